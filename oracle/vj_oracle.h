@@ -1,0 +1,120 @@
+/*
+ * vj_oracle.h -- CPU restatement ("REF-SI") of the reference's Viola-Jones hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under clfacedetection_b200/ may include, link or
+ * call this; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs use it, and only as the checker / CPU baseline.
+ *
+ * PARITY STATUS: the reference (GabrieleCocco/CLFaceDetection) ships no tests, golden
+ * vectors or recorded outputs, and cannot be compiled here (needs OpenCV 2.4.2, the
+ * author's un-vendored CLUtil library and an OpenCL runtime).  The cascade evaluator
+ * below is therefore "parity unpinned" by the reference itself: it is a literal
+ * restatement of tempcv.cpp (C expression types kept as written).  The pieces that
+ * live in OpenCV (resize, integral, tilted integral, groupRectangles) ARE pinned,
+ * bit-for-bit, against cv2 4.13 in tests/test_oracle_pins.py and by the committed
+ * fixtures under tests/golden/.
+ *
+ * All file:line citations are relative to /root/reference/CLFaceDetection/.
+ */
+#ifndef VJ_ORACLE_H
+#define VJ_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vjo_cascade vjo_cascade;
+
+/* Flat description of a CvHaarClassifierCascade (tempcv.hpp:70-112) as produced by
+ * oracle/cascade_xml.py (restating icvReadHaarClassifier, tempcv.cpp:1750-2089).
+ *   st_*   : one entry per stage
+ *   tr_nnodes : nodes per tree, trees concatenated in stage order
+ *   nd_*   : one entry per node, nodes concatenated in tree order
+ *   nd_rect: [N][3][4] = x,y,w,h   nd_weight: [N][3]
+ *   nd_left/right: >0 = node index in the same tree, <=0 = leaf alpha[-idx]
+ *   alpha  : (nnodes+1) floats per tree, concatenated
+ * Returns NULL (and sets vjo_last_error) on a malformed cascade. */
+vjo_cascade *vjo_cascade_create(int win_w, int win_h, int n_stages,
+                                const int *st_ntrees, const float *st_thr,
+                                const int *st_parent, const int *st_next,
+                                const int *tr_nnodes,
+                                const int *nd_tilted, const int *nd_rect,
+                                const float *nd_weight, const float *nd_thr,
+                                const int *nd_left, const int *nd_right,
+                                const float *alpha);
+void vjo_cascade_free(vjo_cascade *c);
+const char *vjo_last_error(void);
+
+/* bit0 is_tree, bit1 isStumpBased, bit2 has_tilted_features (tempcv.cpp:371,431,465) */
+int vjo_cascade_flags(const vjo_cascade *c);
+int vjo_cascade_counts(const vjo_cascade *c, int *n_stages, int *n_trees, int *n_nodes);
+/* hidden-cascade values at scale 1 (tempcv.cpp:419,453-458,733,752-760) */
+void vjo_cascade_hid(const vjo_cascade *c, float *node_weights /*[N][3]*/,
+                     int *node_nrects /*[N]*/, float *stage_thr /*[S]*/,
+                     int *stage_two_rects /*[S]*/, int *stage_child /*[S]*/);
+
+/* cvResize(INTER_LINEAR) for 8-bit single channel (OpenCV imgproc, external; call
+ * site tempcv.cpp:1301).  Returns 0 on success. */
+int vjo_resize_linear(const uint8_t *src, int sw, int sh, int sstride,
+                      uint8_t *dst, int dw, int dh, int dstride);
+
+/* cvIntegral (external; call site tempcv.cpp:1302).  sum/tilted are int32
+ * [(h+1)][(w+1)], sqsum is double (exact integers).  tilted may be NULL. */
+void vjo_integral(const uint8_t *img, int w, int h, int stride,
+                  int32_t *sum, double *sqsum, int32_t *tilted);
+
+/* Level loop of the CV_HAAR_SCALE_IMAGE path (tempcv.cpp:1230-1234,1268-1288) and the
+ * window grid of the invoker (tempcv.cpp:1013-1021,1079-1080).
+ * Fills up to max_levels entries; returns the number of levels.  A zero max_w/max_h
+ * means "image size" (tempcv.cpp:1230-1234). */
+typedef struct vjo_level {
+    double factor;
+    int img_w, img_h;   /* sz   */
+    int win_w, win_h;   /* winSize (output rect size) */
+    int ystep;
+    int nx, ny;         /* windows per row / rows of windows */
+} vjo_level;
+int vjo_plan_levels(int W, int H, int w0, int h0, double scale_factor,
+                    int min_w, int min_h, int max_w, int max_h,
+                    vjo_level *levels, int max_levels);
+
+typedef struct vjo_stats {
+    int64_t windows;           /* windows evaluated */
+    int64_t weak_evals;        /* weak classifiers (trees) evaluated */
+    int64_t node_evals;        /* tree nodes evaluated */
+    int64_t accepted;          /* windows accepted */
+    int64_t near_stage_thr;    /* windows with |stage_sum-thr| <= 1e-5*|thr| at some stage */
+    int64_t stage_reach[64];   /* windows that evaluated stage i (i<64) */
+} vjo_stats;
+
+/* Whole REF-SI detection of one 8-bit gray frame.
+ *   rects     : out, [cap][4] = x,y,w,h in raster order per level (NULL to skip)
+ *   codes     : out, int16 per window, levels concatenated (level l at offset
+ *               sum_{k<l} nx_k*ny_k); linear cascades: number of stages passed
+ *               (count = accepted); stage-tree cascades: 2*last_stage + accepted.
+ *   near      : out, uint8 per window, 1 if some evaluated stage sum was within
+ *               1e-5 relative of its threshold.  codes / near may be NULL.
+ * Returns the number of accepted windows (may exceed cap; only cap are written),
+ * or -1 on error. */
+int64_t vjo_detect(const vjo_cascade *c, const uint8_t *img, int W, int H, int stride,
+                   double scale_factor, int min_w, int min_h, int max_w, int max_h,
+                   int32_t *rects, int64_t cap, int16_t *codes, uint8_t *near,
+                   vjo_stats *stats, int n_threads);
+
+/* Evaluate every grid window of ONE level whose image is given directly (no resize):
+ * used by unit tests of the evaluator. */
+int64_t vjo_eval_level(const vjo_cascade *c, const uint8_t *img, int w, int h, int stride,
+                       int ystep, int16_t *codes, uint8_t *near, vjo_stats *stats,
+                       int n_threads);
+
+/* AgroupRectangles(rectList, weights, groupThreshold, eps) (tempcv.cpp:130-243).
+ * rects in/out [n][4]; weights out [n]; returns the new count. */
+int vjo_group_rectangles(int32_t *rects, int n, int group_threshold, double eps,
+                         int32_t *weights);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
