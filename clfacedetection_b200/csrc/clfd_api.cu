@@ -1,0 +1,849 @@
+// clfd_api.cu -- implementation of the C ABI (include/clfd_b200.h): contexts, cascade
+// objects, the pyramid / integral plan, the detector plan and its enqueue / fetch calls.
+// Host-side planning restates the level loop of cvHaarDetectObjectsForROC's
+// CV_HAAR_SCALE_IMAGE branch (tempcv.cpp:1230-1234,1268-1288) and the window grid of its
+// invoker (tempcv.cpp:1013-1021); all pixel work is in kernels_clif.cu / kernels_clod.cu.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "clfd_pack.h"
+#include "kernels.h"
+
+using namespace clfd;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            set_error("CUDA error %s (%s) at %s:%d: %s", cudaGetErrorName(e_), cudaGetErrorString(e_), \
+                      __FILE__, __LINE__, #call);                                                  \
+            return CLFD_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+#define INVALID(...) do { set_error(__VA_ARGS__); return CLFD_ERR_INVALID; } while (0)
+
+static inline int cv_round(double v) { return (int)lrint(v); }
+static inline int cv_floor(double v) { int i = (int)v; return i - (i > v); }
+static inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------
+// objects
+// ------------------------------------------------------------------------------------
+struct clfd_context {
+    int device = 0;
+    int n_sms = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    struct PyramidPlan *scratch = nullptr;   // cached plan of clfd_integral / clfd_resize
+};
+
+struct clfd_cascade {
+    HostCascade host;
+    PackedCascade packed;
+};
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t count) {
+        if (p) { cudaFree(p); p = nullptr; }
+        n = count;
+        if (count == 0) return 0;
+        CK(cudaMalloc((void **)&p, count * sizeof(T)));
+        return 0;
+    }
+    int upload(const std::vector<T> &v, cudaStream_t s) {
+        int rc = alloc(v.size());
+        if (rc) return rc;
+        if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+        return 0;
+    }
+};
+
+// Pyramid + integral plan for frames of W x H and a list of level sizes.
+struct PyramidPlan {
+    int W = 0, H = 0, max_batch = 0;
+    bool want_tilted = false;
+    std::vector<PyrLevel> levels;
+    size_t pyr_frame_stride = 0, sum_frame_stride = 0, col_frame_stride = 0, col_plane_stride = 0;
+    int max_level_w = 0;
+    int64_t pyramid_pixels = 0, bytes_resize = 0, bytes_integral = 0;
+    DevBuf<uint8_t> pyr;
+    DevBuf<int32_t> sum, tilted;
+    DevBuf<unsigned long long> sq;
+    DevBuf<uint32_t> col;
+    DevBuf<PyrLevel> d_levels;
+    DevBuf<int> xofs, yofs;
+    DevBuf<short2> xalpha, ybeta;
+    DevBuf<int4> resize_items, colscan_items, tilted_items, integral_items[6];
+
+    int build(int W_, int H_, const std::vector<std::pair<int, int>> &sizes, int batch, bool tilt, cudaStream_t s);
+    void fill_args(PyramidArgs &a, const uint8_t *frames, size_t frame_stride, int row_stride, int n_frames) const;
+    int run(clfd_context *ctx, const uint8_t *frames, size_t frame_stride, int row_stride, int n_frames,
+            cudaStream_t s, cudaEvent_t *ev, int *n_launch);
+};
+
+int PyramidPlan::build(int W_, int H_, const std::vector<std::pair<int, int>> &sizes, int batch, bool tilt,
+                       cudaStream_t s) {
+    W = W_; H = H_; max_batch = batch; want_tilted = tilt;
+    levels.clear();
+    std::vector<int> h_xofs, h_yofs;
+    std::vector<short2> h_xalpha, h_ybeta;
+    std::vector<int4> h_resize, h_colscan, h_tilted, h_integral[6];
+    size_t pyr_off = 0, sum_off = 0, col_off = 0;
+    max_level_w = 0; pyramid_pixels = 0; bytes_resize = 0; bytes_integral = 0;
+    for (size_t li = 0; li < sizes.size(); li++) {
+        const int w = sizes[li].first, h = sizes[li].second;
+        if (w <= 0 || h <= 0) INVALID("pyramid level %zu has empty size %dx%d", li, w, h);
+        PyrLevel L;
+        memset(&L, 0, sizeof L);
+        L.w = w; L.h = h;
+        L.pyr_pitch = (int)round_up(w, 16);
+        L.sum_pitch = (int)round_up(w + 1, 8);
+        L.nrb = (h + kRowBlock - 1) / kRowBlock;
+        L.xtab_off = (int)h_xofs.size(); L.ytab_off = (int)h_yofs.size();
+        L.pyr_off = (long long)pyr_off; L.sum_off = (long long)sum_off; L.col_off = (long long)col_off;
+        pyr_off += round_up((size_t)L.pyr_pitch * h, 256);
+        sum_off += round_up((size_t)L.sum_pitch * (h + 1), 64);
+        col_off += (size_t)L.nrb * L.sum_pitch;
+        max_level_w = std::max(max_level_w, w);
+        pyramid_pixels += (int64_t)w * h;
+        // algorithmic bytes: resize min(W*H, 4*w*h) + w*h ; integral w*h + (w+1)(h+1)(4+8+4T)
+        bytes_resize += std::min<int64_t>((int64_t)W * H, 4ll * w * h) + (int64_t)w * h;
+        bytes_integral += (int64_t)w * h + (int64_t)(w + 1) * (h + 1) * (4 + 8 + (tilt ? 4 : 0));
+
+        // cv::resize INTER_LINEAR coefficient tables (OpenCV imgproc)
+        const double scale_x = 1. / ((double)w / W), scale_y = 1. / ((double)h / H);
+        for (int dx = 0; dx < w; dx++) {
+            float fx = (float)((dx + 0.5) * scale_x - 0.5);
+            int sx = cv_floor(fx);
+            fx -= sx;
+            if (sx < 0) { fx = 0; sx = 0; }
+            if (sx >= W - 1) { fx = 0; sx = W - 1; }
+            h_xofs.push_back(sx);
+            h_xalpha.push_back(make_short2((short)lrintf((1.f - fx) * 2048), (short)lrintf(fx * 2048)));
+        }
+        for (int dy = 0; dy < h; dy++) {
+            float fy = (float)((dy + 0.5) * scale_y - 0.5);
+            int sy = cv_floor(fy);
+            fy -= sy;
+            h_yofs.push_back(sy);
+            h_ybeta.push_back(make_short2((short)lrintf((1.f - fy) * 2048), (short)lrintf(fy * 2048)));
+        }
+        const int xspan = std::max(L.pyr_pitch, L.sum_pitch);
+        for (int rb = 0; rb < L.nrb; rb++)
+            for (int c = 0; c * 512 < xspan; c++) h_resize.push_back(make_int4((int)li, rb, c, 0));
+        for (int c = 0; c * 512 < L.sum_pitch; c++) h_colscan.push_back(make_int4((int)li, c, 0, 0));
+        int cls = 0;
+        while (cls < 6 && (32 << cls) * 8 < L.sum_pitch) cls++;
+        if (cls >= 6) INVALID("level width %d exceeds the supported maximum of 8191 pixels", w);
+        for (int rb = 0; rb < L.nrb; rb++) h_integral[cls].push_back(make_int4((int)li, rb, 0, 0));
+        h_tilted.push_back(make_int4((int)li, 0, 0, 0));
+        levels.push_back(L);
+    }
+    pyr_frame_stride = round_up(pyr_off, 256);
+    sum_frame_stride = round_up(sum_off + 1024, 64);   // slack: tile rows may read past a level's last row
+    col_plane_stride = round_up(col_off, 8);
+    col_frame_stride = 2 * col_plane_stride;
+
+    int rc = 0;
+    if ((rc = pyr.alloc(pyr_frame_stride * batch + 256))) return rc;
+    if ((rc = sum.alloc(sum_frame_stride * batch + 4096))) return rc;
+    if ((rc = sq.alloc(sum_frame_stride * batch + 4096))) return rc;
+    if (tilt && (rc = tilted.alloc(sum_frame_stride * batch + 4096))) return rc;
+    if ((rc = col.alloc(col_frame_stride * batch + 64))) return rc;
+    if ((rc = d_levels.upload(levels, s))) return rc;
+    if ((rc = xofs.upload(h_xofs, s)) || (rc = yofs.upload(h_yofs, s))) return rc;
+    if ((rc = xalpha.upload(h_xalpha, s)) || (rc = ybeta.upload(h_ybeta, s))) return rc;
+    if ((rc = resize_items.upload(h_resize, s)) || (rc = colscan_items.upload(h_colscan, s))) return rc;
+    if ((rc = tilted_items.upload(h_tilted, s))) return rc;
+    for (int k = 0; k < 6; k++)
+        if ((rc = integral_items[k].upload(h_integral[k], s))) return rc;
+    // the slack regions are read (never used) by TMA row copies: keep them defined
+    CK(cudaMemsetAsync(sum.p, 0, sum.n * sizeof(int32_t), s));
+    CK(cudaStreamSynchronize(s));   // host vectors go out of scope
+    return 0;
+}
+
+void PyramidPlan::fill_args(PyramidArgs &a, const uint8_t *frames, size_t frame_stride, int row_stride,
+                            int n_frames) const {
+    memset(&a, 0, sizeof a);
+    a.frames = frames; a.frame_stride = frame_stride; a.row_stride = row_stride; a.W = W; a.H = H;
+    a.n_frames = n_frames;
+    a.pyr = pyr.p; a.pyr_frame_stride = pyr_frame_stride;
+    a.col = col.p; a.col_frame_stride = col_frame_stride; a.col_plane_stride = col_plane_stride;
+    a.sum = sum.p; a.sq = sq.p; a.tilted = want_tilted ? tilted.p : nullptr;
+    a.sum_frame_stride = sum_frame_stride;
+    a.levels = d_levels.p; a.n_levels = (int)levels.size();
+    a.xofs = xofs.p; a.xalpha = xalpha.p; a.yofs = yofs.p; a.ybeta = ybeta.p;
+    a.resize_items = resize_items.p; a.n_resize_items = (int)resize_items.n;
+    a.colscan_items = colscan_items.p; a.n_colscan_items = (int)colscan_items.n;
+    for (int k = 0; k < 6; k++) { a.integral_items[k] = integral_items[k].p; a.n_integral_items[k] = (int)integral_items[k].n; }
+    a.tilted_items = tilted_items.p; a.n_tilted_items = want_tilted ? (int)tilted_items.n : 0;
+    a.max_level_w = max_level_w;
+}
+
+// ev (optional): 5 events recorded before K1, K2, K3, K4 and after K4
+int PyramidPlan::run(clfd_context *ctx, const uint8_t *frames, size_t frame_stride, int row_stride, int n_frames,
+                     cudaStream_t s, cudaEvent_t *ev, int *n_launch) {
+    if (n_frames <= 0 || n_frames > max_batch) INVALID("n_frames %d outside 1..%d", n_frames, max_batch);
+    if (row_stride < W) INVALID("row stride %d smaller than the frame width %d", row_stride, W);
+    PyramidArgs a;
+    fill_args(a, frames, frame_stride, row_stride, n_frames);
+    int launches = 0, nint = 0;
+    if (ev) CK(cudaEventRecord(ev[0], s));
+    CK(launch_resize_colsum(a, s)); launches++;
+    if (ev) CK(cudaEventRecord(ev[1], s));
+    CK(launch_colscan(a, s)); launches++;
+    if (ev) CK(cudaEventRecord(ev[2], s));
+    CK(launch_integral_rows(a, s, &nint)); launches += nint;
+    if (ev) CK(cudaEventRecord(ev[3], s));
+    if (want_tilted) { CK(launch_tilted(a, s)); launches++; }
+    if (ev) CK(cudaEventRecord(ev[4], s));
+    ctx->launches += launches;
+    if (n_launch) *n_launch = launches;
+    return 0;
+}
+
+struct CascadePlan {
+    const clfd_cascade *cascade = nullptr;
+    std::vector<CasLevel> levels;
+    std::vector<clfd_level> pub_levels;
+    int n_tiles = 0;
+    long long windows_per_frame = 0;
+    int64_t bytes_cascade = 0;
+    DevBuf<CasLevel> d_levels;
+    DevBuf<DeepStage> d_stages;
+    DevBuf<DeepNode> d_nodes;
+    DevBuf<int> d_tree_first;
+    DevBuf<float> d_alpha;
+    DevBuf<int16_t> d_codes;
+    DevBuf<unsigned long long> d_counters;
+    unsigned long long h_counters[4] = {0, 0, 0, 0};
+};
+
+struct clfd_detector {
+    clfd_context *ctx = nullptr;
+    clfd_detector_config cfg;
+    PyramidPlan pyr;
+    std::vector<std::unique_ptr<CascadePlan>> cas;
+    DevBuf<QueueItem> queue;
+    DevBuf<DevRect> rects;
+    DevBuf<uint8_t> dev_frames;      // staging for host input (clfd_detect)
+    DevRect *h_rects = nullptr;      // pinned
+    unsigned long long *h_counters = nullptr;  // pinned, 4 per cascade
+    unsigned long long rect_cap = 0, queue_cap = 0;
+    int last_frames = 0;
+    clfd_run_stats stats;
+    bool profiling = false;
+    cudaEvent_t ev[16] = {nullptr};
+    float kernel_ms[8] = {0};
+    bool have_events = false;
+    ~clfd_detector() {
+        if (h_rects) cudaFreeHost(h_rects);
+        if (h_counters) cudaFreeHost(h_counters);
+        for (auto &e : ev) if (e) cudaEventDestroy(e);
+    }
+};
+
+// ------------------------------------------------------------------------------------
+// misc
+// ------------------------------------------------------------------------------------
+extern "C" {
+
+const char *clfd_last_error(void) { return get_error(); }
+const char *clfd_version(void) { return "clfd_b200 0.1 (sm_100a)"; }
+
+int clfd_device_count(int *count) {
+    if (!count) INVALID("count is NULL");
+    CK(cudaGetDeviceCount(count));
+    return 0;
+}
+
+int clfd_context_create(int device_index, clfd_context **out) {
+    if (!out) INVALID("out is NULL");
+    *out = nullptr;
+    int n = 0;
+    CK(cudaGetDeviceCount(&n));
+    if (n <= 0) { set_error("no CUDA device is visible: this library has no CPU fallback"); return CLFD_ERR_CUDA; }
+    if (device_index < 0 || device_index >= n) INVALID("device index %d outside 0..%d", device_index, n - 1);
+    CK(cudaSetDevice(device_index));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device_index));
+    if (prop.major < 10) {
+        set_error("device %d (%s) is sm_%d%d; this library is built for sm_100a only", device_index, prop.name,
+                  prop.major, prop.minor);
+        return CLFD_ERR_CUDA;
+    }
+    std::unique_ptr<clfd_context> ctx(new clfd_context());
+    ctx->device = device_index;
+    ctx->n_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    *out = ctx.release();
+    return 0;
+}
+
+void clfd_context_destroy(clfd_context *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    delete ctx->scratch;
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int clfd_context_device(const clfd_context *ctx) { return ctx ? ctx->device : -1; }
+int64_t clfd_context_launch_count(const clfd_context *ctx) { return ctx ? ctx->launches : 0; }
+int clfd_context_synchronize(clfd_context *ctx) {
+    if (!ctx) INVALID("ctx is NULL");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// cascades
+// ------------------------------------------------------------------------------------
+int clfd_cascade_load_xml(const char *path, clfd_cascade **out) {
+    if (!path || !out) INVALID("NULL argument");
+    *out = nullptr;
+    std::unique_ptr<clfd_cascade> c(new clfd_cascade());
+    int rc = load_cascade_xml(path, c->host);
+    if (rc) return rc;
+    pack_cascade(c->host, c->packed);
+    *out = c.release();
+    return 0;
+}
+
+int clfd_cascade_from_arrays(int win_w, int win_h, int n_stages, const int *st_ntrees, const float *st_thr,
+                             const int *st_parent, const int *st_next, const int *tr_nnodes,
+                             const int *nd_tilted, const int *nd_rect, const float *nd_weight,
+                             const float *nd_thr, const int *nd_left, const int *nd_right, const float *alpha,
+                             clfd_cascade **out) {
+    if (!out || !st_ntrees || !st_thr || !st_parent || !st_next || !tr_nnodes || !nd_tilted || !nd_rect ||
+        !nd_weight || !nd_thr || !nd_left || !nd_right || !alpha)
+        INVALID("NULL argument");
+    *out = nullptr;
+    if (n_stages <= 0) { set_error("Number of stages should be positive"); return CLFD_ERR_FORMAT; }
+    std::unique_ptr<clfd_cascade> c(new clfd_cascade());
+    HostCascade &h = c->host;
+    h.win_w = win_w; h.win_h = win_h;
+    long T = 0, N = 0;
+    for (int i = 0; i < n_stages; i++) {
+        if (st_ntrees[i] <= 0) { set_error("header of the stage classifier #%d is invalid", i); return CLFD_ERR_FORMAT; }
+        T += st_ntrees[i];
+    }
+    for (long t = 0; t < T; t++) {
+        if (tr_nnodes[t] <= 0) { set_error("Tree node is not a valid sequence. (tree %ld)", t); return CLFD_ERR_FORMAT; }
+        N += tr_nnodes[t];
+    }
+    h.st_ntrees.assign(st_ntrees, st_ntrees + n_stages);
+    h.st_thr.assign(st_thr, st_thr + n_stages);
+    h.st_parent.assign(st_parent, st_parent + n_stages);
+    h.st_next.assign(st_next, st_next + n_stages);
+    h.tr_nnodes.assign(tr_nnodes, tr_nnodes + T);
+    h.nodes.resize(N);
+    for (long n = 0; n < N; n++) {
+        HostNode &nd = h.nodes[n];
+        nd.tilted = nd_tilted[n] != 0;
+        for (int k = 0; k < 3; k++) {
+            for (int q = 0; q < 4; q++) nd.rect[k][q] = nd_rect[(n * 3 + k) * 4 + q];
+            nd.weight[k] = nd_weight[n * 3 + k];
+        }
+        nd.threshold = nd_thr[n];
+        nd.left = nd_left[n]; nd.right = nd_right[n];
+    }
+    h.alpha.assign(alpha, alpha + N + T);
+    int rc = build_hidden(h);
+    if (rc) return rc;
+    pack_cascade(h, c->packed);
+    *out = c.release();
+    return 0;
+}
+
+void clfd_cascade_destroy(clfd_cascade *c) { delete c; }
+
+int clfd_cascade_get_info(const clfd_cascade *c, clfd_cascade_info *info) {
+    if (!c || !info) INVALID("NULL argument");
+    const HostCascade &h = c->host;
+    memset(info, 0, sizeof *info);
+    info->win_w = h.win_w; info->win_h = h.win_h;
+    info->n_stages = h.n_stages(); info->n_trees = h.n_trees(); info->n_nodes = h.n_nodes();
+    info->is_tree = h.is_tree; info->is_stump_based = h.is_stump_based; info->has_tilted = h.has_tilted;
+    for (int n = 0; n < h.n_nodes(); n++) {
+        info->n_tilted_nodes += h.nodes[n].tilted != 0;
+        info->n_three_rect_nodes += h.hid_nrects[n] == 3;
+    }
+    for (int v : h.st_ntrees) info->max_trees_per_stage = std::max(info->max_trees_per_stage, v);
+    for (int v : h.tr_nnodes) info->max_nodes_per_tree = std::max(info->max_nodes_per_tree, v);
+    info->dense_stages = c->packed.dense.n_stages;
+    info->dense_stumps = c->packed.dense_stumps;
+    for (int v : h.order_free) info->order_free_stages += v;
+    info->packed_bytes = (int)(c->packed.deep_stages.size() * sizeof(DeepStage) + c->packed.deep_nodes.size() * sizeof(DeepNode) +
+                               c->packed.tree_first_node.size() * 4 + c->packed.alpha.size() * 4 + sizeof(DenseParams));
+    return 0;
+}
+
+int clfd_cascade_get_arrays(const clfd_cascade *c, int *st_ntrees, float *st_thr, int *st_parent, int *st_next,
+                            int *st_child, int *tr_nnodes, int *nd_tilted, int *nd_rect, float *nd_weight,
+                            float *nd_thr, int *nd_left, int *nd_right, float *alpha) {
+    if (!c) INVALID("NULL cascade");
+    const HostCascade &h = c->host;
+    const int S = h.n_stages(), T = h.n_trees(), N = h.n_nodes();
+    if (st_ntrees) memcpy(st_ntrees, h.st_ntrees.data(), S * sizeof(int));
+    if (st_thr) memcpy(st_thr, h.st_thr.data(), S * sizeof(float));
+    if (st_parent) memcpy(st_parent, h.st_parent.data(), S * sizeof(int));
+    if (st_next) memcpy(st_next, h.st_next.data(), S * sizeof(int));
+    if (st_child) memcpy(st_child, h.st_child.data(), S * sizeof(int));
+    if (tr_nnodes) memcpy(tr_nnodes, h.tr_nnodes.data(), T * sizeof(int));
+    for (int n = 0; n < N; n++) {
+        const HostNode &nd = h.nodes[n];
+        if (nd_tilted) nd_tilted[n] = nd.tilted;
+        if (nd_rect) memcpy(nd_rect + (size_t)n * 12, nd.rect, 12 * sizeof(int));
+        if (nd_weight) memcpy(nd_weight + (size_t)n * 3, nd.weight, 3 * sizeof(float));
+        if (nd_thr) nd_thr[n] = nd.threshold;
+        if (nd_left) nd_left[n] = nd.left;
+        if (nd_right) nd_right[n] = nd.right;
+    }
+    if (alpha) memcpy(alpha, h.alpha.data(), (size_t)(N + T) * sizeof(float));
+    return 0;
+}
+
+int clfd_cascade_get_hidden(const clfd_cascade *c, float *node_weights, int *node_nrects, float *stage_thr,
+                            int *stage_two_rects) {
+    if (!c) INVALID("NULL cascade");
+    const HostCascade &h = c->host;
+    if (node_weights) memcpy(node_weights, h.hid_weight.data(), h.hid_weight.size() * sizeof(float));
+    if (node_nrects) memcpy(node_nrects, h.hid_nrects.data(), h.hid_nrects.size() * sizeof(int));
+    if (stage_thr) memcpy(stage_thr, h.hid_thr.data(), h.hid_thr.size() * sizeof(float));
+    if (stage_two_rects) memcpy(stage_two_rects, h.two_rects.data(), h.two_rects.size() * sizeof(int));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// clif: stand-alone integral / resize / gray
+// ------------------------------------------------------------------------------------
+static int scratch_plan(clfd_context *ctx, int W, int H, int lw, int lh, bool tilt, PyramidPlan **out) {
+    PyramidPlan *p = ctx->scratch;
+    if (!p || p->W != W || p->H != H || p->levels.size() != 1 || p->levels[0].w != lw || p->levels[0].h != lh ||
+        (tilt && !p->want_tilted)) {
+        delete ctx->scratch;
+        ctx->scratch = nullptr;
+        p = new PyramidPlan();
+        int rc = p->build(W, H, {{lw, lh}}, 1, tilt, ctx->stream);
+        if (rc) { delete p; return rc; }
+        ctx->scratch = p;
+    }
+    *out = p;
+    return 0;
+}
+
+// copies a host or device 8-bit image into a fresh device buffer when it lives on the host
+struct InputImage {
+    const uint8_t *dev = nullptr;
+    uint8_t *owned = nullptr;
+    int stride = 0;
+    ~InputImage() { if (owned) cudaFree(owned); }
+    int set(const uint8_t *img, int wbytes, int h, int stride_, int on_device, cudaStream_t s) {
+        if (on_device) { dev = img; stride = stride_; return 0; }
+        stride = (int)round_up(wbytes, 16);
+        CK(cudaMalloc((void **)&owned, (size_t)stride * h + 16));
+        CK(cudaMemcpy2DAsync(owned, stride, img, stride_, wbytes, h, cudaMemcpyHostToDevice, s));
+        dev = owned;
+        return 0;
+    }
+};
+
+int clfd_integral(clfd_context *ctx, const uint8_t *img, int w, int h, int stride, int img_on_device,
+                  int32_t *sum, uint64_t *sqsum, int32_t *tilted, int out_on_device) {
+    if (!ctx || !img) INVALID("NULL argument");
+    if (w <= 0 || h <= 0 || stride < w) INVALID("bad image geometry %dx%d stride %d", w, h, stride);
+    CK(cudaSetDevice(ctx->device));
+    PyramidPlan *p = nullptr;
+    int rc = scratch_plan(ctx, w, h, w, h, tilted != nullptr, &p);
+    if (rc) return rc;
+    InputImage in;
+    if ((rc = in.set(img, w, h, stride, img_on_device, ctx->stream))) return rc;
+    const bool keep_tilt = p->want_tilted;
+    p->want_tilted = tilted != nullptr;
+    rc = p->run(ctx, in.dev, 0, in.stride, 1, ctx->stream, nullptr, nullptr);
+    p->want_tilted = keep_tilt;
+    if (rc) return rc;
+    const PyrLevel &L = p->levels[0];
+    const cudaMemcpyKind kind = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const size_t W1 = (size_t)w + 1;
+    if (sum) CK(cudaMemcpy2DAsync(sum, W1 * 4, p->sum.p + L.sum_off, (size_t)L.sum_pitch * 4, W1 * 4, h + 1, kind, ctx->stream));
+    if (sqsum) CK(cudaMemcpy2DAsync(sqsum, W1 * 8, p->sq.p + L.sum_off, (size_t)L.sum_pitch * 8, W1 * 8, h + 1, kind, ctx->stream));
+    if (tilted) CK(cudaMemcpy2DAsync(tilted, W1 * 4, p->tilted.p + L.sum_off, (size_t)L.sum_pitch * 4, W1 * 4, h + 1, kind, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int clfd_resize(clfd_context *ctx, const uint8_t *src, int sw, int sh, int sstride, int src_on_device,
+                uint8_t *dst, int dw, int dh, int dstride, int dst_on_device) {
+    if (!ctx || !src || !dst) INVALID("NULL argument");
+    if (sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0 || sstride < sw || dstride < dw) INVALID("bad geometry");
+    CK(cudaSetDevice(ctx->device));
+    PyramidPlan *p = nullptr;
+    int rc = scratch_plan(ctx, sw, sh, dw, dh, false, &p);
+    if (rc) return rc;
+    InputImage in;
+    if ((rc = in.set(src, sw, sh, sstride, src_on_device, ctx->stream))) return rc;
+    PyramidArgs a;
+    p->fill_args(a, in.dev, 0, in.stride, 1);
+    CK(launch_resize_colsum(a, ctx->stream));
+    ctx->launches++;
+    const PyrLevel &L = p->levels[0];
+    CK(cudaMemcpy2DAsync(dst, dstride, p->pyr.p + L.pyr_off, L.pyr_pitch, dw, dh,
+                         dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int clfd_bgr_to_gray(clfd_context *ctx, const uint8_t *bgr, int w, int h, int stride, int channels,
+                     int src_on_device, uint8_t *gray, int gstride, int dst_on_device) {
+    if (!ctx || !bgr || !gray) INVALID("NULL argument");
+    if (w <= 0 || h <= 0 || (channels != 3 && channels != 4) || stride < w * channels || gstride < w)
+        INVALID("bad geometry");
+    CK(cudaSetDevice(ctx->device));
+    InputImage in;
+    int rc = in.set(bgr, w * channels, h, stride, src_on_device, ctx->stream);
+    if (rc) return rc;
+    uint8_t *out = gray;
+    int ostride = gstride;
+    DevBuf<uint8_t> tmp;
+    if (!dst_on_device) {
+        ostride = (int)round_up(w, 16);
+        if ((rc = tmp.alloc((size_t)ostride * h))) return rc;
+        out = tmp.p;
+    }
+    CK(launch_bgr_to_gray(in.dev, w, h, in.stride, channels, out, ostride, ctx->stream));
+    ctx->launches++;
+    if (!dst_on_device) CK(cudaMemcpy2DAsync(gray, gstride, out, ostride, w, h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// detector
+// ------------------------------------------------------------------------------------
+int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades, int n_cascades,
+                         const clfd_detector_config *cfg, clfd_detector **out) {
+    if (!ctx || !cascades || !cfg || !out) INVALID("NULL argument");
+    *out = nullptr;
+    if (n_cascades <= 0 || n_cascades > 16) INVALID("n_cascades %d outside 1..16", n_cascades);
+    if (cfg->width <= 0 || cfg->height <= 0 || cfg->max_batch <= 0 || cfg->max_batch > 65535)
+        INVALID("bad frame geometry / batch");
+    if (!(cfg->scale_factor > 1)) INVALID("scale factor must be > 1");   // tempcv.cpp:1224-1225
+    if (cfg->width > 65535 || cfg->height > 65535) INVALID("frame too large");
+    CK(cudaSetDevice(ctx->device));
+    std::unique_ptr<clfd_detector> det(new clfd_detector());
+    det->ctx = ctx; det->cfg = *cfg;
+    memset(&det->stats, 0, sizeof det->stats);
+    const int W = cfg->width, H = cfg->height;
+    int max_w = cfg->max_w, max_h = cfg->max_h;
+    if (max_h == 0 || max_w == 0) { max_h = H; max_w = W; }   // tempcv.cpp:1230-1234
+
+    // level loop, all cascades in lock step over the shared factor sequence
+    std::vector<std::pair<int, int>> sizes;          // union pyramid
+    std::map<int, int> pyr_index;                    // factor index -> pyramid level
+    std::vector<bool> done(n_cascades, false);
+    bool any_tilted = false;
+    for (int ci = 0; ci < n_cascades; ci++) {
+        if (!cascades[ci]) INVALID("cascade %d is NULL", ci);
+        det->cas.emplace_back(new CascadePlan());
+        det->cas.back()->cascade = cascades[ci];
+        any_tilted |= cascades[ci]->host.has_tilted;
+    }
+    double factor = 1;
+    for (int k = 0;; k++, factor *= cfg->scale_factor) {
+        bool all_done = true;
+        if (k >= 255) INVALID("more than 255 pyramid levels");
+        const int sz_w = cv_round(W / factor), sz_h = cv_round(H / factor);
+        for (int ci = 0; ci < n_cascades; ci++) {
+            if (done[ci]) continue;
+            const HostCascade &hc = cascades[ci]->host;
+            const int win_w = cv_round(hc.win_w * factor), win_h = cv_round(hc.win_h * factor);
+            const int sz1_w = sz_w - hc.win_w + 1, sz1_h = sz_h - hc.win_h + 1;
+            if (sz1_w <= 0 || sz1_h <= 0) { done[ci] = true; continue; }                 // :1283
+            if (win_w > max_w || win_h > max_h) { done[ci] = true; continue; }           // :1285
+            all_done = false;
+            if (win_w < cfg->min_w || win_h < cfg->min_h) continue;                      // :1287
+            const int ystep = factor > 2 ? 1 : 2;                                        // :1021
+            const int xe = sz_w - hc.win_w, ye = sz_h - hc.win_h;                        // :1015-1020
+            const int nx = xe > 0 ? (xe + ystep - 1) / ystep : 0, ny = ye > 0 ? (ye + ystep - 1) / ystep : 0;
+            if (nx == 0 || ny == 0) continue;
+            if (!pyr_index.count(k)) { pyr_index[k] = (int)sizes.size(); sizes.push_back({sz_w, sz_h}); }
+            CascadePlan &cp = *det->cas[ci];
+            CasLevel CL;
+            memset(&CL, 0, sizeof CL);
+            CL.pyr_level = pyr_index[k];
+            CL.nx = nx; CL.ny = ny; CL.ystep = ystep; CL.win_w = win_w; CL.win_h = win_h;
+            CL.tiles_x = (nx + kTileW - 1) / kTileW; CL.tiles_y = (ny + kTileH - 1) / kTileH;
+            CL.tile_base = cp.n_tiles; CL.win_base = cp.windows_per_frame; CL.factor = factor;
+            cp.n_tiles += CL.tiles_x * CL.tiles_y;
+            cp.windows_per_frame += (long long)nx * ny;
+            cp.bytes_cascade += (int64_t)(sz_w + 1) * (sz_h + 1) * (4 + 8 + (hc.has_tilted ? 4 : 0));
+            if (cp.levels.size() >= 255) INVALID("more than 255 levels");
+            cp.levels.push_back(CL);
+            clfd_level pl;
+            pl.factor = factor; pl.img_w = sz_w; pl.img_h = sz_h; pl.win_w = win_w; pl.win_h = win_h;
+            pl.ystep = ystep; pl.nx = nx; pl.ny = ny; pl.win_base = CL.win_base;
+            cp.pub_levels.push_back(pl);
+        }
+        if (all_done) break;
+    }
+    cudaStream_t s = ctx->stream;
+    int rc = 0;
+    if (!sizes.empty() && (rc = det->pyr.build(W, H, sizes, cfg->max_batch, any_tilted, s))) return rc;
+    else if (sizes.empty()) { det->pyr.W = W; det->pyr.H = H; det->pyr.max_batch = cfg->max_batch; }
+
+    long long max_wpf = 0;
+    for (auto &cpp : det->cas) {
+        CascadePlan &cp = *cpp;
+        const PackedCascade &pk = cp.cascade->packed;
+        if ((rc = cp.d_levels.upload(cp.levels, s)) || (rc = cp.d_stages.upload(pk.deep_stages, s)) ||
+            (rc = cp.d_nodes.upload(pk.deep_nodes, s)) || (rc = cp.d_tree_first.upload(pk.tree_first_node, s)) ||
+            (rc = cp.d_alpha.upload(pk.alpha, s)))
+            return rc;
+        if ((rc = cp.d_counters.alloc(4))) return rc;
+        if (cfg->want_codes && (rc = cp.d_codes.alloc((size_t)std::max<long long>(cp.windows_per_frame, 1) * cfg->max_batch)))
+            return rc;
+        max_wpf = std::max(max_wpf, cp.windows_per_frame);
+        cp.bytes_cascade += cp.cascade->packed.deep_nodes.size() * sizeof(DeepNode);
+    }
+    det->queue_cap = (unsigned long long)std::max<long long>(max_wpf, 1) * cfg->max_batch;
+    det->rect_cap = cfg->max_rects > 0 ? (unsigned long long)cfg->max_rects : (1ull << 20);
+    if ((rc = det->queue.alloc(det->queue_cap)) || (rc = det->rects.alloc(det->rect_cap))) return rc;
+    CK(cudaMallocHost((void **)&det->h_rects, det->rect_cap * sizeof(DevRect)));
+    CK(cudaMallocHost((void **)&det->h_counters, 4 * 16 * sizeof(unsigned long long)));
+    CK(cudaStreamSynchronize(s));
+    det->stats.pyramid_pixels = det->pyr.pyramid_pixels;
+    det->stats.bytes_resize = det->pyr.bytes_resize;
+    det->stats.bytes_integral = det->pyr.bytes_integral;
+    for (auto &cpp : det->cas) det->stats.bytes_cascade += cpp->bytes_cascade;
+    *out = det.release();
+    return 0;
+}
+
+void clfd_detector_destroy(clfd_detector *det) {
+    if (!det) return;
+    cudaSetDevice(det->ctx->device);
+    cudaDeviceSynchronize();
+    delete det;
+}
+
+int clfd_detector_num_levels(const clfd_detector *det, int cascade) {
+    if (!det || cascade < 0 || cascade >= (int)det->cas.size()) return CLFD_ERR_INVALID;
+    return (int)det->cas[cascade]->pub_levels.size();
+}
+
+int clfd_detector_get_levels(const clfd_detector *det, int cascade, clfd_level *levels, int max_levels) {
+    if (!det || !levels || cascade < 0 || cascade >= (int)det->cas.size()) INVALID("bad argument");
+    const auto &v = det->cas[cascade]->pub_levels;
+    if ((int)v.size() > max_levels) { set_error("need room for %zu levels", v.size()); return CLFD_ERR_CAPACITY; }
+    memcpy(levels, v.data(), v.size() * sizeof(clfd_level));
+    return (int)v.size();
+}
+
+int64_t clfd_detector_windows_per_frame(const clfd_detector *det, int cascade) {
+    if (!det || cascade < 0 || cascade >= (int)det->cas.size()) return CLFD_ERR_INVALID;
+    return det->cas[cascade]->windows_per_frame;
+}
+
+int clfd_detector_set_profiling(clfd_detector *det, int enable) {
+    if (!det) INVALID("NULL detector");
+    CK(cudaSetDevice(det->ctx->device));
+    det->profiling = enable != 0;
+    if (det->profiling)
+        for (auto &e : det->ev)
+            if (!e) CK(cudaEventCreate(&e));
+    return 0;
+}
+
+int clfd_detector_enqueue(clfd_detector *det, const uint8_t *frames_dev, int n_frames, size_t frame_stride,
+                          int row_stride, void *cuda_stream) {
+    if (!det || !frames_dev) INVALID("NULL argument");
+    clfd_context *ctx = det->ctx;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    if (n_frames <= 0 || n_frames > det->cfg.max_batch) INVALID("n_frames %d outside 1..%d", n_frames, det->cfg.max_batch);
+    det->last_frames = n_frames;
+    int launches = 0;
+    cudaEvent_t *ev = det->profiling ? det->ev : nullptr;
+    if (!det->pyr.levels.empty()) {
+        int rc = det->pyr.run(ctx, frames_dev, frame_stride, row_stride, n_frames, s, ev, &launches);
+        if (rc) return rc;
+    }
+    const int pyr_launches = launches;
+    for (auto &cpp : det->cas) CK(cudaMemsetAsync(cpp->d_counters.p, 0, 4 * sizeof(unsigned long long), s));
+    int ci = 0;
+    for (auto &cpp : det->cas) {
+        CascadePlan &cp = *cpp;
+        if (cp.windows_per_frame > 0) {
+            const PackedCascade &pk = cp.cascade->packed;
+            CascadeArgs a;
+            memset(&a, 0, sizeof a);
+            a.sum = det->pyr.sum.p; a.sq = det->pyr.sq.p; a.tilted = det->pyr.want_tilted ? det->pyr.tilted.p : nullptr;
+            a.sum_frame_stride = det->pyr.sum_frame_stride;
+            a.levels = det->pyr.d_levels.p; a.cas_levels = cp.d_levels.p;
+            a.n_cas_levels = (int)cp.levels.size(); a.n_tiles = cp.n_tiles; a.n_frames = n_frames;
+            a.cascade_index = ci; a.windows_per_frame = cp.windows_per_frame;
+            a.codes = det->cfg.want_codes ? cp.d_codes.p : nullptr;
+            a.queue = det->queue.p; a.queue_cap = det->queue_cap;
+            a.rects = det->rects.p; a.rect_cap = det->rect_cap;
+            a.counters = cp.d_counters.p;
+            a.deep.stages = cp.d_stages.p; a.deep.tree_first_node = cp.d_tree_first.p;
+            a.deep.nodes = cp.d_nodes.p; a.deep.alpha = cp.d_alpha.p;
+            a.deep.n_stages = cp.cascade->host.n_stages(); a.deep.is_tree = cp.cascade->host.is_tree;
+            a.deep.has_tilted = cp.cascade->host.has_tilted;
+            a.deep.win_w = cp.cascade->host.win_w; a.deep.win_h = cp.cascade->host.win_h;
+            a.deep.inv_area = pk.dense.inv_area;
+            if (ev && ci == 0) CK(cudaEventRecord(ev[5], s));
+            if (pk.dense.n_stages > 0) CK(launch_cascade_tiles(pk.dense, a, s));
+            else CK(launch_enqueue_all(a, s));
+            launches++;
+            if (ev && ci == 0) CK(cudaEventRecord(ev[6], s));
+            if (pk.dense.n_stages < pk.dense.total_stages) { CK(launch_cascade_deep(a, ctx->n_sms, s)); launches++; }
+            if (ev && ci == 0) CK(cudaEventRecord(ev[7], s));
+        }
+        // all cascades append to one rect buffer: carry the rect count over
+        if (ci + 1 < (int)det->cas.size())
+            CK(cudaMemcpyAsync(det->cas[ci + 1]->d_counters.p, cp.d_counters.p, sizeof(unsigned long long),
+                               cudaMemcpyDeviceToDevice, s));
+        ci++;
+    }
+    det->have_events = ev != nullptr;
+    ctx->launches += launches - pyr_launches;   // PyramidPlan::run counted its own
+    det->stats.kernel_launches = launches;
+    return 0;
+}
+
+int clfd_detector_fetch(clfd_detector *det, clfd_rect *rects, int64_t cap, int64_t *n_rects, void *cuda_stream) {
+    if (!det || !n_rects) INVALID("NULL argument");
+    clfd_context *ctx = det->ctx;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    const int nc = (int)det->cas.size();
+    for (int ci = 0; ci < nc; ci++)
+        CK(cudaMemcpyAsync(det->h_counters + 4 * ci, det->cas[ci]->d_counters.p, 4 * sizeof(unsigned long long),
+                           cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    unsigned long long total = det->h_counters[4 * (nc - 1)];
+    unsigned long long deep = 0, rect_over = 0, queue_over = 0;
+    for (int ci = 0; ci < nc; ci++) {
+        memcpy(det->cas[ci]->h_counters, det->h_counters + 4 * ci, 4 * sizeof(unsigned long long));
+        deep += det->h_counters[4 * ci + 1];
+        rect_over += det->h_counters[4 * ci + 2];
+        queue_over += det->h_counters[4 * ci + 3];
+    }
+    if (queue_over) { set_error("survivor queue overflow (%llu windows dropped)", queue_over); return CLFD_ERR_CAPACITY; }
+    det->stats.rects = (int64_t)total;
+    det->stats.deep_windows = (int64_t)deep;
+    det->stats.windows = 0;
+    for (auto &cpp : det->cas) det->stats.windows += cpp->windows_per_frame * det->last_frames;
+    *n_rects = (int64_t)total;
+    if (rect_over || total > det->rect_cap) {
+        set_error("device rect buffer overflow: %llu accepted windows, capacity %llu (raise max_rects)", total, det->rect_cap);
+        return CLFD_ERR_CAPACITY;
+    }
+    if (det->have_events) {
+        // [0] resize+colsum [1] colscan [2] integral rows [3] tilted [4] tile kernel [5] deep kernel
+        cudaEventElapsedTime(&det->kernel_ms[0], det->ev[0], det->ev[1]);
+        cudaEventElapsedTime(&det->kernel_ms[1], det->ev[1], det->ev[2]);
+        cudaEventElapsedTime(&det->kernel_ms[2], det->ev[2], det->ev[3]);
+        cudaEventElapsedTime(&det->kernel_ms[3], det->ev[3], det->ev[4]);
+        cudaEventElapsedTime(&det->kernel_ms[4], det->ev[5], det->ev[6]);
+        cudaEventElapsedTime(&det->kernel_ms[5], det->ev[6], det->ev[7]);
+    }
+    if (total == 0 || !rects) return 0;
+    if ((int64_t)total > cap) { set_error("rect buffer too small: need %llu, have %lld", total, (long long)cap); return CLFD_ERR_CAPACITY; }
+    CK(cudaMemcpyAsync(det->h_rects, det->rects.p, total * sizeof(DevRect), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    static_assert(sizeof(DevRect) == sizeof(clfd_rect), "rect layout");
+    memcpy(rects, det->h_rects, total * sizeof(DevRect));
+    return 0;
+}
+
+int clfd_detect(clfd_detector *det, const uint8_t *frames_host, int n_frames, size_t frame_stride, int row_stride,
+                clfd_rect *rects, int64_t cap, int64_t *n_rects) {
+    if (!det || !frames_host) INVALID("NULL argument");
+    clfd_context *ctx = det->ctx;
+    CK(cudaSetDevice(ctx->device));
+    const int W = det->cfg.width, H = det->cfg.height;
+    if (n_frames <= 0 || n_frames > det->cfg.max_batch) INVALID("n_frames %d outside 1..%d", n_frames, det->cfg.max_batch);
+    if (row_stride < W) INVALID("row stride %d smaller than the frame width %d", row_stride, W);
+    const size_t dstride = round_up(W, 16), dframe = dstride * H;
+    if (!det->dev_frames.p) {
+        int rc = det->dev_frames.alloc(dframe * det->cfg.max_batch + 64);
+        if (rc) return rc;
+    }
+    if ((size_t)row_stride == dstride && frame_stride == dframe) {
+        CK(cudaMemcpyAsync(det->dev_frames.p, frames_host, dframe * n_frames, cudaMemcpyHostToDevice, ctx->stream));
+    } else if (frame_stride == (size_t)row_stride * H) {
+        CK(cudaMemcpy2DAsync(det->dev_frames.p, dstride, frames_host, row_stride, W, (size_t)H * n_frames,
+                             cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        for (int f = 0; f < n_frames; f++)
+            CK(cudaMemcpy2DAsync(det->dev_frames.p + f * dframe, dstride, frames_host + f * frame_stride, row_stride, W, H,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    }
+    int rc = clfd_detector_enqueue(det, det->dev_frames.p, n_frames, dframe, (int)dstride, nullptr);
+    if (rc) return rc;
+    return clfd_detector_fetch(det, rects, cap, n_rects, nullptr);
+}
+
+int clfd_detector_get_codes(clfd_detector *det, int cascade, int16_t *codes, int64_t cap) {
+    if (!det || !codes || cascade < 0 || cascade >= (int)det->cas.size()) INVALID("bad argument");
+    if (!det->cfg.want_codes) INVALID("detector was created without want_codes");
+    CK(cudaSetDevice(det->ctx->device));
+    CascadePlan &cp = *det->cas[cascade];
+    const int64_t n = cp.windows_per_frame * det->last_frames;
+    if (n > cap) { set_error("codes buffer too small: need %lld", (long long)n); return CLFD_ERR_CAPACITY; }
+    CK(cudaDeviceSynchronize());
+    if (n > 0) CK(cudaMemcpy(codes, cp.d_codes.p, n * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int clfd_detector_read_level(clfd_detector *det, int cascade, int level, int frame, uint8_t *pyr, int32_t *sum,
+                             uint64_t *sqsum, int32_t *tilted) {
+    if (!det || cascade < 0 || cascade >= (int)det->cas.size()) INVALID("bad argument");
+    CascadePlan &cp = *det->cas[cascade];
+    if (level < 0 || level >= (int)cp.levels.size()) INVALID("level %d outside 0..%zu", level, cp.levels.size());
+    if (frame < 0 || frame >= det->last_frames) INVALID("frame %d outside the last batch", frame);
+    if (tilted && !det->pyr.want_tilted) INVALID("detector has no tilted integral (no cascade with tilted features)");
+    CK(cudaSetDevice(det->ctx->device));
+    CK(cudaDeviceSynchronize());
+    const PyrLevel &L = det->pyr.levels[cp.levels[level].pyr_level];
+    const size_t W1 = (size_t)L.w + 1;
+    const size_t so = (size_t)frame * det->pyr.sum_frame_stride + L.sum_off;
+    if (pyr) CK(cudaMemcpy2D(pyr, L.w, det->pyr.pyr.p + (size_t)frame * det->pyr.pyr_frame_stride + L.pyr_off, L.pyr_pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    if (sum) CK(cudaMemcpy2D(sum, W1 * 4, det->pyr.sum.p + so, (size_t)L.sum_pitch * 4, W1 * 4, L.h + 1, cudaMemcpyDeviceToHost));
+    if (sqsum) CK(cudaMemcpy2D(sqsum, W1 * 8, det->pyr.sq.p + so, (size_t)L.sum_pitch * 8, W1 * 8, L.h + 1, cudaMemcpyDeviceToHost));
+    if (tilted) CK(cudaMemcpy2D(tilted, W1 * 4, det->pyr.tilted.p + so, (size_t)L.sum_pitch * 4, W1 * 4, L.h + 1, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int clfd_detector_get_stats(clfd_detector *det, clfd_run_stats *stats) {
+    if (!det || !stats) INVALID("NULL argument");
+    *stats = det->stats;
+    return 0;
+}
+
+int clfd_detector_get_kernel_ms(clfd_detector *det, float ms[8]) {
+    if (!det || !ms) INVALID("NULL argument");
+    if (!det->have_events) INVALID("profiling was not enabled for the last enqueue");
+    memcpy(ms, det->kernel_ms, sizeof det->kernel_ms);
+    return 0;
+}
+
+}  // extern "C"

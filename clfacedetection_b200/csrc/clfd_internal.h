@@ -1,0 +1,151 @@
+// clfd_internal.h -- structures shared by the host side (loader, packer, planner) and the
+// CUDA kernels.  Not part of the ABI (include/clfd_b200.h is).
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "clfd_b200.h"
+
+namespace clfd {
+
+// ------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
+
+// ------------------------------------------------------------------------------------
+// Host cascade: CvHaarClassifierCascade content (tempcv.hpp:70-112) + hidden cascade
+// ------------------------------------------------------------------------------------
+struct HostNode {
+    int tilted;
+    int rect[3][4];   // x,y,w,h
+    float weight[3];  // as in the XML
+    float threshold;
+    int left, right;
+};
+
+struct HostCascade {
+    std::string name;
+    int win_w = 0, win_h = 0;
+    std::vector<int> st_ntrees, st_parent, st_next, st_child;
+    std::vector<float> st_thr;
+    std::vector<int> tr_nnodes;
+    std::vector<HostNode> nodes;
+    std::vector<float> alpha;
+    // hidden cascade (filled by build_hidden)
+    bool is_tree = false, is_stump_based = true, has_tilted = false;
+    std::vector<float> hid_weight;  // [N][3]
+    std::vector<int> hid_nrects;    // [N]
+    std::vector<float> hid_thr;     // [S]  xml - 0.0001f
+    std::vector<int> two_rects;     // [S]
+    std::vector<int> order_free;    // [S]  alpha sum exact in any order
+    std::vector<int> st_first_tree; // [S+1]
+    std::vector<int> tr_first_node; // [T+1]
+    int n_stages() const { return (int)st_ntrees.size(); }
+    int n_trees() const { return (int)tr_nnodes.size(); }
+    int n_nodes() const { return (int)nodes.size(); }
+};
+
+// haar_xml.cpp: restates icvReadHaarClassifier (tempcv.cpp:1750-2089). 0 or clfd_status.
+int load_cascade_xml(const char *path, HostCascade &out);
+// haar_pack.cpp: validation + icvCreateHidHaarClassifierCascade + scale-1 weights.
+int build_hidden(HostCascade &c);
+
+// ------------------------------------------------------------------------------------
+// Device blobs
+// ------------------------------------------------------------------------------------
+// Tile geometry of the smem-tile ("dense") cascade kernel: TW x TH windows per CTA.
+constexpr int kTileW = 64;
+constexpr int kTileH = 32;
+constexpr int kTileWindows = kTileW * kTileH;
+constexpr int kDenseThreads = 256;
+constexpr int kMaxDenseStumps = 600;
+constexpr int kMaxDenseStages = 32;
+constexpr int kHandoffWindows = 8;  // <= this many survivors in a tile: hand them to the deep kernel
+
+// One stump of the dense kernel, 48 B, read through the constant bank (kernel params).
+struct DenseStump {
+    uint16_t off[12];  // BYTE offsets into the smem tile of p0..p3 of rect 0,1,2 (rect 2: zeros if absent)
+    float w[3];        // hidden weights (w[2] = 0 if absent)
+    float thr;
+    float a0, a1;      // alpha[0] (sum < t), alpha[1] (sum >= t)
+};
+struct DenseStage {
+    uint16_t first, count;
+    float thr;         // biased threshold
+    uint32_t flags;    // bit0 two_rects (double products), bit1 any 3-rect stump
+    uint32_t pad;
+};
+struct DenseParams {
+    int n_stages;       // dense stages (prefix of the cascade)
+    int total_stages;   // stages in the whole cascade
+    int tile_stride;    // ints per smem tile row
+    int win_w, win_h;
+    int pad[3];
+    double inv_area;
+    DenseStage stage[kMaxDenseStages];
+    DenseStump stump[kMaxDenseStumps];
+};
+
+// Generic ("deep") cascade in global memory: any tree shape, tilted, stage tree.
+struct DeepNode {          // 64 B
+    uint8_t dx[12], dy[12];  // corner coordinates of p0..p3 of rect 0,1,2 relative to the window
+    float w[3];
+    float thr;
+    int left, right;         // >0 node index in tree, <=0 leaf -idx
+    int flags;               // bit0 tilted, bits 8.. nrects
+    int pad[3];
+};
+struct DeepStage {         // 32 B
+    int first_tree, ntrees;
+    float thr;
+    int flags;               // bit0 two_rects, bit1 order_free, bit2 all trees are stumps
+    int parent, next, child;
+    int pad;
+};
+struct DeepCascadeDev {
+    const DeepStage *stages;
+    const int *tree_first_node;  // [T+1]; alpha base of tree t = tree_first_node[t] + t
+    const DeepNode *nodes;
+    const float *alpha;
+    int n_stages, is_tree, has_tilted, win_w, win_h;
+    double inv_area;
+};
+
+// Pyramid level (shared by all cascades of a detector)
+struct PyrLevel {
+    int w, h;
+    int pyr_pitch;       // bytes, multiple of 16
+    int sum_pitch;       // elements, multiple of 8 (>= w+1)
+    int nrb;             // row blocks of kRowBlock rows
+    int xtab_off, ytab_off;
+    int pad;
+    long long pyr_off;   // byte offset inside a frame's pyramid block
+    long long sum_off;   // element offset inside a frame's sum / sqsum / tilted block
+    long long col_off;   // element offset inside a frame's column-sum block
+};
+constexpr int kRowBlock = 32;
+
+// Per cascade, per level it evaluates
+struct CasLevel {
+    int pyr_level;
+    int nx, ny, ystep;
+    int win_w, win_h;     // output rect size
+    int tiles_x, tiles_y, tile_base;
+    int pad;
+    long long win_base;
+    double factor;
+};
+
+struct QueueItem {        // survivor handed to the deep kernel
+    uint32_t key;           // frame << 16 | cas_level << 8 | next_stage
+    uint32_t xy;            // y << 16 | x   (window origin, pixels of the level)
+};
+
+struct DevRect {
+    int x, y, w, h, frame, cascade;
+};
+
+}  // namespace clfd

@@ -1,0 +1,23 @@
+// clfd_pack.h -- host-side packed cascade (device-ready arrays) and helpers.
+#pragma once
+#include "clfd_internal.h"
+
+namespace clfd {
+
+struct PackedCascade {
+    DenseParams dense;                 // kernel-parameter blob of the smem-tile kernel
+    int dense_stumps = 0;
+    std::vector<DeepStage> deep_stages;  // global-memory blob of the deep kernel
+    std::vector<DeepNode> deep_nodes;
+    std::vector<int> tree_first_node;
+    std::vector<float> alpha;
+};
+
+void pack_cascade(const HostCascade &c, PackedCascade &out);
+const char *get_error();
+
+int dense_tile_stride(int win_w);            // ints per smem tile row (ystep-2 worst case)
+int dense_tile_rows(int win_h, int ystep);   // integral rows a tile needs
+int dense_tile_cols(int win_w, int ystep);   // integral columns a tile needs (multiple of 4)
+
+}  // namespace clfd

@@ -1,0 +1,94 @@
+// group_rects.cpp -- host-side rectangle grouping (the north star keeps it on the host).
+// Semantics of AgroupRectangles(rectList, weights, groupThreshold, eps)
+// (tempcv.cpp:145-243) with ASimilarRects (tempcv.cpp:130-143); cv::partition (external
+// OpenCV, call site tempcv.cpp:160) = connected components of the similarity relation,
+// classes numbered by their first member.  Replaces the reference's own filterResult
+// (clod.cpp:282-357), which is defective.
+#include <climits>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "clfd_internal.h"
+
+namespace {
+
+struct R4 { int x, y, w, h; };
+
+inline bool similar(const R4 &a, const R4 &b, double eps) {
+    const double delta = eps * (std::min(a.w, b.w) + std::min(a.h, b.h)) * 0.5;
+    return std::abs(a.x - b.x) <= delta && std::abs(a.y - b.y) <= delta &&
+           std::abs(a.x + a.w - b.x - b.w) <= delta && std::abs(a.y + a.h - b.y - b.h) <= delta;
+}
+
+struct DisjointSets {
+    std::vector<int> parent;
+    explicit DisjointSets(int n) : parent(n) { std::iota(parent.begin(), parent.end(), 0); }
+    int find(int i) {
+        int r = i;
+        while (parent[r] != r) r = parent[r];
+        while (parent[i] != r) { int nx = parent[i]; parent[i] = r; i = nx; }
+        return r;
+    }
+    void unite(int a, int b) { a = find(a); b = find(b); if (a != b) parent[std::max(a, b)] = std::min(a, b); }
+};
+
+inline int trunc_sat(float v) { return v > (float)INT_MAX ? INT_MAX : (int)v; }
+
+}  // namespace
+
+extern "C" int clfd_group_rectangles(int32_t *rects_xywh, int *n_io, int group_threshold, double eps,
+                                     int32_t *weights) {
+    if (!rects_xywh || !n_io || *n_io < 0) { clfd::set_error("bad argument"); return CLFD_ERR_INVALID; }
+    const int n = *n_io;
+    if (group_threshold <= 0 || n == 0) {  // tempcv.cpp:147-157
+        if (weights) for (int i = 0; i < n; i++) weights[i] = 1;
+        return 0;
+    }
+    const R4 *in = reinterpret_cast<const R4 *>(rects_xywh);
+    DisjointSets ds(n);
+    for (int i = 0; i < n; i++)
+        for (int j = i + 1; j < n; j++)
+            if (similar(in[i], in[j], eps)) ds.unite(i, j);
+    // with min-index roots, a class's root IS its first member: label order = root order
+    std::vector<int> label(n, -1);
+    int nclasses = 0;
+    for (int i = 0; i < n; i++)
+        if (ds.find(i) == i) label[i] = nclasses++;
+    std::vector<long long> acc((size_t)nclasses * 4, 0);
+    std::vector<int> count(nclasses, 0);
+    for (int i = 0; i < n; i++) {  // :167-175 (int accumulation in the reference)
+        const int c = label[ds.find(i)];
+        acc[c * 4 + 0] += in[i].x; acc[c * 4 + 1] += in[i].y; acc[c * 4 + 2] += in[i].w; acc[c * 4 + 3] += in[i].h;
+        count[c]++;
+    }
+    std::vector<R4> mean(nclasses);
+    for (int c = 0; c < nclasses; c++) {  // :191-199: float reciprocal, truncation
+        const float s = 1.f / count[c];
+        mean[c].x = trunc_sat((int)acc[c * 4 + 0] * s); mean[c].y = trunc_sat((int)acc[c * 4 + 1] * s);
+        mean[c].w = trunc_sat((int)acc[c * 4 + 2] * s); mean[c].h = trunc_sat((int)acc[c * 4 + 3] * s);
+    }
+    int out = 0;
+    std::vector<R4> kept;
+    std::vector<int> kept_w;
+    for (int i = 0; i < nclasses; i++) {  // :207-242
+        const R4 r1 = mean[i];
+        const int n1 = count[i];
+        if (n1 <= group_threshold) continue;
+        bool nested = false;
+        for (int j = 0; j < nclasses && !nested; j++) {
+            const int n2 = count[j];
+            if (j == i || n2 <= group_threshold) continue;
+            const R4 r2 = mean[j];
+            const int dx = trunc_sat((float)(r2.w * eps)), dy = trunc_sat((float)(r2.h * eps));
+            nested = r1.x >= r2.x - dx && r1.y >= r2.y - dy && r1.x + r1.w <= r2.x + r2.w + dx &&
+                     r1.y + r1.h <= r2.y + r2.h + dy && (n2 > std::max(3, n1) || n1 < 3);
+        }
+        if (!nested) { kept.push_back(r1); kept_w.push_back(n1); out++; }
+    }
+    memcpy(rects_xywh, kept.data(), (size_t)out * sizeof(R4));
+    if (weights) memcpy(weights, kept_w.data(), (size_t)out * sizeof(int));
+    *n_io = out;
+    return 0;
+}

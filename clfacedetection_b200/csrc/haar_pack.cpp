@@ -1,0 +1,269 @@
+// haar_pack.cpp -- hidden-cascade construction and device packing.
+//
+// build_hidden restates, for scale = 1 (the only scale REF-SI uses, tempcv.cpp:1321):
+//   * icvCreateHidHaarClassifierCascade (tempcv.cpp:308-467): rectangle bounds checks,
+//     stage threshold bias (-0.0001f, :419), two_rects (:421,453-458), isStumpBased (:465),
+//     is_tree (:431), has_tilted_features (:371);
+//   * cvSetImagesForHaarClassifierCascade (tempcv.cpp:549-768): weight_k =
+//     (float)(xml_weight_k * inv_area * (tilted ? 0.5 : 1)) (:733,752) and weight_0 =
+//     (float)(-sum_{k>=1} weight_k*w_k*h_k / (w_0*h_0)) (:754-760), C expression types kept.
+// This replaces the per-scale precomputeKernelCascade of clod.cpp:529-578: in the pyramid
+// formulation the packed cascade is scale independent and is built once per cascade.
+//
+// This translation unit must be compiled with -ffp-contract=off.
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "clfd_pack.h"
+
+namespace clfd {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+}
+const char *get_error() { return g_error; }
+
+#define FMT_FAIL(...) do { set_error(__VA_ARGS__); return CLFD_ERR_FORMAT; } while (0)
+
+int build_hidden(HostCascade &c) {
+    const int S = c.n_stages();
+    if (S <= 0) FMT_FAIL("Number of stages should be positive");
+    if (c.win_w <= 2 || c.win_h <= 2) FMT_FAIL("cascade window %dx%d is too small", c.win_w, c.win_h);
+    if ((int)c.st_thr.size() != S || (int)c.st_parent.size() != S || (int)c.st_next.size() != S)
+        FMT_FAIL("stage arrays have inconsistent sizes");
+    c.st_first_tree.assign(S + 1, 0);
+    for (int i = 0; i < S; i++) {
+        if (c.st_ntrees[i] <= 0)
+            FMT_FAIL("header of the stage classifier #%d is invalid (has null pointers or non-positive classfier count)", i);
+        c.st_first_tree[i + 1] = c.st_first_tree[i] + c.st_ntrees[i];
+    }
+    const int T = c.st_first_tree[S];
+    if ((int)c.tr_nnodes.size() != T) FMT_FAIL("tree count does not match the stage headers");
+    c.tr_first_node.assign(T + 1, 0);
+    for (int t = 0; t < T; t++) {
+        if (c.tr_nnodes[t] <= 0) FMT_FAIL("Tree node is not a valid sequence. (tree %d)", t);
+        c.tr_first_node[t + 1] = c.tr_first_node[t] + c.tr_nnodes[t];
+    }
+    const int N = c.tr_first_node[T];
+    if ((int)c.nodes.size() != N) FMT_FAIL("node count does not match the tree headers");
+    if ((int)c.alpha.size() != N + T) FMT_FAIL("alpha count does not match the tree headers");
+
+    if ((int)c.st_child.size() != S) {  // derive child links (tempcv.cpp:2076-2083)
+        c.st_child.assign(S, -1);
+        for (int i = 0; i < S; i++) {
+            int p = c.st_parent[i];
+            if (p != -1 && c.st_child[p] == -1) c.st_child[p] = i;
+        }
+    }
+
+    c.is_tree = false; c.is_stump_based = true; c.has_tilted = false;
+    c.hid_weight.assign((size_t)N * 3, 0.f);
+    c.hid_nrects.assign(N, 2);
+    c.hid_thr.assign(S, 0.f);
+    c.two_rects.assign(S, 1);
+    c.order_free.assign(S, 0);
+
+    const float stage_threshold_bias = 0.0001f;  // tempcv.cpp:262
+    const int eq_w = c.win_w - 2, eq_h = c.win_h - 2;  // equRect at scale 1 (tempcv.cpp:614-616)
+    const double weight_scale = 1. / (eq_w * eq_h);    // :617
+
+    for (int i = 0; i < S; i++) {
+        if (c.st_parent[i] < -1 || c.st_parent[i] >= S) FMT_FAIL("parent must be integer number. (stage %d)", i);
+        if (c.st_next[i] < -1 || c.st_next[i] >= S) FMT_FAIL("next must be integer number. (stage %d)", i);
+        c.hid_thr[i] = c.st_thr[i] - stage_threshold_bias;  // float - float, :419
+        c.is_tree |= c.st_next[i] != -1;                    // :431
+        for (int t = c.st_first_tree[i]; t < c.st_first_tree[i + 1]; t++) {
+            const int cnt = c.tr_nnodes[t];
+            c.is_stump_based &= cnt == 1;  // :465
+            for (int l = 0; l < cnt; l++) {
+                const int n = c.tr_first_node[t] + l;
+                const HostNode &nd = c.nodes[n];
+                if (nd.left >= cnt || nd.right >= cnt || -nd.left > cnt || -nd.right > cnt)
+                    FMT_FAIL("Tree structure is broken (stage %d, tree %d, node %d)", i, t - c.st_first_tree[i], l);
+                for (int k = 0; k < 3; k++) {  // :365-387
+                    const int *r = nd.rect[k];
+                    if (!r[2]) continue;
+                    c.has_tilted |= nd.tilted != 0;
+                    if (r[2] < 0 || r[3] < 0 || r[1] < 0 || r[0] + r[2] > c.win_w ||
+                        (!nd.tilted && (r[0] < 0 || r[1] + r[3] > c.win_h)) ||
+                        (nd.tilted && (r[0] - r[3] < 0 || r[1] + r[2] + r[3] > c.win_h)))
+                        FMT_FAIL("rectangle #%d of the classifier #%d of the stage classifier #%d is not inside "
+                                 "the reference (original) cascade window", k, t - c.st_first_tree[i], i);
+                }
+                int nr = 3;  // :453-458
+                if (fabs(nd.weight[2]) < DBL_EPSILON || nd.rect[2][2] == 0 || nd.rect[2][3] == 0)
+                    nr = 2;
+                else
+                    c.two_rects[i] = 0;
+                c.hid_nrects[n] = nr;
+                if (nd.rect[0][2] <= 0 || nd.rect[0][3] <= 0 || nd.rect[1][2] <= 0 || nd.rect[1][3] <= 0)
+                    FMT_FAIL("node needs at least two rectangles (stage %d, tree %d, node %d)", i, t - c.st_first_tree[i], l);
+                // scale-1 weights, tempcv.cpp:692-760 (tr == r at scale 1)
+                double sum0 = 0, area0 = 0;
+                float *hw = &c.hid_weight[(size_t)n * 3];
+                const double correction_ratio = weight_scale * (!nd.tilted ? 1 : 0.5);  // :733
+                for (int k = 0; k < nr; k++) {
+                    const int tw = nd.rect[k][2], th = nd.rect[k][3];
+                    hw[k] = (float)(nd.weight[k] * correction_ratio);  // :752
+                    if (k == 0)
+                        area0 = tw * th;
+                    else
+                        sum0 += hw[k] * tw * th;  // float*int*int evaluated in float, :757
+                }
+                hw[0] = (float)(-sum0 / area0);  // :760
+            }
+        }
+        // Is the stage's alpha sum exact in double whatever the order?  Every alpha is a
+        // multiple of 2^(e_min-23); if sum|alpha| < 2^53 * 2^(e_min-23) every partial sum of
+        // any subset is representable, so a parallel reduction equals the sequential one.
+        {
+            int e_min = 1 << 20;
+            double abs_sum = 0;
+            bool ok = true;
+            for (int t = c.st_first_tree[i]; t < c.st_first_tree[i + 1]; t++) {
+                const int a0 = c.tr_first_node[t] + t, a1 = a0 + c.tr_nnodes[t] + 1;
+                float amax = 0;
+                for (int a = a0; a < a1; a++) {
+                    float v = c.alpha[a];
+                    if (!std::isfinite(v)) { ok = false; continue; }
+                    if (v == 0.f) continue;
+                    int e;
+                    frexpf(fabsf(v), &e);  // |v| = m * 2^e, m in [0.5,1): multiple of 2^(e-24)
+                    if (e - 24 < e_min) e_min = e - 24;
+                    if (fabsf(v) > amax) amax = fabsf(v);
+                }
+                abs_sum += amax;  // one leaf per tree contributes
+            }
+            if (ok) {
+                if (e_min == (1 << 20)) c.order_free[i] = 1;  // all zeros
+                else c.order_free[i] = abs_sum < ldexp(1.0, 52 + e_min) ? 1 : 0;
+            }
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// device packing
+// ------------------------------------------------------------------------------------
+static void corner_coords(const HostNode &nd, int k, int dx[4], int dy[4]) {
+    const int x = nd.rect[k][0], y = nd.rect[k][1], w = nd.rect[k][2], h = nd.rect[k][3];
+    if (!nd.tilted) {  // tempcv.cpp:738-741
+        dy[0] = y;     dx[0] = x;
+        dy[1] = y;     dx[1] = x + w;
+        dy[2] = y + h; dx[2] = x;
+        dy[3] = y + h; dx[3] = x + w;
+    } else {           // tempcv.cpp:745-749
+        dy[0] = y;         dx[0] = x;
+        dy[1] = y + h;     dx[1] = x - h;
+        dy[2] = y + w;     dx[2] = x + w;
+        dy[3] = y + w + h; dx[3] = x + w - h;
+    }
+}
+
+int dense_tile_stride(int win_w) {
+    int cols = (kTileW - 1) * 2 + win_w + 1;
+    return (cols + 3) & ~3;
+}
+int dense_tile_rows(int win_h, int ystep) { return (kTileH - 1) * ystep + win_h + 1; }
+int dense_tile_cols(int win_w, int ystep) { return ((kTileW - 1) * ystep + win_w + 1 + 3) & ~3; }
+
+void pack_cascade(const HostCascade &c, PackedCascade &out) {
+    const int S = c.n_stages(), T = c.n_trees(), N = c.n_nodes();
+    out.deep_stages.resize(S);
+    out.deep_nodes.resize(N);
+    out.tree_first_node = c.tr_first_node;
+    out.alpha = c.alpha;
+    for (int i = 0; i < S; i++) {
+        DeepStage &s = out.deep_stages[i];
+        memset(&s, 0, sizeof s);
+        s.first_tree = c.st_first_tree[i];
+        s.ntrees = c.st_ntrees[i];
+        s.thr = c.hid_thr[i];
+        bool stumps = true;
+        for (int t = s.first_tree; t < s.first_tree + s.ntrees; t++) stumps &= c.tr_nnodes[t] == 1;
+        // double products only on the reference's stump fast path (tempcv.cpp:862,872); stage trees
+        // and multi-node cascades go through icvEvalHidHaarClassifier (float products, :782-786)
+        const bool dbl = !c.is_tree && c.is_stump_based && c.two_rects[i];
+        s.flags = (dbl ? 1 : 0) | (c.order_free[i] ? 2 : 0) | (stumps ? 4 : 0);
+        s.parent = c.st_parent[i]; s.next = c.st_next[i]; s.child = c.st_child[i];
+    }
+    for (int n = 0; n < N; n++) {
+        DeepNode &d = out.deep_nodes[n];
+        memset(&d, 0, sizeof d);
+        const HostNode &nd = c.nodes[n];
+        for (int k = 0; k < c.hid_nrects[n]; k++) {
+            int dx[4], dy[4];
+            corner_coords(nd, k, dx, dy);
+            for (int q = 0; q < 4; q++) { d.dx[k * 4 + q] = (uint8_t)dx[q]; d.dy[k * 4 + q] = (uint8_t)dy[q]; }
+            d.w[k] = c.hid_weight[(size_t)n * 3 + k];
+        }
+        d.thr = nd.threshold;
+        d.left = nd.left; d.right = nd.right;
+        d.flags = (nd.tilted ? 1 : 0) | (c.hid_nrects[n] << 8);
+    }
+    (void)T;
+
+    // dense prefix: leading stages of a stump-based, upright, linear-prefix cascade whose
+    // stumps fit the kernel-parameter budget and whose smem offsets fit 16 bits.
+    DenseParams &P = out.dense;
+    memset(&P, 0, sizeof P);
+    P.total_stages = S;
+    P.win_w = c.win_w; P.win_h = c.win_h;
+    P.tile_stride = dense_tile_stride(c.win_w);
+    P.inv_area = 1. / ((c.win_w - 2) * (c.win_h - 2));
+    P.pad[0] = c.is_tree ? 1 : 0;
+    out.dense_stumps = 0;
+    const size_t tile_bytes = (size_t)dense_tile_rows(c.win_h, 2) * P.tile_stride * 4;
+    bool dense_ok = tile_bytes <= 65536 && c.win_w <= 255 && c.win_h <= 255;
+    int ns = 0, nstump = 0;
+    while (dense_ok && ns < S && ns < kMaxDenseStages) {
+        // in a stage tree only the unconditional linear prefix can be dense: stage i must
+        // be the single child of stage i-1 and have no `next` alternative.
+        if (c.is_tree && (c.st_next[ns] != -1 || c.st_parent[ns] != ns - 1 ||
+                          (ns > 0 && c.st_child[ns - 1] != ns)))
+            break;
+        const int t0 = c.st_first_tree[ns], t1 = c.st_first_tree[ns + 1];
+        if (nstump + (t1 - t0) > kMaxDenseStumps) break;
+        bool ok = true, any3 = false;
+        for (int t = t0; t < t1 && ok; t++) {
+            if (c.tr_nnodes[t] != 1) { ok = false; break; }
+            const int n = c.tr_first_node[t];
+            if (c.nodes[n].tilted) { ok = false; break; }
+            any3 |= c.hid_nrects[n] == 3;
+        }
+        if (!ok) break;
+        DenseStage &ds = P.stage[ns];
+        ds.first = (uint16_t)nstump; ds.count = (uint16_t)(t1 - t0);
+        ds.thr = c.hid_thr[ns];
+        ds.flags = ((!c.is_tree && c.is_stump_based && c.two_rects[ns]) ? 1u : 0u) | (any3 ? 2u : 0u);
+        for (int t = t0; t < t1; t++) {
+            const int n = c.tr_first_node[t];
+            const HostNode &nd = c.nodes[n];
+            DenseStump &st = P.stump[nstump++];
+            for (int k = 0; k < c.hid_nrects[n]; k++) {
+                int dx[4], dy[4];
+                corner_coords(nd, k, dx, dy);
+                for (int q = 0; q < 4; q++) st.off[k * 4 + q] = (uint16_t)((dy[q] * P.tile_stride + dx[q]) * 4);
+                st.w[k] = c.hid_weight[(size_t)n * 3 + k];
+            }
+            st.thr = nd.threshold;
+            const int a = c.tr_first_node[t] + t;  // alpha base of tree t
+            st.a0 = c.alpha[a + (-nd.left)];       // sum <  t -> left  (tempcv.cpp:788)
+            st.a1 = c.alpha[a + (-nd.right)];      // sum >= t -> right
+        }
+        ns++;
+    }
+    P.n_stages = ns;
+    out.dense_stumps = nstump;
+}
+
+}  // namespace clfd

@@ -1,0 +1,61 @@
+// kernels.h -- launchers of the sm_100a kernels (kernels_*.cu).  Every launcher enqueues
+// on `stream` and returns the cudaError_t of the launch.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "clfd_internal.h"
+
+namespace clfd {
+
+// ---- pyramid + integral (clif) ------------------------------------------------------
+struct PyramidArgs {
+    const uint8_t *frames;      // device, n_frames x (H rows of row_stride bytes), frame_stride apart
+    size_t frame_stride;
+    int row_stride, W, H, n_frames;
+    uint8_t *pyr;  size_t pyr_frame_stride;     // bytes
+    uint32_t *col; size_t col_frame_stride;     // elements; plane 0 = sums, plane 1 = squares
+    size_t col_plane_stride;                    // elements
+    int32_t *sum; unsigned long long *sq; int32_t *tilted;   // tilted may be NULL
+    size_t sum_frame_stride;                    // elements (same for sum / sq / tilted)
+    const PyrLevel *levels;                     // device
+    int n_levels;
+    const int *xofs; const short2 *xalpha; const int *yofs; const short2 *ybeta;   // device tables
+    const int4 *resize_items; int n_resize_items;      // (level, row block, column chunk, -)
+    const int4 *colscan_items; int n_colscan_items;    // (level, column chunk, -, -)
+    // integral row-block items grouped by CTA width class: class k uses 32<<k threads
+    const int4 *integral_items[6]; int n_integral_items[6];
+    const int4 *tilted_items; int n_tilted_items;      // (level, -, -, -)
+    int max_level_w;
+};
+cudaError_t launch_resize_colsum(const PyramidArgs &a, cudaStream_t stream);
+cudaError_t launch_colscan(const PyramidArgs &a, cudaStream_t stream);
+cudaError_t launch_integral_rows(const PyramidArgs &a, cudaStream_t stream, int *n_launches);
+cudaError_t launch_tilted(const PyramidArgs &a, cudaStream_t stream);
+
+cudaError_t launch_bgr_to_gray(const uint8_t *bgr, int w, int h, int stride, int channels,
+                               uint8_t *gray, int gstride, cudaStream_t stream);
+
+// ---- cascade (clod) -----------------------------------------------------------------
+struct CascadeArgs {
+    const int32_t *sum; const unsigned long long *sq; const int32_t *tilted;
+    size_t sum_frame_stride;
+    const PyrLevel *levels;         // device
+    const CasLevel *cas_levels;     // device
+    int n_cas_levels, n_tiles, n_frames, cascade_index;
+    long long windows_per_frame;
+    int16_t *codes;                 // device, [n_frames][windows_per_frame] or NULL
+    QueueItem *queue; unsigned long long queue_cap;
+    DevRect *rects; unsigned long long rect_cap;
+    unsigned long long *counters;   // [0] rects  [1] queue items  [2] rect overflow [3] queue overflow
+    DeepCascadeDev deep;
+};
+// dense tile kernel (+ hand-off of survivors to the queue)
+cudaError_t launch_cascade_tiles(const DenseParams &P, const CascadeArgs &a, cudaStream_t stream);
+// fill the queue with every window (cascades without a dense prefix)
+cudaError_t launch_enqueue_all(const CascadeArgs &a, cudaStream_t stream);
+// warp-per-window evaluation of the queue
+cudaError_t launch_cascade_deep(const CascadeArgs &a, int n_sms, cudaStream_t stream);
+
+size_t dense_smem_bytes(const DenseParams &P);
+
+}  // namespace clfd

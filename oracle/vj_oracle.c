@@ -406,7 +406,7 @@ int vjo_plan_levels(int W, int H, int w0, int h0, double scale_factor,
         L->nx = xe > 0 ? (xe + L->ystep - 1) / L->ystep : 0;
         L->ny = ye > 0 ? (ye + L->ystep - 1) / L->ystep : 0;
         if (sz_w + 1 <= 1 + w0) { L->nx = 0; } /* :1017 */
-        if (L->nx == 0 || L->ny == 0) { L->nx = L->ny = 0; }
+        if (L->nx == 0 || L->ny == 0) n--; /* no window fits the grid (:1017-1018): nothing to do */
     }
     return n;
 }

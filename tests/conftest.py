@@ -1,0 +1,40 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DATA = os.path.join(ROOT, "data", "haarcascades")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def cascade_path(name: str) -> str:
+    return os.path.join(DATA, f"haarcascade_{name}.xml")
+
+
+ALL_CASCADES = ["frontalface_alt", "frontalface_default", "frontalface_alt_tree", "eye", "profileface",
+                "fullbody", "frontalface_alt2", "eye_tree_eyeglasses", "mcs_nose"]
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx():
+    import clfacedetection_b200 as clfd
+    ctx = clfd.Context(0)   # raises (no fallback) when there is no GPU / no built library
+    yield ctx
+    ctx.close()
+
+
+_oracle_cache = {}
+
+
+def oracle_cascade(name):
+    import oracle
+    if name not in _oracle_cache:
+        _oracle_cache[name] = oracle.Cascade(cascade_path(name))
+    return _oracle_cache[name]
