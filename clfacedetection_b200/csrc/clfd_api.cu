@@ -220,6 +220,7 @@ struct CascadePlan {
     std::vector<CasLevel> levels;
     std::vector<clfd_level> pub_levels;
     int n_tiles = 0;
+    int n_tiles_y2 = 0;   // tiles of the ystep-2 levels (they come first)
     long long windows_per_frame = 0;
     int64_t bytes_cascade = 0;
     DevBuf<CasLevel> d_levels;
@@ -385,7 +386,7 @@ int clfd_cascade_get_info(const clfd_cascade *c, clfd_cascade_info *info) {
     }
     for (int v : h.st_ntrees) info->max_trees_per_stage = std::max(info->max_trees_per_stage, v);
     for (int v : h.tr_nnodes) info->max_nodes_per_tree = std::max(info->max_nodes_per_tree, v);
-    info->dense_stages = c->packed.dense.n_stages;
+    info->dense_stages = c->packed.dense[0].n_stages;
     info->dense_stumps = c->packed.dense_stumps;
     for (int v : h.order_free) info->order_free_stages += v;
     info->packed_bytes = (int)(c->packed.deep_stages.size() * sizeof(DeepStage) + c->packed.deep_nodes.size() * sizeof(DeepNode) +
@@ -591,6 +592,7 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
             CL.tiles_x = (nx + kTileW - 1) / kTileW; CL.tiles_y = (ny + kTileH - 1) / kTileH;
             CL.tile_base = cp.n_tiles; CL.win_base = cp.windows_per_frame; CL.factor = factor;
             cp.n_tiles += CL.tiles_x * CL.tiles_y;
+            if (ystep == 2) cp.n_tiles_y2 = cp.n_tiles;
             cp.windows_per_frame += (long long)nx * ny;
             cp.bytes_cascade += (int64_t)(sz_w + 1) * (sz_h + 1) * (4 + 8 + (hc.has_tilted ? 4 : 0));
             if (cp.levels.size() >= 255) INVALID("more than 255 levels");
@@ -707,13 +709,21 @@ int clfd_detector_enqueue(clfd_detector *det, const uint8_t *frames_dev, int n_f
             a.deep.n_stages = cp.cascade->host.n_stages(); a.deep.is_tree = cp.cascade->host.is_tree;
             a.deep.has_tilted = cp.cascade->host.has_tilted;
             a.deep.win_w = cp.cascade->host.win_w; a.deep.win_h = cp.cascade->host.win_h;
-            a.deep.inv_area = pk.dense.inv_area;
+            a.deep.inv_area = pk.dense[0].inv_area;
             if (ev && ci == 0) CK(cudaEventRecord(ev[5], s));
-            if (pk.dense.n_stages > 0) CK(launch_cascade_tiles(pk.dense, a, s));
-            else CK(launch_enqueue_all(a, s));
-            launches++;
+            if (pk.dense[0].n_stages > 0) {
+                // ystep-2 levels (de-interleaved tile layout) and ystep-1 levels (natural layout)
+                if (cp.n_tiles_y2 > 0) { CK(launch_cascade_tiles(pk.dense[1], a, 0, cp.n_tiles_y2, s)); launches++; }
+                if (cp.n_tiles > cp.n_tiles_y2) {
+                    CK(launch_cascade_tiles(pk.dense[0], a, cp.n_tiles_y2, cp.n_tiles - cp.n_tiles_y2, s));
+                    launches++;
+                }
+            } else {
+                CK(launch_enqueue_all(a, s));
+                launches++;
+            }
             if (ev && ci == 0) CK(cudaEventRecord(ev[6], s));
-            if (pk.dense.n_stages < pk.dense.total_stages) { CK(launch_cascade_deep(a, ctx->n_sms, s)); launches++; }
+            if (pk.dense[0].n_stages < pk.dense[0].total_stages) { CK(launch_cascade_deep(a, ctx->n_sms, s)); launches++; }
             if (ev && ci == 0) CK(cudaEventRecord(ev[7], s));
         }
         // all cascades append to one rect buffer: carry the rect count over

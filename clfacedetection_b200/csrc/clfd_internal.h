@@ -58,32 +58,44 @@ int build_hidden(HostCascade &c);
 // ------------------------------------------------------------------------------------
 // Tile geometry of the smem-tile ("dense") cascade kernel: TW x TH windows per CTA.
 constexpr int kTileW = 64;
-constexpr int kTileH = 32;
+constexpr int kTileH = 16;
 constexpr int kTileWindows = kTileW * kTileH;
 constexpr int kDenseThreads = 256;
-constexpr int kMaxDenseStumps = 600;
+constexpr int kDenseWarps = kDenseThreads / 32;
+constexpr int kDenseSlots = kTileWindows / kDenseThreads;   // windows per thread (4)
+constexpr int kBucketCap = kTileWindows / 32;                // windows per bank bucket (32)
+constexpr int kMaxDenseStumps = 568;
 constexpr int kMaxDenseStages = 32;
 constexpr int kHandoffWindows = 8;  // <= this many survivors in a tile: hand them to the deep kernel
 
-// One stump of the dense kernel, 48 B, read through the constant bank (kernel params).
+// One stump of the dense kernel, 56 B, read through the constant bank (the packed cascade
+// is a kernel parameter) with uniform loads: the whole warp evaluates the same stump.
 struct DenseStump {
-    uint16_t off[12];  // BYTE offsets into the smem tile of p0..p3 of rect 0,1,2 (rect 2: zeros if absent)
+    uint32_t offp[6];  // 12 x u16 BYTE offsets into the smem tile: p0..p3 of rect 0,1,2 (rect 2: zeros if absent)
     float w[3];        // hidden weights (w[2] = 0 if absent)
     float thr;
-    float a0, a1;      // alpha[0] (sum < t), alpha[1] (sum >= t)
+    double a0, a1;     // alpha[0] (sum < t), alpha[1] (sum >= t), pre-converted (exact)
 };
 struct DenseStage {
     uint16_t first, count;
     float thr;         // biased threshold
-    uint32_t flags;    // bit0 two_rects (double products), bit1 any 3-rect stump
+    uint32_t flags;    // bit0 double-product stage (two_rects fast path), bit1 any 3-rect stump
     uint32_t pad;
 };
+// Two blobs per cascade: [0] for ystep-1 levels (natural tile layout, addr = y*S + x) and
+// [1] for ystep-2 levels (columns de-interleaved: addr = y*S + (x&1)*S/2 + (x>>1)), so that in
+// both a window's base address is  f(wy)*S + wx  with S a multiple of 32 words: the bank of
+// every corner load is (wx + const) mod 32 and lanes holding distinct wx mod 32 never conflict.
 struct DenseParams {
     int n_stages;       // dense stages (prefix of the cascade)
     int total_stages;   // stages in the whole cascade
-    int tile_stride;    // ints per smem tile row
+    int tile_stride;    // ints per smem tile row (multiple of 32)
     int win_w, win_h;
-    int pad[3];
+    int is_tree;        // stage-tree cascade: exit codes are 2*last_stage (+accept)
+    int ystep;          // 1 or 2
+    int force_exact;    // test hook: skip the FP32 filter, evaluate every stage in FP64
+    float filter_eps;   // FP32 filter guard band (2^-20), see kernels_clod.cu
+    int pad;
     double inv_area;
     DenseStage stage[kMaxDenseStages];
     DenseStump stump[kMaxDenseStumps];

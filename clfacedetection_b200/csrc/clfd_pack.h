@@ -5,7 +5,7 @@
 namespace clfd {
 
 struct PackedCascade {
-    DenseParams dense;                 // kernel-parameter blob of the smem-tile kernel
+    DenseParams dense[2];              // kernel-parameter blobs of the smem-tile kernel: [ystep-1]
     int dense_stumps = 0;
     std::vector<DeepStage> deep_stages;  // global-memory blob of the deep kernel
     std::vector<DeepNode> deep_nodes;
@@ -16,8 +16,8 @@ struct PackedCascade {
 void pack_cascade(const HostCascade &c, PackedCascade &out);
 const char *get_error();
 
-int dense_tile_stride(int win_w);            // ints per smem tile row (ystep-2 worst case)
-int dense_tile_rows(int win_h, int ystep);   // integral rows a tile needs
-int dense_tile_cols(int win_w, int ystep);   // integral columns a tile needs (multiple of 4)
+int dense_tile_stride(int win_w, int ystep);  // ints per smem tile row (multiple of 32)
+int dense_tile_rows(int win_h, int ystep);    // integral rows a tile needs
+int dense_tile_cols(int win_w, int ystep);    // integral columns a tile needs (multiple of 4)
 
 }  // namespace clfd

@@ -169,12 +169,15 @@ static void corner_coords(const HostNode &nd, int k, int dx[4], int dy[4]) {
     }
 }
 
-int dense_tile_stride(int win_w) {
-    int cols = (kTileW - 1) * 2 + win_w + 1;
-    return (cols + 3) & ~3;
-}
-int dense_tile_rows(int win_h, int ystep) { return (kTileH - 1) * ystep + win_h + 1; }
 int dense_tile_cols(int win_w, int ystep) { return ((kTileW - 1) * ystep + win_w + 1 + 3) & ~3; }
+int dense_tile_rows(int win_h, int ystep) { return (kTileH - 1) * ystep + win_h + 1; }
+int dense_tile_stride(int win_w, int ystep) {
+    // ystep 1: natural layout, stride >= cols.  ystep 2: even columns in the first half of a
+    // row, odd columns in the second half, stride/2 >= cols/2.  Multiple of 32 words either way.
+    const int cols = dense_tile_cols(win_w, ystep);
+    const int need = ystep == 1 ? cols : 2 * ((cols + 1) / 2);
+    return (need + 31) & ~31;
+}
 
 void pack_cascade(const HostCascade &c, PackedCascade &out) {
     const int S = c.n_stages(), T = c.n_trees(), N = c.n_nodes();
@@ -214,56 +217,66 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
 
     // dense prefix: leading stages of a stump-based, upright, linear-prefix cascade whose
     // stumps fit the kernel-parameter budget and whose smem offsets fit 16 bits.
-    DenseParams &P = out.dense;
-    memset(&P, 0, sizeof P);
-    P.total_stages = S;
-    P.win_w = c.win_w; P.win_h = c.win_h;
-    P.tile_stride = dense_tile_stride(c.win_w);
-    P.inv_area = 1. / ((c.win_w - 2) * (c.win_h - 2));
-    P.pad[0] = c.is_tree ? 1 : 0;
-    out.dense_stumps = 0;
-    const size_t tile_bytes = (size_t)dense_tile_rows(c.win_h, 2) * P.tile_stride * 4;
-    bool dense_ok = tile_bytes <= 65536 && c.win_w <= 255 && c.win_h <= 255;
-    int ns = 0, nstump = 0;
-    while (dense_ok && ns < S && ns < kMaxDenseStages) {
-        // in a stage tree only the unconditional linear prefix can be dense: stage i must
-        // be the single child of stage i-1 and have no `next` alternative.
-        if (c.is_tree && (c.st_next[ns] != -1 || c.st_parent[ns] != ns - 1 ||
-                          (ns > 0 && c.st_child[ns - 1] != ns)))
-            break;
-        const int t0 = c.st_first_tree[ns], t1 = c.st_first_tree[ns + 1];
-        if (nstump + (t1 - t0) > kMaxDenseStumps) break;
-        bool ok = true, any3 = false;
-        for (int t = t0; t < t1 && ok; t++) {
-            if (c.tr_nnodes[t] != 1) { ok = false; break; }
-            const int n = c.tr_first_node[t];
-            if (c.nodes[n].tilted) { ok = false; break; }
-            any3 |= c.hid_nrects[n] == 3;
-        }
-        if (!ok) break;
-        DenseStage &ds = P.stage[ns];
-        ds.first = (uint16_t)nstump; ds.count = (uint16_t)(t1 - t0);
-        ds.thr = c.hid_thr[ns];
-        ds.flags = ((!c.is_tree && c.is_stump_based && c.two_rects[ns]) ? 1u : 0u) | (any3 ? 2u : 0u);
-        for (int t = t0; t < t1; t++) {
-            const int n = c.tr_first_node[t];
-            const HostNode &nd = c.nodes[n];
-            DenseStump &st = P.stump[nstump++];
-            for (int k = 0; k < c.hid_nrects[n]; k++) {
-                int dx[4], dy[4];
-                corner_coords(nd, k, dx, dy);
-                for (int q = 0; q < 4; q++) st.off[k * 4 + q] = (uint16_t)((dy[q] * P.tile_stride + dx[q]) * 4);
-                st.w[k] = c.hid_weight[(size_t)n * 3 + k];
+    for (int yi = 0; yi < 2; yi++) {
+        const int ystep = yi + 1;
+        DenseParams &P = out.dense[yi];
+        memset(&P, 0, sizeof P);
+        P.total_stages = S;
+        P.win_w = c.win_w; P.win_h = c.win_h;
+        P.tile_stride = dense_tile_stride(c.win_w, ystep);
+        P.is_tree = c.is_tree ? 1 : 0;
+        P.ystep = ystep;
+        P.filter_eps = 9.5367431640625e-07f;  // 2^-20
+        P.inv_area = 1. / ((c.win_w - 2) * (c.win_h - 2));
+        const size_t tile_bytes = (size_t)dense_tile_rows(c.win_h, ystep) * P.tile_stride * 4;
+        bool dense_ok = tile_bytes <= 65536 && c.win_w <= 255 && c.win_h <= 255;
+        int ns = 0, nstump = 0;
+        while (dense_ok && ns < S && ns < kMaxDenseStages) {
+            // in a stage tree only the unconditional linear prefix can be dense: stage i must
+            // be the single child of stage i-1 and have no `next` alternative.
+            if (c.is_tree && (c.st_next[ns] != -1 || c.st_parent[ns] != ns - 1 ||
+                              (ns > 0 && c.st_child[ns - 1] != ns)))
+                break;
+            const int t0 = c.st_first_tree[ns], t1 = c.st_first_tree[ns + 1];
+            if (nstump + (t1 - t0) > kMaxDenseStumps) break;
+            bool ok = true, any3 = false;
+            for (int t = t0; t < t1 && ok; t++) {
+                if (c.tr_nnodes[t] != 1) { ok = false; break; }
+                const int n = c.tr_first_node[t];
+                if (c.nodes[n].tilted) { ok = false; break; }
+                any3 |= c.hid_nrects[n] == 3;
             }
-            st.thr = nd.threshold;
-            const int a = c.tr_first_node[t] + t;  // alpha base of tree t
-            st.a0 = c.alpha[a + (-nd.left)];       // sum <  t -> left  (tempcv.cpp:788)
-            st.a1 = c.alpha[a + (-nd.right)];      // sum >= t -> right
+            if (!ok) break;
+            DenseStage &ds = P.stage[ns];
+            ds.first = (uint16_t)nstump; ds.count = (uint16_t)(t1 - t0);
+            ds.thr = c.hid_thr[ns];
+            ds.flags = ((!c.is_tree && c.is_stump_based && c.two_rects[ns]) ? 1u : 0u) | (any3 ? 2u : 0u);
+            for (int t = t0; t < t1; t++) {
+                const int n = c.tr_first_node[t];
+                const HostNode &nd = c.nodes[n];
+                DenseStump &st = P.stump[nstump++];
+                uint16_t off[12] = {0};
+                for (int k = 0; k < c.hid_nrects[n]; k++) {
+                    int dx[4], dy[4];
+                    corner_coords(nd, k, dx, dy);
+                    for (int q = 0; q < 4; q++) {
+                        const int word = ystep == 1 ? dy[q] * P.tile_stride + dx[q]
+                                                    : dy[q] * P.tile_stride + (dx[q] & 1) * (P.tile_stride / 2) + (dx[q] >> 1);
+                        off[k * 4 + q] = (uint16_t)(word * 4);
+                    }
+                    st.w[k] = c.hid_weight[(size_t)n * 3 + k];
+                }
+                for (int q = 0; q < 6; q++) st.offp[q] = (uint32_t)off[2 * q] | ((uint32_t)off[2 * q + 1] << 16);
+                st.thr = nd.threshold;
+                const int a = c.tr_first_node[t] + t;            // alpha base of tree t
+                st.a0 = (double)c.alpha[a + (-nd.left)];         // sum <  t -> left  (tempcv.cpp:788)
+                st.a1 = (double)c.alpha[a + (-nd.right)];        // sum >= t -> right
+            }
+            ns++;
         }
-        ns++;
+        P.n_stages = ns;
+        out.dense_stumps = nstump;
     }
-    P.n_stages = ns;
-    out.dense_stumps = nstump;
 }
 
 }  // namespace clfd

@@ -50,7 +50,8 @@ struct CascadeArgs {
     DeepCascadeDev deep;
 };
 // dense tile kernel (+ hand-off of survivors to the queue)
-cudaError_t launch_cascade_tiles(const DenseParams &P, const CascadeArgs &a, cudaStream_t stream);
+// tiles [tile0, tile0 + n_tiles) must all belong to levels with ystep == P.ystep
+cudaError_t launch_cascade_tiles(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, cudaStream_t stream);
 // fill the queue with every window (cascades without a dense prefix)
 cudaError_t launch_enqueue_all(const CascadeArgs &a, cudaStream_t stream);
 // warp-per-window evaluation of the queue

@@ -85,194 +85,343 @@ __device__ __forceinline__ void emit_rect(const CascadeArgs &a, const CasLevel &
 
 // ------------------------------------------------------------------------------------
 // dense tile kernel
+//
+// Shared-memory plan per CTA (one 64x16-window tile):
+//   tile    int32 [rows][S]      S = tile_stride, a multiple of 32 words.  ystep-1 levels use
+//                                the natural layout (staged by TMA bulk row copies); ystep-2
+//                                levels store even columns in [0,S/2) and odd columns in
+//                                [S/2,S) of each row (staged by LDG.128 + 2 x STS.64), so a
+//                                window's base word is  f(wy)*S + wx  in both.
+//   sigma   double [1024]        per-window variance normaliser (FP64, exact)
+//   list    u16 [2][32 slots][32 buckets]   surviving windows, bucket = wx mod 32
+//   cnt     int [3][32]          bucket fill counts (rotating: read / append / being reset)
+// Lane l of every warp only ever evaluates windows of bucket l.  All lanes execute the same
+// stump, i.e. add the same offset to their base, so the 32 addresses of every LDS fall into
+// 32 different banks: the compaction is bank-conflict free by construction, at the price of
+// bucket imbalance.  A thread carries up to 4 windows through a stage at once (ILP, and the
+// uniform stump loads / offset unpacking are amortised over them).
+//
+// Stage arithmetic: an FP32 filter decides each stump; whenever |s32 - t32| is inside a
+// guard band (2^-20 |t32| plus the cancellation terms) the window's whole stage is redone by
+// dense_eval_stage_exact(), which reproduces the reference's C expressions bit for bit.
+// Outside the band both agree by the error analysis in DESIGN.md, so results are identical
+// to the all-FP64 evaluation (tests also run with force_exact = 1 and compare).
 // ------------------------------------------------------------------------------------
-struct DenseSmem {
-    // [tile ints][sigma doubles][list0][list1][ctl]
-    static __host__ __device__ size_t tile_bytes(const DenseParams &P) {
-        return (size_t)((kTileH - 1) * 2 + P.win_h + 1) * P.tile_stride * 4;
-    }
-};
-
-size_t dense_smem_bytes(const DenseParams &P) {
-    size_t tile = (DenseSmem::tile_bytes(P) + 127) & ~(size_t)127;
-    return tile + kTileWindows * sizeof(double) + 2 * kTileWindows * sizeof(uint16_t) + 64;
-}
-
 #define TILE_LD(base, off) (*reinterpret_cast<const int *>((base) + (off)))
 
-__device__ __forceinline__ bool dense_eval_stage(const DenseParams &P, int s, const unsigned char *base, double sigma) {
+struct DenseSmemPlan {
+    size_t tile, sigma, list, cnt, bar, total;
+};
+__host__ __device__ inline DenseSmemPlan dense_smem_plan(const DenseParams &P) {
+    DenseSmemPlan p;
+    const size_t rows = (size_t)(kTileH - 1) * P.ystep + P.win_h + 1;
+    p.tile = 0;
+    p.sigma = (rows * P.tile_stride * 4 + 127) & ~(size_t)127;
+    p.list = p.sigma + kTileWindows * sizeof(double);
+    p.cnt = p.list + 2 * kTileWindows * sizeof(uint16_t);
+    p.bar = p.cnt + 3 * 32 * sizeof(int);
+    p.total = p.bar + 16;
+    return p;
+}
+size_t dense_smem_bytes(const DenseParams &P) { return dense_smem_plan(P).total; }
+
+// Exact evaluation of one dense stage for one window (the reference's arithmetic).
+__device__ __noinline__ bool dense_eval_stage_exact(const DenseParams &P, int s, const unsigned char *base, double sigma) {
     const int first = P.stage[s].first, count = P.stage[s].count;
-    const uint32_t flags = P.stage[s].flags;
+    const bool dbl = P.stage[s].flags & 1u;
     double S = 0.0;
-    if (flags & 1u) {  // two_rects stage of a stump cascade: double products (tempcv.cpp:872-898)
-        for (int j = 0; j < count; j++) {
-            const DenseStump &q = P.stump[first + j];
-            const int r0 = TILE_LD(base, q.off[0]) - TILE_LD(base, q.off[1]) - TILE_LD(base, q.off[2]) + TILE_LD(base, q.off[3]);
-            const int r1 = TILE_LD(base, q.off[4]) - TILE_LD(base, q.off[5]) - TILE_LD(base, q.off[6]) + TILE_LD(base, q.off[7]);
-            const double t = __dmul_rn((double)q.thr, sigma);
-            // both products are exact in double (|r| < 2^24, 24-bit weights) => fma == mul, mul, add
-            const double sum = __fma_rn((double)r1, (double)q.w[1], __dmul_rn((double)r0, (double)q.w[0]));
-            S = __dadd_rn(S, (double)(sum >= t ? q.a1 : q.a0));
-        }
-    } else {  // float products, double accumulation (tempcv.cpp:899-930, 782-786)
-        for (int j = 0; j < count; j++) {
-            const DenseStump &q = P.stump[first + j];
-            const int r0 = TILE_LD(base, q.off[0]) - TILE_LD(base, q.off[1]) - TILE_LD(base, q.off[2]) + TILE_LD(base, q.off[3]);
-            const int r1 = TILE_LD(base, q.off[4]) - TILE_LD(base, q.off[5]) - TILE_LD(base, q.off[6]) + TILE_LD(base, q.off[7]);
-            const double t = __dmul_rn((double)q.thr, sigma);
-            double sum = __dadd_rn((double)__fmul_rn(__int2float_rn(r0), q.w[0]), (double)__fmul_rn(__int2float_rn(r1), q.w[1]));
-            if (q.off[11] != 0) {  // warp-uniform: third rectangle present
-                const int r2 = TILE_LD(base, q.off[8]) - TILE_LD(base, q.off[9]) - TILE_LD(base, q.off[10]) + TILE_LD(base, q.off[11]);
+    for (int j = 0; j < count; j++) {
+        const DenseStump &q = P.stump[first + j];
+        const uint32_t o0 = q.offp[0], o1 = q.offp[1], o2 = q.offp[2], o3 = q.offp[3];
+        const int r0 = TILE_LD(base, o0 & 0xffffu) - TILE_LD(base, o0 >> 16) - TILE_LD(base, o1 & 0xffffu) + TILE_LD(base, o1 >> 16);
+        const int r1 = TILE_LD(base, o2 & 0xffffu) - TILE_LD(base, o2 >> 16) - TILE_LD(base, o3 & 0xffffu) + TILE_LD(base, o3 >> 16);
+        const double t = __dmul_rn((double)q.thr, sigma);
+        double sum;
+        if (dbl) {  // tempcv.cpp:872-898; both products are exact in double, so fma == mul, mul, add
+            sum = __fma_rn((double)r1, (double)q.w[1], __dmul_rn((double)r0, (double)q.w[0]));
+        } else {    // tempcv.cpp:899-930 / 782-786: float products, double accumulation
+            sum = __dadd_rn((double)__fmul_rn(__int2float_rn(r0), q.w[0]), (double)__fmul_rn(__int2float_rn(r1), q.w[1]));
+            const uint32_t o4 = q.offp[4], o5 = q.offp[5];
+            if (o5 != 0) {
+                const int r2 = TILE_LD(base, o4 & 0xffffu) - TILE_LD(base, o4 >> 16) - TILE_LD(base, o5 & 0xffffu) + TILE_LD(base, o5 >> 16);
                 sum = __dadd_rn(sum, (double)__fmul_rn(__int2float_rn(r2), q.w[2]));
             }
-            S = __dadd_rn(S, (double)(sum >= t ? q.a1 : q.a0));
         }
+        S = __dadd_rn(S, sum >= t ? q.a1 : q.a0);
     }
     return S >= (double)P.stage[s].thr;
 }
 
-__global__ void __launch_bounds__(kDenseThreads)
-k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ CascadeArgs a) {
+// FP32-filtered evaluation of stage s for K windows of this thread.  Everything indexed by
+// the stump loop is warp-uniform (constant bank, uniform registers).
+template <int K, bool DBL, bool HAS3>
+__device__ __forceinline__ void dense_filter_stage(const DenseParams &P, int s, const unsigned char *const (&base)[K],
+                                                   const float (&sg)[K], double (&S)[K], bool (&near)[K]) {
+    const int first = P.stage[s].first, count = P.stage[s].count;
+    const float eps = P.filter_eps, eps4 = eps * 0.25f;
+#pragma unroll 1
+    for (int j = 0; j < count; j++) {
+        const DenseStump &q = P.stump[first + j];
+        const uint32_t o0 = q.offp[0], o1 = q.offp[1], o2 = q.offp[2], o3 = q.offp[3];
+        const uint32_t a00 = o0 & 0xffffu, a01 = o0 >> 16, a02 = o1 & 0xffffu, a03 = o1 >> 16;
+        const uint32_t a10 = o2 & 0xffffu, a11 = o2 >> 16, a12 = o3 & 0xffffu, a13 = o3 >> 16;
+        const float w0 = q.w[0], w1 = q.w[1], thr = q.thr;
+        const double al0 = q.a0, al1 = q.a1;
+        const uint32_t o4 = q.offp[4], o5 = q.offp[5];
+        const bool three = HAS3 && (o5 != 0);   // warp-uniform
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const unsigned char *b = base[k];
+            const int r0 = TILE_LD(b, a00) - TILE_LD(b, a01) - TILE_LD(b, a02) + TILE_LD(b, a03);
+            const int r1 = TILE_LD(b, a10) - TILE_LD(b, a11) - TILE_LD(b, a12) + TILE_LD(b, a13);
+            const float p0 = __fmul_rn(__int2float_rn(r0), w0), p1 = __fmul_rn(__int2float_rn(r1), w1);
+            float s32 = __fadd_rn(p0, p1);
+            const float t32 = __fmul_rn(thr, sg[k]);
+            float m = __fmul_rn(fabsf(t32), eps);
+            if (DBL) {
+                // reference adds the two EXACT products: fp32 product errors do not cancel
+                m = __fadd_rn(m, __fmul_rn(__fadd_rn(fabsf(p0), fabsf(p1)), eps4));
+            }
+            if (HAS3) {
+                if (three) {
+                    const int r2 = TILE_LD(b, o4 & 0xffffu) - TILE_LD(b, o4 >> 16) - TILE_LD(b, o5 & 0xffffu) + TILE_LD(b, o5 >> 16);
+                    m = __fadd_rn(m, __fmul_rn(fabsf(s32), eps4));   // rounding of the first add
+                    s32 = __fadd_rn(s32, __fmul_rn(__int2float_rn(r2), q.w[2]));
+                }
+            }
+            const float d = __fadd_rn(s32, -t32);
+            near[k] = near[k] || (fabsf(d) <= m);
+            S[k] = __dadd_rn(S[k], d >= 0.f ? al1 : al0);
+        }
+    }
+}
+
+struct DenseCtx {
+    const DenseParams *P;
+    const CascadeArgs *a;
+    unsigned char *tile;
+    double *sigma;
+    uint16_t *list;   // [2][kBucketCap][32]
+    int *cnt;         // [3][32]
+    int16_t *codes;   // this frame + level, or nullptr
+    int row_mul;      // bytes between window rows in the tile
+    int tx, ty, nx;
+    int code_mul;
+};
+
+// evaluate stage s for the K windows (wid[], active[]) of this thread, append survivors to
+// bucket `lane` of list `nxt_list` / `nxt_cnt`
+template <int K>
+__device__ __forceinline__ void dense_run_stage(const DenseCtx &c, int s, const int (&wid)[K], const bool (&act)[K],
+                                                int lane, uint16_t *nxt_list, int *nxt_cnt) {
+    const DenseParams &P = *c.P;
+    const unsigned char *base[K];
+    float sg[K];
+    double S[K];
+    bool near[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const int wx = wid[k] & (kTileW - 1), wy = wid[k] / kTileW;
+        base[k] = c.tile + wy * c.row_mul + wx * 4;
+        sg[k] = (float)c.sigma[wid[k]];
+        S[k] = 0.0;
+        near[k] = P.force_exact != 0;
+    }
+    const uint32_t flags = P.stage[s].flags;
+    if (flags & 1u) dense_filter_stage<K, true, false>(P, s, base, sg, S, near);
+    else if (flags & 2u) dense_filter_stage<K, false, true>(P, s, base, sg, S, near);
+    else dense_filter_stage<K, false, false>(P, s, base, sg, S, near);
+    const double sthr = (double)P.stage[s].thr;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        if (!act[k]) continue;
+        bool pass = S[k] >= sthr;
+        if (near[k]) pass = dense_eval_stage_exact(P, s, base[k], c.sigma[wid[k]]);
+        if (pass) {
+            const int slot = atomicAdd(&nxt_cnt[lane], 1);
+            nxt_list[slot * 32 + lane] = (uint16_t)wid[k];
+        } else if (c.codes) {
+            const int wx = wid[k] & (kTileW - 1), wy = wid[k] / kTileW;
+            c.codes[(size_t)(c.ty * kTileH + wy) * c.nx + c.tx * kTileW + wx] = (int16_t)(s * c.code_mul);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kDenseThreads, 4)
+k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ CascadeArgs a, const int tile0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const size_t tile_sz = (DenseSmem::tile_bytes(P) + 127) & ~(size_t)127;
-    unsigned char *tile = smem_raw;
-    double *sigma = reinterpret_cast<double *>(smem_raw + tile_sz);
-    uint16_t *list0 = reinterpret_cast<uint16_t *>(sigma + kTileWindows);
-    uint16_t *list1 = list0 + kTileWindows;
-    int *ctl = reinterpret_cast<int *>(list1 + kTileWindows);   // [0],[1] list counters, [2] queue base
-    uint64_t *bar = reinterpret_cast<uint64_t *>(ctl + 4);
+    const DenseSmemPlan plan = dense_smem_plan(P);
+    unsigned char *tile = smem_raw + plan.tile;
+    double *sigma = reinterpret_cast<double *>(smem_raw + plan.sigma);
+    uint16_t *list = reinterpret_cast<uint16_t *>(smem_raw + plan.list);
+    int *cnt = reinterpret_cast<int *>(smem_raw + plan.cnt);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + plan.bar);
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.y;
+    const int tile_id = tile0 + blockIdx.x;
 
-    // which level does this tile belong to?
-    int cl = 0;
+    int cl = 0;   // which level does this tile belong to?
     {
         int lo = 0, hi = a.n_cas_levels - 1;
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
-            if (__ldg(&a.cas_levels[mid].tile_base) <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+            if (__ldg(&a.cas_levels[mid].tile_base) <= tile_id) lo = mid; else hi = mid - 1;
         }
         cl = lo;
     }
     const CasLevel CL = a.cas_levels[cl];
     const PyrLevel L = a.levels[CL.pyr_level];
-    const int local = blockIdx.x - CL.tile_base;
+    const int local = tile_id - CL.tile_base;
     const int tx = local % CL.tiles_x, ty = local / CL.tiles_x;
-    const int ystep = CL.ystep;
+    const int ystep = P.ystep;   // == CL.ystep by construction of the launch
     const int px0 = tx * kTileW * ystep, py0 = ty * kTileH * ystep;   // tile origin in the integral image
     const int n_wx = min(kTileW, CL.nx - tx * kTileW), n_wy = min(kTileH, CL.ny - ty * kTileH);
     const int rows = min((kTileH - 1) * ystep + P.win_h + 1, L.h + 1 - py0);
     const int cols = ((kTileW - 1) * ystep + P.win_w + 1 + 3) & ~3;
-    const int stride_b = P.tile_stride * 4;
+    const int S = P.tile_stride;
 
     const size_t frame_off = (size_t)frame * a.sum_frame_stride + L.sum_off;
     const int32_t *__restrict__ gsum = a.sum + frame_off + (size_t)py0 * L.sum_pitch + px0;
     const ull *__restrict__ gsq = a.sq + frame_off + (size_t)py0 * L.sum_pitch + px0;
 
-    // ---- stage the integral tile: one TMA bulk copy per row ----
-    if (tid == 0) {
-        ctl[0] = 0; ctl[1] = 0; ctl[2] = 0;
-        mbar_init(bar, 1);
-    }
-    __syncthreads();
-    if (tid == 0) mbar_expect_tx(bar, (uint32_t)(rows * cols * 4));
-    for (int r = tid; r < rows; r += kDenseThreads)
-        tma_bulk_g2s(tile + (size_t)r * stride_b, gsum + (size_t)r * L.sum_pitch, (uint32_t)(cols * 4), bar);
-    mbar_wait(bar, 0);
-
-    const int eq_w = P.win_w - 2, eq_h = P.win_h - 2;
-    const int e0 = (1 * P.tile_stride + 1) * 4, e1 = e0 + eq_w * 4;
-    const int e2 = ((1 + eq_h) * P.tile_stride + 1) * 4, e3 = e2 + eq_w * 4;
-    const int g0 = L.sum_pitch + 1, g1 = g0 + eq_w, g2 = (1 + eq_h) * L.sum_pitch + 1, g3 = g2 + eq_w;
-    const int code_mul = P.pad[0] ? 2 : 1;   // stage-tree cascades report 2*last_stage (+accept)
-    int16_t *__restrict__ codes = a.codes ? a.codes + (size_t)frame * a.windows_per_frame + CL.win_base : nullptr;
-
-    // ---- pass A: sigma + stage 0 for every window of the tile ----
-    for (int w0 = 0; w0 < kTileWindows; w0 += kDenseThreads) {
-        const int wid = w0 + tid;
-        const int wx = wid & (kTileW - 1), wy = wid / kTileW;
-        const bool valid = wx < n_wx && wy < n_wy;
-        bool pass = false;
-        if (valid) {
-            const unsigned char *base = tile + ((size_t)(wy * ystep) * P.tile_stride + wx * ystep) * 4;
-            const int s4 = TILE_LD(base, e0) - TILE_LD(base, e1) - TILE_LD(base, e2) + TILE_LD(base, e3);
-            const ull *q = gsq + (size_t)(wy * ystep) * L.sum_pitch + wx * ystep;
-            const ull q4 = __ldg(q + g0) - __ldg(q + g1) - __ldg(q + g2) + __ldg(q + g3);
-            const double sg = window_sigma(s4, q4, P.inv_area);
-            sigma[wid] = sg;
-            pass = dense_eval_stage(P, 0, base, sg);
-            if (!pass && codes) codes[(size_t)(ty * kTileH + wy) * CL.nx + tx * kTileW + wx] = 0;
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, pass);
-        if (bal) {
-            int wbase = 0;
-            if (lane == 0) wbase = atomicAdd(&ctl[0], __popc(bal));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (pass) list0[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)wid;
-        }
-    }
-    __syncthreads();
-
-    // ---- remaining dense stages, compacting after each ----
-    uint16_t *lin = list0, *lout = list1;
-    int cur = 0;            // ctl index of the input list counter
-    int s = 1;
-    int n = ctl[0];
-    while (n > 0 && s < P.n_stages && !(n <= kHandoffWindows && P.n_stages < P.total_stages)) {
-        if (tid == 0) ctl[cur ^ 1] = 0;
+    // ---- stage the integral tile ----
+    if (tid < 96) cnt[tid] = 0;
+    if (ystep == 1) {   // natural layout: one TMA bulk copy per row
+        if (tid == 0) mbar_init(bar, 1);
         __syncthreads();
-        for (int i0 = (tid & ~31); i0 < n; i0 += kDenseThreads) {
-            const int i = i0 + lane;
-            bool pass = false;
-            int wid = 0;
-            if (i < n) {
-                wid = lin[i];
-                const int wx = wid & (kTileW - 1), wy = wid / kTileW;
-                const unsigned char *base = tile + ((size_t)(wy * ystep) * P.tile_stride + wx * ystep) * 4;
-                pass = dense_eval_stage(P, s, base, sigma[wid]);
-                if (!pass && codes)
-                    codes[(size_t)(ty * kTileH + wy) * CL.nx + tx * kTileW + wx] = (int16_t)(s * code_mul);
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, pass);
-            if (bal) {
-                int wbase = 0;
-                if (lane == 0) wbase = atomicAdd(&ctl[cur ^ 1], __popc(bal));
-                wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                if (pass) lout[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)wid;
-            }
+        if (tid == 0) mbar_expect_tx(bar, (uint32_t)(rows * cols * 4));
+        for (int r = tid; r < rows; r += kDenseThreads)
+            tma_bulk_g2s(tile + (size_t)r * S * 4, gsum + (size_t)r * L.sum_pitch, (uint32_t)(cols * 4), bar);
+        mbar_wait(bar, 0);
+    } else {            // de-interleave columns: x -> (x&1)*S/2 + (x>>1)
+        const int c4 = cols >> 2, total = rows * c4;
+        for (int i = tid; i < total; i += kDenseThreads) {
+            const int r = i / c4, cq = i - r * c4;
+            const int4 v = __ldg(reinterpret_cast<const int4 *>(gsum + (size_t)r * L.sum_pitch) + cq);
+            int *row = reinterpret_cast<int *>(tile) + r * S;
+            *reinterpret_cast<int2 *>(row + 2 * cq) = make_int2(v.x, v.z);
+            *reinterpret_cast<int2 *>(row + (S >> 1) + 2 * cq) = make_int2(v.y, v.w);
         }
         __syncthreads();
-        cur ^= 1;
-        n = ctl[cur];
-        uint16_t *tmp = lin; lin = lout; lout = tmp;
-        s++;
     }
-    if (n == 0) return;
+
+    DenseCtx c;
+    c.P = &P; c.a = &a; c.tile = tile; c.sigma = sigma; c.list = list; c.cnt = cnt;
+    c.codes = a.codes ? a.codes + (size_t)frame * a.windows_per_frame + CL.win_base : nullptr;
+    c.row_mul = ystep * S * 4;
+    c.tx = tx; c.ty = ty; c.nx = CL.nx;
+    c.code_mul = P.is_tree ? 2 : 1;
+
+    // ---- pass A: sigma + stage 0 for every window of the tile (natural order: lane = wx mod 32) ----
+    {
+        const int eq_w = P.win_w - 2, eq_h = P.win_h - 2;
+        // equRect corners (1,1),(1,1+eq_w),(1+eq_h,1),(1+eq_h,1+eq_w) in tile byte offsets
+        int e[4];
+        {
+            const int ys[4] = {1, 1, 1 + eq_h, 1 + eq_h}, xs[4] = {1, 1 + eq_w, 1, 1 + eq_w};
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                e[q] = 4 * (ystep == 1 ? ys[q] * S + xs[q] : ys[q] * S + (xs[q] & 1) * (S >> 1) + (xs[q] >> 1));
+        }
+        const int g0 = L.sum_pitch + 1, g1 = g0 + eq_w, g2 = (1 + eq_h) * L.sum_pitch + 1, g3 = g2 + eq_w;
+        int wid[kDenseSlots];
+        bool act[kDenseSlots];
+#pragma unroll
+        for (int k = 0; k < kDenseSlots; k++) {
+            const int w = k * kDenseThreads + tid;
+            const int wx = w & (kTileW - 1), wy = w / kTileW;
+            act[k] = wx < n_wx && wy < n_wy;
+            wid[k] = act[k] ? w : lane;   // dummy: window (0, lane) keeps loads in range and banks distinct
+            if (act[k]) {
+                const unsigned char *base = tile + wy * c.row_mul + wx * 4;
+                const int s4 = TILE_LD(base, e[0]) - TILE_LD(base, e[1]) - TILE_LD(base, e[2]) + TILE_LD(base, e[3]);
+                const ull *q = gsq + (size_t)(wy * ystep) * L.sum_pitch + wx * ystep;
+                const ull q4 = __ldg(q + g0) - __ldg(q + g1) - __ldg(q + g2) + __ldg(q + g3);
+                sigma[w] = window_sigma(s4, q4, P.inv_area);
+            }
+        }
+        // a thread reads back only sigmas it wrote itself: no barrier needed
+        const int n_act = __reduce_add_sync(0xffffffffu, (int)act[0] + act[1] + act[2] + act[3]);
+        if (n_act) dense_run_stage<kDenseSlots>(c, 0, wid, act, lane, list, cnt);
+    }
+    __syncthreads();
+
+    // ---- remaining dense stages; compaction (per bank bucket) after each ----
+    int s = 1, cur = 0, curl = 0;   // cur: counter set (mod 3) of the input list, curl: list buffer (mod 2)
+    int my_cnt, n_alive;
+    for (;;) {
+        my_cnt = cnt[cur * 32 + lane];
+        n_alive = __reduce_add_sync(0xffffffffu, my_cnt);
+        if (n_alive == 0) return;
+        if (s >= P.n_stages || (n_alive <= kHandoffWindows && P.n_stages < P.total_stages)) break;
+        const int nxt = cur == 2 ? 0 : cur + 1, nxt2 = nxt == 2 ? 0 : nxt + 1;
+        if (warp == 0) cnt[nxt2 * 32 + lane] = 0;   // not read or appended to during this stage
+        const int kmax = __reduce_max_sync(0xffffffffu, my_cnt);
+        const int K = kmax > warp ? (kmax - warp + kDenseWarps - 1) / kDenseWarps : 0;
+        const uint16_t *lin = list + curl * kTileWindows;
+        uint16_t *lout = list + (curl ^ 1) * kTileWindows;
+        int *ncnt = cnt + nxt * 32;
+        int wid[kDenseSlots];
+        bool act[kDenseSlots];
+#pragma unroll
+        for (int k = 0; k < kDenseSlots; k++) {
+            const int slot = warp + k * kDenseWarps;
+            act[k] = slot < my_cnt;
+            wid[k] = act[k] ? lin[slot * 32 + lane] : lane;
+        }
+        if (K == 1) {
+            const int w1[1] = {wid[0]}; const bool a1[1] = {act[0]};
+            dense_run_stage<1>(c, s, w1, a1, lane, lout, ncnt);
+        } else if (K == 2) {
+            const int w2[2] = {wid[0], wid[1]}; const bool a2[2] = {act[0], act[1]};
+            dense_run_stage<2>(c, s, w2, a2, lane, lout, ncnt);
+        } else if (K == 3) {
+            const int w3[3] = {wid[0], wid[1], wid[2]}; const bool a3[3] = {act[0], act[1], act[2]};
+            dense_run_stage<3>(c, s, w3, a3, lane, lout, ncnt);
+        } else if (K >= 4) {
+            dense_run_stage<4>(c, s, wid, act, lane, lout, ncnt);
+        }
+        __syncthreads();
+        cur = nxt; curl ^= 1; s++;
+    }
 
     // ---- survivors: accepted (whole cascade was dense) or handed to the deep kernel ----
+    const uint16_t *lin = list + curl * kTileWindows;
     if (s >= P.total_stages) {
-        for (int i = tid; i < n; i += kDenseThreads) {
-            const int wid = lin[i];
-            const int wx = wid & (kTileW - 1), wy = wid / kTileW;
+        for (int slot = warp; slot < my_cnt; slot += kDenseWarps) {
+            const int w = lin[slot * 32 + lane];
+            const int wx = w & (kTileW - 1), wy = w / kTileW;
             emit_rect(a, CL, frame, px0 + wx * ystep, py0 + wy * ystep);
-            if (codes) codes[(size_t)(ty * kTileH + wy) * CL.nx + tx * kTileW + wx] = (int16_t)P.total_stages;
+            if (c.codes) c.codes[(size_t)(ty * kTileH + wy) * CL.nx + tx * kTileW + wx] = (int16_t)P.total_stages;
         }
     } else {
-        if (tid == 0) {
-            const ull b = atomicAdd(a.counters + 1, (ull)n);
-            reinterpret_cast<ull *>(ctl)[1] = b;   // ctl[2..3]
+        // exclusive prefix of the bucket counts gives every lane its slice of the queue block
+        int incl = my_cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        ull qb = 0;
+        if (warp == 0) {
+            if (lane == 0) qb = atomicAdd(a.counters + 1, (ull)n_alive);
+            qb = __shfl_sync(0xffffffffu, qb, 0);
+            // broadcast to the other warps through the (now unused) sigma area
+            if (lane == 0) *reinterpret_cast<ull *>(sigma) = qb;
         }
         __syncthreads();
-        const ull qb = reinterpret_cast<ull *>(ctl)[1];
-        for (int i = tid; i < n; i += kDenseThreads) {
-            const int wid = lin[i];
-            const int wx = wid & (kTileW - 1), wy = wid / kTileW;
-            if (qb + i < a.queue_cap) {
+        qb = *reinterpret_cast<const ull *>(sigma);
+        const ull lane_base = qb + (ull)(incl - my_cnt);
+        for (int slot = warp; slot < my_cnt; slot += kDenseWarps) {
+            const int w = lin[slot * 32 + lane];
+            const int wx = w & (kTileW - 1), wy = w / kTileW;
+            const ull pos = lane_base + slot;
+            if (pos < a.queue_cap) {
                 QueueItem it;
                 it.key = ((uint32_t)frame << 16) | ((uint32_t)cl << 8) | (uint32_t)s;
                 it.xy = ((uint32_t)(py0 + wy * ystep) << 16) | (uint32_t)(px0 + wx * ystep);
-                a.queue[qb + i] = it;
+                a.queue[pos] = it;
             } else {
                 atomicAdd(a.counters + 3, 1ull);
             }
@@ -280,8 +429,8 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     }
 }
 
-cudaError_t launch_cascade_tiles(const DenseParams &P, const CascadeArgs &a, cudaStream_t stream) {
-    if (a.n_tiles == 0 || a.n_frames == 0) return cudaSuccess;
+cudaError_t launch_cascade_tiles(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, cudaStream_t stream) {
+    if (n_tiles <= 0 || a.n_frames == 0) return cudaSuccess;
     const size_t smem = dense_smem_bytes(P);
     static size_t configured = 0;
     if (smem > configured) {
@@ -289,7 +438,7 @@ cudaError_t launch_cascade_tiles(const DenseParams &P, const CascadeArgs &a, cud
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    k_cascade_tiles<<<dim3(a.n_tiles, a.n_frames), kDenseThreads, smem, stream>>>(P, a);
+    k_cascade_tiles<<<dim3(n_tiles, a.n_frames), kDenseThreads, smem, stream>>>(P, a, tile0);
     return cudaGetLastError();
 }
 
