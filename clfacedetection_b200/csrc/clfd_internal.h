@@ -60,18 +60,18 @@ int build_hidden(HostCascade &c);
 constexpr int kTileW = 64;
 constexpr int kTileH = 16;
 constexpr int kTileWindows = kTileW * kTileH;
-constexpr int kDenseThreads = 256;
+constexpr int kDenseThreads = 128;
 constexpr int kDenseWarps = kDenseThreads / 32;
-constexpr int kDenseSlots = kTileWindows / kDenseThreads;   // windows per thread (4)
-constexpr int kBucketCap = kTileWindows / 32;                // windows per bank bucket (32)
-constexpr int kMaxDenseStumps = 568;
+constexpr int kDenseSlots = kTileWindows / kDenseThreads;   // windows per thread (8)
+constexpr int kDenseChunk = 4;                               // windows a thread carries through a stage at once
+constexpr int kMaxDenseStumps = 396;
 constexpr int kMaxDenseStages = 32;
 constexpr int kHandoffWindows = 8;  // <= this many survivors in a tile: hand them to the deep kernel
 
-// One stump of the dense kernel, 56 B, read through the constant bank (the packed cascade
-// is a kernel parameter) with uniform loads: the whole warp evaluates the same stump.
+// One stump of the dense kernel, 80 B, read through the constant bank (the packed cascade
+// is a kernel parameter); the whole warp evaluates the same stump.
 struct DenseStump {
-    uint32_t offp[6];  // 12 x u16 BYTE offsets into the smem tile: p0..p3 of rect 0,1,2 (rect 2: zeros if absent)
+    uint32_t off[12];  // BYTE offsets into the smem tile: p0..p3 of rect 0,1,2 (rect 2: zeros if absent)
     float w[3];        // hidden weights (w[2] = 0 if absent)
     float thr;
     double a0, a1;     // alpha[0] (sum < t), alpha[1] (sum >= t), pre-converted (exact)
@@ -95,7 +95,7 @@ struct DenseParams {
     int ystep;          // 1 or 2
     int force_exact;    // test hook: skip the FP32 filter, evaluate every stage in FP64
     float filter_eps;   // FP32 filter guard band (2^-20), see kernels_clod.cu
-    int pad;
+    int n_fixed;        // leading stages run in fixed geometry (no compaction), <= n_stages
     double inv_area;
     DenseStage stage[kMaxDenseStages];
     DenseStump stump[kMaxDenseStumps];

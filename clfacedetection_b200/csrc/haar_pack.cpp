@@ -255,18 +255,17 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
                 const int n = c.tr_first_node[t];
                 const HostNode &nd = c.nodes[n];
                 DenseStump &st = P.stump[nstump++];
-                uint16_t off[12] = {0};
+                for (int q = 0; q < 12; q++) st.off[q] = 0;
                 for (int k = 0; k < c.hid_nrects[n]; k++) {
                     int dx[4], dy[4];
                     corner_coords(nd, k, dx, dy);
                     for (int q = 0; q < 4; q++) {
                         const int word = ystep == 1 ? dy[q] * P.tile_stride + dx[q]
                                                     : dy[q] * P.tile_stride + (dx[q] & 1) * (P.tile_stride / 2) + (dx[q] >> 1);
-                        off[k * 4 + q] = (uint16_t)(word * 4);
+                        st.off[k * 4 + q] = (uint32_t)(word * 4);
                     }
                     st.w[k] = c.hid_weight[(size_t)n * 3 + k];
                 }
-                for (int q = 0; q < 6; q++) st.offp[q] = (uint32_t)off[2 * q] | ((uint32_t)off[2 * q + 1] << 16);
                 st.thr = nd.threshold;
                 const int a = c.tr_first_node[t] + t;            // alpha base of tree t
                 st.a0 = (double)c.alpha[a + (-nd.left)];         // sum <  t -> left  (tempcv.cpp:788)
@@ -275,6 +274,7 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
             ns++;
         }
         P.n_stages = ns;
+        P.n_fixed = ns < 3 ? ns : 3;
         out.dense_stumps = nstump;
     }
 }

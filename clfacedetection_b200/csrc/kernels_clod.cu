@@ -86,20 +86,24 @@ __device__ __forceinline__ void emit_rect(const CascadeArgs &a, const CasLevel &
 // ------------------------------------------------------------------------------------
 // dense tile kernel
 //
-// Shared-memory plan per CTA (one 64x16-window tile):
-//   tile    int32 [rows][S]      S = tile_stride, a multiple of 32 words.  ystep-1 levels use
-//                                the natural layout (staged by TMA bulk row copies); ystep-2
-//                                levels store even columns in [0,S/2) and odd columns in
-//                                [S/2,S) of each row (staged by LDG.128 + 2 x STS.64), so a
-//                                window's base word is  f(wy)*S + wx  in both.
-//   sigma   double [1024]        per-window variance normaliser (FP64, exact)
-//   list    u16 [2][32 slots][32 buckets]   surviving windows, bucket = wx mod 32
-//   cnt     int [3][32]          bucket fill counts (rotating: read / append / being reset)
-// Lane l of every warp only ever evaluates windows of bucket l.  All lanes execute the same
-// stump, i.e. add the same offset to their base, so the 32 addresses of every LDS fall into
-// 32 different banks: the compaction is bank-conflict free by construction, at the price of
-// bucket imbalance.  A thread carries up to 4 windows through a stage at once (ILP, and the
-// uniform stump loads / offset unpacking are amortised over them).
+// One CTA (128 threads) per 64x16-window tile.  Shared memory:
+//   tile    int32 [rows][S]   ystep-1 levels: natural layout, staged by TMA bulk row copies;
+//                             ystep-2 levels: even columns in [0,S/2), odd columns in [S/2,S)
+//                             of each row (LDG.128 + 2 x STS.64), so that in both layouts a
+//                             window's base word is f(wy)*S + wx and the 32 lanes of a warp
+//                             (consecutive wx) hit 32 different banks on every corner load.
+//   sigma   double [1024]     per-window variance normaliser (FP64, exact)
+//   list    u16 [2][1024]     compacted survivor lists (ping-pong)
+//
+// Phase 1, "fixed geometry" (stages 0 .. n_fixed-1, where most windows are still alive):
+//   thread t owns the column of 8 windows (wx = t & 63, wy = (t >> 6) + 2k).  Their tile
+//   addresses differ by a compile-time constant, so a corner address is computed ONCE per
+//   stump and the 4 windows of a chunk are read with immediate offsets (LDS [R + k*ROWSTEP]):
+//   no per-window address arithmetic, no compaction traffic, conflict-free banks.  Dead
+//   windows ride along; a chunk whose 4 x 32 windows are all dead is skipped (warp-uniform).
+// Phase 2, compacted (remaining dense stages): survivors are stream-compacted with a warp
+//   ballot after every stage; a warp takes rows of 32 list entries, up to 4 rows per pass.
+// Survivors of the last dense stage are appended to the global queue of the deep kernel.
 //
 // Stage arithmetic: an FP32 filter decides each stump; whenever |s32 - t32| is inside a
 // guard band (2^-20 |t32| plus the cancellation terms) the window's whole stage is redone by
@@ -110,7 +114,7 @@ __device__ __forceinline__ void emit_rect(const CascadeArgs &a, const CasLevel &
 #define TILE_LD(base, off) (*reinterpret_cast<const int *>((base) + (off)))
 
 struct DenseSmemPlan {
-    size_t tile, sigma, list, cnt, bar, total;
+    size_t tile, sigma, list, ctl, bar, total;
 };
 __host__ __device__ inline DenseSmemPlan dense_smem_plan(const DenseParams &P) {
     DenseSmemPlan p;
@@ -118,8 +122,8 @@ __host__ __device__ inline DenseSmemPlan dense_smem_plan(const DenseParams &P) {
     p.tile = 0;
     p.sigma = (rows * P.tile_stride * 4 + 127) & ~(size_t)127;
     p.list = p.sigma + kTileWindows * sizeof(double);
-    p.cnt = p.list + 2 * kTileWindows * sizeof(uint16_t);
-    p.bar = p.cnt + 3 * 32 * sizeof(int);
+    p.ctl = p.list + 2 * kTileWindows * sizeof(uint16_t);
+    p.bar = p.ctl + 32;
     p.total = p.bar + 16;
     return p;
 }
@@ -132,18 +136,16 @@ __device__ __noinline__ bool dense_eval_stage_exact(const DenseParams &P, int s,
     double S = 0.0;
     for (int j = 0; j < count; j++) {
         const DenseStump &q = P.stump[first + j];
-        const uint32_t o0 = q.offp[0], o1 = q.offp[1], o2 = q.offp[2], o3 = q.offp[3];
-        const int r0 = TILE_LD(base, o0 & 0xffffu) - TILE_LD(base, o0 >> 16) - TILE_LD(base, o1 & 0xffffu) + TILE_LD(base, o1 >> 16);
-        const int r1 = TILE_LD(base, o2 & 0xffffu) - TILE_LD(base, o2 >> 16) - TILE_LD(base, o3 & 0xffffu) + TILE_LD(base, o3 >> 16);
+        const int r0 = TILE_LD(base, q.off[0]) - TILE_LD(base, q.off[1]) - TILE_LD(base, q.off[2]) + TILE_LD(base, q.off[3]);
+        const int r1 = TILE_LD(base, q.off[4]) - TILE_LD(base, q.off[5]) - TILE_LD(base, q.off[6]) + TILE_LD(base, q.off[7]);
         const double t = __dmul_rn((double)q.thr, sigma);
         double sum;
         if (dbl) {  // tempcv.cpp:872-898; both products are exact in double, so fma == mul, mul, add
             sum = __fma_rn((double)r1, (double)q.w[1], __dmul_rn((double)r0, (double)q.w[0]));
         } else {    // tempcv.cpp:899-930 / 782-786: float products, double accumulation
             sum = __dadd_rn((double)__fmul_rn(__int2float_rn(r0), q.w[0]), (double)__fmul_rn(__int2float_rn(r1), q.w[1]));
-            const uint32_t o4 = q.offp[4], o5 = q.offp[5];
-            if (o5 != 0) {
-                const int r2 = TILE_LD(base, o4 & 0xffffu) - TILE_LD(base, o4 >> 16) - TILE_LD(base, o5 & 0xffffu) + TILE_LD(base, o5 >> 16);
+            if (q.off[11] != 0) {
+                const int r2 = TILE_LD(base, q.off[8]) - TILE_LD(base, q.off[9]) - TILE_LD(base, q.off[10]) + TILE_LD(base, q.off[11]);
                 sum = __dadd_rn(sum, (double)__fmul_rn(__int2float_rn(r2), q.w[2]));
             }
         }
@@ -152,9 +154,10 @@ __device__ __noinline__ bool dense_eval_stage_exact(const DenseParams &P, int s,
     return S >= (double)P.stage[s].thr;
 }
 
-// FP32-filtered evaluation of stage s for K windows of this thread.  Everything indexed by
-// the stump loop is warp-uniform (constant bank, uniform registers).
-template <int K, bool DBL, bool HAS3>
+// FP32-filtered evaluation of stage s for K windows of this thread.
+//   FIXED = true : window k lives at base0 + k*ROWSTEP (compile-time) -> immediate offsets
+//   FIXED = false: window k lives at base[k]
+template <int K, bool DBL, bool HAS3, bool FIXED, int ROWSTEP>
 __device__ __forceinline__ void dense_filter_stage(const DenseParams &P, int s, const unsigned char *const (&base)[K],
                                                    const float (&sg)[K], double (&S)[K], bool (&near)[K]) {
     const int first = P.stage[s].first, count = P.stage[s].count;
@@ -162,18 +165,23 @@ __device__ __forceinline__ void dense_filter_stage(const DenseParams &P, int s, 
 #pragma unroll 1
     for (int j = 0; j < count; j++) {
         const DenseStump &q = P.stump[first + j];
-        const uint32_t o0 = q.offp[0], o1 = q.offp[1], o2 = q.offp[2], o3 = q.offp[3];
-        const uint32_t a00 = o0 & 0xffffu, a01 = o0 >> 16, a02 = o1 & 0xffffu, a03 = o1 >> 16;
-        const uint32_t a10 = o2 & 0xffffu, a11 = o2 >> 16, a12 = o3 & 0xffffu, a13 = o3 >> 16;
         const float w0 = q.w[0], w1 = q.w[1], thr = q.thr;
         const double al0 = q.a0, al1 = q.a1;
-        const uint32_t o4 = q.offp[4], o5 = q.offp[5];
-        const bool three = HAS3 && (o5 != 0);   // warp-uniform
+        const bool three = HAS3 && (q.off[11] != 0);   // warp-uniform
+        // corner pointers of window 0 (shared by all K windows in fixed geometry)
+        const unsigned char *c00 = base[0] + q.off[0], *c01 = base[0] + q.off[1], *c02 = base[0] + q.off[2], *c03 = base[0] + q.off[3];
+        const unsigned char *c10 = base[0] + q.off[4], *c11 = base[0] + q.off[5], *c12 = base[0] + q.off[6], *c13 = base[0] + q.off[7];
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            const unsigned char *b = base[k];
-            const int r0 = TILE_LD(b, a00) - TILE_LD(b, a01) - TILE_LD(b, a02) + TILE_LD(b, a03);
-            const int r1 = TILE_LD(b, a10) - TILE_LD(b, a11) - TILE_LD(b, a12) + TILE_LD(b, a13);
+            int r0, r1;
+            if (FIXED) {
+                r0 = TILE_LD(c00, k * ROWSTEP) - TILE_LD(c01, k * ROWSTEP) - TILE_LD(c02, k * ROWSTEP) + TILE_LD(c03, k * ROWSTEP);
+                r1 = TILE_LD(c10, k * ROWSTEP) - TILE_LD(c11, k * ROWSTEP) - TILE_LD(c12, k * ROWSTEP) + TILE_LD(c13, k * ROWSTEP);
+            } else {
+                const unsigned char *b = base[k];
+                r0 = TILE_LD(b, q.off[0]) - TILE_LD(b, q.off[1]) - TILE_LD(b, q.off[2]) + TILE_LD(b, q.off[3]);
+                r1 = TILE_LD(b, q.off[4]) - TILE_LD(b, q.off[5]) - TILE_LD(b, q.off[6]) + TILE_LD(b, q.off[7]);
+            }
             const float p0 = __fmul_rn(__int2float_rn(r0), w0), p1 = __fmul_rn(__int2float_rn(r1), w1);
             float s32 = __fadd_rn(p0, p1);
             const float t32 = __fmul_rn(thr, sg[k]);
@@ -184,7 +192,8 @@ __device__ __forceinline__ void dense_filter_stage(const DenseParams &P, int s, 
             }
             if (HAS3) {
                 if (three) {
-                    const int r2 = TILE_LD(b, o4 & 0xffffu) - TILE_LD(b, o4 >> 16) - TILE_LD(b, o5 & 0xffffu) + TILE_LD(b, o5 >> 16);
+                    const unsigned char *b = FIXED ? base[0] + k * ROWSTEP : base[k];
+                    const int r2 = TILE_LD(b, q.off[8]) - TILE_LD(b, q.off[9]) - TILE_LD(b, q.off[10]) + TILE_LD(b, q.off[11]);
                     m = __fadd_rn(m, __fmul_rn(fabsf(s32), eps4));   // rounding of the first add
                     s32 = __fadd_rn(s32, __fmul_rn(__int2float_rn(r2), q.w[2]));
                 }
@@ -196,25 +205,34 @@ __device__ __forceinline__ void dense_filter_stage(const DenseParams &P, int s, 
     }
 }
 
+template <int K, bool FIXED, int ROWSTEP>
+__device__ __forceinline__ void dense_dispatch_stage(const DenseParams &P, int s, const unsigned char *const (&base)[K],
+                                                     const float (&sg)[K], double (&S)[K], bool (&near)[K]) {
+    const uint32_t flags = P.stage[s].flags;
+    if (flags & 1u) dense_filter_stage<K, true, false, FIXED, ROWSTEP>(P, s, base, sg, S, near);
+    else if (flags & 2u) dense_filter_stage<K, false, true, FIXED, ROWSTEP>(P, s, base, sg, S, near);
+    else dense_filter_stage<K, false, false, FIXED, ROWSTEP>(P, s, base, sg, S, near);
+}
+
 struct DenseCtx {
-    const DenseParams *P;
-    const CascadeArgs *a;
     unsigned char *tile;
     double *sigma;
-    uint16_t *list;   // [2][kBucketCap][32]
-    int *cnt;         // [3][32]
     int16_t *codes;   // this frame + level, or nullptr
     int row_mul;      // bytes between window rows in the tile
     int tx, ty, nx;
     int code_mul;
 };
 
-// evaluate stage s for the K windows (wid[], active[]) of this thread, append survivors to
-// bucket `lane` of list `nxt_list` / `nxt_cnt`
+__device__ __forceinline__ void dense_write_code(const DenseCtx &c, int wid, int code) {
+    const int wx = wid & (kTileW - 1), wy = wid / kTileW;
+    c.codes[(size_t)(c.ty * kTileH + wy) * c.nx + c.tx * kTileW + wx] = (int16_t)code;
+}
+
+// compacted phase: evaluate stage s for K list entries of this thread; survivors are appended
+// to `lout` with a warp ballot (one shared-memory atomic per warp and row)
 template <int K>
-__device__ __forceinline__ void dense_run_stage(const DenseCtx &c, int s, const int (&wid)[K], const bool (&act)[K],
-                                                int lane, uint16_t *nxt_list, int *nxt_cnt) {
-    const DenseParams &P = *c.P;
+__device__ __forceinline__ void dense_run_rows(const DenseParams &P, const DenseCtx &c, int s, const int (&wid)[K],
+                                               const bool (&act)[K], int lane, uint16_t *lout, int *out_cnt) {
     const unsigned char *base[K];
     float sg[K];
     double S[K];
@@ -227,34 +245,37 @@ __device__ __forceinline__ void dense_run_stage(const DenseCtx &c, int s, const 
         S[k] = 0.0;
         near[k] = P.force_exact != 0;
     }
-    const uint32_t flags = P.stage[s].flags;
-    if (flags & 1u) dense_filter_stage<K, true, false>(P, s, base, sg, S, near);
-    else if (flags & 2u) dense_filter_stage<K, false, true>(P, s, base, sg, S, near);
-    else dense_filter_stage<K, false, false>(P, s, base, sg, S, near);
+    dense_dispatch_stage<K, false, 0>(P, s, base, sg, S, near);
     const double sthr = (double)P.stage[s].thr;
 #pragma unroll
     for (int k = 0; k < K; k++) {
-        if (!act[k]) continue;
-        bool pass = S[k] >= sthr;
-        if (near[k]) pass = dense_eval_stage_exact(P, s, base[k], c.sigma[wid[k]]);
-        if (pass) {
-            const int slot = atomicAdd(&nxt_cnt[lane], 1);
-            nxt_list[slot * 32 + lane] = (uint16_t)wid[k];
-        } else if (c.codes) {
-            const int wx = wid[k] & (kTileW - 1), wy = wid[k] / kTileW;
-            c.codes[(size_t)(c.ty * kTileH + wy) * c.nx + c.tx * kTileW + wx] = (int16_t)(s * c.code_mul);
+        bool pass = false;
+        if (act[k]) {
+            pass = S[k] >= sthr;
+            if (near[k]) pass = dense_eval_stage_exact(P, s, base[k], c.sigma[wid[k]]);
+            if (!pass && c.codes) dense_write_code(c, wid[k], s * c.code_mul);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (bal) {
+            int wbase = 0;
+            if (lane == 0) wbase = atomicAdd(out_cnt, __popc(bal));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (pass) lout[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)wid[k];
         }
     }
 }
 
-__global__ void __launch_bounds__(kDenseThreads, 4)
+// ROWSTEP_T: compile-time byte distance between a thread's consecutive windows in phase 1
+// (= 2 window rows), or 0 to use the runtime value (generic window sizes).
+template <int ROWSTEP_T>
+__global__ void __launch_bounds__(kDenseThreads)
 k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ CascadeArgs a, const int tile0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const DenseSmemPlan plan = dense_smem_plan(P);
     unsigned char *tile = smem_raw + plan.tile;
     double *sigma = reinterpret_cast<double *>(smem_raw + plan.sigma);
     uint16_t *list = reinterpret_cast<uint16_t *>(smem_raw + plan.list);
-    int *cnt = reinterpret_cast<int *>(smem_raw + plan.cnt);
+    int *ctl = reinterpret_cast<int *>(smem_raw + plan.ctl);   // [0..2] rotating list counters, [4..5] queue base
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + plan.bar);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -286,7 +307,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     const ull *__restrict__ gsq = a.sq + frame_off + (size_t)py0 * L.sum_pitch + px0;
 
     // ---- stage the integral tile ----
-    if (tid < 96) cnt[tid] = 0;
+    if (tid < 8) ctl[tid] = 0;
     if (ystep == 1) {   // natural layout: one TMA bulk copy per row
         if (tid == 0) mbar_init(bar, 1);
         __syncthreads();
@@ -307,17 +328,20 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     }
 
     DenseCtx c;
-    c.P = &P; c.a = &a; c.tile = tile; c.sigma = sigma; c.list = list; c.cnt = cnt;
+    c.tile = tile; c.sigma = sigma;
     c.codes = a.codes ? a.codes + (size_t)frame * a.windows_per_frame + CL.win_base : nullptr;
     c.row_mul = ystep * S * 4;
     c.tx = tx; c.ty = ty; c.nx = CL.nx;
     c.code_mul = P.is_tree ? 2 : 1;
 
-    // ---- pass A: sigma + stage 0 for every window of the tile (natural order: lane = wx mod 32) ----
+    // ---- phase 1: sigma, then the fixed-geometry stages ----
+    constexpr int kRowsPerSlot = kDenseThreads / kTileW;   // window rows between a thread's slots (2)
+    const int rowstep = ROWSTEP_T ? ROWSTEP_T : kRowsPerSlot * c.row_mul;
+    const int wx = tid & (kTileW - 1), wy0 = tid / kTileW;
+    uint32_t alive = 0;   // bit k: window (wx, wy0 + 2k) still alive
     {
         const int eq_w = P.win_w - 2, eq_h = P.win_h - 2;
-        // equRect corners (1,1),(1,1+eq_w),(1+eq_h,1),(1+eq_h,1+eq_w) in tile byte offsets
-        int e[4];
+        int e[4];   // equRect corners (1,1),(1,1+eq_w),(1+eq_h,1),(1+eq_h,1+eq_w) as tile byte offsets
         {
             const int ys[4] = {1, 1, 1 + eq_h, 1 + eq_h}, xs[4] = {1, 1 + eq_w, 1, 1 + eq_w};
 #pragma unroll
@@ -325,62 +349,108 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
                 e[q] = 4 * (ystep == 1 ? ys[q] * S + xs[q] : ys[q] * S + (xs[q] & 1) * (S >> 1) + (xs[q] >> 1));
         }
         const int g0 = L.sum_pitch + 1, g1 = g0 + eq_w, g2 = (1 + eq_h) * L.sum_pitch + 1, g3 = g2 + eq_w;
-        int wid[kDenseSlots];
-        bool act[kDenseSlots];
 #pragma unroll
         for (int k = 0; k < kDenseSlots; k++) {
-            const int w = k * kDenseThreads + tid;
-            const int wx = w & (kTileW - 1), wy = w / kTileW;
-            act[k] = wx < n_wx && wy < n_wy;
-            wid[k] = act[k] ? w : lane;   // dummy: window (0, lane) keeps loads in range and banks distinct
-            if (act[k]) {
+            const int wy = wy0 + k * kRowsPerSlot;
+            if (wx < n_wx && wy < n_wy) {
+                alive |= 1u << k;
                 const unsigned char *base = tile + wy * c.row_mul + wx * 4;
                 const int s4 = TILE_LD(base, e[0]) - TILE_LD(base, e[1]) - TILE_LD(base, e[2]) + TILE_LD(base, e[3]);
                 const ull *q = gsq + (size_t)(wy * ystep) * L.sum_pitch + wx * ystep;
                 const ull q4 = __ldg(q + g0) - __ldg(q + g1) - __ldg(q + g2) + __ldg(q + g3);
-                sigma[w] = window_sigma(s4, q4, P.inv_area);
+                sigma[wy * kTileW + wx] = window_sigma(s4, q4, P.inv_area);
+            } else {
+                sigma[wy * kTileW + wx] = 1.0;
             }
         }
-        // a thread reads back only sigmas it wrote itself: no barrier needed
-        const int n_act = __reduce_add_sync(0xffffffffu, (int)act[0] + act[1] + act[2] + act[3]);
-        if (n_act) dense_run_stage<kDenseSlots>(c, 0, wid, act, lane, list, cnt);
+    }
+    // a thread reads back only sigmas it wrote itself: no barrier needed in phase 1
+    int s = 0;
+    for (; s < P.n_fixed; s++) {
+#pragma unroll 1
+        for (int k0 = 0; k0 < kDenseSlots; k0 += kDenseChunk) {
+            const uint32_t m4 = (alive >> k0) & ((1u << kDenseChunk) - 1u);
+            if (!__any_sync(0xffffffffu, m4 != 0)) continue;   // whole 4 x 32 block is dead
+            const unsigned char *base[kDenseChunk];
+            float sg[kDenseChunk];
+            double Ssum[kDenseChunk];
+            bool near[kDenseChunk];
+#pragma unroll
+            for (int k = 0; k < kDenseChunk; k++) {
+                const int wy = wy0 + (k0 + k) * kRowsPerSlot;
+                base[k] = tile + wy * c.row_mul + wx * 4;   // == base[0] + k * rowstep
+                sg[k] = (float)sigma[wy * kTileW + wx];
+                Ssum[k] = 0.0;
+                near[k] = P.force_exact != 0;
+            }
+            if (ROWSTEP_T) dense_dispatch_stage<kDenseChunk, true, ROWSTEP_T>(P, s, base, sg, Ssum, near);
+            else dense_dispatch_stage<kDenseChunk, false, 0>(P, s, base, sg, Ssum, near);
+            const double sthr = (double)P.stage[s].thr;
+#pragma unroll
+            for (int k = 0; k < kDenseChunk; k++) {
+                if (!((m4 >> k) & 1u)) continue;
+                const int wid = (wy0 + (k0 + k) * kRowsPerSlot) * kTileW + wx;
+                bool pass = Ssum[k] >= sthr;
+                if (near[k]) pass = dense_eval_stage_exact(P, s, base[k], sigma[wid]);
+                if (!pass) {
+                    alive &= ~(1u << (k0 + k));
+                    if (c.codes) dense_write_code(c, wid, s * c.code_mul);
+                }
+            }
+        }
+    }
+    (void)rowstep;
+
+    // ---- compaction of the phase-1 survivors (row-major order inside the tile) ----
+#pragma unroll
+    for (int k = 0; k < kDenseSlots; k++) {
+        const bool pass = (alive >> k) & 1u;
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (bal) {
+            int wbase = 0;
+            if (lane == 0) wbase = atomicAdd(&ctl[0], __popc(bal));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (pass) list[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((wy0 + k * kRowsPerSlot) * kTileW + wx);
+        }
     }
     __syncthreads();
 
-    // ---- remaining dense stages; compaction (per bank bucket) after each ----
-    int s = 1, cur = 0, curl = 0;   // cur: counter set (mod 3) of the input list, curl: list buffer (mod 2)
-    int my_cnt, n_alive;
+    // ---- phase 2: remaining dense stages on compacted lists ----
+    int cur = 0, curl = 0;   // cur: counter (mod 3) of the input list, curl: list buffer (mod 2)
+    int n_alive;
     for (;;) {
-        my_cnt = cnt[cur * 32 + lane];
-        n_alive = __reduce_add_sync(0xffffffffu, my_cnt);
+        n_alive = ctl[cur];
         if (n_alive == 0) return;
         if (s >= P.n_stages || (n_alive <= kHandoffWindows && P.n_stages < P.total_stages)) break;
         const int nxt = cur == 2 ? 0 : cur + 1, nxt2 = nxt == 2 ? 0 : nxt + 1;
-        if (warp == 0) cnt[nxt2 * 32 + lane] = 0;   // not read or appended to during this stage
-        const int kmax = __reduce_max_sync(0xffffffffu, my_cnt);
-        const int K = kmax > warp ? (kmax - warp + kDenseWarps - 1) / kDenseWarps : 0;
+        if (tid == 0) ctl[nxt2] = 0;   // neither read nor appended to during this stage
         const uint16_t *lin = list + curl * kTileWindows;
         uint16_t *lout = list + (curl ^ 1) * kTileWindows;
-        int *ncnt = cnt + nxt * 32;
-        int wid[kDenseSlots];
-        bool act[kDenseSlots];
+        const int n_rows = (n_alive + 31) >> 5;
+        for (int r0 = warp; r0 < n_rows; r0 += kDenseWarps * kDenseChunk) {
+            int wid[kDenseChunk];
+            bool act[kDenseChunk];
+            int K = 0;
 #pragma unroll
-        for (int k = 0; k < kDenseSlots; k++) {
-            const int slot = warp + k * kDenseWarps;
-            act[k] = slot < my_cnt;
-            wid[k] = act[k] ? lin[slot * 32 + lane] : lane;
-        }
-        if (K == 1) {
-            const int w1[1] = {wid[0]}; const bool a1[1] = {act[0]};
-            dense_run_stage<1>(c, s, w1, a1, lane, lout, ncnt);
-        } else if (K == 2) {
-            const int w2[2] = {wid[0], wid[1]}; const bool a2[2] = {act[0], act[1]};
-            dense_run_stage<2>(c, s, w2, a2, lane, lout, ncnt);
-        } else if (K == 3) {
-            const int w3[3] = {wid[0], wid[1], wid[2]}; const bool a3[3] = {act[0], act[1], act[2]};
-            dense_run_stage<3>(c, s, w3, a3, lane, lout, ncnt);
-        } else if (K >= 4) {
-            dense_run_stage<4>(c, s, wid, act, lane, lout, ncnt);
+            for (int k = 0; k < kDenseChunk; k++) {
+                const int row = r0 + k * kDenseWarps;
+                const int i = row * 32 + lane;
+                act[k] = row < n_rows && i < n_alive;
+                wid[k] = act[k] ? lin[i] : lane;
+                K += row < n_rows;
+            }
+            if (K == 1) {
+                const int w1[1] = {wid[0]}; const bool a1[1] = {act[0]};
+                dense_run_rows<1>(P, c, s, w1, a1, lane, lout, &ctl[nxt]);
+            } else if (K == 2) {
+                const int w2[2] = {wid[0], wid[1]}; const bool a2[2] = {act[0], act[1]};
+                dense_run_rows<2>(P, c, s, w2, a2, lane, lout, &ctl[nxt]);
+            } else if (K == 3) {
+                const int w3[3] = {wid[0], wid[1], wid[2]}; const bool a3[3] = {act[0], act[1], act[2]};
+                dense_run_rows<3>(P, c, s, w3, a3, lane, lout, &ctl[nxt]);
+            } else {
+                dense_run_rows<4>(P, c, s, wid, act, lane, lout, &ctl[nxt]);
+            }
         }
         __syncthreads();
         cur = nxt; curl ^= 1; s++;
@@ -389,39 +459,22 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     // ---- survivors: accepted (whole cascade was dense) or handed to the deep kernel ----
     const uint16_t *lin = list + curl * kTileWindows;
     if (s >= P.total_stages) {
-        for (int slot = warp; slot < my_cnt; slot += kDenseWarps) {
-            const int w = lin[slot * 32 + lane];
-            const int wx = w & (kTileW - 1), wy = w / kTileW;
-            emit_rect(a, CL, frame, px0 + wx * ystep, py0 + wy * ystep);
-            if (c.codes) c.codes[(size_t)(ty * kTileH + wy) * CL.nx + tx * kTileW + wx] = (int16_t)P.total_stages;
+        for (int i = tid; i < n_alive; i += kDenseThreads) {
+            const int w = lin[i];
+            emit_rect(a, CL, frame, px0 + (w & (kTileW - 1)) * ystep, py0 + (w / kTileW) * ystep);
+            if (c.codes) dense_write_code(c, w, P.total_stages);
         }
     } else {
-        // exclusive prefix of the bucket counts gives every lane its slice of the queue block
-        int incl = my_cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
-        }
-        ull qb = 0;
-        if (warp == 0) {
-            if (lane == 0) qb = atomicAdd(a.counters + 1, (ull)n_alive);
-            qb = __shfl_sync(0xffffffffu, qb, 0);
-            // broadcast to the other warps through the (now unused) sigma area
-            if (lane == 0) *reinterpret_cast<ull *>(sigma) = qb;
-        }
+        if (tid == 0) *reinterpret_cast<ull *>(ctl + 4) = atomicAdd(a.counters + 1, (ull)n_alive);
         __syncthreads();
-        qb = *reinterpret_cast<const ull *>(sigma);
-        const ull lane_base = qb + (ull)(incl - my_cnt);
-        for (int slot = warp; slot < my_cnt; slot += kDenseWarps) {
-            const int w = lin[slot * 32 + lane];
-            const int wx = w & (kTileW - 1), wy = w / kTileW;
-            const ull pos = lane_base + slot;
-            if (pos < a.queue_cap) {
+        const ull qb = *reinterpret_cast<const ull *>(ctl + 4);
+        for (int i = tid; i < n_alive; i += kDenseThreads) {
+            const int w = lin[i];
+            if (qb + i < a.queue_cap) {
                 QueueItem it;
                 it.key = ((uint32_t)frame << 16) | ((uint32_t)cl << 8) | (uint32_t)s;
-                it.xy = ((uint32_t)(py0 + wy * ystep) << 16) | (uint32_t)(px0 + wx * ystep);
-                a.queue[pos] = it;
+                it.xy = ((uint32_t)(py0 + (w / kTileW) * ystep) << 16) | (uint32_t)(px0 + (w & (kTileW - 1)) * ystep);
+                a.queue[qb + i] = it;
             } else {
                 atomicAdd(a.counters + 3, 1ull);
             }
@@ -429,17 +482,28 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     }
 }
 
-cudaError_t launch_cascade_tiles(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, cudaStream_t stream) {
-    if (n_tiles <= 0 || a.n_frames == 0) return cudaSuccess;
-    const size_t smem = dense_smem_bytes(P);
+template <int ROWSTEP_T>
+static cudaError_t launch_tiles_t(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, size_t smem, cudaStream_t stream) {
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_cascade_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_cascade_tiles<ROWSTEP_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    k_cascade_tiles<<<dim3(n_tiles, a.n_frames), kDenseThreads, smem, stream>>>(P, a, tile0);
+    k_cascade_tiles<ROWSTEP_T><<<dim3(n_tiles, a.n_frames), kDenseThreads, smem, stream>>>(P, a, tile0);
     return cudaGetLastError();
+}
+
+cudaError_t launch_cascade_tiles(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, cudaStream_t stream) {
+    if (n_tiles <= 0 || a.n_frames == 0) return cudaSuccess;
+    const size_t smem = dense_smem_bytes(P);
+    // byte distance between a thread's consecutive phase-1 windows: 2 window rows
+    const int rowstep = (kDenseThreads / kTileW) * P.ystep * P.tile_stride * 4;
+    switch (rowstep) {   // common window sizes get immediate-offset code (20x20 / 24x24 cascades)
+        case 2 * 1 * 96 * 4:  return launch_tiles_t<2 * 1 * 96 * 4>(P, a, tile0, n_tiles, smem, stream);
+        case 2 * 2 * 160 * 4: return launch_tiles_t<2 * 2 * 160 * 4>(P, a, tile0, n_tiles, smem, stream);
+        default:              return launch_tiles_t<0>(P, a, tile0, n_tiles, smem, stream);
+    }
 }
 
 // ------------------------------------------------------------------------------------
