@@ -62,7 +62,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -70,7 +70,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """start of the timed region: earlier samples are dropped"""
+        self.t0 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -79,7 +83,10 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0 = getattr(self, "t0", 0.0)
+        for ts, ln in self.lines:
+            if ts < t0:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -143,7 +150,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU")
@@ -196,6 +203,8 @@ def main():
     def step_e2e():
         return det.detect(host)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()   # nvidia-smi needs ~0.5 s to start: launch it before the warm-up
     for _ in range(max(args.warmup, 3)):
         res = step_device()
     n_rects = len(res.rects)
@@ -203,10 +212,9 @@ def main():
     # ---- timed: device-resident input ------------------------------------------------------
     det.set_profiling(True)
     kernel_ms = np.zeros(8)
-    sampler = ClockSampler(local_rank)
     launches0 = ctx.launch_count
     barrier()
-    sampler.start()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()

@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "clfd_pack.h"
@@ -274,7 +275,11 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
             ns++;
         }
         P.n_stages = ns;
-        P.n_fixed = ns < 3 ? ns : 3;
+        {   // stages evaluated in fixed geometry before the first compaction (tunable for experiments)
+            int nf = 3;
+            if (const char *e = getenv("CLFD_N_FIXED")) nf = atoi(e);
+            P.n_fixed = nf < 0 ? 0 : (nf > ns ? ns : nf);
+        }
         out.dense_stumps = nstump;
     }
 }

@@ -114,16 +114,20 @@ __device__ __forceinline__ void emit_rect(const CascadeArgs &a, const CasLevel &
 #define TILE_LD(base, off) (*reinterpret_cast<const int *>((base) + (off)))
 
 struct DenseSmemPlan {
-    size_t tile, sigma, list, ctl, bar, total;
+    size_t tile, sigma, list, blist, ctl, bar, total;
 };
+// control block (ints): [0..31] bucket counts, [32..63] snapshot of the counts, [64..95] round
+// masks, [96..127] round prefixes, [128] survivors, [130..131] queue base
+constexpr int kCtlBcnt = 0, kCtlBcopy = 32, kCtlRmask = 64, kCtlRpref = 96, kCtlAlive = 128, kCtlQueue = 130, kCtlInts = 136;
 __host__ __device__ inline DenseSmemPlan dense_smem_plan(const DenseParams &P) {
     DenseSmemPlan p;
     const size_t rows = (size_t)(kTileH - 1) * P.ystep + P.win_h + 1;
     p.tile = 0;
     p.sigma = (rows * P.tile_stride * 4 + 127) & ~(size_t)127;
     p.list = p.sigma + kTileWindows * sizeof(double);
-    p.ctl = p.list + 2 * kTileWindows * sizeof(uint16_t);
-    p.bar = p.ctl + 32;
+    p.blist = p.list + kTileWindows * sizeof(uint16_t);
+    p.ctl = p.blist + kTileWindows * sizeof(uint16_t);
+    p.bar = p.ctl + kCtlInts * sizeof(int);
     p.total = p.bar + 16;
     return p;
 }
@@ -228,11 +232,17 @@ __device__ __forceinline__ void dense_write_code(const DenseCtx &c, int wid, int
     c.codes[(size_t)(c.ty * kTileH + wy) * c.nx + c.tx * kTileW + wx] = (int16_t)code;
 }
 
-// compacted phase: evaluate stage s for K list entries of this thread; survivors are appended
-// to `lout` with a warp ballot (one shared-memory atomic per warp and row)
+// survivors go to the bucket of their bank residue (wx mod 32): blist[slot][bucket]
+__device__ __forceinline__ void dense_append(uint16_t *blist, int *bcnt, int wid) {
+    const int b = wid & 31;
+    const int slot = atomicAdd(&bcnt[b], 1);
+    blist[slot * 32 + b] = (uint16_t)wid;
+}
+
+// compacted phase: evaluate stage s for K list entries of this thread
 template <int K>
 __device__ __forceinline__ void dense_run_rows(const DenseParams &P, const DenseCtx &c, int s, const int (&wid)[K],
-                                               const bool (&act)[K], int lane, uint16_t *lout, int *out_cnt) {
+                                               const bool (&act)[K], uint16_t *blist, int *bcnt) {
     const unsigned char *base[K];
     float sg[K];
     double S[K];
@@ -249,20 +259,52 @@ __device__ __forceinline__ void dense_run_rows(const DenseParams &P, const Dense
     const double sthr = (double)P.stage[s].thr;
 #pragma unroll
     for (int k = 0; k < K; k++) {
-        bool pass = false;
-        if (act[k]) {
-            pass = S[k] >= sthr;
-            if (near[k]) pass = dense_eval_stage_exact(P, s, base[k], c.sigma[wid[k]]);
-            if (!pass && c.codes) dense_write_code(c, wid[k], s * c.code_mul);
+        if (!act[k]) continue;
+        bool pass = S[k] >= sthr;
+        if (near[k]) pass = dense_eval_stage_exact(P, s, base[k], c.sigma[wid[k]]);
+        if (pass) dense_append(blist, bcnt, wid[k]);
+        else if (c.codes) dense_write_code(c, wid[k], s * c.code_mul);
+    }
+}
+
+// Turn the bucketed survivors into a linear list in ROUND-ROBIN bucket order (slot 0 of every
+// non-empty bucket, then slot 1, ...): a row of 32 consecutive entries then holds (nearly)
+// distinct bank residues, so phase-2 corner loads are (nearly) conflict free while rows stay
+// full.  Returns the number of survivors.  Three barriers; all threads must call it.
+__device__ __forceinline__ int dense_reorder(uint16_t *list, const uint16_t *blist, int *ctl, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    __syncthreads();   // all appends done
+    if (warp == 0) {
+        const int cl = ctl[kCtlBcnt + lane];
+        const int kmax = __reduce_max_sync(0xffffffffu, cl);
+        unsigned mymask = 0;   // lane r keeps the mask of buckets that have a slot r
+        for (int r = 0; r < kmax; r++) {
+            const unsigned m = __ballot_sync(0xffffffffu, cl > r);
+            if (lane == r) mymask = m;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, pass);
-        if (bal) {
-            int wbase = 0;
-            if (lane == 0) wbase = atomicAdd(out_cnt, __popc(bal));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (pass) lout[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)wid[k];
+        const int n = __popc(mymask);
+        int incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        ctl[kCtlRmask + lane] = (int)mymask;
+        ctl[kCtlRpref + lane] = incl - n;
+        ctl[kCtlBcopy + lane] = cl;
+        ctl[kCtlBcnt + lane] = 0;
+        if (lane == 31) ctl[kCtlAlive] = incl;
+    }
+    __syncthreads();
+    {
+        const int mine = ctl[kCtlBcopy + lane];
+        for (int r = warp; r < mine; r += kDenseWarps) {
+            const unsigned m = (unsigned)ctl[kCtlRmask + r];
+            list[ctl[kCtlRpref + r] + __popc(m & ((1u << lane) - 1u))] = blist[r * 32 + lane];
         }
     }
+    __syncthreads();
+    return ctl[kCtlAlive];
 }
 
 // ROWSTEP_T: compile-time byte distance between a thread's consecutive windows in phase 1
@@ -275,7 +317,8 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     unsigned char *tile = smem_raw + plan.tile;
     double *sigma = reinterpret_cast<double *>(smem_raw + plan.sigma);
     uint16_t *list = reinterpret_cast<uint16_t *>(smem_raw + plan.list);
-    int *ctl = reinterpret_cast<int *>(smem_raw + plan.ctl);   // [0..2] rotating list counters, [4..5] queue base
+    uint16_t *blist = reinterpret_cast<uint16_t *>(smem_raw + plan.blist);
+    int *ctl = reinterpret_cast<int *>(smem_raw + plan.ctl);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + plan.bar);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -307,7 +350,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     const ull *__restrict__ gsq = a.sq + frame_off + (size_t)py0 * L.sum_pitch + px0;
 
     // ---- stage the integral tile ----
-    if (tid < 8) ctl[tid] = 0;
+    for (int i = tid; i < kCtlInts; i += kDenseThreads) ctl[i] = 0;
     if (ystep == 1) {   // natural layout: one TMA bulk copy per row
         if (tid == 0) mbar_init(bar, 1);
         __syncthreads();
@@ -401,31 +444,16 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     }
     (void)rowstep;
 
-    // ---- compaction of the phase-1 survivors (row-major order inside the tile) ----
+    // ---- phase-1 survivors -> buckets -> bank-friendly linear list ----
 #pragma unroll
-    for (int k = 0; k < kDenseSlots; k++) {
-        const bool pass = (alive >> k) & 1u;
-        const unsigned bal = __ballot_sync(0xffffffffu, pass);
-        if (bal) {
-            int wbase = 0;
-            if (lane == 0) wbase = atomicAdd(&ctl[0], __popc(bal));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (pass) list[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((wy0 + k * kRowsPerSlot) * kTileW + wx);
-        }
-    }
-    __syncthreads();
+    for (int k = 0; k < kDenseSlots; k++)
+        if ((alive >> k) & 1u) dense_append(blist, ctl + kCtlBcnt, (wy0 + k * kRowsPerSlot) * kTileW + wx);
+    int n_alive = dense_reorder(list, blist, ctl, tid);
 
     // ---- phase 2: remaining dense stages on compacted lists ----
-    int cur = 0, curl = 0;   // cur: counter (mod 3) of the input list, curl: list buffer (mod 2)
-    int n_alive;
     for (;;) {
-        n_alive = ctl[cur];
         if (n_alive == 0) return;
         if (s >= P.n_stages || (n_alive <= kHandoffWindows && P.n_stages < P.total_stages)) break;
-        const int nxt = cur == 2 ? 0 : cur + 1, nxt2 = nxt == 2 ? 0 : nxt + 1;
-        if (tid == 0) ctl[nxt2] = 0;   // neither read nor appended to during this stage
-        const uint16_t *lin = list + curl * kTileWindows;
-        uint16_t *lout = list + (curl ^ 1) * kTileWindows;
         const int n_rows = (n_alive + 31) >> 5;
         for (int r0 = warp; r0 < n_rows; r0 += kDenseWarps * kDenseChunk) {
             int wid[kDenseChunk];
@@ -436,28 +464,28 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
                 const int row = r0 + k * kDenseWarps;
                 const int i = row * 32 + lane;
                 act[k] = row < n_rows && i < n_alive;
-                wid[k] = act[k] ? lin[i] : lane;
+                wid[k] = act[k] ? list[i] : lane;
                 K += row < n_rows;
             }
             if (K == 1) {
                 const int w1[1] = {wid[0]}; const bool a1[1] = {act[0]};
-                dense_run_rows<1>(P, c, s, w1, a1, lane, lout, &ctl[nxt]);
+                dense_run_rows<1>(P, c, s, w1, a1, blist, ctl + kCtlBcnt);
             } else if (K == 2) {
                 const int w2[2] = {wid[0], wid[1]}; const bool a2[2] = {act[0], act[1]};
-                dense_run_rows<2>(P, c, s, w2, a2, lane, lout, &ctl[nxt]);
+                dense_run_rows<2>(P, c, s, w2, a2, blist, ctl + kCtlBcnt);
             } else if (K == 3) {
                 const int w3[3] = {wid[0], wid[1], wid[2]}; const bool a3[3] = {act[0], act[1], act[2]};
-                dense_run_rows<3>(P, c, s, w3, a3, lane, lout, &ctl[nxt]);
+                dense_run_rows<3>(P, c, s, w3, a3, blist, ctl + kCtlBcnt);
             } else {
-                dense_run_rows<4>(P, c, s, wid, act, lane, lout, &ctl[nxt]);
+                dense_run_rows<4>(P, c, s, wid, act, blist, ctl + kCtlBcnt);
             }
         }
-        __syncthreads();
-        cur = nxt; curl ^= 1; s++;
+        n_alive = dense_reorder(list, blist, ctl, tid);
+        s++;
     }
 
     // ---- survivors: accepted (whole cascade was dense) or handed to the deep kernel ----
-    const uint16_t *lin = list + curl * kTileWindows;
+    const uint16_t *lin = list;
     if (s >= P.total_stages) {
         for (int i = tid; i < n_alive; i += kDenseThreads) {
             const int w = lin[i];
@@ -465,9 +493,9 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
             if (c.codes) dense_write_code(c, w, P.total_stages);
         }
     } else {
-        if (tid == 0) *reinterpret_cast<ull *>(ctl + 4) = atomicAdd(a.counters + 1, (ull)n_alive);
+        if (tid == 0) *reinterpret_cast<ull *>(ctl + kCtlQueue) = atomicAdd(a.counters + 1, (ull)n_alive);
         __syncthreads();
-        const ull qb = *reinterpret_cast<const ull *>(ctl + 4);
+        const ull qb = *reinterpret_cast<const ull *>(ctl + kCtlQueue);
         for (int i = tid; i < n_alive; i += kDenseThreads) {
             const int w = lin[i];
             if (qb + i < a.queue_cap) {
