@@ -228,6 +228,7 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
         P.is_tree = c.is_tree ? 1 : 0;
         P.ystep = ystep;
         P.filter_eps = 9.5367431640625e-07f;  // 2^-20
+        if (const char *e = getenv("CLFD_FORCE_EXACT")) P.force_exact = atoi(e) != 0;   // test hook: bypass the FP32 filter
         P.inv_area = 1. / ((c.win_w - 2) * (c.win_h - 2));
         const size_t tile_bytes = (size_t)dense_tile_rows(c.win_h, ystep) * P.tile_stride * 4;
         bool dense_ok = tile_bytes <= 65536 && c.win_w <= 255 && c.win_h <= 255;

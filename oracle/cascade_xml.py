@@ -57,8 +57,16 @@ class CascadeFormatError(ValueError):
     pass
 
 
+_INT_TOKEN = re.compile(r"^[+-]?\d+$")
+
+
 def _f32(text: str) -> np.float32:
-    return np.float32(float(text))
+    """CvFileStorage types a bare integer token as INT, and the reference then rejects it where
+    it wants CV_NODE_IS_REAL (tempcv.cpp:1925,1952,1981,2019,2049); reals carry '.' or an exponent."""
+    tok = text.strip()
+    if _INT_TOKEN.match(tok):
+        raise CascadeFormatError(f"value must be real number, got integer token {tok!r}")
+    return np.float32(float(tok))
 
 
 def load_cascade_xml(path: str) -> FlatCascade:

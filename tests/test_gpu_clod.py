@@ -96,3 +96,45 @@ def test_device_resident_enqueue_matches_host_path(gpu_ctx):
         assert np.array_equal(a.frame_rects(f), b.frame_rects(f))
     assert b.stats["windows"] == 3 * det.windows_per_frame()
     det.close()
+
+
+def test_fp32_filter_equals_all_fp64_evaluation(gpu_ctx, monkeypatch):
+    """The tile kernel decides stumps with an FP32 filter and redoes a window's stage in FP64
+    inside the guard band.  CLFD_FORCE_EXACT=1 makes every stage take the FP64 path: both
+    must give the same exit codes (and both equal the oracle, checked by _compare)."""
+    frames = np.stack([octave_frame(640, 480, 9), uniform_frame(640, 480, 9)])
+    monkeypatch.setenv("CLFD_FORCE_EXACT", "1")
+    _compare(gpu_ctx, ["frontalface_alt", "frontalface_default"], frames, 1.2)
+    monkeypatch.delenv("CLFD_FORCE_EXACT")
+    _compare(gpu_ctx, ["frontalface_alt", "frontalface_default"], frames, 1.2)
+
+
+@pytest.mark.parametrize("nf", [0, 1, 5])
+def test_any_split_between_fixed_and_compacted_stages(gpu_ctx, monkeypatch, nf):
+    monkeypatch.setenv("CLFD_N_FIXED", str(nf))
+    _compare(gpu_ctx, ["frontalface_alt"], np.stack([octave_frame(800, 600, 3)]), 1.2)
+
+
+def test_other_window_shapes_use_the_generic_tile_kernel(gpu_ctx):
+    # lowerbody-like shapes are not shipped here; fullbody (14x28) exercises the non-templated
+    # row step of the tile kernel for its two dense stages, then the deep kernel with tilted features
+    _compare(gpu_ctx, ["fullbody"], np.stack([octave_frame(700, 500, 6)]), 1.25)
+
+
+def test_full_size_properties_batch(gpu_ctx):
+    """At BASELINE sizes the oracle is too slow for every frame; check size-independent
+    properties instead: (i) a batch gives the same per-frame results as single-frame calls,
+    (ii) duplicated frames give duplicated detections, (iii) accepted windows == rect count."""
+    cas = clfd.Cascade(cascade_path("frontalface_alt"))
+    frames = np.stack([octave_frame(1920, 1080, i % 3) for i in range(6)])
+    det = clfd.Detector(gpu_ctx, cas, 1920, 1080, max_batch=6, scale_factor=1.2, want_codes=True)
+    res = det.detect(frames)
+    codes = det.codes(0, 6)
+    for f in range(3):
+        assert np.array_equal(res.frame_rects(f), res.frame_rects(f + 3))
+        assert np.array_equal(codes[f], codes[f + 3])
+    assert int((codes == cas.info.n_stages).sum()) == len(res.rects)
+    single = clfd.Detector(gpu_ctx, cas, 1920, 1080, max_batch=1, scale_factor=1.2)
+    for f in range(3):
+        assert np.array_equal(single.detect(frames[f:f + 1]).frame_rects(0), res.frame_rects(f))
+    det.close(); single.close()

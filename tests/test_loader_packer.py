@@ -1,0 +1,117 @@
+"""The product's C++ cascade loader / hidden-cascade builder (csrc/haar_xml.cpp,
+haar_pack.cpp, reached through the C ABI -- no GPU needed) against the oracle's independent
+Python reader + C hidden cascade, and against the census of SURVEY.md Appendix B."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import clfacedetection_b200 as clfd
+import oracle
+from conftest import ALL_CASCADES, cascade_path, oracle_cascade
+
+# file: (win_w, win_h, stages, trees, nodes, max trees/stage, max nodes/tree, tilted nodes, 3-rect nodes, stage tree)
+CENSUS = {
+    "eye": (20, 20, 24, 1066, 1066, 93, 1, 0, 167, 0),
+    "eye_tree_eyeglasses": (20, 20, 30, 851, 2553, 47, 3, 577, 295, 0),
+    "frontalface_alt": (20, 20, 22, 2135, 2135, 213, 1, 0, 360, 0),
+    "frontalface_alt2": (20, 20, 20, 1047, 2094, 109, 2, 0, 347, 0),
+    "frontalface_alt_tree": (20, 20, 47, 8468, 8468, 406, 1, 0, 1545, 1),
+    "frontalface_default": (24, 24, 25, 2913, 2913, 211, 1, 0, 557, 0),
+    "fullbody": (14, 28, 30, 1464, 1464, 107, 1, 201, 227, 0),
+    "mcs_nose": (18, 15, 20, 3365, 3365, 377, 1, 990, 557, 0),
+    "profileface": (20, 20, 26, 2609, 2609, 195, 1, 0, 415, 0),
+}
+
+
+@pytest.mark.parametrize("name", ALL_CASCADES)
+def test_census(name):
+    i = clfd.Cascade(cascade_path(name)).info
+    got = (i.win_w, i.win_h, i.n_stages, i.n_trees, i.n_nodes, i.max_trees_per_stage, i.max_nodes_per_tree,
+           i.n_tilted_nodes, i.n_three_rect_nodes, i.is_tree)
+    assert got == CENSUS[name]
+    assert bool(i.is_stump_based) == (i.max_nodes_per_tree == 1)
+    assert bool(i.has_tilted) == (i.n_tilted_nodes > 0)
+
+
+@pytest.mark.parametrize("name", ALL_CASCADES)
+def test_loader_equals_oracle_reader_bit_for_bit(name):
+    ours = clfd.Cascade(cascade_path(name)).arrays()
+    ref = oracle.load_cascade_xml(cascade_path(name))
+    for k in ("st_ntrees", "st_thr", "st_parent", "st_next", "tr_nnodes", "nd_tilted", "nd_rect", "nd_weight",
+              "nd_thr", "nd_left", "nd_right", "alpha"):
+        a, b = ours[k], getattr(ref, k)
+        assert a.shape == b.shape and a.tobytes() == b.tobytes(), k
+
+
+@pytest.mark.parametrize("name", ALL_CASCADES)
+def test_hidden_cascade_equals_oracle(name):
+    """scale-1 weights, kept-rect counts, biased stage thresholds, two_rects (tempcv.cpp:419,453-458,752-760)"""
+    w, nr, thr, two = clfd.Cascade(cascade_path(name)).hidden()
+    ow, onr, othr, otwo, _ = oracle_cascade(name).hidden()
+    assert w.tobytes() == ow.tobytes()
+    assert np.array_equal(nr, onr) and thr.tobytes() == othr.tobytes() and np.array_equal(two, otwo)
+
+
+def test_from_arrays_round_trip_and_child_links():
+    flat = oracle.load_cascade_xml(cascade_path("frontalface_alt_tree"))
+    c = clfd.Cascade(flat=flat)
+    a = c.arrays()
+    assert c.info.is_tree == 1
+    child = a["st_child"]
+    # SURVEY Appendix B topology: 0-4 linear, stage 4 -> child 5 (next 6); odd chain ends at 39
+    assert child[:5].tolist() == [1, 2, 3, 4, 5] and a["st_next"][5] == 6 and child[39] == -1
+    assert c.info.dense_stages == 5   # only the unconditional linear prefix can be tile-evaluated
+
+
+def test_dense_prefix_rules():
+    assert clfd.Cascade(cascade_path("frontalface_alt")).info.dense_stages >= 8
+    assert clfd.Cascade(cascade_path("frontalface_alt2")).info.dense_stages == 0     # multi-node trees
+    assert clfd.Cascade(cascade_path("fullbody")).info.dense_stages == 2             # first tilted stump in stage 2
+    assert clfd.Cascade(cascade_path("mcs_nose")).info.dense_stages == 0
+
+
+def _mutate(name, old, new, count=1):
+    text = open(cascade_path(name), encoding="latin-1").read()
+    assert old in text
+    f = tempfile.NamedTemporaryFile("w", suffix=".xml", delete=False, encoding="latin-1")
+    f.write(text.replace(old, new, count))
+    f.close()
+    return f.name
+
+
+@pytest.mark.parametrize("old,new,msg", [
+    ("<size>20 20</size>", "<size>20</size>", "size node is not a valid sequence"),
+    ("<_>3 7 14 4 -1.</_>", "<_>3 7 19 4 -1.</_>", "width must be positive integer and (x + width) must not exceed window width"),
+    ("<_>3 7 14 4 -1.</_>", "<_>3 7 14 4 -1</_>", "weight must be real number"),
+    ("<tilted>0</tilted>", "", "tilted must be 0 or 1"),
+    ("<left_val>", "<left_vall>", None),
+    ("<parent>-1</parent>", "<parent>99</parent>", "parent must be integer number. (stage 0)"),
+    ("<stage_threshold>", "<stage_thresholdx>", None),
+])
+def test_malformed_cascades_fail_loudly(old, new, msg):
+    path = _mutate("frontalface_alt", old, new)
+    try:
+        with pytest.raises(clfd.ClfdError) as e:
+            clfd.Cascade(path)
+        assert e.value.status == -3
+        if msg:
+            assert msg in str(e.value)
+        with pytest.raises(Exception):
+            oracle.load_cascade_xml(path)
+    finally:
+        os.unlink(path)
+
+
+def test_missing_and_foreign_files():
+    with pytest.raises(clfd.ClfdError) as e:
+        clfd.Cascade("/nonexistent/haarcascade.xml")
+    assert e.value.status == -4
+    f = tempfile.NamedTemporaryFile("w", suffix=".xml", delete=False)
+    f.write("<?xml version='1.0'?><opencv_storage><cascade type_id=\"opencv-cascade-classifier\"></cascade></opencv_storage>")
+    f.close()
+    with pytest.raises(clfd.ClfdError) as e:
+        clfd.Cascade(f.name)
+    assert "opencv-haar-classifier" in str(e.value)
+    os.unlink(f.name)
