@@ -242,24 +242,16 @@ def main():
     d2h = int(len(r.rects) * 24 + 32)
 
     # ---- the single gather of detection rects (no collective in the hot loop) ---------------
+    from clfacedetection_b200 import sharding
+    t_g0 = time.perf_counter()
+    local = sharding.rects_to_array(res.rects, frame_offset=rank * B)   # rank r owns frames [r*B, (r+1)*B)
+    gathered = sharding.gather_rects(local, device="cuda")
+    gather_ms = 1e3 * (time.perf_counter() - t_g0)
+    total_rects = len(gathered)
     if world > 1:
-        t = torch.tensor([ms, e2e_s, float(n_rects)], device="cuda", dtype=torch.float64)
-        mx = t.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        counts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-        dist.all_gather(counts, torch.tensor([n_rects], dtype=torch.int64, device="cuda"))
-        cap = int(max(c.item() for c in counts))
-        mine = torch.zeros((max(cap, 1), 6), dtype=torch.int32, device="cuda")
-        if n_rects:
-            rr = res.rects
-            mine[:n_rects] = torch.from_numpy(
-                np.stack([rr[k] for k in ("x", "y", "w", "h", "frame", "cascade")], 1).astype(np.int32)).cuda()
-        gathered = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(gathered, mine)
-        ms, e2e_s = float(mx[0].item()), float(mx[1].item())
-        total_rects = int(sum(c.item() for c in counts))
-    else:
-        total_rects = n_rects
+        t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)   # timing: max over ranks
+        ms, e2e_s = float(t[0].item()), float(t[1].item())
 
     if rank == 0:
         stats = det.stats()
@@ -292,6 +284,7 @@ def main():
             "windows_per_sec": round(fps * wpf, 1),
             "wall_s": round(wall, 4),
             "rects_per_step": total_rects,
+            "rect_gather_ms": round(gather_ms, 3),
             "deep_windows_per_step": stats["deep_windows"],
             "e2e": {"value": round(B * world * args.steps / e2e_s, 2), "unit": "frames/s",
                     "h2d_bytes_per_step": int(B * W * H), "d2h_bytes_per_step": d2h},
