@@ -1,0 +1,71 @@
+#!/usr/bin/env python3
+"""Turn an `ncu --set full` report (.ncu-rep, scratch under gpurun_out/) into the small
+per-kernel CSV summary that is committed under profiles/.
+
+usage: python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/r1_xxx_full.csv
+"""
+import csv
+import subprocess
+import sys
+
+KEEP = [
+    "ID", "Kernel Name", "Grid Size", "Block Size",
+    "gpu__time_duration.sum",
+    "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
+    "l1tex__t_bytes.sum", "l1tex__t_sector_hit_rate.pct",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed.avg.per_cycle_elapsed",
+    "sm__inst_issued.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_adu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
+    "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "smsp__thread_inst_executed_per_inst_executed.pct",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem", "launch__shared_mem_per_block_dynamic",
+    "launch__shared_mem_per_block_static", "launch__waves_per_multiprocessor",
+    "smsp__inst_executed.sum",
+    "smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+    "smsp__average_warp_latency_issue_stalled_barrier.ratio",
+    "smsp__average_warp_latency_issue_stalled_mio_throttle.ratio",
+    "smsp__average_warp_latency_issue_stalled_lg_throttle.ratio",
+    "smsp__average_warp_latency_issue_stalled_not_selected.ratio",
+    "smsp__average_warp_latency_issue_stalled_wait.ratio",
+    "smsp__average_warp_latency_issue_stalled_math_pipe_throttle.ratio",
+    "smsp__average_warp_latency_issue_stalled_dispatch_stall.ratio",
+    "smsp__average_warp_latency_issue_stalled_branch_resolving.ratio",
+]
+
+
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"],
+                         check=True, capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    head, units, body = rows[0], rows[1], rows[2:]
+    cols = [(k, head.index(k)) for k in KEEP if k in head]
+    with open(out, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["metric", "unit"] + ["%s | %s" % (r[head.index("ID")], r[head.index("Kernel Name")]) for r in body])
+        for k, i in cols:
+            if k in ("ID", "Kernel Name"):
+                continue
+            w.writerow([k, units[i]] + [r[i] for r in body])
+    print("wrote", out, len(body), "launches,", len(cols), "metrics")
+
+
+if __name__ == "__main__":
+    main()
