@@ -228,6 +228,8 @@ struct CascadePlan {
     DevBuf<DeepNode> d_nodes;
     DevBuf<int> d_tree_first;
     DevBuf<float> d_alpha;
+    DevBuf<TailStump> d_tail[2];   // warp-per-window tail records of the tile kernel, [ystep-1]
+    DenseParams dense[2];          // the cascade's parameter blobs with this detector's tail pointers
     DevBuf<int16_t> d_codes;
     DevBuf<unsigned long long> d_counters;
     unsigned long long h_counters[4] = {0, 0, 0, 0};
@@ -617,6 +619,12 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
             (rc = cp.d_nodes.upload(pk.deep_nodes, s)) || (rc = cp.d_tree_first.upload(pk.tree_first_node, s)) ||
             (rc = cp.d_alpha.upload(pk.alpha, s)))
             return rc;
+        for (int yi = 0; yi < 2; yi++) {
+            cp.dense[yi] = pk.dense[yi];
+            if (!pk.tail[yi].empty() && (rc = cp.d_tail[yi].upload(pk.tail[yi], s))) return rc;
+            cp.dense[yi].tail = cp.d_tail[yi].p;
+            if (!cp.d_tail[yi].p) cp.dense[yi].tail_stages = 0;
+        }
         if ((rc = cp.d_counters.alloc(4))) return rc;
         if (cfg->want_codes && (rc = cp.d_codes.alloc((size_t)std::max<long long>(cp.windows_per_frame, 1) * cfg->max_batch)))
             return rc;
@@ -713,9 +721,9 @@ int clfd_detector_enqueue(clfd_detector *det, const uint8_t *frames_dev, int n_f
             if (ev && ci == 0) CK(cudaEventRecord(ev[5], s));
             if (pk.dense[0].n_stages > 0) {
                 // ystep-2 levels (de-interleaved tile layout) and ystep-1 levels (natural layout)
-                if (cp.n_tiles_y2 > 0) { CK(launch_cascade_tiles(pk.dense[1], a, 0, cp.n_tiles_y2, s)); launches++; }
+                if (cp.n_tiles_y2 > 0) { CK(launch_cascade_tiles(cp.dense[1], a, 0, cp.n_tiles_y2, s)); launches++; }
                 if (cp.n_tiles > cp.n_tiles_y2) {
-                    CK(launch_cascade_tiles(pk.dense[0], a, cp.n_tiles_y2, cp.n_tiles - cp.n_tiles_y2, s));
+                    CK(launch_cascade_tiles(cp.dense[0], a, cp.n_tiles_y2, cp.n_tiles - cp.n_tiles_y2, s));
                     launches++;
                 }
             } else {
@@ -723,7 +731,9 @@ int clfd_detector_enqueue(clfd_detector *det, const uint8_t *frames_dev, int n_f
                 launches++;
             }
             if (ev && ci == 0) CK(cudaEventRecord(ev[6], s));
-            if (pk.dense[0].n_stages < pk.dense[0].total_stages) { CK(launch_cascade_deep(a, ctx->n_sms, s)); launches++; }
+            // cascades the tile kernel finishes itself (tail_stages) never fill the queue
+            const bool tiles_finish = pk.dense[0].n_stages > 0 && cp.dense[0].tail_stages && cp.dense[1].tail_stages;
+            if (!tiles_finish && pk.dense[0].n_stages < pk.dense[0].total_stages) { CK(launch_cascade_deep(a, ctx->n_sms, s)); launches++; }
             if (ev && ci == 0) CK(cudaEventRecord(ev[7], s));
         }
         // all cascades append to one rect buffer: carry the rect count over

@@ -66,7 +66,9 @@ constexpr int kDenseSlots = kTileWindows / kDenseThreads;   // windows per threa
 constexpr int kDenseChunk = 4;                               // windows a thread carries through a stage at once
 constexpr int kMaxDenseStumps = 396;
 constexpr int kMaxDenseStages = 32;
-constexpr int kHandoffWindows = 8;  // <= this many survivors in a tile: hand them to the deep kernel
+constexpr int kHandoffWindows = 8;  // <= this many survivors in a tile: warp-per-window tail (or the deep kernel)
+constexpr int kGroupRows = 4;       // list rows (of 32 windows) a warp carries through a compacted stage at once
+constexpr int kGroupWindows = kGroupRows * 32;
 
 // One stump of the dense kernel, 80 B, read through the constant bank (the packed cascade
 // is a kernel parameter); the whole warp evaluates the same stump.
@@ -77,26 +79,40 @@ struct DenseStump {
     double a0, a1;     // alpha[0] (sum < t), alpha[1] (sum >= t), pre-converted (exact)
 };
 struct DenseStage {
-    uint16_t first, count;
-    float thr;         // biased threshold
-    uint32_t flags;    // bit0 double-product stage (two_rects fast path), bit1 any 3-rect stump
-    uint32_t pad;
+    uint16_t first, count;   // first: index into DenseParams::stump (stages < n_stages only)
+    float thr;               // biased threshold
+    uint32_t flags;          // bit0 double-product stage (two_rects fast path), bit1 any 3-rect stump,
+                             // bit2 alpha sum exact in any order (HostCascade::order_free)
+    uint32_t tail_first;     // index of the stage's first stump in the global TailStump array
+};
+// The same stump for the warp-per-window tail of the tile kernel (lanes stride over the stumps
+// of a stage, so records are read from global memory, 48 B = 3 x LDG.128 per lane).
+struct TailStump {
+    uint16_t off[12];  // BYTE offsets into the smem tile (tile <= 64 KB)
+    float w[3];
+    float thr;
+    float a0, a1;
 };
 // Two blobs per cascade: [0] for ystep-1 levels (natural tile layout, addr = y*S + x) and
 // [1] for ystep-2 levels (columns de-interleaved: addr = y*S + (x&1)*S/2 + (x>>1)), so that in
-// both a window's base address is  f(wy)*S + wx  with S a multiple of 32 words: the bank of
-// every corner load is (wx + const) mod 32 and lanes holding distinct wx mod 32 never conflict.
+// both a window's base word is  ystep*wy*S + wx  with ystep*S = 8 (mod 32): the bank of every
+// corner load is (wx + 8*wy + const) mod 32, so lanes whose windows have distinct
+// (wx + 8*wy) mod 32 never conflict, and a compact blob of survivors spreads over the banks.
 struct DenseParams {
     int n_stages;       // dense stages (prefix of the cascade)
     int total_stages;   // stages in the whole cascade
-    int tile_stride;    // ints per smem tile row (multiple of 32)
+    int tile_stride;    // ints per smem tile row (ystep * stride = 8 mod 32)
     int win_w, win_h;
     int is_tree;        // stage-tree cascade: exit codes are 2*last_stage (+accept)
     int ystep;          // 1 or 2
     int force_exact;    // test hook: skip the FP32 filter, evaluate every stage in FP64
     float filter_eps;   // FP32 filter guard band (2^-20), see kernels_clod.cu
     int n_fixed;        // leading stages run in fixed geometry (no compaction), <= n_stages
+    int tail_stages;    // == total_stages when the tile kernel can finish the cascade itself (stump based,
+                        // upright, linear, <= kMaxDenseStages stages): no queue / deep kernel; else 0
+    int handoff;        // <= this many survivors in a tile: leave the compacted phase
     double inv_area;
+    const TailStump *tail;   // device, layout of this blob's ystep (patched in by the detector)
     DenseStage stage[kMaxDenseStages];
     DenseStump stump[kMaxDenseStumps];
 };

@@ -7,6 +7,7 @@ namespace clfd {
 struct PackedCascade {
     DenseParams dense[2];              // kernel-parameter blobs of the smem-tile kernel: [ystep-1]
     int dense_stumps = 0;
+    std::vector<TailStump> tail[2];    // every stump of the cascade in tile-offset form, [ystep-1]; empty if no tail
     std::vector<DeepStage> deep_stages;  // global-memory blob of the deep kernel
     std::vector<DeepNode> deep_nodes;
     std::vector<int> tree_first_node;
@@ -16,7 +17,7 @@ struct PackedCascade {
 void pack_cascade(const HostCascade &c, PackedCascade &out);
 const char *get_error();
 
-int dense_tile_stride(int win_w, int ystep);  // ints per smem tile row (multiple of 32)
+int dense_tile_stride(int win_w, int ystep);  // ints per smem tile row (ystep * stride = 8 mod 32)
 int dense_tile_rows(int win_h, int ystep);    // integral rows a tile needs
 int dense_tile_cols(int win_w, int ystep);    // integral columns a tile needs (multiple of 4)
 

@@ -174,10 +174,14 @@ int dense_tile_cols(int win_w, int ystep) { return ((kTileW - 1) * ystep + win_w
 int dense_tile_rows(int win_h, int ystep) { return (kTileH - 1) * ystep + win_h + 1; }
 int dense_tile_stride(int win_w, int ystep) {
     // ystep 1: natural layout, stride >= cols.  ystep 2: even columns in the first half of a
-    // row, odd columns in the second half, stride/2 >= cols/2.  Multiple of 32 words either way.
+    // row, odd columns in the second half, stride/2 >= cols/2.  In both the word distance
+    // between consecutive WINDOW rows, ystep * stride, is 8 (mod 32) and the stride is a
+    // multiple of 4 words (16-byte rows for the TMA bulk copies / 8-byte halves for STS.64).
     const int cols = dense_tile_cols(win_w, ystep);
-    const int need = ystep == 1 ? cols : 2 * ((cols + 1) / 2);
-    return (need + 31) & ~31;
+    int s = ystep == 1 ? cols : 2 * ((cols + 1) / 2);
+    s = (s + 3) & ~3;
+    while ((ystep * s) % 32 != 8) s += 4;
+    return s;
 }
 
 void pack_cascade(const HostCascade &c, PackedCascade &out) {
@@ -214,7 +218,6 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
         d.left = nd.left; d.right = nd.right;
         d.flags = (nd.tilted ? 1 : 0) | (c.hid_nrects[n] << 8);
     }
-    (void)T;
 
     // dense prefix: leading stages of a stump-based, upright, linear-prefix cascade whose
     // stumps fit the kernel-parameter budget and whose smem offsets fit 16 bits.
@@ -232,6 +235,48 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
         P.inv_area = 1. / ((c.win_w - 2) * (c.win_h - 2));
         const size_t tile_bytes = (size_t)dense_tile_rows(c.win_h, ystep) * P.tile_stride * 4;
         bool dense_ok = tile_bytes <= 65536 && c.win_w <= 255 && c.win_h <= 255;
+        // Can the tile kernel finish the cascade on its own (warp-per-window tail over global
+        // TailStump records)?  Needs a linear, upright, stump-based cascade.
+        bool tail_ok = dense_ok && !c.is_tree && c.is_stump_based && !c.has_tilted && S <= kMaxDenseStages;
+        out.tail[yi].clear();
+        if (tail_ok) {
+            out.tail[yi].resize(T);
+            for (int i = 0; i < S; i++) {
+                DenseStage &ds = P.stage[i];
+                ds.first = 0; ds.count = (uint16_t)c.st_ntrees[i];
+                ds.thr = c.hid_thr[i];
+                bool any3 = false;
+                for (int t = c.st_first_tree[i]; t < c.st_first_tree[i + 1]; t++) any3 |= c.hid_nrects[c.tr_first_node[t]] == 3;
+                ds.flags = (c.two_rects[i] ? 1u : 0u) | (any3 ? 2u : 0u) | (c.order_free[i] ? 4u : 0u);
+                ds.tail_first = (uint32_t)c.st_first_tree[i];
+            }
+            for (int t = 0; t < T; t++) {
+                const int n = c.tr_first_node[t];
+                const HostNode &nd = c.nodes[n];
+                TailStump &ts = out.tail[yi][t];
+                memset(&ts, 0, sizeof ts);
+                for (int k = 0; k < c.hid_nrects[n]; k++) {
+                    int dx[4], dy[4];
+                    corner_coords(nd, k, dx, dy);
+                    for (int q = 0; q < 4; q++) {
+                        const int word = ystep == 1 ? dy[q] * P.tile_stride + dx[q]
+                                                    : dy[q] * P.tile_stride + (dx[q] & 1) * (P.tile_stride / 2) + (dx[q] >> 1);
+                        ts.off[k * 4 + q] = (uint16_t)(word * 4);
+                    }
+                    ts.w[k] = c.hid_weight[(size_t)n * 3 + k];
+                }
+                ts.thr = nd.threshold;
+                const int a = c.tr_first_node[t] + t;
+                ts.a0 = c.alpha[a + (-nd.left)];
+                ts.a1 = c.alpha[a + (-nd.right)];
+            }
+            P.tail_stages = S;
+        }
+        {
+            int ho = kHandoffWindows;
+            if (const char *e = getenv("CLFD_HANDOFF")) ho = atoi(e);
+            P.handoff = ho < 0 ? 0 : ho;
+        }
         int ns = 0, nstump = 0;
         while (dense_ok && ns < S && ns < kMaxDenseStages) {
             // in a stage tree only the unconditional linear prefix can be dense: stage i must
@@ -252,7 +297,9 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
             DenseStage &ds = P.stage[ns];
             ds.first = (uint16_t)nstump; ds.count = (uint16_t)(t1 - t0);
             ds.thr = c.hid_thr[ns];
-            ds.flags = ((!c.is_tree && c.is_stump_based && c.two_rects[ns]) ? 1u : 0u) | (any3 ? 2u : 0u);
+            ds.flags = ((!c.is_tree && c.is_stump_based && c.two_rects[ns]) ? 1u : 0u) | (any3 ? 2u : 0u) |
+                       (c.order_free[ns] ? 4u : 0u);
+            ds.tail_first = (uint32_t)t0;
             for (int t = t0; t < t1; t++) {
                 const int n = c.tr_first_node[t];
                 const HostNode &nd = c.nodes[n];

@@ -4,19 +4,23 @@
 // window semantics of cvRunHaarClassifierCascadeSum (tempcv.cpp:795-972) on the pyramid
 // grid of HaarDetectObjects_ScaleImage_Invoker (tempcv.cpp:1011-1103).
 //
-// Two kernels per cascade per batch, no host round trip in between:
-//   k_cascade_tiles : one CTA per 64x32-window tile of one level of one frame.  The int32
-//       integral tile is staged into shared memory with TMA bulk row copies
-//       (cp.async.bulk + mbarrier), sigma is computed once per window in FP64, and the
-//       leading ("dense") stages are evaluated one thread per window with a warp-ballot
-//       stream compaction of the surviving window list after EVERY stage, so warps stay
-//       full despite the steep early-exit profile.  Stumps come from the constant bank
-//       (the packed cascade is a __grid_constant__ kernel parameter, <= 32 KB).
-//   k_cascade_deep  : survivors of the dense prefix from all tiles / levels / frames are
-//       pooled in one global queue and evaluated one WARP per window, lanes striding over
-//       the trees of a stage (handles multi-node trees, tilted features and the alt_tree
-//       stage tree).  The stage sum is reduced with shuffles when the packer proved the
-//       alpha sum exact in any order, otherwise accumulated in tree order.
+// One or two kernels per cascade per batch, no host round trip in between:
+//   k_cascade_tiles : one CTA per 64x16-window tile of one level of one frame.  The int32
+//       integral tile is staged into shared memory (TMA bulk row copies, cp.async.bulk +
+//       mbarrier, on ystep-1 levels), sigma is computed once per window in FP64, and the
+//       cascade is evaluated in three phases of shrinking window count: fixed geometry
+//       (thread per window column, no compaction), compacted conflict-free rows with the
+//       stumps of a stage split over the warps, and a warp-per-window tail.  Stumps of the
+//       leading stages come from the constant bank (the packed cascade is a
+//       __grid_constant__ kernel parameter, <= 32 KB), the rest from global memory.
+//       Stump-based upright cascades (frontalface_alt / _default, eye, profileface) are
+//       finished inside this kernel.
+//   k_cascade_deep  : for cascades the tile kernel cannot finish (multi-node trees, tilted
+//       features, the alt_tree stage tree) the survivors of the dense prefix from all tiles /
+//       levels / frames are pooled in one global queue and evaluated one WARP per window,
+//       lanes striding over the trees of a stage.  The stage sum is reduced with shuffles
+//       when the packer proved the alpha sum exact in any order, otherwise accumulated in
+//       tree order.
 //
 // Arithmetic is bit-identical to the reference's C expressions: integer rect sums; FP64
 // variance with separately rounded mul/sub/sqrt; two_rects stages multiply in double
@@ -89,52 +93,104 @@ __device__ __forceinline__ void emit_rect(const CascadeArgs &a, const CasLevel &
 // One CTA (128 threads) per 64x16-window tile.  Shared memory:
 //   tile    int32 [rows][S]   ystep-1 levels: natural layout, staged by TMA bulk row copies;
 //                             ystep-2 levels: even columns in [0,S/2), odd columns in [S/2,S)
-//                             of each row (LDG.128 + 2 x STS.64), so that in both layouts a
-//                             window's base word is f(wy)*S + wx and the 32 lanes of a warp
-//                             (consecutive wx) hit 32 different banks on every corner load.
-//   sigma   double [1024]     per-window variance normaliser (FP64, exact)
-//   list    u16 [2][1024]     compacted survivor lists (ping-pong)
+//                             of each row (LDG.128 + 2 x STS.64).  In both layouts a window's
+//                             base word is ystep*wy*S + wx with ystep*S = 8 (mod 32), so its
+//                             bank class is (wx + 8*wy) mod 32: the 32 lanes of a warp with
+//                             consecutive wx never conflict, and neither do compacted rows
+//                             whose windows have distinct classes.
+//   sgf     float [1024]      per-window sigma rounded to FP32 (the FP64 value is recomputed
+//                             on the rare exact fallback)
+//   list    u16 [1024]        compacted survivors, rows of 32 (see dense_reorder)
+//   blist   u16 [32][32]      survivors bucketed by bank class
+//   part    double [4][128]   per-warp partial stage sums of one group of 4 list rows
 //
 // Phase 1, "fixed geometry" (stages 0 .. n_fixed-1, where most windows are still alive):
 //   thread t owns the column of 8 windows (wx = t & 63, wy = (t >> 6) + 2k).  Their tile
 //   addresses differ by a compile-time constant, so a corner address is computed ONCE per
 //   stump and the 4 windows of a chunk are read with immediate offsets (LDS [R + k*ROWSTEP]):
-//   no per-window address arithmetic, no compaction traffic, conflict-free banks.  Dead
-//   windows ride along; a chunk whose 4 x 32 windows are all dead is skipped (warp-uniform).
-// Phase 2, compacted (remaining dense stages): survivors are stream-compacted with a warp
-//   ballot after every stage; a warp takes rows of 32 list entries, up to 4 rows per pass.
-// Survivors of the last dense stage are appended to the global queue of the deep kernel.
+//   no per-window address arithmetic, no compaction traffic, conflict-free banks.
+// Phase 2, compacted, stump-split (remaining stages of the parameter-resident prefix): the
+//   survivors are laid out in conflict-free rows of 32; EVERY warp evaluates the same group
+//   of up to 4 rows (4 windows per lane: shared stump loads, 4-way ILP) but only every 4th
+//   stump of the stage; the four partial sums meet in shared memory.  All warps carry the
+//   same load whatever the number of survivors, and a stage's latency is a quarter of the
+//   sequential one.  Adding partial sums in a different order is bit-exact because the packer
+//   proved the stage's alpha sum exact in any order (DenseStage flags bit2); stages without
+//   the proof go through the sequential FP64 path.
+// Phase 3, tail (<= handoff survivors, or the stages beyond the parameter budget): one WARP
+//   per window, lanes stride over the stumps of a stage (records from global memory, tile
+//   still in shared memory), exact arithmetic, until the window is rejected or accepted.
+//   Cascades the tail cannot express (trees, tilted features, stage trees) hand their
+//   survivors to the queue of k_cascade_deep instead.
 //
-// Stage arithmetic: an FP32 filter decides each stump; whenever |s32 - t32| is inside a
-// guard band (2^-20 |t32| plus the cancellation terms) the window's whole stage is redone by
-// dense_eval_stage_exact(), which reproduces the reference's C expressions bit for bit.
+// Stage arithmetic (phases 1-2): an FP32 filter decides each stump; whenever |s32 - t32| is
+// inside a guard band (2^-20 |t32| plus the cancellation terms) the window's whole stage is
+// redone by dense_stage_exact(), which reproduces the reference's C expressions bit for bit.
 // Outside the band both agree by the error analysis in DESIGN.md, so results are identical
 // to the all-FP64 evaluation (tests also run with force_exact = 1 and compare).
 // ------------------------------------------------------------------------------------
 #define TILE_LD(base, off) (*reinterpret_cast<const int *>((base) + (off)))
 
 struct DenseSmemPlan {
-    size_t tile, sigma, list, blist, ctl, bar, total;
+    size_t tile, sgf, list, blist, part, ctl, bar, total;
 };
-// control block (ints): [0..31] bucket counts, [32..63] snapshot of the counts, [64..95] round
-// masks, [96..127] round prefixes, [128] survivors, [130..131] queue base
-constexpr int kCtlBcnt = 0, kCtlBcopy = 32, kCtlRmask = 64, kCtlRpref = 96, kCtlAlive = 128, kCtlQueue = 130, kCtlInts = 136;
+// control block (ints): [0..63] two generations of bucket counts, [64..65] queue base
+constexpr int kCtlBcnt = 0, kCtlQueue = 64, kCtlInts = 72;
 __host__ __device__ inline DenseSmemPlan dense_smem_plan(const DenseParams &P) {
     DenseSmemPlan p;
     const size_t rows = (size_t)(kTileH - 1) * P.ystep + P.win_h + 1;
     p.tile = 0;
-    p.sigma = (rows * P.tile_stride * 4 + 127) & ~(size_t)127;
-    p.list = p.sigma + kTileWindows * sizeof(double);
+    p.sgf = (rows * P.tile_stride * 4 + 127) & ~(size_t)127;
+    p.list = p.sgf + kTileWindows * sizeof(float);
     p.blist = p.list + kTileWindows * sizeof(uint16_t);
-    p.ctl = p.blist + kTileWindows * sizeof(uint16_t);
+    p.part = p.blist + kTileWindows * sizeof(uint16_t);
+    p.ctl = p.part + (size_t)kDenseWarps * kGroupWindows * sizeof(double);
     p.bar = p.ctl + kCtlInts * sizeof(int);
     p.total = p.bar + 16;
     return p;
 }
 size_t dense_smem_bytes(const DenseParams &P) { return dense_smem_plan(P).total; }
 
-// Exact evaluation of one dense stage for one window (the reference's arithmetic).
-__device__ __noinline__ bool dense_eval_stage_exact(const DenseParams &P, int s, const unsigned char *base, double sigma) {
+struct DenseCtx {
+    unsigned char *tile;
+    float *sgf;
+    const ull *gsq;   // squared integral at the tile origin
+    int16_t *codes;   // this frame + level, or nullptr
+    int sq_pitch;     // elements
+    int row_mul;      // bytes between window rows in the tile
+    int ystep, S;
+    int tx, ty, nx;
+    int code_mul;
+};
+
+__device__ __forceinline__ const unsigned char *dense_base(const DenseCtx &c, int wid) {
+    return c.tile + (wid / kTileW) * c.row_mul + (wid & (kTileW - 1)) * 4;
+}
+__device__ __forceinline__ int dense_tile_off(const DenseCtx &c, int y, int x) {   // byte offset of integral (y, x) from a window base
+    return 4 * (c.ystep == 1 ? y * c.S + x : y * c.S + (x & 1) * (c.S >> 1) + (x >> 1));
+}
+__device__ __forceinline__ void dense_write_code(const DenseCtx &c, int wid, int code) {
+    const int wx = wid & (kTileW - 1), wy = wid / kTileW;
+    c.codes[(size_t)(c.ty * kTileH + wy) * c.nx + c.tx * kTileW + wx] = (int16_t)code;
+}
+
+// FP64 sigma of window `wid` (tempcv.cpp:824-832): int32 corners from the tile, uint64 from global
+__device__ __forceinline__ double dense_sigma(const DenseParams &P, const DenseCtx &c, int wid) {
+    const int wx = wid & (kTileW - 1), wy = wid / kTileW;
+    const int eq_w = P.win_w - 2, eq_h = P.win_h - 2;
+    const unsigned char *base = c.tile + wy * c.row_mul + wx * 4;
+    const int s4 = TILE_LD(base, dense_tile_off(c, 1, 1)) - TILE_LD(base, dense_tile_off(c, 1, 1 + eq_w)) -
+                   TILE_LD(base, dense_tile_off(c, 1 + eq_h, 1)) + TILE_LD(base, dense_tile_off(c, 1 + eq_h, 1 + eq_w));
+    const ull *q = c.gsq + (size_t)(wy * c.ystep) * c.sq_pitch + wx * c.ystep;
+    const int g0 = c.sq_pitch + 1, g1 = g0 + eq_w, g2 = (1 + eq_h) * c.sq_pitch + 1, g3 = g2 + eq_w;
+    const ull q4 = __ldg(q + g0) - __ldg(q + g1) - __ldg(q + g2) + __ldg(q + g3);
+    return window_sigma(s4, q4, P.inv_area);
+}
+
+// Exact evaluation of one parameter-resident stage for one window (the reference's arithmetic).
+__device__ __noinline__ bool dense_stage_exact(const DenseParams &P, const DenseCtx &c, int s, int wid) {
+    const unsigned char *base = dense_base(c, wid);
+    const double sigma = dense_sigma(P, c, wid);
     const int first = P.stage[s].first, count = P.stage[s].count;
     const bool dbl = P.stage[s].flags & 1u;
     double S = 0.0;
@@ -158,16 +214,17 @@ __device__ __noinline__ bool dense_eval_stage_exact(const DenseParams &P, int s,
     return S >= (double)P.stage[s].thr;
 }
 
-// FP32-filtered evaluation of stage s for K windows of this thread.
+// FP32-filtered evaluation of stumps j0, j0 + jstep, ... of stage s for K windows of this thread.
 //   FIXED = true : window k lives at base0 + k*ROWSTEP (compile-time) -> immediate offsets
 //   FIXED = false: window k lives at base[k]
 template <int K, bool DBL, bool HAS3, bool FIXED, int ROWSTEP>
-__device__ __forceinline__ void dense_filter_stage(const DenseParams &P, int s, const unsigned char *const (&base)[K],
-                                                   const float (&sg)[K], double (&S)[K], bool (&near)[K]) {
+__device__ __forceinline__ void dense_filter_stage(const DenseParams &P, int s, int j0, int jstep,
+                                                   const unsigned char *const (&base)[K], const float (&sg)[K],
+                                                   double (&S)[K], bool (&near)[K]) {
     const int first = P.stage[s].first, count = P.stage[s].count;
     const float eps = P.filter_eps, eps4 = eps * 0.25f;
 #pragma unroll 1
-    for (int j = 0; j < count; j++) {
+    for (int j = j0; j < count; j += jstep) {
         const DenseStump &q = P.stump[first + j];
         const float w0 = q.w[0], w1 = q.w[1], thr = q.thr;
         const double al0 = q.a0, al1 = q.a1;
@@ -210,101 +267,92 @@ __device__ __forceinline__ void dense_filter_stage(const DenseParams &P, int s, 
 }
 
 template <int K, bool FIXED, int ROWSTEP>
-__device__ __forceinline__ void dense_dispatch_stage(const DenseParams &P, int s, const unsigned char *const (&base)[K],
-                                                     const float (&sg)[K], double (&S)[K], bool (&near)[K]) {
+__device__ __forceinline__ void dense_dispatch_stage(const DenseParams &P, int s, int j0, int jstep,
+                                                     const unsigned char *const (&base)[K], const float (&sg)[K],
+                                                     double (&S)[K], bool (&near)[K]) {
     const uint32_t flags = P.stage[s].flags;
-    if (flags & 1u) dense_filter_stage<K, true, false, FIXED, ROWSTEP>(P, s, base, sg, S, near);
-    else if (flags & 2u) dense_filter_stage<K, false, true, FIXED, ROWSTEP>(P, s, base, sg, S, near);
-    else dense_filter_stage<K, false, false, FIXED, ROWSTEP>(P, s, base, sg, S, near);
+    if (flags & 1u) dense_filter_stage<K, true, false, FIXED, ROWSTEP>(P, s, j0, jstep, base, sg, S, near);
+    else if (flags & 2u) dense_filter_stage<K, false, true, FIXED, ROWSTEP>(P, s, j0, jstep, base, sg, S, near);
+    else dense_filter_stage<K, false, false, FIXED, ROWSTEP>(P, s, j0, jstep, base, sg, S, near);
 }
 
-struct DenseCtx {
-    unsigned char *tile;
-    double *sigma;
-    int16_t *codes;   // this frame + level, or nullptr
-    int row_mul;      // bytes between window rows in the tile
-    int tx, ty, nx;
-    int code_mul;
-};
+// bank class of a window: (wx + 8*wy) mod 32
+__device__ __forceinline__ int dense_bank_class(int wid) { return (wid + 8 * (wid / kTileW)) & 31; }
 
-__device__ __forceinline__ void dense_write_code(const DenseCtx &c, int wid, int code) {
-    const int wx = wid & (kTileW - 1), wy = wid / kTileW;
-    c.codes[(size_t)(c.ty * kTileH + wy) * c.nx + c.tx * kTileW + wx] = (int16_t)code;
-}
-
-// survivors go to the bucket of their bank residue (wx mod 32): blist[slot][bucket]
+// survivors go to the bucket of their bank class: blist[slot][bucket]
 __device__ __forceinline__ void dense_append(uint16_t *blist, int *bcnt, int wid) {
-    const int b = wid & 31;
+    const int b = dense_bank_class(wid);
     const int slot = atomicAdd(&bcnt[b], 1);
     blist[slot * 32 + b] = (uint16_t)wid;
 }
 
-// compacted phase: evaluate stage s for K list entries of this thread
+// The compacted survivor list.  N survivors, sorted by bank class (i = rank in that order),
+// are laid out COLUMN-major in R = ceil(N/32) rows of 32:
+//     entry i  ->  row i % R, column i / R.
+// Rows are full (the kernel is issue-bound: every row costs a full instruction stream) and
+// balanced (row r has (N - r + R - 1) / R entries, columns 0 .. cnt-1), and because the
+// entries of one bucket are consecutive in i, a bucket of c windows puts at most ceil(c/R) of
+// them into one row: the bank-conflict degree of every corner load is ceil(max bucket / R),
+// the minimum any arrangement with R rows can reach.
+struct DenseList {
+    int n, rows;
+};
+__device__ __forceinline__ int dense_row_count(const DenseList &l, int row) { return row < l.rows ? (l.n - row + l.rows - 1) / l.rows : 0; }
+
+// Build the list from the buckets of generation `gen`; zero the counters of the other
+// generation for the next stage.  Two barriers; all threads must call it.  Every warp
+// computes the (tiny) prefix itself, so no broadcast through shared memory is needed.
+__device__ __forceinline__ DenseList dense_reorder(uint16_t *list, const uint16_t *blist, int *ctl, int gen, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    __syncthreads();   // all appends of this generation done
+    const int cnt = ctl[kCtlBcnt + gen * 32 + lane];
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    DenseList l;
+    l.n = __shfl_sync(0xffffffffu, incl, 31);
+    l.rows = (l.n + 31) >> 5;
+    if (warp == 0) ctl[kCtlBcnt + (gen ^ 1) * 32 + lane] = 0;
+    if (l.n > 0) {
+        const float inv_rows = 1.0f / (float)l.rows;
+        const int excl = incl - cnt;
+        for (int sl = warp; sl < cnt; sl += kDenseWarps) {
+            const int i = excl + sl;
+            const int col = (int)(((float)i + 0.5f) * inv_rows);   // exact: i < 1024, rows <= 32
+            const int row = i - col * l.rows;
+            list[row * 32 + col] = blist[sl * 32 + lane];
+        }
+    }
+    __syncthreads();
+    return l;
+}
+
+// compacted phase: this warp's share (stumps warp, warp+4, ...) of stage s for K list rows
 template <int K>
-__device__ __forceinline__ void dense_run_rows(const DenseParams &P, const DenseCtx &c, int s, const int (&wid)[K],
-                                               const bool (&act)[K], uint16_t *blist, int *bcnt) {
+__device__ __forceinline__ void dense_rows_partial(const DenseParams &P, const DenseCtx &c, int s, const DenseList &l,
+                                                   const uint16_t *list, int row0, double *part, int warp, int lane) {
     const unsigned char *base[K];
     float sg[K];
     double S[K];
     bool near[K];
+    const bool all_near = P.force_exact != 0 || !(P.stage[s].flags & 4u);
 #pragma unroll
     for (int k = 0; k < K; k++) {
-        const int wx = wid[k] & (kTileW - 1), wy = wid[k] / kTileW;
-        base[k] = c.tile + wy * c.row_mul + wx * 4;
-        sg[k] = (float)c.sigma[wid[k]];
+        const int row = row0 + k;
+        // idle lanes shadow column 0 of their row (a broadcast, no extra wavefront)
+        const int wid = list[row * 32 + (lane < dense_row_count(l, row) ? lane : 0)];
+        base[k] = dense_base(c, wid);
+        sg[k] = c.sgf[wid];
         S[k] = 0.0;
-        near[k] = P.force_exact != 0;
+        near[k] = all_near;
     }
-    dense_dispatch_stage<K, false, 0>(P, s, base, sg, S, near);
-    const double sthr = (double)P.stage[s].thr;
+    dense_dispatch_stage<K, false, 0>(P, s, warp, kDenseWarps, base, sg, S, near);
 #pragma unroll
-    for (int k = 0; k < K; k++) {
-        if (!act[k]) continue;
-        bool pass = S[k] >= sthr;
-        if (near[k]) pass = dense_eval_stage_exact(P, s, base[k], c.sigma[wid[k]]);
-        if (pass) dense_append(blist, bcnt, wid[k]);
-        else if (c.codes) dense_write_code(c, wid[k], s * c.code_mul);
-    }
-}
-
-// Turn the bucketed survivors into a linear list in ROUND-ROBIN bucket order (slot 0 of every
-// non-empty bucket, then slot 1, ...): a row of 32 consecutive entries then holds (nearly)
-// distinct bank residues, so phase-2 corner loads are (nearly) conflict free while rows stay
-// full.  Returns the number of survivors.  Three barriers; all threads must call it.
-__device__ __forceinline__ int dense_reorder(uint16_t *list, const uint16_t *blist, int *ctl, int tid) {
-    const int lane = tid & 31, warp = tid >> 5;
-    __syncthreads();   // all appends done
-    if (warp == 0) {
-        const int cl = ctl[kCtlBcnt + lane];
-        const int kmax = __reduce_max_sync(0xffffffffu, cl);
-        unsigned mymask = 0;   // lane r keeps the mask of buckets that have a slot r
-        for (int r = 0; r < kmax; r++) {
-            const unsigned m = __ballot_sync(0xffffffffu, cl > r);
-            if (lane == r) mymask = m;
-        }
-        const int n = __popc(mymask);
-        int incl = n;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
-        }
-        ctl[kCtlRmask + lane] = (int)mymask;
-        ctl[kCtlRpref + lane] = incl - n;
-        ctl[kCtlBcopy + lane] = cl;
-        ctl[kCtlBcnt + lane] = 0;
-        if (lane == 31) ctl[kCtlAlive] = incl;
-    }
-    __syncthreads();
-    {
-        const int mine = ctl[kCtlBcopy + lane];
-        for (int r = warp; r < mine; r += kDenseWarps) {
-            const unsigned m = (unsigned)ctl[kCtlRmask + r];
-            list[ctl[kCtlRpref + r] + __popc(m & ((1u << lane) - 1u))] = blist[r * 32 + lane];
-        }
-    }
-    __syncthreads();
-    return ctl[kCtlAlive];
+    for (int k = 0; k < K; k++)   // NaN marks "redo this window's stage exactly"
+        part[warp * kGroupWindows + k * 32 + lane] = near[k] ? __longlong_as_double(0x7ff8000000000000ll) : S[k];
 }
 
 // ROWSTEP_T: compile-time byte distance between a thread's consecutive windows in phase 1
@@ -315,9 +363,10 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const DenseSmemPlan plan = dense_smem_plan(P);
     unsigned char *tile = smem_raw + plan.tile;
-    double *sigma = reinterpret_cast<double *>(smem_raw + plan.sigma);
+    float *sgf = reinterpret_cast<float *>(smem_raw + plan.sgf);
     uint16_t *list = reinterpret_cast<uint16_t *>(smem_raw + plan.list);
     uint16_t *blist = reinterpret_cast<uint16_t *>(smem_raw + plan.blist);
+    double *part = reinterpret_cast<double *>(smem_raw + plan.part);
     int *ctl = reinterpret_cast<int *>(smem_raw + plan.ctl);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + plan.bar);
 
@@ -371,40 +420,27 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     }
 
     DenseCtx c;
-    c.tile = tile; c.sigma = sigma;
+    c.tile = tile; c.sgf = sgf; c.gsq = gsq;
     c.codes = a.codes ? a.codes + (size_t)frame * a.windows_per_frame + CL.win_base : nullptr;
+    c.sq_pitch = L.sum_pitch;
     c.row_mul = ystep * S * 4;
+    c.ystep = ystep; c.S = S;
     c.tx = tx; c.ty = ty; c.nx = CL.nx;
     c.code_mul = P.is_tree ? 2 : 1;
 
     // ---- phase 1: sigma, then the fixed-geometry stages ----
     constexpr int kRowsPerSlot = kDenseThreads / kTileW;   // window rows between a thread's slots (2)
-    const int rowstep = ROWSTEP_T ? ROWSTEP_T : kRowsPerSlot * c.row_mul;
     const int wx = tid & (kTileW - 1), wy0 = tid / kTileW;
     uint32_t alive = 0;   // bit k: window (wx, wy0 + 2k) still alive
-    {
-        const int eq_w = P.win_w - 2, eq_h = P.win_h - 2;
-        int e[4];   // equRect corners (1,1),(1,1+eq_w),(1+eq_h,1),(1+eq_h,1+eq_w) as tile byte offsets
-        {
-            const int ys[4] = {1, 1, 1 + eq_h, 1 + eq_h}, xs[4] = {1, 1 + eq_w, 1, 1 + eq_w};
 #pragma unroll
-            for (int q = 0; q < 4; q++)
-                e[q] = 4 * (ystep == 1 ? ys[q] * S + xs[q] : ys[q] * S + (xs[q] & 1) * (S >> 1) + (xs[q] >> 1));
-        }
-        const int g0 = L.sum_pitch + 1, g1 = g0 + eq_w, g2 = (1 + eq_h) * L.sum_pitch + 1, g3 = g2 + eq_w;
-#pragma unroll
-        for (int k = 0; k < kDenseSlots; k++) {
-            const int wy = wy0 + k * kRowsPerSlot;
-            if (wx < n_wx && wy < n_wy) {
-                alive |= 1u << k;
-                const unsigned char *base = tile + wy * c.row_mul + wx * 4;
-                const int s4 = TILE_LD(base, e[0]) - TILE_LD(base, e[1]) - TILE_LD(base, e[2]) + TILE_LD(base, e[3]);
-                const ull *q = gsq + (size_t)(wy * ystep) * L.sum_pitch + wx * ystep;
-                const ull q4 = __ldg(q + g0) - __ldg(q + g1) - __ldg(q + g2) + __ldg(q + g3);
-                sigma[wy * kTileW + wx] = window_sigma(s4, q4, P.inv_area);
-            } else {
-                sigma[wy * kTileW + wx] = 1.0;
-            }
+    for (int k = 0; k < kDenseSlots; k++) {
+        const int wy = wy0 + k * kRowsPerSlot;
+        const int wid = wy * kTileW + wx;
+        if (wx < n_wx && wy < n_wy) {
+            alive |= 1u << k;
+            sgf[wid] = (float)dense_sigma(P, c, wid);
+        } else {
+            sgf[wid] = 1.0f;
         }
     }
     // a thread reads back only sigmas it wrote itself: no barrier needed in phase 1
@@ -422,19 +458,19 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
             for (int k = 0; k < kDenseChunk; k++) {
                 const int wy = wy0 + (k0 + k) * kRowsPerSlot;
                 base[k] = tile + wy * c.row_mul + wx * 4;   // == base[0] + k * rowstep
-                sg[k] = (float)sigma[wy * kTileW + wx];
+                sg[k] = sgf[wy * kTileW + wx];
                 Ssum[k] = 0.0;
                 near[k] = P.force_exact != 0;
             }
-            if (ROWSTEP_T) dense_dispatch_stage<kDenseChunk, true, ROWSTEP_T>(P, s, base, sg, Ssum, near);
-            else dense_dispatch_stage<kDenseChunk, false, 0>(P, s, base, sg, Ssum, near);
+            if (ROWSTEP_T) dense_dispatch_stage<kDenseChunk, true, ROWSTEP_T>(P, s, 0, 1, base, sg, Ssum, near);
+            else dense_dispatch_stage<kDenseChunk, false, 0>(P, s, 0, 1, base, sg, Ssum, near);
             const double sthr = (double)P.stage[s].thr;
 #pragma unroll
             for (int k = 0; k < kDenseChunk; k++) {
                 if (!((m4 >> k) & 1u)) continue;
                 const int wid = (wy0 + (k0 + k) * kRowsPerSlot) * kTileW + wx;
                 bool pass = Ssum[k] >= sthr;
-                if (near[k]) pass = dense_eval_stage_exact(P, s, base[k], sigma[wid]);
+                if (near[k]) pass = dense_stage_exact(P, c, s, wid);
                 if (!pass) {
                     alive &= ~(1u << (k0 + k));
                     if (c.codes) dense_write_code(c, wid, s * c.code_mul);
@@ -442,67 +478,127 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
             }
         }
     }
-    (void)rowstep;
 
-    // ---- phase-1 survivors -> buckets -> bank-friendly linear list ----
+    // ---- phase-1 survivors -> buckets -> conflict-free list ----
+    int gen = 0;
 #pragma unroll
     for (int k = 0; k < kDenseSlots; k++)
         if ((alive >> k) & 1u) dense_append(blist, ctl + kCtlBcnt, (wy0 + k * kRowsPerSlot) * kTileW + wx);
-    int n_alive = dense_reorder(list, blist, ctl, tid);
+    DenseList l = dense_reorder(list, blist, ctl, gen, tid);
 
-    // ---- phase 2: remaining dense stages on compacted lists ----
+    // ---- phase 2: remaining parameter-resident stages, all warps on the same rows, stumps split ----
+    const bool can_leave = P.tail_stages != 0 || P.n_stages < P.total_stages;   // somebody finishes the cascade
     for (;;) {
-        if (n_alive == 0) return;
-        if (s >= P.n_stages || (n_alive <= kHandoffWindows && P.n_stages < P.total_stages)) break;
-        const int n_rows = (n_alive + 31) >> 5;
-        for (int r0 = warp; r0 < n_rows; r0 += kDenseWarps * kDenseChunk) {
-            int wid[kDenseChunk];
-            bool act[kDenseChunk];
-            int K = 0;
+        if (l.n == 0) return;
+        if (s >= P.n_stages || (l.n <= P.handoff && can_leave)) break;
+        gen ^= 1;
+        int *bcnt = ctl + kCtlBcnt + gen * 32;
+        const double sthr = (double)P.stage[s].thr;
+        for (int row0 = 0; row0 < l.rows; row0 += kGroupRows) {
+            const int K = min(kGroupRows, l.rows - row0);
+            if (row0 > 0) __syncthreads();   // the previous group's partial sums have been consumed
+            if (K == 1) dense_rows_partial<1>(P, c, s, l, list, row0, part, warp, lane);
+            else if (K == 2) dense_rows_partial<2>(P, c, s, l, list, row0, part, warp, lane);
+            else if (K == 3) dense_rows_partial<3>(P, c, s, l, list, row0, part, warp, lane);
+            else dense_rows_partial<4>(P, c, s, l, list, row0, part, warp, lane);
+            __syncthreads();
+            for (int t = tid; t < kGroupWindows; t += kDenseThreads) {
+                const int row = row0 + (t >> 5), col = t & 31;
+                if (col >= dense_row_count(l, row)) continue;
+                const int wid = list[row * 32 + col];
+                double Ssum = part[t];
 #pragma unroll
-            for (int k = 0; k < kDenseChunk; k++) {
-                const int row = r0 + k * kDenseWarps;
-                const int i = row * 32 + lane;
-                act[k] = row < n_rows && i < n_alive;
-                wid[k] = act[k] ? list[i] : lane;
-                K += row < n_rows;
-            }
-            if (K == 1) {
-                const int w1[1] = {wid[0]}; const bool a1[1] = {act[0]};
-                dense_run_rows<1>(P, c, s, w1, a1, blist, ctl + kCtlBcnt);
-            } else if (K == 2) {
-                const int w2[2] = {wid[0], wid[1]}; const bool a2[2] = {act[0], act[1]};
-                dense_run_rows<2>(P, c, s, w2, a2, blist, ctl + kCtlBcnt);
-            } else if (K == 3) {
-                const int w3[3] = {wid[0], wid[1], wid[2]}; const bool a3[3] = {act[0], act[1], act[2]};
-                dense_run_rows<3>(P, c, s, w3, a3, blist, ctl + kCtlBcnt);
-            } else {
-                dense_run_rows<4>(P, c, s, wid, act, blist, ctl + kCtlBcnt);
+                for (int w = 1; w < kDenseWarps; w++) Ssum = __dadd_rn(Ssum, part[w * kGroupWindows + t]);
+                bool pass = Ssum >= sthr;
+                if (Ssum != Ssum) pass = dense_stage_exact(P, c, s, wid);
+                if (pass) dense_append(blist, bcnt, wid);
+                else if (c.codes) dense_write_code(c, wid, s * c.code_mul);
             }
         }
-        n_alive = dense_reorder(list, blist, ctl, tid);
+        l = dense_reorder(list, blist, ctl, gen, tid);
         s++;
     }
 
-    // ---- survivors: accepted (whole cascade was dense) or handed to the deep kernel ----
-    const uint16_t *lin = list;
     if (s >= P.total_stages) {
-        for (int i = tid; i < n_alive; i += kDenseThreads) {
-            const int w = lin[i];
+        // ---- the whole cascade was parameter resident: survivors are detections ----
+        for (int i = tid; i < l.rows * 32; i += kDenseThreads) {
+            if ((i & 31) >= dense_row_count(l, i >> 5)) continue;
+            const int w = list[i];
             emit_rect(a, CL, frame, px0 + (w & (kTileW - 1)) * ystep, py0 + (w / kTileW) * ystep);
             if (c.codes) dense_write_code(c, w, P.total_stages);
         }
+    } else if (P.tail_stages) {
+        // ---- phase 3: warp per window, lanes over the stumps of a stage, exact arithmetic ----
+        const TailStump *__restrict__ tail = P.tail;
+        for (int n = warp; n < l.n; n += kDenseWarps) {
+            const int col = n / l.rows, row = n - col * l.rows;
+            const int wid = list[row * 32 + col];
+            const unsigned char *base = dense_base(c, wid);
+            const double sigma = dense_sigma(P, c, wid);
+            int ss = s;
+            bool accepted = false;
+            for (;;) {
+                const DenseStage st = P.stage[ss];
+                const bool dbl = st.flags & 1u, order_free = st.flags & 4u;
+                double Ssum = 0.0, acc = 0.0;
+                for (int j0 = 0; j0 < st.count; j0 += 32) {
+                    const int j = j0 + lane;
+                    float av = 0.f;
+                    if (j < st.count) {
+                        const uint4 *rec = reinterpret_cast<const uint4 *>(tail + st.tail_first + j);
+                        const uint4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+                        // q0 = off[0..7]; q1 = off[8..11], w0, w1; q2 = w2, thr, a0, a1
+                        const int r0 = TILE_LD(base, q0.x & 0xffffu) - TILE_LD(base, q0.x >> 16) - TILE_LD(base, q0.y & 0xffffu) + TILE_LD(base, q0.y >> 16);
+                        const int r1 = TILE_LD(base, q0.z & 0xffffu) - TILE_LD(base, q0.z >> 16) - TILE_LD(base, q0.w & 0xffffu) + TILE_LD(base, q0.w >> 16);
+                        const float w0 = __uint_as_float(q1.z), w1 = __uint_as_float(q1.w);
+                        const double t = __dmul_rn((double)__uint_as_float(q2.y), sigma);
+                        double sv;
+                        if (dbl) {
+                            sv = __fma_rn((double)r1, (double)w1, __dmul_rn((double)r0, (double)w0));
+                        } else {
+                            sv = __dadd_rn((double)__fmul_rn(__int2float_rn(r0), w0), (double)__fmul_rn(__int2float_rn(r1), w1));
+                            if ((q1.y >> 16) != 0) {
+                                const int r2 = TILE_LD(base, q1.x & 0xffffu) - TILE_LD(base, q1.x >> 16) - TILE_LD(base, q1.y & 0xffffu) + TILE_LD(base, q1.y >> 16);
+                                sv = __dadd_rn(sv, (double)__fmul_rn(__int2float_rn(r2), __uint_as_float(q2.x)));
+                            }
+                        }
+                        av = __uint_as_float(sv >= t ? q2.w : q2.z);
+                    }
+                    if (order_free) {
+                        acc = __dadd_rn(acc, (double)av);
+                    } else {
+                        const int cnt = min(32, (int)st.count - j0);
+                        for (int k = 0; k < cnt; k++) Ssum = __dadd_rn(Ssum, (double)__shfl_sync(0xffffffffu, av, k));
+                    }
+                }
+                if (order_free) {
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, d));
+                    Ssum = acc;
+                }
+                if (!(Ssum >= (double)st.thr)) break;
+                if (++ss >= P.total_stages) { accepted = true; break; }
+            }
+            if (lane == 0) {
+                if (accepted) emit_rect(a, CL, frame, px0 + (wid & (kTileW - 1)) * ystep, py0 + (wid / kTileW) * ystep);
+                if (c.codes) dense_write_code(c, wid, ss);
+            }
+        }
     } else {
-        if (tid == 0) *reinterpret_cast<ull *>(ctl + kCtlQueue) = atomicAdd(a.counters + 1, (ull)n_alive);
+        // ---- hand the survivors to the deep kernel ----
+        if (tid == 0) *reinterpret_cast<ull *>(ctl + kCtlQueue) = atomicAdd(a.counters + 1, (ull)l.n);
         __syncthreads();
         const ull qb = *reinterpret_cast<const ull *>(ctl + kCtlQueue);
-        for (int i = tid; i < n_alive; i += kDenseThreads) {
-            const int w = lin[i];
-            if (qb + i < a.queue_cap) {
+        for (int i = tid; i < l.rows * 32; i += kDenseThreads) {
+            const int row = i >> 5, col = i & 31;
+            if (col >= dense_row_count(l, row)) continue;
+            const int w = list[i];
+            const ull slot = qb + (ull)(col * l.rows + row);
+            if (slot < a.queue_cap) {
                 QueueItem it;
                 it.key = ((uint32_t)frame << 16) | ((uint32_t)cl << 8) | (uint32_t)s;
                 it.xy = ((uint32_t)(py0 + (w / kTileW) * ystep) << 16) | (uint32_t)(px0 + (w & (kTileW - 1)) * ystep);
-                a.queue[qb + i] = it;
+                a.queue[slot] = it;
             } else {
                 atomicAdd(a.counters + 3, 1ull);
             }
@@ -522,15 +618,30 @@ static cudaError_t launch_tiles_t(const DenseParams &P, const CascadeArgs &a, in
     return cudaGetLastError();
 }
 
+// row steps of the stock window sizes (bytes between a thread's consecutive phase-1 windows)
+constexpr int dense_stride_ce(int win_w, int ystep) {
+    int cols = ((kTileW - 1) * ystep + win_w + 1 + 3) & ~3;
+    int s = ystep == 1 ? cols : 2 * ((cols + 1) / 2);
+    s = (s + 3) & ~3;
+    while ((ystep * s) % 32 != 8) s += 4;
+    return s;
+}
+constexpr int dense_rowstep_ce(int win_w, int ystep) { return (kDenseThreads / kTileW) * ystep * dense_stride_ce(win_w, ystep) * 4; }
+
 cudaError_t launch_cascade_tiles(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, cudaStream_t stream) {
     if (n_tiles <= 0 || a.n_frames == 0) return cudaSuccess;
     const size_t smem = dense_smem_bytes(P);
     // byte distance between a thread's consecutive phase-1 windows: 2 window rows
     const int rowstep = (kDenseThreads / kTileW) * P.ystep * P.tile_stride * 4;
-    switch (rowstep) {   // common window sizes get immediate-offset code (20x20 / 24x24 cascades)
-        case 2 * 1 * 96 * 4:  return launch_tiles_t<2 * 1 * 96 * 4>(P, a, tile0, n_tiles, smem, stream);
-        case 2 * 2 * 160 * 4: return launch_tiles_t<2 * 2 * 160 * 4>(P, a, tile0, n_tiles, smem, stream);
-        default:              return launch_tiles_t<0>(P, a, tile0, n_tiles, smem, stream);
+    // the common window widths (20 and 24 pixels) get immediate-offset code
+    constexpr int r20_1 = dense_rowstep_ce(20, 1), r20_2 = dense_rowstep_ce(20, 2);
+    constexpr int r24_1 = dense_rowstep_ce(24, 1), r24_2 = dense_rowstep_ce(24, 2);
+    static_assert(r20_1 == r24_1 && r20_2 != r24_2 && r20_2 != r20_1 && r24_2 != r20_1, "row steps must be distinct switch labels");
+    switch (rowstep) {
+        case r20_1: return launch_tiles_t<r20_1>(P, a, tile0, n_tiles, smem, stream);
+        case r20_2: return launch_tiles_t<r20_2>(P, a, tile0, n_tiles, smem, stream);
+        case r24_2: return launch_tiles_t<r24_2>(P, a, tile0, n_tiles, smem, stream);
+        default:    return launch_tiles_t<0>(P, a, tile0, n_tiles, smem, stream);
     }
 }
 
