@@ -623,7 +623,7 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
             cp.dense[yi] = pk.dense[yi];
             if (!pk.tail[yi].empty() && (rc = cp.d_tail[yi].upload(pk.tail[yi], s))) return rc;
             cp.dense[yi].tail = cp.d_tail[yi].p;
-            if (!cp.d_tail[yi].p) cp.dense[yi].tail_stages = 0;
+            if (!cp.d_tail[yi].p) cp.dense[yi].tail_stages = 0;   // (then n_stages is 0 too and the tile kernel is not launched)
         }
         if ((rc = cp.d_counters.alloc(4))) return rc;
         if (cfg->want_codes && (rc = cp.d_codes.alloc((size_t)std::max<long long>(cp.windows_per_frame, 1) * cfg->max_batch)))
@@ -732,8 +732,8 @@ int clfd_detector_enqueue(clfd_detector *det, const uint8_t *frames_dev, int n_f
             }
             if (ev && ci == 0) CK(cudaEventRecord(ev[6], s));
             // cascades the tile kernel finishes itself (tail_stages) never fill the queue
-            const bool tiles_finish = pk.dense[0].n_stages > 0 && cp.dense[0].tail_stages && cp.dense[1].tail_stages;
-            if (!tiles_finish && pk.dense[0].n_stages < pk.dense[0].total_stages) { CK(launch_cascade_deep(a, ctx->n_sms, s)); launches++; }
+            const bool tiles_finish = pk.dense[0].n_stages > 0 && cp.dense[0].tail_stages == pk.dense[0].total_stages;
+            if (!tiles_finish) { CK(launch_cascade_deep(a, ctx->n_sms, s)); launches++; }
             if (ev && ci == 0) CK(cudaEventRecord(ev[7], s));
         }
         // all cascades append to one rect buffer: carry the rect count over

@@ -235,43 +235,6 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
         P.inv_area = 1. / ((c.win_w - 2) * (c.win_h - 2));
         const size_t tile_bytes = (size_t)dense_tile_rows(c.win_h, ystep) * P.tile_stride * 4;
         bool dense_ok = tile_bytes <= 65536 && c.win_w <= 255 && c.win_h <= 255;
-        // Can the tile kernel finish the cascade on its own (warp-per-window tail over global
-        // TailStump records)?  Needs a linear, upright, stump-based cascade.
-        bool tail_ok = dense_ok && !c.is_tree && c.is_stump_based && !c.has_tilted && S <= kMaxDenseStages;
-        out.tail[yi].clear();
-        if (tail_ok) {
-            out.tail[yi].resize(T);
-            for (int i = 0; i < S; i++) {
-                DenseStage &ds = P.stage[i];
-                ds.first = 0; ds.count = (uint16_t)c.st_ntrees[i];
-                ds.thr = c.hid_thr[i];
-                bool any3 = false;
-                for (int t = c.st_first_tree[i]; t < c.st_first_tree[i + 1]; t++) any3 |= c.hid_nrects[c.tr_first_node[t]] == 3;
-                ds.flags = (c.two_rects[i] ? 1u : 0u) | (any3 ? 2u : 0u) | (c.order_free[i] ? 4u : 0u);
-                ds.tail_first = (uint32_t)c.st_first_tree[i];
-            }
-            for (int t = 0; t < T; t++) {
-                const int n = c.tr_first_node[t];
-                const HostNode &nd = c.nodes[n];
-                TailStump &ts = out.tail[yi][t];
-                memset(&ts, 0, sizeof ts);
-                for (int k = 0; k < c.hid_nrects[n]; k++) {
-                    int dx[4], dy[4];
-                    corner_coords(nd, k, dx, dy);
-                    for (int q = 0; q < 4; q++) {
-                        const int word = ystep == 1 ? dy[q] * P.tile_stride + dx[q]
-                                                    : dy[q] * P.tile_stride + (dx[q] & 1) * (P.tile_stride / 2) + (dx[q] >> 1);
-                        ts.off[k * 4 + q] = (uint16_t)(word * 4);
-                    }
-                    ts.w[k] = c.hid_weight[(size_t)n * 3 + k];
-                }
-                ts.thr = nd.threshold;
-                const int a = c.tr_first_node[t] + t;
-                ts.a0 = c.alpha[a + (-nd.left)];
-                ts.a1 = c.alpha[a + (-nd.right)];
-            }
-            P.tail_stages = S;
-        }
         {
             int ho = kHandoffWindows;
             if (const char *e = getenv("CLFD_HANDOFF")) ho = atoi(e);
@@ -323,6 +286,44 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
             ns++;
         }
         P.n_stages = ns;
+        // Stages the warp-autonomous phase of the tile kernel may evaluate (TailStump records in
+        // global memory): the whole cascade when it is linear, upright and stump based (then no
+        // queue / deep kernel is needed), otherwise just the dense prefix.
+        const bool full = ns > 0 && !c.is_tree && c.is_stump_based && !c.has_tilted && S <= kMaxDenseStages;
+        const int tail_n = full ? S : ns;
+        out.tail[yi].clear();
+        out.tail[yi].resize(c.st_first_tree[tail_n]);
+        for (int i = 0; i < tail_n; i++) {
+            DenseStage &ds = P.stage[i];
+            bool any3 = false;
+            for (int t = c.st_first_tree[i]; t < c.st_first_tree[i + 1]; t++) any3 |= c.hid_nrects[c.tr_first_node[t]] == 3;
+            if (i >= ns) ds.first = 0;
+            ds.count = (uint16_t)c.st_ntrees[i];
+            ds.thr = c.hid_thr[i];
+            ds.flags = ((!c.is_tree && c.is_stump_based && c.two_rects[i]) ? 1u : 0u) | (any3 ? 2u : 0u) | (c.order_free[i] ? 4u : 0u);
+            ds.tail_first = (uint32_t)c.st_first_tree[i];
+        }
+        for (int t = 0; t < c.st_first_tree[tail_n]; t++) {
+            const int n = c.tr_first_node[t];
+            const HostNode &nd = c.nodes[n];
+            TailStump &ts = out.tail[yi][t];
+            memset(&ts, 0, sizeof ts);
+            for (int k = 0; k < c.hid_nrects[n]; k++) {
+                int dx[4], dy[4];
+                corner_coords(nd, k, dx, dy);
+                for (int q = 0; q < 4; q++) {
+                    const int word = ystep == 1 ? dy[q] * P.tile_stride + dx[q]
+                                                : dy[q] * P.tile_stride + (dx[q] & 1) * (P.tile_stride / 2) + (dx[q] >> 1);
+                    ts.off[k * 4 + q] = (uint16_t)(word * 4);
+                }
+                ts.w[k] = c.hid_weight[(size_t)n * 3 + k];
+            }
+            ts.thr = nd.threshold;
+            const int a = c.tr_first_node[t] + t;
+            ts.a0 = c.alpha[a + (-nd.left)];
+            ts.a1 = c.alpha[a + (-nd.right)];
+        }
+        P.tail_stages = tail_n;
         {   // stages evaluated in fixed geometry before the first compaction (tunable for experiments)
             int nf = 3;
             if (const char *e = getenv("CLFD_N_FIXED")) nf = atoi(e);

@@ -8,11 +8,11 @@
 //   k_cascade_tiles : one CTA per 64x16-window tile of one level of one frame.  The int32
 //       integral tile is staged into shared memory (TMA bulk row copies, cp.async.bulk +
 //       mbarrier, on ystep-1 levels), sigma is computed once per window in FP64, and the
-//       cascade is evaluated in three phases of shrinking window count: fixed geometry
-//       (thread per window column, no compaction), compacted conflict-free rows with the
-//       stumps of a stage split over the warps, and a warp-per-window tail.  Stumps of the
-//       leading stages come from the constant bank (the packed cascade is a
-//       __grid_constant__ kernel parameter, <= 32 KB), the rest from global memory.
+//       cascade is evaluated in two phases: fixed geometry (thread per window column, no
+//       compaction, stumps from the constant bank: the packed cascade is a __grid_constant__
+//       kernel parameter, <= 32 KB) while most windows are alive, then warp-autonomous: a
+//       warp carries 32 survivors through all remaining stages, re-dividing its lanes between
+//       windows and stumps as windows die (stump records from global memory).
 //       Stump-based upright cascades (frontalface_alt / _default, eye, profileface) are
 //       finished inside this kernel.
 //   k_cascade_deep  : for cascades the tile kernel cannot finish (multi-node trees, tilted
@@ -98,53 +98,42 @@ __device__ __forceinline__ void emit_rect(const CascadeArgs &a, const CasLevel &
 //                             bank class is (wx + 8*wy) mod 32: the 32 lanes of a warp with
 //                             consecutive wx never conflict, and neither do compacted rows
 //                             whose windows have distinct classes.
-//   sgf     float [1024]      per-window sigma rounded to FP32 (the FP64 value is recomputed
-//                             on the rare exact fallback)
-//   list    u16 [1024]        compacted survivors, rows of 32 (see dense_reorder)
-//   blist   u16 [32][32]      survivors bucketed by bank class
-//   part    double [4][128]   per-warp partial stage sums of one group of 4 list rows
+//   sgf     float [1024]      per-window sigma rounded to FP32 for the phase-1 filter (the FP64
+//                             value is recomputed where exact arithmetic needs it)
+//   list    u16 [1024]        survivors of phase 1
+//   scr     384 B per warp    re-packing scratch of phase 2
 //
 // Phase 1, "fixed geometry" (stages 0 .. n_fixed-1, where most windows are still alive):
 //   thread t owns the column of 8 windows (wx = t & 63, wy = (t >> 6) + 2k).  Their tile
 //   addresses differ by a compile-time constant, so a corner address is computed ONCE per
 //   stump and the 4 windows of a chunk are read with immediate offsets (LDS [R + k*ROWSTEP]):
-//   no per-window address arithmetic, no compaction traffic, conflict-free banks.
-// Phase 2, compacted, stump-split (remaining stages of the parameter-resident prefix): the
-//   survivors are laid out in conflict-free rows of 32; EVERY warp evaluates the same group
-//   of up to 4 rows (4 windows per lane: shared stump loads, 4-way ILP) but only every 4th
-//   stump of the stage; the four partial sums meet in shared memory.  All warps carry the
-//   same load whatever the number of survivors, and a stage's latency is a quarter of the
-//   sequential one.  Adding partial sums in a different order is bit-exact because the packer
-//   proved the stage's alpha sum exact in any order (DenseStage flags bit2); stages without
-//   the proof go through the sequential FP64 path.
-// Phase 3, tail (<= handoff survivors, or the stages beyond the parameter budget): one WARP
-//   per window, lanes stride over the stumps of a stage (records from global memory, tile
-//   still in shared memory), exact arithmetic, until the window is rejected or accepted.
-//   Cascades the tail cannot express (trees, tilted features, stage trees) hand their
-//   survivors to the queue of k_cascade_deep instead.
-//
-// Stage arithmetic (phases 1-2): an FP32 filter decides each stump; whenever |s32 - t32| is
-// inside a guard band (2^-20 |t32| plus the cancellation terms) the window's whole stage is
-// redone by dense_stage_exact(), which reproduces the reference's C expressions bit for bit.
-// Outside the band both agree by the error analysis in DESIGN.md, so results are identical
-// to the all-FP64 evaluation (tests also run with force_exact = 1 and compare).
+//   no per-window address arithmetic, no compaction traffic, conflict-free banks.  Stumps
+//   come from the constant bank (the packed cascade is a kernel parameter).  An FP32 filter
+//   decides each stump; whenever |s32 - t32| is inside a guard band (2^-20 |t32| plus the
+//   cancellation terms) the window's whole stage is redone by dense_stage_exact(), which
+//   reproduces the reference's C expressions bit for bit.  Outside the band both agree by the
+//   error analysis in DESIGN.md, so results are identical to the all-FP64 evaluation (tests
+//   also run with force_exact = 1 and compare).
+// Phase 2, warp-autonomous (all remaining stages the tile kernel knows): see
+//   dense_warp_finish().  Stump-based upright cascades are finished here; the others hand
+//   the survivors of their dense prefix to the queue of k_cascade_deep.
 // ------------------------------------------------------------------------------------
 #define TILE_LD(base, off) (*reinterpret_cast<const int *>((base) + (off)))
 
 struct DenseSmemPlan {
-    size_t tile, sgf, list, blist, part, ctl, bar, total;
+    size_t tile, sgf, list, scr, ctl, bar, total;
 };
-// control block (ints): [0..63] two generations of bucket counts, [64..65] queue base
-constexpr int kCtlBcnt = 0, kCtlQueue = 64, kCtlInts = 72;
+// control block (ints): [0] survivors of phase 1
+constexpr int kCtlAlive = 0, kCtlInts = 8;
+constexpr int kScrBytesPerWarp = 32 * (sizeof(double) + sizeof(int));
 __host__ __device__ inline DenseSmemPlan dense_smem_plan(const DenseParams &P) {
     DenseSmemPlan p;
     const size_t rows = (size_t)(kTileH - 1) * P.ystep + P.win_h + 1;
     p.tile = 0;
     p.sgf = (rows * P.tile_stride * 4 + 127) & ~(size_t)127;
     p.list = p.sgf + kTileWindows * sizeof(float);
-    p.blist = p.list + kTileWindows * sizeof(uint16_t);
-    p.part = p.blist + kTileWindows * sizeof(uint16_t);
-    p.ctl = p.part + (size_t)kDenseWarps * kGroupWindows * sizeof(double);
+    p.scr = p.list + kTileWindows * sizeof(uint16_t);
+    p.ctl = p.scr + (size_t)kDenseWarps * kScrBytesPerWarp;
     p.bar = p.ctl + kCtlInts * sizeof(int);
     p.total = p.bar + 16;
     return p;
@@ -276,83 +265,93 @@ __device__ __forceinline__ void dense_dispatch_stage(const DenseParams &P, int s
     else dense_filter_stage<K, false, false, FIXED, ROWSTEP>(P, s, j0, jstep, base, sg, S, near);
 }
 
-// bank class of a window: (wx + 8*wy) mod 32
-__device__ __forceinline__ int dense_bank_class(int wid) { return (wid + 8 * (wid / kTileW)) & 31; }
-
-// survivors go to the bucket of their bank class: blist[slot][bucket]
-__device__ __forceinline__ void dense_append(uint16_t *blist, int *bcnt, int wid) {
-    const int b = dense_bank_class(wid);
-    const int slot = atomicAdd(&bcnt[b], 1);
-    blist[slot * 32 + b] = (uint16_t)wid;
-}
-
-// The compacted survivor list.  N survivors, sorted by bank class (i = rank in that order),
-// are laid out COLUMN-major in R = ceil(N/32) rows of 32:
-//     entry i  ->  row i % R, column i / R.
-// Rows are full (the kernel is issue-bound: every row costs a full instruction stream) and
-// balanced (row r has (N - r + R - 1) / R entries, columns 0 .. cnt-1), and because the
-// entries of one bucket are consecutive in i, a bucket of c windows puts at most ceil(c/R) of
-// them into one row: the bank-conflict degree of every corner load is ceil(max bucket / R),
-// the minimum any arrangement with R rows can reach.
-struct DenseList {
-    int n, rows;
-};
-__device__ __forceinline__ int dense_row_count(const DenseList &l, int row) { return row < l.rows ? (l.n - row + l.rows - 1) / l.rows : 0; }
-
-// Build the list from the buckets of generation `gen`; zero the counters of the other
-// generation for the next stage.  Two barriers; all threads must call it.  Every warp
-// computes the (tiny) prefix itself, so no broadcast through shared memory is needed.
-__device__ __forceinline__ DenseList dense_reorder(uint16_t *list, const uint16_t *blist, int *ctl, int gen, int tid) {
-    const int lane = tid & 31, warp = tid >> 5;
-    __syncthreads();   // all appends of this generation done
-    const int cnt = ctl[kCtlBcnt + gen * 32 + lane];
-    int incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
-    }
-    DenseList l;
-    l.n = __shfl_sync(0xffffffffu, incl, 31);
-    l.rows = (l.n + 31) >> 5;
-    if (warp == 0) ctl[kCtlBcnt + (gen ^ 1) * 32 + lane] = 0;
-    if (l.n > 0) {
-        const float inv_rows = 1.0f / (float)l.rows;
-        const int excl = incl - cnt;
-        for (int sl = warp; sl < cnt; sl += kDenseWarps) {
-            const int i = excl + sl;
-            const int col = (int)(((float)i + 0.5f) * inv_rows);   // exact: i < 1024, rows <= 32
-            const int row = i - col * l.rows;
-            list[row * 32 + col] = blist[sl * 32 + lane];
+// Phase 2: a warp takes up to 32 surviving windows (lane k holds window k) through ALL the
+// remaining stages on its own -- no block barrier, no shared survivor list.  For every stage
+// the 32 lanes are arranged as  w window slots x G stump groups  (w = smallest power of two
+// >= live windows, G = 32 / w): lane (slot, grp) evaluates stumps grp, grp + G, ... of the
+// stage for window `slot`, and the G partial sums of a window meet through xor-shuffles.
+// With 32 windows this is thread-per-window; as windows die the lanes they free take over a
+// share of the stumps (one window left: 32 stumps per pass), so lanes stay busy without
+// re-compaction across warps.  Survivors are re-packed to the low lanes through a 384-byte
+// scratch.  Stump records come from global memory (TailStump, 3 x LDG.128 per lane); the
+// arithmetic is the reference's exact one (no filter).  Summing partial sums out of order is
+// bit-exact because the packer proved the stage's alpha sum exact in any order (flags bit2);
+// a stage without the proof keeps w = 32, G = 1, i.e. tree order.
+__device__ __forceinline__ void dense_warp_finish(const DenseParams &P, const DenseCtx &c, const CascadeArgs &a,
+                                                  const CasLevel &CL, int frame, int cl, int px0, int py0, int s0, int wid,
+                                                  double *scr_sigma, int *scr_wid, int lane) {
+    const TailStump *__restrict__ tail = P.tail;
+    int nw = __popc(__ballot_sync(0xffffffffu, wid >= 0));   // the windows sit in lanes 0 .. nw-1
+    double sigma = wid >= 0 ? dense_sigma(P, c, wid) : 1.0;
+    int ss = s0;
+    while (nw > 0 && ss < P.tail_stages) {
+        const DenseStage st = P.stage[ss];
+        const bool dbl = st.flags & 1u;
+        int lw = 5;
+        if (st.flags & 4u) while (lw > 0 && (1 << (lw - 1)) >= nw) lw--;
+        const int w = 1 << lw, G = 32 >> lw;
+        const int slot = lane & (w - 1), grp = lane >> lw;
+        const int swid = __shfl_sync(0xffffffffu, wid, slot);
+        const double ssig = __shfl_sync(0xffffffffu, sigma, slot);
+        double acc = 0.0;
+        if (slot < nw) {
+            const unsigned char *base = dense_base(c, swid);
+            const uint4 *rec = reinterpret_cast<const uint4 *>(tail + st.tail_first + grp);
+            for (int j = grp; j < st.count; j += G, rec += 3 * G) {
+                const uint4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+                // q0 = off[0..7]; q1 = off[8..11], w0, w1; q2 = w2, thr, a0, a1
+                const int r0 = TILE_LD(base, q0.x & 0xffffu) - TILE_LD(base, q0.x >> 16) - TILE_LD(base, q0.y & 0xffffu) + TILE_LD(base, q0.y >> 16);
+                const int r1 = TILE_LD(base, q0.z & 0xffffu) - TILE_LD(base, q0.z >> 16) - TILE_LD(base, q0.w & 0xffffu) + TILE_LD(base, q0.w >> 16);
+                const float w0 = __uint_as_float(q1.z), w1 = __uint_as_float(q1.w);
+                const double t = __dmul_rn((double)__uint_as_float(q2.y), ssig);
+                double sv;
+                if (dbl) {  // tempcv.cpp:872-898; both products are exact in double, so fma == mul, mul, add
+                    sv = __fma_rn((double)r1, (double)w1, __dmul_rn((double)r0, (double)w0));
+                } else {    // tempcv.cpp:899-930 / 782-786: float products, double accumulation
+                    sv = __dadd_rn((double)__fmul_rn(__int2float_rn(r0), w0), (double)__fmul_rn(__int2float_rn(r1), w1));
+                    if ((q1.y >> 16) != 0) {
+                        const int r2 = TILE_LD(base, q1.x & 0xffffu) - TILE_LD(base, q1.x >> 16) - TILE_LD(base, q1.y & 0xffffu) + TILE_LD(base, q1.y >> 16);
+                        sv = __dadd_rn(sv, (double)__fmul_rn(__int2float_rn(r2), __uint_as_float(q2.x)));
+                    }
+                }
+                acc = __dadd_rn(acc, (double)__uint_as_float(sv >= t ? q2.w : q2.z));
+            }
+        }
+        for (int d = w; d < 32; d <<= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, d));
+        const bool mine = lane < nw;   // then slot == lane: acc is this lane's own window
+        const bool pass = acc >= (double)st.thr;
+        const unsigned surv = __ballot_sync(0xffffffffu, mine && pass);
+        if (mine && !pass && c.codes) dense_write_code(c, wid, ss * c.code_mul);
+        ss++;
+        const int n2 = __popc(surv);
+        if (n2 != nw) {   // re-pack the survivors into lanes 0 .. n2-1
+            if (mine && pass) {
+                const int d = __popc(surv & ((1u << lane) - 1u));
+                scr_wid[d] = wid;
+                scr_sigma[d] = sigma;
+            }
+            __syncwarp();
+            nw = n2;
+            if (lane < nw) { wid = scr_wid[lane]; sigma = scr_sigma[lane]; } else wid = -1;
+            __syncwarp();
         }
     }
-    __syncthreads();
-    return l;
-}
-
-// compacted phase: this warp's share (stumps warp, warp+4, ...) of stage s for K list rows
-template <int K>
-__device__ __forceinline__ void dense_rows_partial(const DenseParams &P, const DenseCtx &c, int s, const DenseList &l,
-                                                   const uint16_t *list, int row0, double *part, int warp, int lane) {
-    const unsigned char *base[K];
-    float sg[K];
-    double S[K];
-    bool near[K];
-    const bool all_near = P.force_exact != 0 || !(P.stage[s].flags & 4u);
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        const int row = row0 + k;
-        // idle lanes shadow column 0 of their row (a broadcast, no extra wavefront)
-        const int wid = list[row * 32 + (lane < dense_row_count(l, row) ? lane : 0)];
-        base[k] = dense_base(c, wid);
-        sg[k] = c.sgf[wid];
-        S[k] = 0.0;
-        near[k] = all_near;
+    if (nw == 0 || lane >= nw) return;
+    const int x = px0 + (wid & (kTileW - 1)) * c.ystep, y = py0 + (wid / kTileW) * c.ystep;
+    if (ss >= P.total_stages) {          // passed every stage: a detection
+        emit_rect(a, CL, frame, x, y);
+        if (c.codes) dense_write_code(c, wid, P.total_stages);
+    } else {                             // the rest of the cascade belongs to the deep kernel
+        const ull slot = atomicAdd(a.counters + 1, 1ull);
+        if (slot < a.queue_cap) {
+            QueueItem it;
+            it.key = ((uint32_t)frame << 16) | ((uint32_t)cl << 8) | (uint32_t)ss;
+            it.xy = ((uint32_t)y << 16) | (uint32_t)x;
+            a.queue[slot] = it;
+        } else {
+            atomicAdd(a.counters + 3, 1ull);
+        }
     }
-    dense_dispatch_stage<K, false, 0>(P, s, warp, kDenseWarps, base, sg, S, near);
-#pragma unroll
-    for (int k = 0; k < K; k++)   // NaN marks "redo this window's stage exactly"
-        part[warp * kGroupWindows + k * 32 + lane] = near[k] ? __longlong_as_double(0x7ff8000000000000ll) : S[k];
 }
 
 // ROWSTEP_T: compile-time byte distance between a thread's consecutive windows in phase 1
@@ -365,8 +364,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     unsigned char *tile = smem_raw + plan.tile;
     float *sgf = reinterpret_cast<float *>(smem_raw + plan.sgf);
     uint16_t *list = reinterpret_cast<uint16_t *>(smem_raw + plan.list);
-    uint16_t *blist = reinterpret_cast<uint16_t *>(smem_raw + plan.blist);
-    double *part = reinterpret_cast<double *>(smem_raw + plan.part);
+    unsigned char *scr = smem_raw + plan.scr + (size_t)(threadIdx.x >> 5) * kScrBytesPerWarp;
     int *ctl = reinterpret_cast<int *>(smem_raw + plan.ctl);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + plan.bar);
 
@@ -479,130 +477,31 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
         }
     }
 
-    // ---- phase-1 survivors -> buckets -> conflict-free list ----
-    int gen = 0;
+    // ---- phase-1 survivors -> one list (warp-aggregated append; a warp's entries keep
+    //      consecutive wx, i.e. distinct banks) ----
 #pragma unroll
-    for (int k = 0; k < kDenseSlots; k++)
-        if ((alive >> k) & 1u) dense_append(blist, ctl + kCtlBcnt, (wy0 + k * kRowsPerSlot) * kTileW + wx);
-    DenseList l = dense_reorder(list, blist, ctl, gen, tid);
-
-    // ---- phase 2: remaining parameter-resident stages, all warps on the same rows, stumps split ----
-    const bool can_leave = P.tail_stages != 0 || P.n_stages < P.total_stages;   // somebody finishes the cascade
-    for (;;) {
-        if (l.n == 0) return;
-        if (s >= P.n_stages || (l.n <= P.handoff && can_leave)) break;
-        gen ^= 1;
-        int *bcnt = ctl + kCtlBcnt + gen * 32;
-        const double sthr = (double)P.stage[s].thr;
-        for (int row0 = 0; row0 < l.rows; row0 += kGroupRows) {
-            const int K = min(kGroupRows, l.rows - row0);
-            if (row0 > 0) __syncthreads();   // the previous group's partial sums have been consumed
-            if (K == 1) dense_rows_partial<1>(P, c, s, l, list, row0, part, warp, lane);
-            else if (K == 2) dense_rows_partial<2>(P, c, s, l, list, row0, part, warp, lane);
-            else if (K == 3) dense_rows_partial<3>(P, c, s, l, list, row0, part, warp, lane);
-            else dense_rows_partial<4>(P, c, s, l, list, row0, part, warp, lane);
-            __syncthreads();
-            for (int t = tid; t < kGroupWindows; t += kDenseThreads) {
-                const int row = row0 + (t >> 5), col = t & 31;
-                if (col >= dense_row_count(l, row)) continue;
-                const int wid = list[row * 32 + col];
-                double Ssum = part[t];
-#pragma unroll
-                for (int w = 1; w < kDenseWarps; w++) Ssum = __dadd_rn(Ssum, part[w * kGroupWindows + t]);
-                bool pass = Ssum >= sthr;
-                if (Ssum != Ssum) pass = dense_stage_exact(P, c, s, wid);
-                if (pass) dense_append(blist, bcnt, wid);
-                else if (c.codes) dense_write_code(c, wid, s * c.code_mul);
-            }
+    for (int k = 0; k < kDenseSlots; k++) {
+        const bool al = (alive >> k) & 1u;
+        const unsigned m = __ballot_sync(0xffffffffu, al);
+        if (m) {
+            int b = 0;
+            if (lane == 0) b = atomicAdd(ctl + kCtlAlive, __popc(m));
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (al) list[b + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((wy0 + k * kRowsPerSlot) * kTileW + wx);
         }
-        l = dense_reorder(list, blist, ctl, gen, tid);
-        s++;
     }
+    __syncthreads();
+    const int n_alive = ctl[kCtlAlive];
+    if (n_alive == 0) return;
 
-    if (s >= P.total_stages) {
-        // ---- the whole cascade was parameter resident: survivors are detections ----
-        for (int i = tid; i < l.rows * 32; i += kDenseThreads) {
-            if ((i & 31) >= dense_row_count(l, i >> 5)) continue;
-            const int w = list[i];
-            emit_rect(a, CL, frame, px0 + (w & (kTileW - 1)) * ystep, py0 + (w / kTileW) * ystep);
-            if (c.codes) dense_write_code(c, w, P.total_stages);
-        }
-    } else if (P.tail_stages) {
-        // ---- phase 3: warp per window, lanes over the stumps of a stage, exact arithmetic ----
-        const TailStump *__restrict__ tail = P.tail;
-        for (int n = warp; n < l.n; n += kDenseWarps) {
-            const int col = n / l.rows, row = n - col * l.rows;
-            const int wid = list[row * 32 + col];
-            const unsigned char *base = dense_base(c, wid);
-            const double sigma = dense_sigma(P, c, wid);
-            int ss = s;
-            bool accepted = false;
-            for (;;) {
-                const DenseStage st = P.stage[ss];
-                const bool dbl = st.flags & 1u, order_free = st.flags & 4u;
-                double Ssum = 0.0, acc = 0.0;
-                for (int j0 = 0; j0 < st.count; j0 += 32) {
-                    const int j = j0 + lane;
-                    float av = 0.f;
-                    if (j < st.count) {
-                        const uint4 *rec = reinterpret_cast<const uint4 *>(tail + st.tail_first + j);
-                        const uint4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
-                        // q0 = off[0..7]; q1 = off[8..11], w0, w1; q2 = w2, thr, a0, a1
-                        const int r0 = TILE_LD(base, q0.x & 0xffffu) - TILE_LD(base, q0.x >> 16) - TILE_LD(base, q0.y & 0xffffu) + TILE_LD(base, q0.y >> 16);
-                        const int r1 = TILE_LD(base, q0.z & 0xffffu) - TILE_LD(base, q0.z >> 16) - TILE_LD(base, q0.w & 0xffffu) + TILE_LD(base, q0.w >> 16);
-                        const float w0 = __uint_as_float(q1.z), w1 = __uint_as_float(q1.w);
-                        const double t = __dmul_rn((double)__uint_as_float(q2.y), sigma);
-                        double sv;
-                        if (dbl) {
-                            sv = __fma_rn((double)r1, (double)w1, __dmul_rn((double)r0, (double)w0));
-                        } else {
-                            sv = __dadd_rn((double)__fmul_rn(__int2float_rn(r0), w0), (double)__fmul_rn(__int2float_rn(r1), w1));
-                            if ((q1.y >> 16) != 0) {
-                                const int r2 = TILE_LD(base, q1.x & 0xffffu) - TILE_LD(base, q1.x >> 16) - TILE_LD(base, q1.y & 0xffffu) + TILE_LD(base, q1.y >> 16);
-                                sv = __dadd_rn(sv, (double)__fmul_rn(__int2float_rn(r2), __uint_as_float(q2.x)));
-                            }
-                        }
-                        av = __uint_as_float(sv >= t ? q2.w : q2.z);
-                    }
-                    if (order_free) {
-                        acc = __dadd_rn(acc, (double)av);
-                    } else {
-                        const int cnt = min(32, (int)st.count - j0);
-                        for (int k = 0; k < cnt; k++) Ssum = __dadd_rn(Ssum, (double)__shfl_sync(0xffffffffu, av, k));
-                    }
-                }
-                if (order_free) {
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, d));
-                    Ssum = acc;
-                }
-                if (!(Ssum >= (double)st.thr)) break;
-                if (++ss >= P.total_stages) { accepted = true; break; }
-            }
-            if (lane == 0) {
-                if (accepted) emit_rect(a, CL, frame, px0 + (wid & (kTileW - 1)) * ystep, py0 + (wid / kTileW) * ystep);
-                if (c.codes) dense_write_code(c, wid, ss);
-            }
-        }
-    } else {
-        // ---- hand the survivors to the deep kernel ----
-        if (tid == 0) *reinterpret_cast<ull *>(ctl + kCtlQueue) = atomicAdd(a.counters + 1, (ull)l.n);
-        __syncthreads();
-        const ull qb = *reinterpret_cast<const ull *>(ctl + kCtlQueue);
-        for (int i = tid; i < l.rows * 32; i += kDenseThreads) {
-            const int row = i >> 5, col = i & 31;
-            if (col >= dense_row_count(l, row)) continue;
-            const int w = list[i];
-            const ull slot = qb + (ull)(col * l.rows + row);
-            if (slot < a.queue_cap) {
-                QueueItem it;
-                it.key = ((uint32_t)frame << 16) | ((uint32_t)cl << 8) | (uint32_t)s;
-                it.xy = ((uint32_t)(py0 + (w / kTileW) * ystep) << 16) | (uint32_t)(px0 + (w & (kTileW - 1)) * ystep);
-                a.queue[slot] = it;
-            } else {
-                atomicAdd(a.counters + 3, 1ull);
-            }
-        }
+    // ---- phase 2: every warp finishes an equal share of the survivors on its own ----
+    const int share = (n_alive + kDenseWarps - 1) / kDenseWarps;
+    const int lo = warp * share, hi = min(n_alive, lo + share);
+    double *scr_sigma = reinterpret_cast<double *>(scr);
+    int *scr_wid = reinterpret_cast<int *>(scr + 32 * sizeof(double));
+    for (int b0 = lo; b0 < hi; b0 += 32) {
+        const int wid = b0 + lane < hi ? (int)list[b0 + lane] : -1;
+        dense_warp_finish(P, c, a, CL, frame, cl, px0, py0, s, wid, scr_sigma, scr_wid, lane);
     }
 }
 
