@@ -388,7 +388,7 @@ int clfd_cascade_get_info(const clfd_cascade *c, clfd_cascade_info *info) {
     }
     for (int v : h.st_ntrees) info->max_trees_per_stage = std::max(info->max_trees_per_stage, v);
     for (int v : h.tr_nnodes) info->max_nodes_per_tree = std::max(info->max_nodes_per_tree, v);
-    info->dense_stages = c->packed.dense[0].n_stages;
+    info->dense_stages = c->packed.dense[0].tail_stages;
     info->dense_stumps = c->packed.dense_stumps;
     for (int v : h.order_free) info->order_free_stages += v;
     info->packed_bytes = (int)(c->packed.deep_stages.size() * sizeof(DeepStage) + c->packed.deep_nodes.size() * sizeof(DeepNode) +
@@ -623,7 +623,6 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
             cp.dense[yi] = pk.dense[yi];
             if (!pk.tail[yi].empty() && (rc = cp.d_tail[yi].upload(pk.tail[yi], s))) return rc;
             cp.dense[yi].tail = cp.d_tail[yi].p;
-            if (!cp.d_tail[yi].p) cp.dense[yi].tail_stages = 0;   // (then n_stages is 0 too and the tile kernel is not launched)
         }
         if ((rc = cp.d_counters.alloc(4))) return rc;
         if (cfg->want_codes && (rc = cp.d_codes.alloc((size_t)std::max<long long>(cp.windows_per_frame, 1) * cfg->max_batch)))
@@ -719,7 +718,7 @@ int clfd_detector_enqueue(clfd_detector *det, const uint8_t *frames_dev, int n_f
             a.deep.win_w = cp.cascade->host.win_w; a.deep.win_h = cp.cascade->host.win_h;
             a.deep.inv_area = pk.dense[0].inv_area;
             if (ev && ci == 0) CK(cudaEventRecord(ev[5], s));
-            if (pk.dense[0].n_stages > 0) {
+            if (pk.dense[0].tail_stages > 0) {
                 // ystep-2 levels (de-interleaved tile layout) and ystep-1 levels (natural layout)
                 if (cp.n_tiles_y2 > 0) { CK(launch_cascade_tiles(cp.dense[1], a, 0, cp.n_tiles_y2, s)); launches++; }
                 if (cp.n_tiles > cp.n_tiles_y2) {
@@ -732,7 +731,7 @@ int clfd_detector_enqueue(clfd_detector *det, const uint8_t *frames_dev, int n_f
             }
             if (ev && ci == 0) CK(cudaEventRecord(ev[6], s));
             // cascades the tile kernel finishes itself (tail_stages) never fill the queue
-            const bool tiles_finish = pk.dense[0].n_stages > 0 && cp.dense[0].tail_stages == pk.dense[0].total_stages;
+            const bool tiles_finish = pk.dense[0].tail_stages > 0 && pk.dense[0].tail_stages == pk.dense[0].total_stages;
             if (!tiles_finish) { CK(launch_cascade_deep(a, ctx->n_sms, s)); launches++; }
             if (ev && ci == 0) CK(cudaEventRecord(ev[7], s));
         }

@@ -64,34 +64,29 @@ constexpr int kDenseThreads = 128;
 constexpr int kDenseWarps = kDenseThreads / 32;
 constexpr int kDenseSlots = kTileWindows / kDenseThreads;   // windows per thread (8)
 constexpr int kDenseChunk = 4;                               // windows a thread carries through a stage at once
-constexpr int kMaxDenseStumps = 396;
-constexpr int kMaxDenseStages = 32;
-constexpr int kHandoffWindows = 8;  // <= this many survivors in a tile: warp-per-window tail (or the deep kernel)
-constexpr int kGroupRows = 4;       // list rows (of 32 windows) a warp carries through a compacted stage at once
-constexpr int kGroupWindows = kGroupRows * 32;
+constexpr int kMaxDenseStumps = 392;   // parameter-resident stumps (constant bank): the leading stages that fit
+constexpr int kMaxDenseStages = 32;    // stages the tile kernel can evaluate (a cascade with more keeps a deep tail)
 
-// One stump of the dense kernel, 80 B, read through the constant bank (the packed cascade
-// is a kernel parameter); the whole warp evaluates the same stump.
+// One stump of the tile kernel, 80 B = 5 x 16 B.  The leading stages' stumps are parameter
+// resident (constant bank: a warp whose lanes all evaluate the same stump reads it with LDC,
+// off the L1 data pipe the corner loads saturate); every tile-evaluated stump also has a copy
+// in global memory (lanes on different stumps, stages beyond the parameter budget).
 struct DenseStump {
     uint32_t off[12];  // BYTE offsets into the smem tile: p0..p3 of rect 0,1,2 (rect 2: zeros if absent)
     float w[3];        // hidden weights (w[2] = 0 if absent)
     float thr;
-    double a0, a1;     // alpha[0] (sum < t), alpha[1] (sum >= t), pre-converted (exact)
+    float a0, a1;      // alpha[0] (sum < t), alpha[1] (sum >= t)
+    float pad[2];
 };
+typedef DenseStump TailStump;
 struct DenseStage {
     uint16_t first, count;   // first: index into DenseParams::stump (stages < n_stages only)
     float thr;               // biased threshold
     uint32_t flags;          // bit0 double-product stage (two_rects fast path), bit1 any 3-rect stump,
                              // bit2 alpha sum exact in any order (HostCascade::order_free)
     uint32_t tail_first;     // index of the stage's first stump in the global TailStump array
-};
-// The same stump for the warp-per-window tail of the tile kernel (lanes stride over the stumps
-// of a stage, so records are read from global memory, 48 B = 3 x LDG.128 per lane).
-struct TailStump {
-    uint16_t off[12];  // BYTE offsets into the smem tile (tile <= 64 KB)
-    float w[3];
-    float thr;
-    float a0, a1;
+    float sum_eps;           // bound on the error of an FP32 sum of the stage's alphas in any order
+    uint32_t pad;
 };
 // Two blobs per cascade: [0] for ystep-1 levels (natural tile layout, addr = y*S + x) and
 // [1] for ystep-2 levels (columns de-interleaved: addr = y*S + (x&1)*S/2 + (x>>1)), so that in
@@ -99,7 +94,7 @@ struct TailStump {
 // corner load is (wx + 8*wy + const) mod 32, so lanes whose windows have distinct
 // (wx + 8*wy) mod 32 never conflict, and a compact blob of survivors spreads over the banks.
 struct DenseParams {
-    int n_stages;       // dense stages (prefix of the cascade)
+    int n_stages;       // stages whose stumps are parameter resident (>= n_fixed)
     int total_stages;   // stages in the whole cascade
     int tile_stride;    // ints per smem tile row (ystep * stride = 8 mod 32)
     int win_w, win_h;
@@ -108,9 +103,9 @@ struct DenseParams {
     int force_exact;    // test hook: skip the FP32 filter, evaluate every stage in FP64
     float filter_eps;   // FP32 filter guard band (2^-20), see kernels_clod.cu
     int n_fixed;        // leading stages run in fixed geometry (no compaction), <= n_stages
-    int tail_stages;    // == total_stages when the tile kernel can finish the cascade itself (stump based,
-                        // upright, linear, <= kMaxDenseStages stages): no queue / deep kernel; else 0
-    int handoff;        // <= this many survivors in a tile: leave the compacted phase
+    int tail_stages;    // leading stages the tile kernel evaluates (upright stumps, linear): == total_stages
+                        // when it finishes the cascade itself, otherwise survivors go to the deep kernel
+    int pad0;
     double inv_area;
     const TailStump *tail;   // device, layout of this blob's ystep (patched in by the detector)
     DenseStage stage[kMaxDenseStages];

@@ -6,8 +6,8 @@ namespace clfd {
 
 struct PackedCascade {
     DenseParams dense[2];              // kernel-parameter blobs of the smem-tile kernel: [ystep-1]
-    int dense_stumps = 0;
-    std::vector<TailStump> tail[2];    // every stump of the cascade in tile-offset form, [ystep-1]; empty if no tail
+    int dense_stumps = 0;              // stumps in the stages the tile kernel evaluates
+    std::vector<TailStump> tail[2];    // stumps of the tile-evaluated stages in tile-offset form, [ystep-1]
     std::vector<DeepStage> deep_stages;  // global-memory blob of the deep kernel
     std::vector<DeepNode> deep_nodes;
     std::vector<int> tree_first_node;

@@ -219,8 +219,11 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
         d.flags = (nd.tilted ? 1 : 0) | (c.hid_nrects[n] << 8);
     }
 
-    // dense prefix: leading stages of a stump-based, upright, linear-prefix cascade whose
-    // stumps fit the kernel-parameter budget and whose smem offsets fit 16 bits.
+    // Tile-kernel blobs.  `elig` = leading stages the tile kernel can evaluate: one-node upright
+    // trees, and in a stage tree only the unconditional linear prefix (stage i the single child
+    // of stage i-1 with no `next` alternative).  Every eligible stump gets a TailStump record
+    // (global memory, warp-autonomous phase); the stumps of the first n_fixed stages are also
+    // parameter resident (DenseStump, fixed-geometry phase).
     for (int yi = 0; yi < 2; yi++) {
         const int ystep = yi + 1;
         DenseParams &P = out.dense[yi];
@@ -231,105 +234,74 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
         P.is_tree = c.is_tree ? 1 : 0;
         P.ystep = ystep;
         P.filter_eps = 9.5367431640625e-07f;  // 2^-20
-        if (const char *e = getenv("CLFD_FORCE_EXACT")) P.force_exact = atoi(e) != 0;   // test hook: bypass the FP32 filter
+        if (const char *e = getenv("CLFD_FORCE_EXACT")) P.force_exact = atoi(e) != 0;   // test hook: bypass the FP32 filters
         P.inv_area = 1. / ((c.win_w - 2) * (c.win_h - 2));
         const size_t tile_bytes = (size_t)dense_tile_rows(c.win_h, ystep) * P.tile_stride * 4;
-        bool dense_ok = tile_bytes <= 65536 && c.win_w <= 255 && c.win_h <= 255;
-        {
-            int ho = kHandoffWindows;
-            if (const char *e = getenv("CLFD_HANDOFF")) ho = atoi(e);
-            P.handoff = ho < 0 ? 0 : ho;
-        }
-        int ns = 0, nstump = 0;
-        while (dense_ok && ns < S && ns < kMaxDenseStages) {
-            // in a stage tree only the unconditional linear prefix can be dense: stage i must
-            // be the single child of stage i-1 and have no `next` alternative.
-            if (c.is_tree && (c.st_next[ns] != -1 || c.st_parent[ns] != ns - 1 ||
-                              (ns > 0 && c.st_child[ns - 1] != ns)))
+        const bool dense_ok = tile_bytes <= 65536 && c.win_w <= 255 && c.win_h <= 255;
+        int elig = 0;
+        while (dense_ok && elig < S && elig < kMaxDenseStages) {
+            if (c.is_tree && (c.st_next[elig] != -1 || c.st_parent[elig] != elig - 1 ||
+                              (elig > 0 && c.st_child[elig - 1] != elig)))
                 break;
-            const int t0 = c.st_first_tree[ns], t1 = c.st_first_tree[ns + 1];
-            if (nstump + (t1 - t0) > kMaxDenseStumps) break;
-            bool ok = true, any3 = false;
-            for (int t = t0; t < t1 && ok; t++) {
-                if (c.tr_nnodes[t] != 1) { ok = false; break; }
-                const int n = c.tr_first_node[t];
-                if (c.nodes[n].tilted) { ok = false; break; }
-                any3 |= c.hid_nrects[n] == 3;
-            }
+            bool ok = true;
+            for (int t = c.st_first_tree[elig]; t < c.st_first_tree[elig + 1] && ok; t++)
+                ok = c.tr_nnodes[t] == 1 && !c.nodes[c.tr_first_node[t]].tilted;
             if (!ok) break;
-            DenseStage &ds = P.stage[ns];
-            ds.first = (uint16_t)nstump; ds.count = (uint16_t)(t1 - t0);
-            ds.thr = c.hid_thr[ns];
-            ds.flags = ((!c.is_tree && c.is_stump_based && c.two_rects[ns]) ? 1u : 0u) | (any3 ? 2u : 0u) |
-                       (c.order_free[ns] ? 4u : 0u);
-            ds.tail_first = (uint32_t)t0;
-            for (int t = t0; t < t1; t++) {
+            elig++;
+        }
+        P.tail_stages = elig;
+        const int n_elig_stumps = c.st_first_tree[elig];
+        out.dense_stumps = n_elig_stumps;
+        out.tail[yi].assign(n_elig_stumps, TailStump());
+        auto tile_offset = [&](int dy, int dx) {
+            const int word = ystep == 1 ? dy * P.tile_stride + dx
+                                        : dy * P.tile_stride + (dx & 1) * (P.tile_stride / 2) + (dx >> 1);
+            return (uint32_t)(word * 4);
+        };
+        for (int i = 0; i < elig; i++) {
+            DenseStage &ds = P.stage[i];
+            bool any3 = false;
+            double abs_sum = 0;
+            for (int t = c.st_first_tree[i]; t < c.st_first_tree[i + 1]; t++) {
                 const int n = c.tr_first_node[t];
                 const HostNode &nd = c.nodes[n];
-                DenseStump &st = P.stump[nstump++];
-                for (int q = 0; q < 12; q++) st.off[q] = 0;
+                any3 |= c.hid_nrects[n] == 3;
+                TailStump &ts = out.tail[yi][t];
+                memset(&ts, 0, sizeof ts);
                 for (int k = 0; k < c.hid_nrects[n]; k++) {
                     int dx[4], dy[4];
                     corner_coords(nd, k, dx, dy);
-                    for (int q = 0; q < 4; q++) {
-                        const int word = ystep == 1 ? dy[q] * P.tile_stride + dx[q]
-                                                    : dy[q] * P.tile_stride + (dx[q] & 1) * (P.tile_stride / 2) + (dx[q] >> 1);
-                        st.off[k * 4 + q] = (uint32_t)(word * 4);
-                    }
-                    st.w[k] = c.hid_weight[(size_t)n * 3 + k];
+                    for (int q = 0; q < 4; q++) ts.off[k * 4 + q] = tile_offset(dy[q], dx[q]);
+                    ts.w[k] = c.hid_weight[(size_t)n * 3 + k];
                 }
-                st.thr = nd.threshold;
+                ts.thr = nd.threshold;
                 const int a = c.tr_first_node[t] + t;            // alpha base of tree t
-                st.a0 = (double)c.alpha[a + (-nd.left)];         // sum <  t -> left  (tempcv.cpp:788)
-                st.a1 = (double)c.alpha[a + (-nd.right)];        // sum >= t -> right
+                ts.a0 = c.alpha[a + (-nd.left)];                 // sum <  t -> left  (tempcv.cpp:788)
+                ts.a1 = c.alpha[a + (-nd.right)];                // sum >= t -> right
+                abs_sum += fmax(fabs((double)ts.a0), fabs((double)ts.a1));
             }
+            ds.first = 0; ds.count = (uint16_t)c.st_ntrees[i];
+            ds.thr = c.hid_thr[i];
+            // double products only on the reference's stump fast path (tempcv.cpp:862,872)
+            ds.flags = ((!c.is_tree && c.is_stump_based && c.two_rects[i]) ? 1u : 0u) | (any3 ? 2u : 0u) |
+                       (c.order_free[i] ? 4u : 0u);
+            ds.tail_first = (uint32_t)c.st_first_tree[i];
+            // FP32 summation of n alphas in any order: |error| <= (n-1) 2^-24 sum|alpha|; 2x slack
+            const double e = (double)c.st_ntrees[i] * ldexp(1.0, -23) * abs_sum;
+            ds.sum_eps = std::isfinite(e) ? (float)(e * 1.0000002) + FLT_MIN : INFINITY;
+        }
+        // parameter-resident copy of the leading stages that fit the kernel-parameter budget
+        int ns = 0, nstump = 0;
+        while (ns < elig && nstump + c.st_ntrees[ns] <= kMaxDenseStumps) {
+            P.stage[ns].first = (uint16_t)nstump;
+            for (int t = c.st_first_tree[ns]; t < c.st_first_tree[ns + 1]; t++) P.stump[nstump++] = out.tail[yi][t];
             ns++;
         }
         P.n_stages = ns;
-        // Stages the warp-autonomous phase of the tile kernel may evaluate (TailStump records in
-        // global memory): the whole cascade when it is linear, upright and stump based (then no
-        // queue / deep kernel is needed), otherwise just the dense prefix.
-        const bool full = ns > 0 && !c.is_tree && c.is_stump_based && !c.has_tilted && S <= kMaxDenseStages;
-        const int tail_n = full ? S : ns;
-        out.tail[yi].clear();
-        out.tail[yi].resize(c.st_first_tree[tail_n]);
-        for (int i = 0; i < tail_n; i++) {
-            DenseStage &ds = P.stage[i];
-            bool any3 = false;
-            for (int t = c.st_first_tree[i]; t < c.st_first_tree[i + 1]; t++) any3 |= c.hid_nrects[c.tr_first_node[t]] == 3;
-            if (i >= ns) ds.first = 0;
-            ds.count = (uint16_t)c.st_ntrees[i];
-            ds.thr = c.hid_thr[i];
-            ds.flags = ((!c.is_tree && c.is_stump_based && c.two_rects[i]) ? 1u : 0u) | (any3 ? 2u : 0u) | (c.order_free[i] ? 4u : 0u);
-            ds.tail_first = (uint32_t)c.st_first_tree[i];
-        }
-        for (int t = 0; t < c.st_first_tree[tail_n]; t++) {
-            const int n = c.tr_first_node[t];
-            const HostNode &nd = c.nodes[n];
-            TailStump &ts = out.tail[yi][t];
-            memset(&ts, 0, sizeof ts);
-            for (int k = 0; k < c.hid_nrects[n]; k++) {
-                int dx[4], dy[4];
-                corner_coords(nd, k, dx, dy);
-                for (int q = 0; q < 4; q++) {
-                    const int word = ystep == 1 ? dy[q] * P.tile_stride + dx[q]
-                                                : dy[q] * P.tile_stride + (dx[q] & 1) * (P.tile_stride / 2) + (dx[q] >> 1);
-                    ts.off[k * 4 + q] = (uint16_t)(word * 4);
-                }
-                ts.w[k] = c.hid_weight[(size_t)n * 3 + k];
-            }
-            ts.thr = nd.threshold;
-            const int a = c.tr_first_node[t] + t;
-            ts.a0 = c.alpha[a + (-nd.left)];
-            ts.a1 = c.alpha[a + (-nd.right)];
-        }
-        P.tail_stages = tail_n;
-        {   // stages evaluated in fixed geometry before the first compaction (tunable for experiments)
-            int nf = 3;
-            if (const char *e = getenv("CLFD_N_FIXED")) nf = atoi(e);
-            P.n_fixed = nf < 0 ? 0 : (nf > ns ? ns : nf);
-        }
-        out.dense_stumps = nstump;
+        // stages run in fixed geometry before the first compaction (tunable for experiments)
+        int nf = 3;
+        if (const char *e = getenv("CLFD_N_FIXED")) nf = atoi(e);
+        P.n_fixed = nf < 0 ? 0 : (nf > ns ? ns : nf);
     }
 }
 

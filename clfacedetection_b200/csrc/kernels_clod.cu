@@ -100,7 +100,7 @@ __device__ __forceinline__ void emit_rect(const CascadeArgs &a, const CasLevel &
 //                             whose windows have distinct classes.
 //   sgf     float [1024]      per-window sigma rounded to FP32 for the phase-1 filter (the FP64
 //                             value is recomputed where exact arithmetic needs it)
-//   list    u16 [1024]        survivors of phase 1
+//   list    u16 [1024]        survivors (phase 1 output; per-warp segments compacted in place in phase 2)
 //   scr     384 B per warp    re-packing scratch of phase 2
 //
 // Phase 1, "fixed geometry" (stages 0 .. n_fixed-1, where most windows are still alive):
@@ -114,26 +114,36 @@ __device__ __forceinline__ void emit_rect(const CascadeArgs &a, const CasLevel &
 //   reproduces the reference's C expressions bit for bit.  Outside the band both agree by the
 //   error analysis in DESIGN.md, so results are identical to the all-FP64 evaluation (tests
 //   also run with force_exact = 1 and compare).
-// Phase 2, warp-autonomous (all remaining stages the tile kernel knows): see
-//   dense_warp_finish().  Stump-based upright cascades are finished here; the others hand
-//   the survivors of their dense prefix to the queue of k_cascade_deep.
+// Phase 2, warp-autonomous (all remaining stages the tile kernel knows; see the kernel body):
+//   stump-based upright cascades are finished here; the others hand the survivors of their
+//   eligible prefix to the queue of k_cascade_deep.
 // ------------------------------------------------------------------------------------
-#define TILE_LD(base, off) (*reinterpret_cast<const int *>((base) + (off)))
+// Tile accesses use 32-bit shared-window addresses and explicit ld.shared (a generic pointer
+// would make the compiler rebuild the shared window base inside every loop).
+__device__ __forceinline__ int lds32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+template <int IMM>
+__device__ __forceinline__ int lds32i(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
 
 struct DenseSmemPlan {
-    size_t tile, sgf, list, scr, ctl, bar, total;
+    size_t tile, sgf, list, ctl, bar, total;
 };
 // control block (ints): [0] survivors of phase 1
 constexpr int kCtlAlive = 0, kCtlInts = 8;
-constexpr int kScrBytesPerWarp = 32 * (sizeof(double) + sizeof(int));
 __host__ __device__ inline DenseSmemPlan dense_smem_plan(const DenseParams &P) {
     DenseSmemPlan p;
     const size_t rows = (size_t)(kTileH - 1) * P.ystep + P.win_h + 1;
     p.tile = 0;
     p.sgf = (rows * P.tile_stride * 4 + 127) & ~(size_t)127;
     p.list = p.sgf + kTileWindows * sizeof(float);
-    p.scr = p.list + kTileWindows * sizeof(uint16_t);
-    p.ctl = p.scr + (size_t)kDenseWarps * kScrBytesPerWarp;
+    p.ctl = p.list + kTileWindows * sizeof(uint16_t);
     p.bar = p.ctl + kCtlInts * sizeof(int);
     p.total = p.bar + 16;
     return p;
@@ -141,8 +151,7 @@ __host__ __device__ inline DenseSmemPlan dense_smem_plan(const DenseParams &P) {
 size_t dense_smem_bytes(const DenseParams &P) { return dense_smem_plan(P).total; }
 
 struct DenseCtx {
-    unsigned char *tile;
-    float *sgf;
+    uint32_t tile;    // shared-window address of the tile
     const ull *gsq;   // squared integral at the tile origin
     int16_t *codes;   // this frame + level, or nullptr
     int sq_pitch;     // elements
@@ -152,11 +161,11 @@ struct DenseCtx {
     int code_mul;
 };
 
-__device__ __forceinline__ const unsigned char *dense_base(const DenseCtx &c, int wid) {
-    return c.tile + (wid / kTileW) * c.row_mul + (wid & (kTileW - 1)) * 4;
+__device__ __forceinline__ uint32_t dense_base(const DenseCtx &c, int wid) {
+    return c.tile + (uint32_t)((wid / kTileW) * c.row_mul + (wid & (kTileW - 1)) * 4);
 }
-__device__ __forceinline__ int dense_tile_off(const DenseCtx &c, int y, int x) {   // byte offset of integral (y, x) from a window base
-    return 4 * (c.ystep == 1 ? y * c.S + x : y * c.S + (x & 1) * (c.S >> 1) + (x >> 1));
+__device__ __forceinline__ uint32_t dense_tile_off(const DenseCtx &c, int y, int x) {   // byte offset of integral (y, x) from a window base
+    return 4u * (uint32_t)(c.ystep == 1 ? y * c.S + x : y * c.S + (x & 1) * (c.S >> 1) + (x >> 1));
 }
 __device__ __forceinline__ void dense_write_code(const DenseCtx &c, int wid, int code) {
     const int wx = wid & (kTileW - 1), wy = wid / kTileW;
@@ -167,191 +176,148 @@ __device__ __forceinline__ void dense_write_code(const DenseCtx &c, int wid, int
 __device__ __forceinline__ double dense_sigma(const DenseParams &P, const DenseCtx &c, int wid) {
     const int wx = wid & (kTileW - 1), wy = wid / kTileW;
     const int eq_w = P.win_w - 2, eq_h = P.win_h - 2;
-    const unsigned char *base = c.tile + wy * c.row_mul + wx * 4;
-    const int s4 = TILE_LD(base, dense_tile_off(c, 1, 1)) - TILE_LD(base, dense_tile_off(c, 1, 1 + eq_w)) -
-                   TILE_LD(base, dense_tile_off(c, 1 + eq_h, 1)) + TILE_LD(base, dense_tile_off(c, 1 + eq_h, 1 + eq_w));
+    const uint32_t base = dense_base(c, wid);
+    const int s4 = lds32(base + dense_tile_off(c, 1, 1)) - lds32(base + dense_tile_off(c, 1, 1 + eq_w)) -
+                   lds32(base + dense_tile_off(c, 1 + eq_h, 1)) + lds32(base + dense_tile_off(c, 1 + eq_h, 1 + eq_w));
     const ull *q = c.gsq + (size_t)(wy * c.ystep) * c.sq_pitch + wx * c.ystep;
     const int g0 = c.sq_pitch + 1, g1 = g0 + eq_w, g2 = (1 + eq_h) * c.sq_pitch + 1, g3 = g2 + eq_w;
     const ull q4 = __ldg(q + g0) - __ldg(q + g1) - __ldg(q + g2) + __ldg(q + g3);
     return window_sigma(s4, q4, P.inv_area);
 }
 
-// Exact evaluation of one parameter-resident stage for one window (the reference's arithmetic).
+// One stump in registers.
+struct StumpRegs {
+    uint32_t o[12];
+    float w0, w1, w2, thr, a0, a1;
+};
+__device__ __forceinline__ StumpRegs stump_from_param(const DenseStump &q) {   // constant bank (LDC)
+    StumpRegs r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.o[i] = q.off[i];
+    r.w0 = q.w[0]; r.w1 = q.w[1]; r.w2 = q.w[2]; r.thr = q.thr; r.a0 = q.a0; r.a1 = q.a1;
+    return r;
+}
+__device__ __forceinline__ StumpRegs stump_from_global(const DenseStump *__restrict__ p, bool any3) {   // 4-5 x LDG.128
+    const uint4 *rec = reinterpret_cast<const uint4 *>(p);
+    const uint4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q3 = __ldg(rec + 3), q4 = __ldg(rec + 4);
+    uint4 q2 = make_uint4(0u, 0u, 0u, 0u);
+    if (any3) q2 = __ldg(rec + 2);
+    StumpRegs r;
+    r.o[0] = q0.x; r.o[1] = q0.y; r.o[2] = q0.z; r.o[3] = q0.w;
+    r.o[4] = q1.x; r.o[5] = q1.y; r.o[6] = q1.z; r.o[7] = q1.w;
+    r.o[8] = q2.x; r.o[9] = q2.y; r.o[10] = q2.z; r.o[11] = q2.w;
+    r.w0 = __uint_as_float(q3.x); r.w1 = __uint_as_float(q3.y); r.w2 = __uint_as_float(q3.z); r.thr = __uint_as_float(q3.w);
+    r.a0 = __uint_as_float(q4.x); r.a1 = __uint_as_float(q4.y);
+    return r;
+}
+
+// Exact evaluation of one stage for one window: the reference's arithmetic, stumps in tree order.
 __device__ __noinline__ bool dense_stage_exact(const DenseParams &P, const DenseCtx &c, int s, int wid) {
-    const unsigned char *base = dense_base(c, wid);
+    const uint32_t base = dense_base(c, wid);
     const double sigma = dense_sigma(P, c, wid);
-    const int first = P.stage[s].first, count = P.stage[s].count;
+    const int count = P.stage[s].count;
     const bool dbl = P.stage[s].flags & 1u;
+    const DenseStump *rec = P.tail + P.stage[s].tail_first;
     double S = 0.0;
     for (int j = 0; j < count; j++) {
-        const DenseStump &q = P.stump[first + j];
-        const int r0 = TILE_LD(base, q.off[0]) - TILE_LD(base, q.off[1]) - TILE_LD(base, q.off[2]) + TILE_LD(base, q.off[3]);
-        const int r1 = TILE_LD(base, q.off[4]) - TILE_LD(base, q.off[5]) - TILE_LD(base, q.off[6]) + TILE_LD(base, q.off[7]);
+        const StumpRegs q = stump_from_global(rec + j, true);
+        const int r0 = lds32(base + q.o[0]) - lds32(base + q.o[1]) - lds32(base + q.o[2]) + lds32(base + q.o[3]);
+        const int r1 = lds32(base + q.o[4]) - lds32(base + q.o[5]) - lds32(base + q.o[6]) + lds32(base + q.o[7]);
         const double t = __dmul_rn((double)q.thr, sigma);
         double sum;
         if (dbl) {  // tempcv.cpp:872-898; both products are exact in double, so fma == mul, mul, add
-            sum = __fma_rn((double)r1, (double)q.w[1], __dmul_rn((double)r0, (double)q.w[0]));
+            sum = __fma_rn((double)r1, (double)q.w1, __dmul_rn((double)r0, (double)q.w0));
         } else {    // tempcv.cpp:899-930 / 782-786: float products, double accumulation
-            sum = __dadd_rn((double)__fmul_rn(__int2float_rn(r0), q.w[0]), (double)__fmul_rn(__int2float_rn(r1), q.w[1]));
-            if (q.off[11] != 0) {
-                const int r2 = TILE_LD(base, q.off[8]) - TILE_LD(base, q.off[9]) - TILE_LD(base, q.off[10]) + TILE_LD(base, q.off[11]);
-                sum = __dadd_rn(sum, (double)__fmul_rn(__int2float_rn(r2), q.w[2]));
+            sum = __dadd_rn((double)__fmul_rn(__int2float_rn(r0), q.w0), (double)__fmul_rn(__int2float_rn(r1), q.w1));
+            if (q.o[11] != 0) {
+                const int r2 = lds32(base + q.o[8]) - lds32(base + q.o[9]) - lds32(base + q.o[10]) + lds32(base + q.o[11]);
+                sum = __dadd_rn(sum, (double)__fmul_rn(__int2float_rn(r2), q.w2));
             }
         }
-        S = __dadd_rn(S, sum >= t ? q.a1 : q.a0);
+        S = __dadd_rn(S, (double)(sum >= t ? q.a1 : q.a0));
     }
     return S >= (double)P.stage[s].thr;
 }
 
-// FP32-filtered evaluation of stumps j0, j0 + jstep, ... of stage s for K windows of this thread.
-//   FIXED = true : window k lives at base0 + k*ROWSTEP (compile-time) -> immediate offsets
+// FP32 filter: one stump for K windows of this thread.  The stump decision sign(s - t) is taken
+// from FP32 arithmetic; near[k] records that |s32 - t32| fell inside the guard band (2^-20 |t32|
+// plus the cancellation terms), S[k] adds the selected alpha in FP32.
+//   FIXED = true : window k lives at base[0] + k*ROWSTEP (compile-time) -> immediate offsets
 //   FIXED = false: window k lives at base[k]
-template <int K, bool DBL, bool HAS3, bool FIXED, int ROWSTEP>
-__device__ __forceinline__ void dense_filter_stage(const DenseParams &P, int s, int j0, int jstep,
-                                                   const unsigned char *const (&base)[K], const float (&sg)[K],
-                                                   double (&S)[K], bool (&near)[K]) {
-    const int first = P.stage[s].first, count = P.stage[s].count;
-    const float eps = P.filter_eps, eps4 = eps * 0.25f;
-#pragma unroll 1
-    for (int j = j0; j < count; j += jstep) {
-        const DenseStump &q = P.stump[first + j];
-        const float w0 = q.w[0], w1 = q.w[1], thr = q.thr;
-        const double al0 = q.a0, al1 = q.a1;
-        const bool three = HAS3 && (q.off[11] != 0);   // warp-uniform
-        // corner pointers of window 0 (shared by all K windows in fixed geometry)
-        const unsigned char *c00 = base[0] + q.off[0], *c01 = base[0] + q.off[1], *c02 = base[0] + q.off[2], *c03 = base[0] + q.off[3];
-        const unsigned char *c10 = base[0] + q.off[4], *c11 = base[0] + q.off[5], *c12 = base[0] + q.off[6], *c13 = base[0] + q.off[7];
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            int r0, r1;
-            if (FIXED) {
-                r0 = TILE_LD(c00, k * ROWSTEP) - TILE_LD(c01, k * ROWSTEP) - TILE_LD(c02, k * ROWSTEP) + TILE_LD(c03, k * ROWSTEP);
-                r1 = TILE_LD(c10, k * ROWSTEP) - TILE_LD(c11, k * ROWSTEP) - TILE_LD(c12, k * ROWSTEP) + TILE_LD(c13, k * ROWSTEP);
-            } else {
-                const unsigned char *b = base[k];
-                r0 = TILE_LD(b, q.off[0]) - TILE_LD(b, q.off[1]) - TILE_LD(b, q.off[2]) + TILE_LD(b, q.off[3]);
-                r1 = TILE_LD(b, q.off[4]) - TILE_LD(b, q.off[5]) - TILE_LD(b, q.off[6]) + TILE_LD(b, q.off[7]);
-            }
-            const float p0 = __fmul_rn(__int2float_rn(r0), w0), p1 = __fmul_rn(__int2float_rn(r1), w1);
-            float s32 = __fadd_rn(p0, p1);
-            const float t32 = __fmul_rn(thr, sg[k]);
-            float m = __fmul_rn(fabsf(t32), eps);
-            if (DBL) {
-                // reference adds the two EXACT products: fp32 product errors do not cancel
-                m = __fadd_rn(m, __fmul_rn(__fadd_rn(fabsf(p0), fabsf(p1)), eps4));
-            }
-            if (HAS3) {
-                if (three) {
-                    const unsigned char *b = FIXED ? base[0] + k * ROWSTEP : base[k];
-                    const int r2 = TILE_LD(b, q.off[8]) - TILE_LD(b, q.off[9]) - TILE_LD(b, q.off[10]) + TILE_LD(b, q.off[11]);
-                    m = __fadd_rn(m, __fmul_rn(fabsf(s32), eps4));   // rounding of the first add
-                    s32 = __fadd_rn(s32, __fmul_rn(__int2float_rn(r2), q.w[2]));
-                }
-            }
-            const float d = __fadd_rn(s32, -t32);
-            near[k] = near[k] || (fabsf(d) <= m);
-            S[k] = __dadd_rn(S[k], d >= 0.f ? al1 : al0);
-        }
+template <int KK, int K, bool FIXED, int ROWSTEP>
+__device__ __forceinline__ void stump_filter_window(const StumpRegs &q, bool dbl, bool three, float eps, const uint32_t (&c)[12],
+                                                    const uint32_t (&base)[K], const float (&sg)[K], float (&S)[K], bool (&near)[K]) {
+    const float eps4 = eps * 0.25f;
+    constexpr int IMM = KK * ROWSTEP;
+    const uint32_t b = base[FIXED ? 0 : KK];
+    int r0, r1;
+    if (FIXED) {   // LDS [corner of window 0 + immediate]
+        r0 = lds32i<IMM>(c[0]) - lds32i<IMM>(c[1]) - lds32i<IMM>(c[2]) + lds32i<IMM>(c[3]);
+        r1 = lds32i<IMM>(c[4]) - lds32i<IMM>(c[5]) - lds32i<IMM>(c[6]) + lds32i<IMM>(c[7]);
+    } else {
+        r0 = lds32(b + q.o[0]) - lds32(b + q.o[1]) - lds32(b + q.o[2]) + lds32(b + q.o[3]);
+        r1 = lds32(b + q.o[4]) - lds32(b + q.o[5]) - lds32(b + q.o[6]) + lds32(b + q.o[7]);
     }
+    const float p0 = __fmul_rn(__int2float_rn(r0), q.w0), p1 = __fmul_rn(__int2float_rn(r1), q.w1);
+    float s32 = __fadd_rn(p0, p1);
+    const float t32 = __fmul_rn(q.thr, sg[KK]);
+    float m = __fmul_rn(fabsf(t32), eps);
+    if (dbl) m = __fadd_rn(m, __fmul_rn(__fadd_rn(fabsf(p0), fabsf(p1)), eps4));   // the reference adds EXACT products: fp32 product errors do not cancel
+    if (three) {
+        int r2;
+        if (FIXED) r2 = lds32i<IMM>(c[8]) - lds32i<IMM>(c[9]) - lds32i<IMM>(c[10]) + lds32i<IMM>(c[11]);
+        else r2 = lds32(b + q.o[8]) - lds32(b + q.o[9]) - lds32(b + q.o[10]) + lds32(b + q.o[11]);
+        m = __fadd_rn(m, __fmul_rn(fabsf(s32), eps4));   // rounding of the first add
+        s32 = __fadd_rn(s32, __fmul_rn(__int2float_rn(r2), q.w2));
+    }
+    const float d = __fadd_rn(s32, -t32);
+    near[KK] = near[KK] || (fabsf(d) <= m);
+    S[KK] = __fadd_rn(S[KK], d >= 0.f ? q.a1 : q.a0);
 }
 
 template <int K, bool FIXED, int ROWSTEP>
-__device__ __forceinline__ void dense_dispatch_stage(const DenseParams &P, int s, int j0, int jstep,
-                                                     const unsigned char *const (&base)[K], const float (&sg)[K],
-                                                     double (&S)[K], bool (&near)[K]) {
-    const uint32_t flags = P.stage[s].flags;
-    if (flags & 1u) dense_filter_stage<K, true, false, FIXED, ROWSTEP>(P, s, j0, jstep, base, sg, S, near);
-    else if (flags & 2u) dense_filter_stage<K, false, true, FIXED, ROWSTEP>(P, s, j0, jstep, base, sg, S, near);
-    else dense_filter_stage<K, false, false, FIXED, ROWSTEP>(P, s, j0, jstep, base, sg, S, near);
+__device__ __forceinline__ void stump_filter(const StumpRegs &q, bool dbl, bool any3, float eps, const uint32_t (&base)[K],
+                                             const float (&sg)[K], float (&S)[K], bool (&near)[K]) {
+    static_assert(K >= 1 && K <= 4, "1..4 windows per thread");
+    const bool three = any3 && q.o[11] != 0u;   // warp-uniform per stump
+    uint32_t c[12];
+    if (FIXED) {   // corner addresses of window 0, shared by all K windows
+#pragma unroll
+        for (int i = 0; i < 12; i++) c[i] = base[0] + q.o[i];
+    }
+    stump_filter_window<0, K, FIXED, ROWSTEP>(q, dbl, three, eps, c, base, sg, S, near);
+    if (K > 1) stump_filter_window<(K > 1 ? 1 : 0), K, FIXED, ROWSTEP>(q, dbl, three, eps, c, base, sg, S, near);
+    if (K > 2) stump_filter_window<(K > 2 ? 2 : 0), K, FIXED, ROWSTEP>(q, dbl, three, eps, c, base, sg, S, near);
+    if (K > 3) stump_filter_window<(K > 3 ? 3 : 0), K, FIXED, ROWSTEP>(q, dbl, three, eps, c, base, sg, S, near);
 }
 
-// Phase 2: a warp takes up to 32 surviving windows (lane k holds window k) through ALL the
-// remaining stages on its own -- no block barrier, no shared survivor list.  For every stage
-// the 32 lanes are arranged as  w window slots x G stump groups  (w = smallest power of two
-// >= live windows, G = 32 / w): lane (slot, grp) evaluates stumps grp, grp + G, ... of the
-// stage for window `slot`, and the G partial sums of a window meet through xor-shuffles.
-// With 32 windows this is thread-per-window; as windows die the lanes they free take over a
-// share of the stumps (one window left: 32 stumps per pass), so lanes stay busy without
-// re-compaction across warps.  Survivors are re-packed to the low lanes through a 384-byte
-// scratch.  Stump records come from global memory (TailStump, 3 x LDG.128 per lane); the
-// arithmetic is the reference's exact one (no filter).  Summing partial sums out of order is
-// bit-exact because the packer proved the stage's alpha sum exact in any order (flags bit2);
-// a stage without the proof keeps w = 32, G = 1, i.e. tree order.
-__device__ __forceinline__ void dense_warp_finish(const DenseParams &P, const DenseCtx &c, const CascadeArgs &a,
-                                                  const CasLevel &CL, int frame, int cl, int px0, int py0, int s0, int wid,
-                                                  double *scr_sigma, int *scr_wid, int lane) {
-    const TailStump *__restrict__ tail = P.tail;
-    int nw = __popc(__ballot_sync(0xffffffffu, wid >= 0));   // the windows sit in lanes 0 .. nw-1
-    double sigma = wid >= 0 ? dense_sigma(P, c, wid) : 1.0;
-    int ss = s0;
-    while (nw > 0 && ss < P.tail_stages) {
-        const DenseStage st = P.stage[ss];
-        const bool dbl = st.flags & 1u;
-        int lw = 5;
-        if (st.flags & 4u) while (lw > 0 && (1 << (lw - 1)) >= nw) lw--;
-        const int w = 1 << lw, G = 32 >> lw;
-        const int slot = lane & (w - 1), grp = lane >> lw;
-        const int swid = __shfl_sync(0xffffffffu, wid, slot);
-        const double ssig = __shfl_sync(0xffffffffu, sigma, slot);
-        double acc = 0.0;
-        if (slot < nw) {
-            const unsigned char *base = dense_base(c, swid);
-            const uint4 *rec = reinterpret_cast<const uint4 *>(tail + st.tail_first + grp);
-            for (int j = grp; j < st.count; j += G, rec += 3 * G) {
-                const uint4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
-                // q0 = off[0..7]; q1 = off[8..11], w0, w1; q2 = w2, thr, a0, a1
-                const int r0 = TILE_LD(base, q0.x & 0xffffu) - TILE_LD(base, q0.x >> 16) - TILE_LD(base, q0.y & 0xffffu) + TILE_LD(base, q0.y >> 16);
-                const int r1 = TILE_LD(base, q0.z & 0xffffu) - TILE_LD(base, q0.z >> 16) - TILE_LD(base, q0.w & 0xffffu) + TILE_LD(base, q0.w >> 16);
-                const float w0 = __uint_as_float(q1.z), w1 = __uint_as_float(q1.w);
-                const double t = __dmul_rn((double)__uint_as_float(q2.y), ssig);
-                double sv;
-                if (dbl) {  // tempcv.cpp:872-898; both products are exact in double, so fma == mul, mul, add
-                    sv = __fma_rn((double)r1, (double)w1, __dmul_rn((double)r0, (double)w0));
-                } else {    // tempcv.cpp:899-930 / 782-786: float products, double accumulation
-                    sv = __dadd_rn((double)__fmul_rn(__int2float_rn(r0), w0), (double)__fmul_rn(__int2float_rn(r1), w1));
-                    if ((q1.y >> 16) != 0) {
-                        const int r2 = TILE_LD(base, q1.x & 0xffffu) - TILE_LD(base, q1.x >> 16) - TILE_LD(base, q1.y & 0xffffu) + TILE_LD(base, q1.y >> 16);
-                        sv = __dadd_rn(sv, (double)__fmul_rn(__int2float_rn(r2), __uint_as_float(q2.x)));
-                    }
-                }
-                acc = __dadd_rn(acc, (double)__uint_as_float(sv >= t ? q2.w : q2.z));
-            }
-        }
-        for (int d = w; d < 32; d <<= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, d));
-        const bool mine = lane < nw;   // then slot == lane: acc is this lane's own window
-        const bool pass = acc >= (double)st.thr;
-        const unsigned surv = __ballot_sync(0xffffffffu, mine && pass);
-        if (mine && !pass && c.codes) dense_write_code(c, wid, ss * c.code_mul);
-        ss++;
-        const int n2 = __popc(surv);
-        if (n2 != nw) {   // re-pack the survivors into lanes 0 .. n2-1
-            if (mine && pass) {
-                const int d = __popc(surv & ((1u << lane) - 1u));
-                scr_wid[d] = wid;
-                scr_sigma[d] = sigma;
-            }
-            __syncwarp();
-            nw = n2;
-            if (lane < nw) { wid = scr_wid[lane]; sigma = scr_sigma[lane]; } else wid = -1;
-            __syncwarp();
-        }
+// Stumps grp, grp + G, ... of stage s for K windows of this lane.  Stumps come from the
+// constant bank when the stage is parameter resident, else from global memory.
+template <int K, bool FIXED, int ROWSTEP>
+__device__ __forceinline__ void stage_filter(const DenseParams &P, int s, int grp, int G, const uint32_t (&base)[K],
+                                             const float (&sg)[K], float (&S)[K], bool (&near)[K]) {
+    const int count = P.stage[s].count;
+    const uint32_t flags = P.stage[s].flags;
+    const bool dbl = flags & 1u, any3 = flags & 2u;
+    const float eps = P.filter_eps;
+    if (s < P.n_stages && G == 1) {   // all lanes on the same stump: constant bank
+        const int first = P.stage[s].first;
+#pragma unroll 1
+        for (int j = grp; j < count; j += G) stump_filter<K, FIXED, ROWSTEP>(stump_from_param(P.stump[first + j]), dbl, any3, eps, base, sg, S, near);
+    } else {
+        const DenseStump *__restrict__ rec = P.tail + P.stage[s].tail_first;
+#pragma unroll 1
+        for (int j = grp; j < count; j += G) stump_filter<K, FIXED, ROWSTEP>(stump_from_global(rec + j, any3), dbl, any3, eps, base, sg, S, near);
     }
-    if (nw == 0 || lane >= nw) return;
-    const int x = px0 + (wid & (kTileW - 1)) * c.ystep, y = py0 + (wid / kTileW) * c.ystep;
-    if (ss >= P.total_stages) {          // passed every stage: a detection
-        emit_rect(a, CL, frame, x, y);
-        if (c.codes) dense_write_code(c, wid, P.total_stages);
-    } else {                             // the rest of the cascade belongs to the deep kernel
-        const ull slot = atomicAdd(a.counters + 1, 1ull);
-        if (slot < a.queue_cap) {
-            QueueItem it;
-            it.key = ((uint32_t)frame << 16) | ((uint32_t)cl << 8) | (uint32_t)ss;
-            it.xy = ((uint32_t)y << 16) | (uint32_t)x;
-            a.queue[slot] = it;
-        } else {
-            atomicAdd(a.counters + 3, 1ull);
-        }
-    }
+}
+
+// Stage verdict of one window from its FP32 stage sum.  |S32 - S| <= sum_eps for any summation
+// order, so outside that band (and with no stump inside its own band) the FP32 verdict is the
+// reference's; inside, the stage is redone exactly.
+__device__ __forceinline__ bool stage_verdict(const DenseParams &P, const DenseCtx &c, int s, float sthr, float seps, int wid,
+                                              float S, bool near) {
+    if (near || !(fabsf(__fadd_rn(S, -sthr)) > seps)) return dense_stage_exact(P, c, s, wid);
+    return S >= sthr;
 }
 
 // ROWSTEP_T: compile-time byte distance between a thread's consecutive windows in phase 1
@@ -364,7 +330,6 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     unsigned char *tile = smem_raw + plan.tile;
     float *sgf = reinterpret_cast<float *>(smem_raw + plan.sgf);
     uint16_t *list = reinterpret_cast<uint16_t *>(smem_raw + plan.list);
-    unsigned char *scr = smem_raw + plan.scr + (size_t)(threadIdx.x >> 5) * kScrBytesPerWarp;
     int *ctl = reinterpret_cast<int *>(smem_raw + plan.ctl);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + plan.bar);
 
@@ -418,13 +383,14 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     }
 
     DenseCtx c;
-    c.tile = tile; c.sgf = sgf; c.gsq = gsq;
+    c.tile = smem_u32(tile); c.gsq = gsq;
     c.codes = a.codes ? a.codes + (size_t)frame * a.windows_per_frame + CL.win_base : nullptr;
     c.sq_pitch = L.sum_pitch;
     c.row_mul = ystep * S * 4;
     c.ystep = ystep; c.S = S;
     c.tx = tx; c.ty = ty; c.nx = CL.nx;
     c.code_mul = P.is_tree ? 2 : 1;
+    const float inf = __int_as_float(0x7f800000);
 
     // ---- phase 1: sigma, then the fixed-geometry stages ----
     constexpr int kRowsPerSlot = kDenseThreads / kTileW;   // window rows between a thread's slots (2)
@@ -444,32 +410,30 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     // a thread reads back only sigmas it wrote itself: no barrier needed in phase 1
     int s = 0;
     for (; s < P.n_fixed; s++) {
+        const float sthr = P.stage[s].thr, seps = P.force_exact ? inf : P.stage[s].sum_eps;
 #pragma unroll 1
         for (int k0 = 0; k0 < kDenseSlots; k0 += kDenseChunk) {
             const uint32_t m4 = (alive >> k0) & ((1u << kDenseChunk) - 1u);
             if (!__any_sync(0xffffffffu, m4 != 0)) continue;   // whole 4 x 32 block is dead
-            const unsigned char *base[kDenseChunk];
+            uint32_t base[kDenseChunk];
             float sg[kDenseChunk];
-            double Ssum[kDenseChunk];
+            float Ssum[kDenseChunk];
             bool near[kDenseChunk];
 #pragma unroll
             for (int k = 0; k < kDenseChunk; k++) {
                 const int wy = wy0 + (k0 + k) * kRowsPerSlot;
-                base[k] = tile + wy * c.row_mul + wx * 4;   // == base[0] + k * rowstep
+                base[k] = c.tile + (uint32_t)(wy * c.row_mul + wx * 4);   // == base[0] + k * rowstep
                 sg[k] = sgf[wy * kTileW + wx];
-                Ssum[k] = 0.0;
-                near[k] = P.force_exact != 0;
+                Ssum[k] = 0.f;
+                near[k] = false;
             }
-            if (ROWSTEP_T) dense_dispatch_stage<kDenseChunk, true, ROWSTEP_T>(P, s, 0, 1, base, sg, Ssum, near);
-            else dense_dispatch_stage<kDenseChunk, false, 0>(P, s, 0, 1, base, sg, Ssum, near);
-            const double sthr = (double)P.stage[s].thr;
+            if (ROWSTEP_T) stage_filter<kDenseChunk, true, ROWSTEP_T>(P, s, 0, 1, base, sg, Ssum, near);
+            else stage_filter<kDenseChunk, false, 0>(P, s, 0, 1, base, sg, Ssum, near);
 #pragma unroll
             for (int k = 0; k < kDenseChunk; k++) {
                 if (!((m4 >> k) & 1u)) continue;
                 const int wid = (wy0 + (k0 + k) * kRowsPerSlot) * kTileW + wx;
-                bool pass = Ssum[k] >= sthr;
-                if (near[k]) pass = dense_stage_exact(P, c, s, wid);
-                if (!pass) {
+                if (!stage_verdict(P, c, s, sthr, seps, wid, Ssum[k], near[k])) {
                     alive &= ~(1u << (k0 + k));
                     if (c.codes) dense_write_code(c, wid, s * c.code_mul);
                 }
@@ -494,14 +458,99 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     const int n_alive = ctl[kCtlAlive];
     if (n_alive == 0) return;
 
-    // ---- phase 2: every warp finishes an equal share of the survivors on its own ----
+    // ---- phase 2: every warp takes an equal share of the survivors through all remaining
+    //      stages on its own: no block barrier, warp-local in-place re-compaction after every
+    //      stage.  More than 16 windows left: thread per window (rows of 32, two rows per pass
+    //      so the stump loads are shared).  16 or fewer: the lanes are arranged as w window
+    //      slots x G stump groups (w = smallest power of two >= windows, G = 32 / w): lane
+    //      (slot, grp) evaluates stumps grp, grp + G, ... for window `slot`, and the G partial
+    //      sums meet through xor-shuffles -- with one window left the warp does 32 stumps per
+    //      pass. ----
     const int share = (n_alive + kDenseWarps - 1) / kDenseWarps;
-    const int lo = warp * share, hi = min(n_alive, lo + share);
-    double *scr_sigma = reinterpret_cast<double *>(scr);
-    int *scr_wid = reinterpret_cast<int *>(scr + 32 * sizeof(double));
-    for (int b0 = lo; b0 < hi; b0 += 32) {
-        const int wid = b0 + lane < hi ? (int)list[b0 + lane] : -1;
-        dense_warp_finish(P, c, a, CL, frame, cl, px0, py0, s, wid, scr_sigma, scr_wid, lane);
+    const int lo = min(n_alive, warp * share);
+    int n = min(n_alive, lo + share) - lo;
+    uint16_t *cur = list + lo;
+    for (; s < P.tail_stages && n > 0; s++) {
+        const float sthr = P.stage[s].thr, seps = P.force_exact ? inf : P.stage[s].sum_eps;
+        int n_next = 0;
+        // append the survivors among this pass's windows at cur[n_next..]: always at or below the
+        // positions the pass has already read (in-place compaction)
+        auto keep = [&](bool valid, int wid, float Ssum, bool near) {
+            const bool pass = valid && stage_verdict(P, c, s, sthr, seps, wid, Ssum, near);
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            if (pass) cur[n_next + __popc(m & ((1u << lane) - 1u))] = (uint16_t)wid;
+            n_next += __popc(m);
+            if (valid && !pass && c.codes) dense_write_code(c, wid, s * c.code_mul);
+        };
+        if (n > 16) {
+            for (int r0 = 0; r0 < n; r0 += 64) {
+                if (r0 + 32 < n) {   // two rows
+                    const bool v1 = r0 + 32 + lane < n;
+                    const int wid0 = cur[r0 + lane], wid1 = cur[v1 ? r0 + 32 + lane : r0 + 32];
+                    __syncwarp();   // both rows are in registers before their slots are overwritten
+                    const uint32_t base[2] = {dense_base(c, wid0), dense_base(c, wid1)};
+                    const float sg[2] = {sgf[wid0], sgf[wid1]};
+                    float Ssum[2] = {0.f, 0.f};
+                    bool near[2] = {false, false};
+                    stage_filter<2, false, 0>(P, s, 0, 1, base, sg, Ssum, near);
+                    keep(true, wid0, Ssum[0], near[0]);
+                    keep(v1, wid1, Ssum[1], near[1]);
+                } else {             // one (possibly partial) row
+                    const bool v0 = r0 + lane < n;
+                    const int wid0 = cur[v0 ? r0 + lane : r0];
+                    __syncwarp();
+                    const uint32_t base[1] = {dense_base(c, wid0)};
+                    const float sg[1] = {sgf[wid0]};
+                    float Ssum[1] = {0.f};
+                    bool near[1] = {false};
+                    stage_filter<1, false, 0>(P, s, 0, 1, base, sg, Ssum, near);
+                    keep(v0, wid0, Ssum[0], near[0]);
+                }
+            }
+        } else {
+            int lw = 4;
+            while (lw > 0 && (1 << (lw - 1)) >= n) lw--;
+            const int slot = lane & ((1 << lw) - 1), grp = lane >> lw, G = 32 >> lw;
+            const bool valid = slot < n;
+            const int wid0 = cur[valid ? slot : 0];
+            __syncwarp();
+            const uint32_t base[1] = {dense_base(c, wid0)};
+            const float sg[1] = {sgf[wid0]};
+            float Ssum[1] = {0.f};
+            bool near[1] = {false};
+            if (valid) stage_filter<1, false, 0>(P, s, grp, G, base, sg, Ssum, near);
+            float acc = Ssum[0];
+            unsigned nr = near[0];
+            for (int d = 1 << lw; d < 32; d <<= 1) {
+                acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, d));
+                nr |= __shfl_xor_sync(0xffffffffu, nr, d);
+            }
+            keep(lane < n, wid0, acc, nr != 0);   // lane < n: slot == lane
+        }
+        __syncwarp();
+        n = n_next;
+    }
+    // ---- survivors: detections, or (cascades with a deep tail) queue items ----
+    if (n == 0) return;
+    ull qb = 0;
+    if (s < P.total_stages) {
+        if (lane == 0) qb = atomicAdd(a.counters + 1, (ull)n);
+        qb = __shfl_sync(0xffffffffu, qb, 0);
+    }
+    for (int i = lane; i < n; i += 32) {
+        const int w = cur[i];
+        const int x = px0 + (w & (kTileW - 1)) * ystep, y = py0 + (w / kTileW) * ystep;
+        if (s >= P.total_stages) {
+            emit_rect(a, CL, frame, x, y);
+            if (c.codes) dense_write_code(c, w, P.total_stages);
+        } else if (qb + i < a.queue_cap) {
+            QueueItem it;
+            it.key = ((uint32_t)frame << 16) | ((uint32_t)cl << 8) | (uint32_t)s;
+            it.xy = ((uint32_t)y << 16) | (uint32_t)x;
+            a.queue[qb + i] = it;
+        } else {
+            atomicAdd(a.counters + 3, 1ull);
+        }
     }
 }
 
