@@ -89,7 +89,8 @@ struct PyramidPlan {
 
     int build(int W_, int H_, const std::vector<std::pair<int, int>> &sizes, int batch, bool tilt, cudaStream_t s);
     void fill_args(PyramidArgs &a, const uint8_t *frames, size_t frame_stride, int row_stride, int n_frames) const;
-    int run(clfd_context *ctx, const uint8_t *frames, size_t frame_stride, int row_stride, int n_frames,
+    // frames: first frame of the range; frame_base: index of that frame in the per-frame device buffers
+    int run(clfd_context *ctx, const uint8_t *frames, size_t frame_stride, int row_stride, int frame_base, int n_frames,
             cudaStream_t s, cudaEvent_t *ev, int *n_launch);
 };
 
@@ -194,12 +195,19 @@ void PyramidPlan::fill_args(PyramidArgs &a, const uint8_t *frames, size_t frame_
 }
 
 // ev (optional): 5 events recorded before K1, K2, K3, K4 and after K4
-int PyramidPlan::run(clfd_context *ctx, const uint8_t *frames, size_t frame_stride, int row_stride, int n_frames,
-                     cudaStream_t s, cudaEvent_t *ev, int *n_launch) {
-    if (n_frames <= 0 || n_frames > max_batch) INVALID("n_frames %d outside 1..%d", n_frames, max_batch);
+int PyramidPlan::run(clfd_context *ctx, const uint8_t *frames, size_t frame_stride, int row_stride, int frame_base,
+                     int n_frames, cudaStream_t s, cudaEvent_t *ev, int *n_launch) {
+    if (n_frames <= 0 || frame_base < 0 || frame_base + n_frames > max_batch)
+        INVALID("frames %d..%d outside 0..%d", frame_base, frame_base + n_frames, max_batch);
     if (row_stride < W) INVALID("row stride %d smaller than the frame width %d", row_stride, W);
     PyramidArgs a;
     fill_args(a, frames, frame_stride, row_stride, n_frames);
+    // the kernels index the per-frame buffers with the frame number inside the launch
+    a.pyr += (size_t)frame_base * a.pyr_frame_stride;
+    a.col += (size_t)frame_base * a.col_frame_stride;
+    a.sum += (size_t)frame_base * a.sum_frame_stride;
+    a.sq += (size_t)frame_base * a.sum_frame_stride;
+    if (a.tilted) a.tilted += (size_t)frame_base * a.sum_frame_stride;
     int launches = 0, nint = 0;
     if (ev) CK(cudaEventRecord(ev[0], s));
     CK(launch_resize_colsum(a, s)); launches++;
@@ -235,6 +243,8 @@ struct CascadePlan {
     unsigned long long h_counters[4] = {0, 0, 0, 0};
 };
 
+constexpr int kMaxChunks = 8;
+
 struct clfd_detector {
     clfd_context *ctx = nullptr;
     clfd_detector_config cfg;
@@ -252,10 +262,17 @@ struct clfd_detector {
     cudaEvent_t ev[16] = {nullptr};
     float kernel_ms[8] = {0};
     bool have_events = false;
+    // clfd_detect pipelines the H2D copy of a batch with its own compute, chunk by chunk
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copied[kMaxChunks] = {nullptr};
+    cudaEvent_t idle = nullptr;
     ~clfd_detector() {
         if (h_rects) cudaFreeHost(h_rects);
         if (h_counters) cudaFreeHost(h_counters);
         for (auto &e : ev) if (e) cudaEventDestroy(e);
+        for (auto &e : copied) if (e) cudaEventDestroy(e);
+        if (idle) cudaEventDestroy(idle);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
     }
 };
 
@@ -478,7 +495,7 @@ int clfd_integral(clfd_context *ctx, const uint8_t *img, int w, int h, int strid
     if ((rc = in.set(img, w, h, stride, img_on_device, ctx->stream))) return rc;
     const bool keep_tilt = p->want_tilted;
     p->want_tilted = tilted != nullptr;
-    rc = p->run(ctx, in.dev, 0, in.stride, 1, ctx->stream, nullptr, nullptr);
+    rc = p->run(ctx, in.dev, 0, in.stride, 0, 1, ctx->stream, nullptr, nullptr);
     p->want_tilted = keep_tilt;
     if (rc) return rc;
     const PyrLevel &L = p->levels[0];
@@ -679,35 +696,40 @@ int clfd_detector_set_profiling(clfd_detector *det, int enable) {
     return 0;
 }
 
-int clfd_detector_enqueue(clfd_detector *det, const uint8_t *frames_dev, int n_frames, size_t frame_stride,
-                          int row_stride, void *cuda_stream) {
-    if (!det || !frames_dev) INVALID("NULL argument");
+// Enqueue every kernel for frames [frame_base, frame_base + n_frames) of the current batch.
+// `first` resets the batch's rect / overflow counters; the kernels see frame numbers relative
+// to the range (the per-frame buffers are passed pre-offset) and add frame_base to the frame
+// index of the rects they emit.
+static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int frame_base, int n_frames, size_t frame_stride,
+                         int row_stride, cudaStream_t s, bool first, int *n_launches) {
     clfd_context *ctx = det->ctx;
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-    if (n_frames <= 0 || n_frames > det->cfg.max_batch) INVALID("n_frames %d outside 1..%d", n_frames, det->cfg.max_batch);
-    det->last_frames = n_frames;
     int launches = 0;
     cudaEvent_t *ev = det->profiling ? det->ev : nullptr;
     if (!det->pyr.levels.empty()) {
-        int rc = det->pyr.run(ctx, frames_dev, frame_stride, row_stride, n_frames, s, ev, &launches);
+        int rc = det->pyr.run(ctx, frames_dev, frame_stride, row_stride, frame_base, n_frames, s, ev, &launches);
         if (rc) return rc;
     }
     const int pyr_launches = launches;
-    for (auto &cpp : det->cas) CK(cudaMemsetAsync(cpp->d_counters.p, 0, 4 * sizeof(unsigned long long), s));
+    for (auto &cpp : det->cas) {
+        if (first) CK(cudaMemsetAsync(cpp->d_counters.p, 0, 4 * sizeof(unsigned long long), s));
+        else CK(cudaMemsetAsync(cpp->d_counters.p + 1, 0, sizeof(unsigned long long), s));   // the queue is per range
+    }
     int ci = 0;
     for (auto &cpp : det->cas) {
         CascadePlan &cp = *cpp;
         if (cp.windows_per_frame > 0) {
             const PackedCascade &pk = cp.cascade->packed;
+            const size_t fo = (size_t)frame_base * det->pyr.sum_frame_stride;
             CascadeArgs a;
             memset(&a, 0, sizeof a);
-            a.sum = det->pyr.sum.p; a.sq = det->pyr.sq.p; a.tilted = det->pyr.want_tilted ? det->pyr.tilted.p : nullptr;
+            a.sum = det->pyr.sum.p + fo; a.sq = det->pyr.sq.p + fo;
+            a.tilted = det->pyr.want_tilted ? det->pyr.tilted.p + fo : nullptr;
             a.sum_frame_stride = det->pyr.sum_frame_stride;
             a.levels = det->pyr.d_levels.p; a.cas_levels = cp.d_levels.p;
             a.n_cas_levels = (int)cp.levels.size(); a.n_tiles = cp.n_tiles; a.n_frames = n_frames;
+            a.frame_base = frame_base;
             a.cascade_index = ci; a.windows_per_frame = cp.windows_per_frame;
-            a.codes = det->cfg.want_codes ? cp.d_codes.p : nullptr;
+            a.codes = det->cfg.want_codes ? cp.d_codes.p + (size_t)frame_base * cp.windows_per_frame : nullptr;
             a.queue = det->queue.p; a.queue_cap = det->queue_cap;
             a.rects = det->rects.p; a.rect_cap = det->rect_cap;
             a.counters = cp.d_counters.p;
@@ -730,7 +752,7 @@ int clfd_detector_enqueue(clfd_detector *det, const uint8_t *frames_dev, int n_f
                 launches++;
             }
             if (ev && ci == 0) CK(cudaEventRecord(ev[6], s));
-            // cascades the tile kernel finishes itself (tail_stages) never fill the queue
+            // cascades the tile kernel finishes itself (tail_stages == total_stages) never fill the queue
             const bool tiles_finish = pk.dense[0].tail_stages > 0 && pk.dense[0].tail_stages == pk.dense[0].total_stages;
             if (!tiles_finish) { CK(launch_cascade_deep(a, ctx->n_sms, s)); launches++; }
             if (ev && ci == 0) CK(cudaEventRecord(ev[7], s));
@@ -743,6 +765,21 @@ int clfd_detector_enqueue(clfd_detector *det, const uint8_t *frames_dev, int n_f
     }
     det->have_events = ev != nullptr;
     ctx->launches += launches - pyr_launches;   // PyramidPlan::run counted its own
+    *n_launches += launches;
+    return 0;
+}
+
+int clfd_detector_enqueue(clfd_detector *det, const uint8_t *frames_dev, int n_frames, size_t frame_stride,
+                          int row_stride, void *cuda_stream) {
+    if (!det || !frames_dev) INVALID("NULL argument");
+    clfd_context *ctx = det->ctx;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    if (n_frames <= 0 || n_frames > det->cfg.max_batch) INVALID("n_frames %d outside 1..%d", n_frames, det->cfg.max_batch);
+    det->last_frames = n_frames;
+    int launches = 0;
+    int rc = enqueue_range(det, frames_dev, 0, n_frames, frame_stride, row_stride, s, true, &launches);
+    if (rc) return rc;
     det->stats.kernel_launches = launches;
     return 0;
 }
@@ -806,18 +843,45 @@ int clfd_detect(clfd_detector *det, const uint8_t *frames_host, int n_frames, si
         int rc = det->dev_frames.alloc(dframe * det->cfg.max_batch + 64);
         if (rc) return rc;
     }
-    if ((size_t)row_stride == dstride && frame_stride == dframe) {
-        CK(cudaMemcpyAsync(det->dev_frames.p, frames_host, dframe * n_frames, cudaMemcpyHostToDevice, ctx->stream));
-    } else if (frame_stride == (size_t)row_stride * H) {
-        CK(cudaMemcpy2DAsync(det->dev_frames.p, dstride, frames_host, row_stride, W, (size_t)H * n_frames,
-                             cudaMemcpyHostToDevice, ctx->stream));
-    } else {
-        for (int f = 0; f < n_frames; f++)
-            CK(cudaMemcpy2DAsync(det->dev_frames.p + f * dframe, dstride, frames_host + f * frame_stride, row_stride, W, H,
-                                 cudaMemcpyHostToDevice, ctx->stream));
+    // Pipeline: the batch is cut into chunks; chunk k+1 is copied on the copy stream while the
+    // kernels of chunk k run on the compute stream (for pinned host memory; pageable memory
+    // degrades to a serial copy).  Multi-cascade detectors carry their rect count from one
+    // cascade to the next inside a range, so they run as one chunk.
+    int n_chunks = 1;
+    if (det->cas.size() == 1 && n_frames >= 8) n_chunks = n_frames >= 32 ? 4 : 2;
+    if (const char *e = getenv("CLFD_DETECT_CHUNKS")) n_chunks = std::max(1, std::min({atoi(e), kMaxChunks, n_frames}));
+    if (det->cas.size() != 1) n_chunks = 1;
+    if (!det->copy_stream) CK(cudaStreamCreateWithFlags(&det->copy_stream, cudaStreamNonBlocking));
+    if (!det->idle) CK(cudaEventCreateWithFlags(&det->idle, cudaEventDisableTiming));
+    for (int k = 0; k < n_chunks; k++)
+        if (!det->copied[k]) CK(cudaEventCreateWithFlags(&det->copied[k], cudaEventDisableTiming));
+    // the staging buffer is free once everything queued on the compute stream so far is done
+    CK(cudaEventRecord(det->idle, ctx->stream));
+    CK(cudaStreamWaitEvent(det->copy_stream, det->idle, 0));
+    det->last_frames = n_frames;
+    int launches = 0;
+    for (int k = 0; k < n_chunks; k++) {
+        const int f0 = (int)((long long)n_frames * k / n_chunks), f1 = (int)((long long)n_frames * (k + 1) / n_chunks);
+        const int nf = f1 - f0;
+        if (nf <= 0) continue;
+        uint8_t *dst = det->dev_frames.p + (size_t)f0 * dframe;
+        const uint8_t *src = frames_host + (size_t)f0 * frame_stride;
+        cudaStream_t cs = det->copy_stream;
+        if ((size_t)row_stride == dstride && frame_stride == dframe) {
+            CK(cudaMemcpyAsync(dst, src, dframe * nf, cudaMemcpyHostToDevice, cs));
+        } else if (frame_stride == (size_t)row_stride * H) {
+            CK(cudaMemcpy2DAsync(dst, dstride, src, row_stride, W, (size_t)H * nf, cudaMemcpyHostToDevice, cs));
+        } else {
+            for (int f = 0; f < nf; f++)
+                CK(cudaMemcpy2DAsync(dst + f * dframe, dstride, src + f * frame_stride, row_stride, W, H,
+                                     cudaMemcpyHostToDevice, cs));
+        }
+        CK(cudaEventRecord(det->copied[k], cs));
+        CK(cudaStreamWaitEvent(ctx->stream, det->copied[k], 0));
+        int rc = enqueue_range(det, dst, f0, nf, dframe, (int)dstride, ctx->stream, k == 0, &launches);
+        if (rc) return rc;
     }
-    int rc = clfd_detector_enqueue(det, det->dev_frames.p, n_frames, dframe, (int)dstride, nullptr);
-    if (rc) return rc;
+    det->stats.kernel_launches = launches;
     return clfd_detector_fetch(det, rects, cap, n_rects, nullptr);
 }
 

@@ -42,6 +42,7 @@ struct CascadeArgs {
     const PyrLevel *levels;         // device
     const CasLevel *cas_levels;     // device
     int n_cas_levels, n_tiles, n_frames, cascade_index;
+    int frame_base;                 // added to the frame index of emitted rects (ranges of a batch)
     long long windows_per_frame;
     int16_t *codes;                 // device, [n_frames][windows_per_frame] or NULL
     QueueItem *queue; unsigned long long queue_cap;
