@@ -80,7 +80,7 @@ __device__ __forceinline__ void emit_rect(const CascadeArgs &a, const CasLevel &
         DevRect r;
         r.x = __double2int_rn(__dmul_rn((double)px, CL.factor));  // cvRound(x*factor), tempcv.cpp:1099
         r.y = __double2int_rn(__dmul_rn((double)py, CL.factor));
-        r.w = CL.win_w; r.h = CL.win_h; r.frame = frame; r.cascade = a.cascade_index;
+        r.w = CL.win_w; r.h = CL.win_h; r.frame = a.frame_base + frame; r.cascade = a.cascade_index;
         a.rects[slot] = r;
     } else {
         atomicAdd(a.counters + 2, 1ull);
