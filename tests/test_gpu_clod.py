@@ -138,3 +138,75 @@ def test_full_size_properties_batch(gpu_ctx):
     for f in range(3):
         assert np.array_equal(single.detect(frames[f:f + 1]).frame_rects(0), res.frame_rects(f))
     det.close(); single.close()
+
+
+@pytest.mark.parametrize("chunks", [1, 2, 3])
+def test_detect_pipelined_chunks_equal_one_shot(gpu_ctx, monkeypatch, chunks):
+    """clfd_detect cuts a batch into ranges whose H2D copy overlaps the previous range's compute.
+    Rect frame indices, exit codes and per-frame intermediates must not depend on the cut."""
+    frames = np.stack([octave_frame(640, 480, i) for i in range(9)])
+    cas = clfd.Cascade(cascade_path("frontalface_alt"))
+    monkeypatch.setenv("CLFD_DETECT_CHUNKS", str(chunks))
+    det = clfd.Detector(gpu_ctx, cas, 640, 480, max_batch=9, scale_factor=1.2, want_codes=True)
+    res = det.detect(frames)
+    codes = det.codes(0, 9)
+    oc = oracle_cascade("frontalface_alt")
+    for f in (0, 4, 8):
+        rects, ocodes, _, _, _ = oc.detect(frames[f], 1.2)
+        assert np.array_equal(codes[f], ocodes)
+        assert np.array_equal(res.frame_rects(f), _sorted(rects))
+        _, s, _, _ = det.read_level(2, frame=f)
+        import oracle
+        lv = det.levels()[2]
+        os_, _, _ = oracle.integral(oracle.resize_linear(frames[f], lv.img_w, lv.img_h))
+        assert np.array_equal(s, os_)
+    assert sorted(set(res.rects["frame"].tolist())) == sorted(f for f in range(9) if len(res.frame_rects(f)))
+    det.close()
+
+
+def _synthetic_cascade(big, n_stages=12):
+    """frontalface_alt's first stages; with `big` != 0 the first stump of every stage votes +big
+    and the last one -big whatever the window: the partial sums in between are rounded at the
+    scale of `big`, so the stage sum depends on the summation order, the order-free proof fails
+    and every order-sensitive shortcut must fall back to the reference's tree order."""
+    from oracle.cascade_xml import FlatCascade, load_cascade_xml
+    f = load_cascade_xml(cascade_path("frontalface_alt"))
+    S = n_stages
+    T = int(np.sum(f.st_ntrees[:S]))
+    alpha = np.array(f.alpha[:2 * T], np.float32).copy()
+    if big:
+        first = np.concatenate([[0], np.cumsum(f.st_ntrees[:S])])
+        for st in range(S):
+            alpha[2 * first[st]:2 * first[st] + 2] = np.float32(big)
+            alpha[2 * first[st + 1] - 2:2 * first[st + 1]] = np.float32(-big)
+    thr = np.ascontiguousarray(f.st_thr[:S], np.float32) - np.float32(0.8 if big else 0.0)   # two stumps lost their vote
+    c = np.ascontiguousarray
+    return FlatCascade(name="synthetic", win_w=f.win_w, win_h=f.win_h, st_ntrees=c(f.st_ntrees[:S], np.int32),
+                       st_thr=thr, st_parent=np.arange(-1, S - 1, dtype=np.int32),
+                       st_next=np.full(S, -1, np.int32), tr_nnodes=np.ones(T, np.int32),
+                       nd_tilted=c(f.nd_tilted[:T], np.int32), nd_rect=c(f.nd_rect[:T], np.int32),
+                       nd_weight=c(f.nd_weight[:T], np.float32), nd_thr=c(f.nd_thr[:T], np.float32),
+                       nd_left=c(f.nd_left[:T], np.int32), nd_right=c(f.nd_right[:T], np.int32), alpha=alpha)
+
+
+@pytest.mark.parametrize("big", [0.0, 2.0 ** 30])
+def test_synthetic_cascade_order_sensitive_sums(gpu_ctx, big):
+    """Stage sums that are NOT exact in any order (alphas spanning > 2^29): the FP32 stage-sum
+    filter and the split of a stage's stumps over lanes must still reproduce the reference's
+    sequential double sum bit for bit (they fall back to dense_stage_exact).  12 stages also
+    puts the last stages beyond the kernel-parameter budget (stumps read from global memory)."""
+    import oracle
+    flat = _synthetic_cascade(big)
+    cas = clfd.Cascade(flat=flat)
+    if big:
+        assert cas.info.order_free_stages == 0
+    assert cas.info.dense_stages == cas.info.n_stages
+    oc = oracle.Cascade(flat)
+    det = clfd.Detector(gpu_ctx, cas, 640, 480, max_batch=2, scale_factor=1.2, want_codes=True)
+    frames = np.stack([octave_frame(640, 480, 11), uniform_frame(640, 480, 11)])
+    res = det.detect(frames)
+    for f in range(2):
+        rects, ocodes, _, _, _ = oc.detect(frames[f], 1.2)
+        assert np.array_equal(det.codes(0, 2)[f], ocodes)
+        assert np.array_equal(res.frame_rects(f), _sorted(rects))
+    det.close()
