@@ -13,8 +13,9 @@ metric configuration: haarcascade_frontalface_alt, 1920x1080, scale 1.2 (SURVEY 
 `e2e`    : frames/s through clfd_detect() -- pinned HOST frames in, H2D inside the timed
            region, host rect list out.
 `roofline`: the dominant kernel (cascade tile kernel) against the measured HBM peak, using the
-           compulsory bytes of SURVEY 8-d; per-kernel numbers for resize / integral are under
-           `kernels`.
+           compulsory bytes of SURVEY 8-d (the contract's figure), plus what actually bounds it:
+           the L1 data pipe (shared-memory corner loads), from the committed ncu capture in
+           profiles/traffic.json.  Per-kernel numbers for resize / integral are under `kernels`.
 """
 from __future__ import annotations
 
@@ -36,6 +37,14 @@ CASCADE = "frontalface_alt"
 SCALE = 1.2
 XML = os.path.join(ROOT, "data", "haarcascades", f"haarcascade_{CASCADE}.xml")
 KERNEL_NAMES = ["resize_colsum", "colscan", "integral_rows", "tilted", "cascade_tiles", "cascade_deep"]
+
+
+def ncu_traffic():
+    """per-kernel DRAM bytes per frame and L1 data-pipe utilisation from the committed ncu capture"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return None
 
 
 def measured_peak_gbs():
@@ -231,15 +240,28 @@ def main():
     kernel_ms /= args.steps
 
     # ---- timed: end to end through the host API ----------------------------------------------
+    # Every step copies its batch from pinned host memory (H2D inside the timed region) and
+    # reads its rect list back to the host.  clfd_detect_submit / _collect keep two batches in
+    # flight, so the copy of step i+1 overlaps the kernels of step i (a frame stream).
     for _ in range(2):
         step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    det.submit(host)
+    for _ in range(args.steps - 1):
+        det.submit(host)
+        r = det.collect()
+    r = det.collect()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    d2h = int(len(r.rects) * 24 + 32)
+    # the blocking single call (one batch at a time, copy overlapped only inside the batch)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         r = step_e2e()
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    d2h = int(len(r.rects) * 24 + 32)
+    e2e_blocking_s = time.perf_counter() - t0
 
     # ---- the single gather of detection rects (no collective in the hot loop) ---------------
     from clfacedetection_b200 import sharding
@@ -249,9 +271,9 @@ def main():
     gather_ms = 1e3 * (time.perf_counter() - t_g0)
     total_rects = len(gathered)
     if world > 1:
-        t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, e2e_blocking_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)   # timing: max over ranks
-        ms, e2e_s = float(t[0].item()), float(t[1].item())
+        ms, e2e_s, e2e_blocking_s = float(t[0].item()), float(t[1].item()), float(t[2].item())
 
     if rank == 0:
         stats = det.stats()
@@ -261,6 +283,7 @@ def main():
         alg = {"resize_colsum": stats["bytes_resize"] * B, "integral_rows": stats["bytes_integral"] * B,
                "cascade_tiles": stats["bytes_cascade"] * B}
         kernels = {}
+        ncu = ncu_traffic()
         for i, nm in enumerate(KERNEL_NAMES):
             if kernel_ms[i] > 0:
                 k = {"ms": round(float(kernel_ms[i]), 4), "share": round(float(kernel_ms[i] / max(kernel_ms.sum(), 1e-9)), 4)}
@@ -268,12 +291,21 @@ def main():
                     k["algorithmic_bytes"] = int(alg[nm])
                     k["achieved_gbs"] = round(alg[nm] / (kernel_ms[i] * 1e-3) / 1e9, 1)
                     k["frac_of_hbm_peak"] = round(k["achieved_gbs"] / peak, 4)
+                if ncu and nm in ncu["kernels"]:
+                    k["ncu_dram_bytes"] = int(ncu["kernels"][nm]["dram_bytes_per_frame"]) * B
+                    k["ncu_l1_data_pipe_pct"] = ncu["kernels"][nm]["l1_data_pipe_pct"]
                 kernels[nm] = k
         dom = "cascade_tiles"
         roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
-                "peak_source": peak_src, "unit": "GB/s", "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": None,
-                "note": "achieved = compulsory bytes (integral tiles read once + packed cascade) / CUDA-event time; "
-                        "the kernel is smem/issue-bound, not HBM-bound (DESIGN.md)"}
+                "peak_source": peak_src, "unit": "GB/s", "frac": kernels[dom]["frac_of_hbm_peak"],
+                "traffic": kernels[dom].get("ncu_dram_bytes"),
+                "launches_per_step": 2,
+                "note": "achieved = compulsory bytes (integral tiles read once + packed cascade) of both tile launches of a "
+                        "step / their CUDA-event time; traffic = ncu DRAM bytes of the same two launches scaled to this "
+                        "batch.  The kernel is NOT HBM-bound: it saturates the SM's L1 data pipe (shared-memory corner "
+                        "loads, one 128-B wavefront per clock per SM), see l1_data_pipe and DESIGN.md",
+                "l1_data_pipe": {"pct_of_peak": kernels[dom].get("ncu_l1_data_pipe_pct"),
+                                 "source": ncu["source"] if ncu else None}}
         line = {
             "metric": "frames_per_sec_1080p", "value": round(fps, 2), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4),
@@ -287,7 +319,9 @@ def main():
             "rect_gather_ms": round(gather_ms, 3),
             "deep_windows_per_step": stats["deep_windows"],
             "e2e": {"value": round(B * world * args.steps / e2e_s, 2), "unit": "frames/s",
-                    "h2d_bytes_per_step": int(B * W * H), "d2h_bytes_per_step": d2h},
+                    "h2d_bytes_per_step": int(B * W * H), "d2h_bytes_per_step": d2h,
+                    "api": "clfd_detect_submit/_collect, 2 batches in flight",
+                    "blocking_call_value": round(B * world * args.steps / e2e_blocking_s, 2)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,

@@ -236,6 +236,25 @@ class Detector:
                                         self._rects.ctypes.data_as(C.POINTER(abi.Rect)), self._rect_cap, C.byref(cnt)))
         return DetectResult(self._rects[:cnt.value].copy(), self.stats())
 
+    # ---- host input, streaming: submit batch i+1 while batch i computes -----------------
+    def submit(self, frames) -> None:
+        """frames as for detect(); must stay alive (and should be pinned) until collected"""
+        if isinstance(frames, np.ndarray):
+            assert frames.ndim == 3 and frames.dtype == np.uint8 and frames.flags.c_contiguous
+            n, H, W = frames.shape
+            fs, rs = frames.strides[0], frames.strides[1]
+        else:
+            n, H, W = frames.shape
+            fs, rs = frames.stride(0), frames.stride(1)
+        assert (H, W) == (self.height, self.width)
+        abi.check(abi.lib().clfd_detect_submit(self._h, _ptr(frames), n, fs, rs))
+
+    def collect(self) -> DetectResult:
+        cnt = C.c_int64()
+        abi.check(abi.lib().clfd_detect_collect(self._h, self._rects.ctypes.data_as(C.POINTER(abi.Rect)),
+                                                self._rect_cap, C.byref(cnt)))
+        return DetectResult(self._rects[:cnt.value].copy(), self.stats())
+
     def codes(self, cascade: int = 0, n_frames: int = 1) -> np.ndarray:
         wpf = self.windows_per_frame(cascade)
         out = np.zeros((n_frames, wpf), np.int16)

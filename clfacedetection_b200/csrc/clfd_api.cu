@@ -244,6 +244,8 @@ struct CascadePlan {
 };
 
 constexpr int kMaxChunks = 8;
+constexpr int kSlots = 2;            // batches in flight through clfd_detect_submit / _collect
+constexpr int kEagerRects = 1 << 16; // rects copied back with the counters; more cost one extra copy
 
 struct clfd_detector {
     clfd_context *ctx = nullptr;
@@ -252,9 +254,14 @@ struct clfd_detector {
     std::vector<std::unique_ptr<CascadePlan>> cas;
     DevBuf<QueueItem> queue;
     DevBuf<DevRect> rects;
-    DevBuf<uint8_t> dev_frames;      // staging for host input (clfd_detect)
-    DevRect *h_rects = nullptr;      // pinned
-    unsigned long long *h_counters = nullptr;  // pinned, 4 per cascade
+    DevBuf<uint8_t> dev_frames[kSlots];   // staging for host input (clfd_detect / clfd_detect_submit)
+    DevBuf<DevRect> rects2;               // rect buffer of slot 1 (slot 0 uses `rects`)
+    DevRect *h_rects = nullptr;           // pinned, kSlots x rect_cap... slot 1 holds kEagerRects only
+    DevRect *h_rects1 = nullptr;
+    unsigned long long *h_counters = nullptr;  // pinned, kSlots x (4 per cascade, 16 cascades)
+    cudaEvent_t done[kSlots] = {nullptr, nullptr};
+    int slot_frames[kSlots] = {0, 0};
+    long long n_submitted = 0, n_collected = 0;
     unsigned long long rect_cap = 0, queue_cap = 0;
     int last_frames = 0;
     clfd_run_stats stats;
@@ -265,13 +272,13 @@ struct clfd_detector {
     // clfd_detect pipelines the H2D copy of a batch with its own compute, chunk by chunk
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copied[kMaxChunks] = {nullptr};
-    cudaEvent_t idle = nullptr;
     ~clfd_detector() {
         if (h_rects) cudaFreeHost(h_rects);
+        if (h_rects1) cudaFreeHost(h_rects1);
         if (h_counters) cudaFreeHost(h_counters);
+        for (auto &e : done) if (e) cudaEventDestroy(e);
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         for (auto &e : copied) if (e) cudaEventDestroy(e);
-        if (idle) cudaEventDestroy(idle);
         if (copy_stream) cudaStreamDestroy(copy_stream);
     }
 };
@@ -641,7 +648,7 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
             if (!pk.tail[yi].empty() && (rc = cp.d_tail[yi].upload(pk.tail[yi], s))) return rc;
             cp.dense[yi].tail = cp.d_tail[yi].p;
         }
-        if ((rc = cp.d_counters.alloc(4))) return rc;
+        if ((rc = cp.d_counters.alloc(4 * kSlots))) return rc;
         if (cfg->want_codes && (rc = cp.d_codes.alloc((size_t)std::max<long long>(cp.windows_per_frame, 1) * cfg->max_batch)))
             return rc;
         max_wpf = std::max(max_wpf, cp.windows_per_frame);
@@ -651,7 +658,7 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
     det->rect_cap = cfg->max_rects > 0 ? (unsigned long long)cfg->max_rects : (1ull << 20);
     if ((rc = det->queue.alloc(det->queue_cap)) || (rc = det->rects.alloc(det->rect_cap))) return rc;
     CK(cudaMallocHost((void **)&det->h_rects, det->rect_cap * sizeof(DevRect)));
-    CK(cudaMallocHost((void **)&det->h_counters, 4 * 16 * sizeof(unsigned long long)));
+    CK(cudaMallocHost((void **)&det->h_counters, kSlots * 4 * 16 * sizeof(unsigned long long)));
     CK(cudaStreamSynchronize(s));
     det->stats.pyramid_pixels = det->pyr.pyramid_pixels;
     det->stats.bytes_resize = det->pyr.bytes_resize;
@@ -701,7 +708,7 @@ int clfd_detector_set_profiling(clfd_detector *det, int enable) {
 // to the range (the per-frame buffers are passed pre-offset) and add frame_base to the frame
 // index of the rects they emit.
 static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int frame_base, int n_frames, size_t frame_stride,
-                         int row_stride, cudaStream_t s, bool first, int *n_launches) {
+                         int row_stride, cudaStream_t s, bool first, int *n_launches, int slot = 0) {
     clfd_context *ctx = det->ctx;
     int launches = 0;
     cudaEvent_t *ev = det->profiling ? det->ev : nullptr;
@@ -711,8 +718,8 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
     }
     const int pyr_launches = launches;
     for (auto &cpp : det->cas) {
-        if (first) CK(cudaMemsetAsync(cpp->d_counters.p, 0, 4 * sizeof(unsigned long long), s));
-        else CK(cudaMemsetAsync(cpp->d_counters.p + 1, 0, sizeof(unsigned long long), s));   // the queue is per range
+        if (first) CK(cudaMemsetAsync(cpp->d_counters.p + 4 * slot, 0, 4 * sizeof(unsigned long long), s));
+        else CK(cudaMemsetAsync(cpp->d_counters.p + 4 * slot + 1, 0, sizeof(unsigned long long), s));   // the queue is per range
     }
     int ci = 0;
     for (auto &cpp : det->cas) {
@@ -731,8 +738,8 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
             a.cascade_index = ci; a.windows_per_frame = cp.windows_per_frame;
             a.codes = det->cfg.want_codes ? cp.d_codes.p + (size_t)frame_base * cp.windows_per_frame : nullptr;
             a.queue = det->queue.p; a.queue_cap = det->queue_cap;
-            a.rects = det->rects.p; a.rect_cap = det->rect_cap;
-            a.counters = cp.d_counters.p;
+            a.rects = slot ? det->rects2.p : det->rects.p; a.rect_cap = det->rect_cap;
+            a.counters = cp.d_counters.p + 4 * slot;
             a.deep.stages = cp.d_stages.p; a.deep.tree_first_node = cp.d_tree_first.p;
             a.deep.nodes = cp.d_nodes.p; a.deep.alpha = cp.d_alpha.p;
             a.deep.n_stages = cp.cascade->host.n_stages(); a.deep.is_tree = cp.cascade->host.is_tree;
@@ -759,7 +766,7 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
         }
         // all cascades append to one rect buffer: carry the rect count over
         if (ci + 1 < (int)det->cas.size())
-            CK(cudaMemcpyAsync(det->cas[ci + 1]->d_counters.p, cp.d_counters.p, sizeof(unsigned long long),
+            CK(cudaMemcpyAsync(det->cas[ci + 1]->d_counters.p + 4 * slot, cp.d_counters.p + 4 * slot, sizeof(unsigned long long),
                                cudaMemcpyDeviceToDevice, s));
         ci++;
     }
@@ -830,41 +837,52 @@ int clfd_detector_fetch(clfd_detector *det, clfd_rect *rects, int64_t cap, int64
     return 0;
 }
 
-int clfd_detect(clfd_detector *det, const uint8_t *frames_host, int n_frames, size_t frame_stride, int row_stride,
-                clfd_rect *rects, int64_t cap, int64_t *n_rects) {
+// Host input, asynchronous: copy + enqueue one batch into the next free slot.
+//   * the batch is cut into ranges; range k+1 is copied on the copy stream while the kernels of
+//     range k run on the compute stream (pinned host memory; pageable memory degrades to a
+//     serial copy).  Multi-cascade detectors carry their rect count from one cascade to the
+//     next inside a range, so they run as one range;
+//   * counters and the first kEagerRects rects are copied back behind the kernels and an event
+//     marks the slot done, so the NEXT batch's host-to-device copy overlaps this batch's compute.
+int clfd_detect_submit(clfd_detector *det, const uint8_t *frames_host, int n_frames, size_t frame_stride, int row_stride) {
     if (!det || !frames_host) INVALID("NULL argument");
     clfd_context *ctx = det->ctx;
     CK(cudaSetDevice(ctx->device));
     const int W = det->cfg.width, H = det->cfg.height;
     if (n_frames <= 0 || n_frames > det->cfg.max_batch) INVALID("n_frames %d outside 1..%d", n_frames, det->cfg.max_batch);
     if (row_stride < W) INVALID("row stride %d smaller than the frame width %d", row_stride, W);
+    if (det->n_submitted - det->n_collected >= kSlots) INVALID("%d batches already in flight: collect one first", kSlots);
+    const int slot = (int)(det->n_submitted % kSlots);
     const size_t dstride = round_up(W, 16), dframe = dstride * H;
-    if (!det->dev_frames.p) {
-        int rc = det->dev_frames.alloc(dframe * det->cfg.max_batch + 64);
-        if (rc) return rc;
+    int rc;
+    if (!det->dev_frames[slot].p && (rc = det->dev_frames[slot].alloc(dframe * det->cfg.max_batch + 64))) return rc;
+    if (slot == 1) {
+        if (!det->rects2.p && (rc = det->rects2.alloc(det->rect_cap))) return rc;
+        if (!det->h_rects1) CK(cudaMallocHost((void **)&det->h_rects1, (size_t)kEagerRects * sizeof(DevRect)));
     }
-    // Pipeline: the batch is cut into chunks; chunk k+1 is copied on the copy stream while the
-    // kernels of chunk k run on the compute stream (for pinned host memory; pageable memory
-    // degrades to a serial copy).  Multi-cascade detectors carry their rect count from one
-    // cascade to the next inside a range, so they run as one chunk.
     int n_chunks = 1;
     if (det->cas.size() == 1 && n_frames >= 8) n_chunks = n_frames >= 32 ? 4 : 2;
+    // with a batch already in flight the whole copy overlaps THAT batch's compute: no need to
+    // pay the extra kernel boundaries of a cut
+    if (det->n_submitted > det->n_collected) n_chunks = 1;
     if (const char *e = getenv("CLFD_DETECT_CHUNKS")) n_chunks = std::max(1, std::min({atoi(e), kMaxChunks, n_frames}));
     if (det->cas.size() != 1) n_chunks = 1;
     if (!det->copy_stream) CK(cudaStreamCreateWithFlags(&det->copy_stream, cudaStreamNonBlocking));
-    if (!det->idle) CK(cudaEventCreateWithFlags(&det->idle, cudaEventDisableTiming));
     for (int k = 0; k < n_chunks; k++)
         if (!det->copied[k]) CK(cudaEventCreateWithFlags(&det->copied[k], cudaEventDisableTiming));
-    // the staging buffer is free once everything queued on the compute stream so far is done
-    CK(cudaEventRecord(det->idle, ctx->stream));
-    CK(cudaStreamWaitEvent(det->copy_stream, det->idle, 0));
+    for (auto &e : det->done)
+        if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // The slot's staging buffer was last read by the batch submitted kSlots submits ago, which has
+    // been collected (its done event was synchronised), so the copy may start right away -- while
+    // the previous batch still computes.
     det->last_frames = n_frames;
+    det->slot_frames[slot] = n_frames;
     int launches = 0;
     for (int k = 0; k < n_chunks; k++) {
         const int f0 = (int)((long long)n_frames * k / n_chunks), f1 = (int)((long long)n_frames * (k + 1) / n_chunks);
         const int nf = f1 - f0;
         if (nf <= 0) continue;
-        uint8_t *dst = det->dev_frames.p + (size_t)f0 * dframe;
+        uint8_t *dst = det->dev_frames[slot].p + (size_t)f0 * dframe;
         const uint8_t *src = frames_host + (size_t)f0 * frame_stride;
         cudaStream_t cs = det->copy_stream;
         if ((size_t)row_stride == dstride && frame_stride == dframe) {
@@ -878,11 +896,72 @@ int clfd_detect(clfd_detector *det, const uint8_t *frames_host, int n_frames, si
         }
         CK(cudaEventRecord(det->copied[k], cs));
         CK(cudaStreamWaitEvent(ctx->stream, det->copied[k], 0));
-        int rc = enqueue_range(det, dst, f0, nf, dframe, (int)dstride, ctx->stream, k == 0, &launches);
+        rc = enqueue_range(det, dst, f0, nf, dframe, (int)dstride, ctx->stream, k == 0, &launches, slot);
         if (rc) return rc;
     }
     det->stats.kernel_launches = launches;
-    return clfd_detector_fetch(det, rects, cap, n_rects, nullptr);
+    // results: counters of every cascade + the first rects, behind the kernels
+    const int nc = (int)det->cas.size();
+    unsigned long long *hc = det->h_counters + (size_t)slot * 4 * 16;
+    for (int ci = 0; ci < nc; ci++)
+        CK(cudaMemcpyAsync(hc + 4 * ci, det->cas[ci]->d_counters.p + 4 * slot, 4 * sizeof(unsigned long long),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t eager = (size_t)std::min<unsigned long long>(det->rect_cap, kEagerRects);
+    CK(cudaMemcpyAsync(slot ? det->h_rects1 : det->h_rects, slot ? det->rects2.p : det->rects.p, eager * sizeof(DevRect),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(det->done[slot], ctx->stream));
+    det->n_submitted++;
+    return 0;
+}
+
+// Wait for the oldest submitted batch and hand out its rects.
+int clfd_detect_collect(clfd_detector *det, clfd_rect *rects, int64_t cap, int64_t *n_rects) {
+    if (!det || !n_rects) INVALID("NULL argument");
+    if (det->n_collected >= det->n_submitted) INVALID("no batch in flight");
+    clfd_context *ctx = det->ctx;
+    CK(cudaSetDevice(ctx->device));
+    const int slot = (int)(det->n_collected % kSlots);
+    det->n_collected++;
+    CK(cudaEventSynchronize(det->done[slot]));
+    const int nc = (int)det->cas.size();
+    const unsigned long long *hc = det->h_counters + (size_t)slot * 4 * 16;
+    const unsigned long long total = hc[4 * (nc - 1)];
+    unsigned long long deep = 0, rect_over = 0, queue_over = 0;
+    for (int ci = 0; ci < nc; ci++) {
+        memcpy(det->cas[ci]->h_counters, hc + 4 * ci, 4 * sizeof(unsigned long long));
+        deep += hc[4 * ci + 1];
+        rect_over += hc[4 * ci + 2];
+        queue_over += hc[4 * ci + 3];
+    }
+    if (queue_over) { set_error("survivor queue overflow (%llu windows dropped)", queue_over); return CLFD_ERR_CAPACITY; }
+    det->stats.rects = (int64_t)total;
+    det->stats.deep_windows = (int64_t)deep;
+    det->stats.windows = 0;
+    for (auto &cpp : det->cas) det->stats.windows += cpp->windows_per_frame * det->slot_frames[slot];
+    *n_rects = (int64_t)total;
+    if (rect_over || total > det->rect_cap) {
+        set_error("device rect buffer overflow: %llu accepted windows, capacity %llu (raise max_rects)", total, det->rect_cap);
+        return CLFD_ERR_CAPACITY;
+    }
+    if (total == 0 || !rects) return 0;
+    if ((int64_t)total > cap) { set_error("rect buffer too small: need %llu, have %lld", total, (long long)cap); return CLFD_ERR_CAPACITY; }
+    static_assert(sizeof(DevRect) == sizeof(clfd_rect), "rect layout");
+    const unsigned long long eager = std::min<unsigned long long>(total, kEagerRects);
+    memcpy(rects, slot ? det->h_rects1 : det->h_rects, eager * sizeof(DevRect));
+    if (total > eager)   // rare: the slot's device buffer is untouched until the slot is submitted again
+        CK(cudaMemcpy(rects + eager, (slot ? det->rects2.p : det->rects.p) + eager, (total - eager) * sizeof(DevRect),
+                      cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// Host input end to end, synchronous: the call a clod user makes.
+int clfd_detect(clfd_detector *det, const uint8_t *frames_host, int n_frames, size_t frame_stride, int row_stride,
+                clfd_rect *rects, int64_t cap, int64_t *n_rects) {
+    if (!det) INVALID("NULL argument");
+    if (det->n_submitted != det->n_collected) INVALID("clfd_detect while submitted batches are in flight");
+    int rc = clfd_detect_submit(det, frames_host, n_frames, frame_stride, row_stride);
+    if (rc) return rc;
+    return clfd_detect_collect(det, rects, cap, n_rects);
 }
 
 int clfd_detector_get_codes(clfd_detector *det, int cascade, int16_t *codes, int64_t cap) {

@@ -181,6 +181,15 @@ CLFD_API int clfd_detector_fetch(clfd_detector *det, clfd_rect *rects, int64_t c
 CLFD_API int clfd_detect(clfd_detector *det, const uint8_t *frames_host, int n_frames,
                          size_t frame_stride, int row_stride, clfd_rect *rects, int64_t cap,
                          int64_t *n_rects);
+/* The same, split in two so that batches overlap: _submit copies batch i+1 (pinned host
+ * memory, copy stream) while batch i still computes, _collect waits for the OLDEST submitted
+ * batch and hands out its rects.  At most 2 batches in flight.  The reference has no such
+ * call (clodDetectObjects blocks per stage, clod.cpp:1256-1302); this is the streaming form of
+ * SURVEY 8-e ("pinned staging buffers, H2D / compute / D2H overlap"). */
+CLFD_API int clfd_detect_submit(clfd_detector *det, const uint8_t *frames_host, int n_frames,
+                                size_t frame_stride, int row_stride);
+CLFD_API int clfd_detect_collect(clfd_detector *det, clfd_rect *rects, int64_t cap,
+                                 int64_t *n_rects);
 /* Exit codes of the last batch (want_codes=1): int16 [n_frames][windows_per_frame(cascade)];
  * linear cascades: stages passed (n_stages = accepted); stage trees: 2*last_stage+accepted. */
 CLFD_API int clfd_detector_get_codes(clfd_detector *det, int cascade, int16_t *codes,

@@ -16,6 +16,9 @@ KEEP = [
     "dram__throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
     "l1tex__t_bytes.sum", "l1tex__t_sector_hit_rate.pct",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts.sum",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",

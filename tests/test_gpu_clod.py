@@ -210,3 +210,31 @@ def test_synthetic_cascade_order_sensitive_sums(gpu_ctx, big):
         assert np.array_equal(det.codes(0, 2)[f], ocodes)
         assert np.array_equal(res.frame_rects(f), _sorted(rects))
     det.close()
+
+
+def test_submit_collect_pipeline_keeps_batches_apart(gpu_ctx):
+    """clfd_detect_submit / _collect: two batches in flight (the copy of batch i+1 overlaps the
+    kernels of batch i).  Results must come back in submission order and equal the blocking call."""
+    import torch
+    cas = clfd.Cascade(cascade_path("frontalface_alt"))
+    det = clfd.Detector(gpu_ctx, cas, 640, 480, max_batch=8, scale_factor=1.2)
+    batches = [np.stack([octave_frame(640, 480, 10 * b + i) for i in range(8)]) for b in range(4)]
+    pinned = [torch.from_numpy(b).pin_memory() for b in batches]
+    want = [det.detect(b) for b in batches]
+    got = []
+    det.submit(pinned[0])
+    for b in range(1, 4):
+        det.submit(pinned[b])
+        got.append(det.collect())
+    got.append(det.collect())
+    for b in range(4):
+        assert got[b].stats["windows"] == 8 * det.windows_per_frame()
+        for f in range(8):
+            assert np.array_equal(got[b].frame_rects(f), want[b].frame_rects(f)), (b, f)
+    with pytest.raises(Exception):
+        det.collect()            # nothing in flight
+    det.submit(pinned[0]); det.submit(pinned[1])
+    with pytest.raises(Exception):
+        det.submit(pinned[2])    # two already in flight
+    det.collect(); det.collect()
+    det.close()
