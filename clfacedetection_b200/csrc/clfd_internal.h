@@ -105,7 +105,7 @@ struct DenseParams {
     int n_fixed;        // leading stages run in fixed geometry (no compaction), <= n_stages
     int tail_stages;    // leading stages the tile kernel evaluates (upright stumps, linear): == total_stages
                         // when it finishes the cascade itself, otherwise survivors go to the deep kernel
-    int pad0;
+    int g1_min;         // phase 2: more than this many windows in a warp -> thread per window (G = 1), max 16
     double inv_area;
     const TailStump *tail;   // device, layout of this blob's ystep (patched in by the detector)
     DenseStage stage[kMaxDenseStages];

@@ -11,6 +11,7 @@
 // formulation the packed cascade is scale independent and is built once per cascade.
 //
 // This translation unit must be compiled with -ffp-contract=off.
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdarg>
@@ -250,6 +251,8 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
             elig++;
         }
         P.tail_stages = elig;
+        P.g1_min = 16;
+        if (const char *e = getenv("CLFD_G1_MIN")) P.g1_min = std::max(1, std::min(16, atoi(e)));
         const int n_elig_stumps = c.st_first_tree[elig];
         out.dense_stumps = n_elig_stumps;
         out.tail[yi].assign(n_elig_stumps, TailStump());

@@ -510,7 +510,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
             n_next += __popc(m);
             if (valid && !pass && c.codes) dense_write_code(c, wid, s * c.code_mul);
         };
-        if (n > 16) {
+        if (n > P.g1_min) {
             const int R = (n + 31) >> 5;
             for (int r = 0; r < R; r += 2) {
                 const int c0 = dealt ? (n - r + R - 1) / R : min(32, n - 32 * r);
@@ -540,7 +540,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
             }
         } else {
             int lw = 4;
-            while (lw > 0 && (1 << (lw - 1)) >= n) lw--;
+            while (lw > 0 && (1 << (lw - 1)) >= n) lw--;   // n <= 16 here
             const int slot = lane & ((1 << lw) - 1), grp = lane >> lw, G = 32 >> lw;
             const bool valid = slot < n;
             const int wid0 = cur[valid ? slot : 0];
