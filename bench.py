@@ -157,6 +157,7 @@ def run_reference(args):
 
 
 def main():
+    global CASCADE, XML
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -166,7 +167,11 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=4, help="frames per step of the CPU reference arm")
     ap.add_argument("--cpu-baseline-frames", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cascade", default=CASCADE, help="stock cascade name (default: the metric's frontalface_alt; "
+                    "frontalface_default is BASELINE.json configs[1])")
     args = ap.parse_args()
+    CASCADE = args.cascade
+    XML = os.path.join(ROOT, "data", "haarcascades", f"haarcascade_{CASCADE}.xml")
     if args.impl == "reference":
         return run_reference(args)
 
