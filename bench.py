@@ -260,6 +260,18 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     d2h = int(len(r.rects) * 24 + 32)
+    # the same stream with the host-side rectangle grouping (min_neighbors 3, tempcv.cpp:1462-1472)
+    # of batch i running while the GPU evaluates batch i+1
+    barrier()
+    t0 = time.perf_counter()
+    det.submit(host)
+    grouped = 0
+    for _ in range(args.steps - 1):
+        det.submit(host)
+        grouped += len(clfd.group_batch(det.collect().rects, 3, 0.2)[0])
+    grouped += len(clfd.group_batch(det.collect().rects, 3, 0.2)[0])
+    torch.cuda.synchronize()
+    e2e_grouped_s = time.perf_counter() - t0
     # the blocking single call (one batch at a time, copy overlapped only inside the batch)
     barrier()
     t0 = time.perf_counter()
@@ -276,9 +288,9 @@ def main():
     gather_ms = 1e3 * (time.perf_counter() - t_g0)
     total_rects = len(gathered)
     if world > 1:
-        t = torch.tensor([ms, e2e_s, e2e_blocking_s], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, e2e_blocking_s, e2e_grouped_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)   # timing: max over ranks
-        ms, e2e_s, e2e_blocking_s = float(t[0].item()), float(t[1].item()), float(t[2].item())
+        ms, e2e_s, e2e_blocking_s, e2e_grouped_s = (float(x) for x in t.tolist())
 
     if rank == 0:
         stats = det.stats()
@@ -326,7 +338,9 @@ def main():
             "e2e": {"value": round(B * world * args.steps / e2e_s, 2), "unit": "frames/s",
                     "h2d_bytes_per_step": int(B * W * H), "d2h_bytes_per_step": d2h,
                     "api": "clfd_detect_submit/_collect, 2 batches in flight",
-                    "blocking_call_value": round(B * world * args.steps / e2e_blocking_s, 2)},
+                    "blocking_call_value": round(B * world * args.steps / e2e_blocking_s, 2),
+                    "with_host_grouping_value": round(B * world * args.steps / e2e_grouped_s, 2),
+                    "grouped_rects_per_step": grouped // args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,

@@ -280,3 +280,16 @@ def group_rectangles(rects: np.ndarray, group_threshold: int, eps: float = 0.2):
     abi.check(abi.lib().clfd_group_rectangles(r.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n), group_threshold,
                                               eps, w.ctypes.data_as(C.POINTER(C.c_int32))))
     return r[:n.value].copy(), w[:n.value].copy()
+
+
+def group_batch(rects: np.ndarray, group_threshold: int, eps: float = 0.2, n_threads: int = 0):
+    """Per-(frame, cascade) AgroupRectangles of a batch's raw rects (RECT_DTYPE) on host threads
+    -> (grouped rects RECT_DTYPE, neighbour counts)."""
+    r = np.ascontiguousarray(rects, RECT_DTYPE)
+    out = np.zeros(max(len(r), 1), RECT_DTYPE)
+    w = np.zeros(max(len(r), 1), np.int32)
+    n = C.c_int64()
+    abi.check(abi.lib().clfd_group_batch(r.ctypes.data_as(C.POINTER(abi.Rect)), len(r), group_threshold, eps, n_threads,
+                                         out.ctypes.data_as(C.POINTER(abi.Rect)), w.ctypes.data_as(C.POINTER(C.c_int32)),
+                                         len(out), C.byref(n)))
+    return out[:n.value].copy(), w[:n.value].copy()

@@ -7,7 +7,10 @@
 #include <climits>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <atomic>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include "clfd_internal.h"
@@ -90,5 +93,74 @@ extern "C" int clfd_group_rectangles(int32_t *rects_xywh, int *n_io, int group_t
     memcpy(rects_xywh, kept.data(), (size_t)out * sizeof(R4));
     if (weights) memcpy(weights, kept_w.data(), (size_t)out * sizeof(int));
     *n_io = out;
+    return 0;
+}
+
+// Batch form: the raw rects of a whole batch, as clfd_detect / _collect return
+// them, grouped per (frame, cascade) on `n_threads` host threads.  With clfd_detect_submit /
+// _collect the caller runs this for batch i while the GPU evaluates batch i+1, so the O(N^2)
+// grouping of tempcv.cpp:1462-1472 leaves the critical path.  Output: grouped rects sorted by
+// (frame, cascade), the neighbour count of each in `weights`.
+extern "C" int clfd_group_batch(const clfd_rect *rects, int64_t n, int group_threshold, double eps, int n_threads,
+                                clfd_rect *out, int32_t *weights, int64_t cap, int64_t *n_out) {
+    if ((!rects && n > 0) || n < 0 || !out || !n_out) { clfd::set_error("bad argument"); return CLFD_ERR_INVALID; }
+    *n_out = 0;
+    if (n == 0) return 0;
+    // bucket by (frame, cascade), keeping the device order inside a bucket out of the result:
+    // sort each bucket by (w, y, x) so the grouping is deterministic whatever the atomics did
+    std::vector<int64_t> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+        const clfd_rect &p = rects[a], &q = rects[b];
+        if (p.frame != q.frame) return p.frame < q.frame;
+        if (p.cascade != q.cascade) return p.cascade < q.cascade;
+        if (p.w != q.w) return p.w < q.w;
+        if (p.y != q.y) return p.y < q.y;
+        return p.x < q.x;
+    });
+    struct Bucket { int64_t first, count; int frame, cascade; std::vector<int32_t> r, w; int m; };
+    std::vector<Bucket> buckets;
+    for (int64_t i = 0; i < n;) {
+        int64_t j = i;
+        const clfd_rect &p = rects[order[i]];
+        while (j < n && rects[order[j]].frame == p.frame && rects[order[j]].cascade == p.cascade) j++;
+        buckets.push_back(Bucket{i, j - i, p.frame, p.cascade, {}, {}, 0});
+        i = j;
+    }
+    std::atomic<size_t> next{0};
+    std::atomic<int> failed{0};
+    auto work = [&]() {
+        for (;;) {
+            const size_t b = next.fetch_add(1);
+            if (b >= buckets.size()) return;
+            Bucket &B = buckets[b];
+            if (B.count > INT_MAX) { failed = 1; continue; }
+            B.r.resize((size_t)B.count * 4);
+            B.w.assign((size_t)B.count, 1);
+            for (int64_t k = 0; k < B.count; k++) {
+                const clfd_rect &p = rects[order[B.first + k]];
+                B.r[k * 4 + 0] = p.x; B.r[k * 4 + 1] = p.y; B.r[k * 4 + 2] = p.w; B.r[k * 4 + 3] = p.h;
+            }
+            B.m = (int)B.count;
+            if (clfd_group_rectangles(B.r.data(), &B.m, group_threshold, eps, B.w.data())) failed = 1;
+        }
+    };
+    const int nt = std::max(1, std::min<int>(n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency(), (int)buckets.size()));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; t++) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    if (failed) { clfd::set_error("rectangle grouping failed"); return CLFD_ERR_INVALID; }
+    int64_t total = 0;
+    for (const Bucket &B : buckets) total += B.m;
+    *n_out = total;
+    if (total > cap) { clfd::set_error("grouped rect buffer too small: need %lld", (long long)total); return CLFD_ERR_CAPACITY; }
+    int64_t o = 0;
+    for (const Bucket &B : buckets)
+        for (int k = 0; k < B.m; k++, o++) {
+            out[o].x = B.r[k * 4 + 0]; out[o].y = B.r[k * 4 + 1]; out[o].w = B.r[k * 4 + 2]; out[o].h = B.r[k * 4 + 3];
+            out[o].frame = B.frame; out[o].cascade = B.cascade;
+            if (weights) weights[o] = B.w[k];
+        }
     return 0;
 }

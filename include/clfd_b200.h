@@ -212,6 +212,16 @@ CLFD_API int clfd_detector_get_kernel_ms(clfd_detector *det, float ms[8]);
 CLFD_API int clfd_group_rectangles(int32_t *rects_xywh, int *n, int group_threshold, double eps,
                                    int32_t *weights);
 
+/* The same for the raw rects of a whole batch (as clfd_detect / clfd_detect_collect return
+ * them): grouped per (frame, cascade) on n_threads host threads (0 = all).  Run it for batch i
+ * while the GPU evaluates batch i+1 (clfd_detect_submit) and the O(N^2) grouping of
+ * tempcv.cpp:1462-1472 leaves the critical path.  Inside a (frame, cascade)
+ * group the rects are first ordered by (w, y, x), so the result does not depend on the order in
+ * which the device appended them.  out is sorted by (frame, cascade). */
+CLFD_API int clfd_group_batch(const clfd_rect *rects, int64_t n, int group_threshold, double eps,
+                              int n_threads, clfd_rect *out, int32_t *weights, int64_t cap,
+                              int64_t *n_out);
+
 #ifdef __cplusplus
 }
 #endif

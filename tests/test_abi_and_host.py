@@ -118,3 +118,43 @@ def test_reference_main_cpp_compiles_unchanged(tmp_path):
 def test_clod_demo_is_built():
     assert os.path.exists(os.path.join(ROOT, "examples", "clod_demo"))
     assert os.path.exists(os.path.join(ROOT, "clfacedetection_b200", "libclfd_clod.so"))
+
+
+def test_group_batch_equals_per_frame_grouping():
+    """clfd_group_batch (host threads, per (frame, cascade)) == the oracle's AgroupRectangles run
+    frame by frame on the same rects, whatever order the device appended them in."""
+    import clfacedetection_b200 as clfd
+    import oracle
+    rng = np.random.default_rng(5)
+    recs = []
+    for frame in range(7):
+        for cascade in range(2):
+            k = int(rng.integers(0, 5))
+            for _ in range(k):   # k clusters of jittered rects
+                cx, cy, s = rng.integers(0, 500, 2).tolist() + [int(rng.integers(20, 120))]
+                for _ in range(int(rng.integers(1, 9))):
+                    j = rng.integers(-2, 3, 3)
+                    recs.append((cx + j[0], cy + j[1], s + j[2], s + j[2], frame, cascade))
+    rects = np.array(recs, dtype=clfd.RECT_DTYPE)
+    shuffled = rects[rng.permutation(len(rects))]
+    for thr in (1, 3):
+        got, w = clfd.group_batch(shuffled, thr, 0.2, n_threads=4)
+        again, w2 = clfd.group_batch(rects, thr, 0.2, n_threads=1)
+        assert np.array_equal(got, again) and np.array_equal(w, w2)   # order / thread independent
+        o = 0
+        for frame in range(7):
+            for cascade in range(2):
+                m = (rects["frame"] == frame) & (rects["cascade"] == cascade)
+                r = rects[m]
+                r = r[np.lexsort((r["x"], r["y"], r["w"]))]
+                xywh = np.stack([r["x"], r["y"], r["w"], r["h"]], axis=1).astype(np.int32) if len(r) else np.zeros((0, 4), np.int32)
+                want, ww = oracle.group_rectangles(xywh, thr, 0.2)
+                n = len(want)
+                g = got[o:o + n]
+                assert np.array_equal(np.stack([g["x"], g["y"], g["w"], g["h"]], axis=1), want.reshape(-1, 4))
+                assert np.all(g["frame"] == frame) and np.all(g["cascade"] == cascade)
+                assert np.array_equal(w[o:o + n], ww)
+                o += n
+        assert o == len(got)
+    empty, _ = clfd.group_batch(rects[:0], 3)
+    assert len(empty) == 0
