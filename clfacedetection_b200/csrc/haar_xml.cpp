@@ -1,6 +1,7 @@
-// haar_xml.cpp -- loader for OpenCV old-format Haar cascade files (type_id
-// "opencv-haar-classifier"): the product-side replacement of cvLoad() as called at
-// main.cpp:36, i.e. of icvReadHaarClassifier (tempcv.cpp:1750-2089).
+// haar_xml.cpp -- loader for OpenCV Haar cascade files: the old format (type_id
+// "opencv-haar-classifier"), i.e. the product-side replacement of cvLoad() as called at
+// main.cpp:36 = icvReadHaarClassifier (tempcv.cpp:1750-2089), and the new "opencv-cascade-
+// classifier" format with HAAR features (read_new_cascade below).
 //
 // The reference reads these through OpenCV's CvFileStorage; here a small tolerant XML
 // tokenizer builds an element tree and the cascade is read from it with the same field
@@ -282,6 +283,115 @@ int read_cascade(const Elem &node, HostCascade &c) {
     return 0;
 }
 
+// New-format files (type_id "opencv-cascade-classifier", the on-disk format next to the one the
+// reference loads: SURVEY 8-f row 4; declared in tempcv.hpp:370-491, no reader in the reference
+// tree).  Only stageType BOOST + featureType HAAR; stages are linear (no stage tree).  The
+// content maps one to one onto the old structure:
+//   internalNodes = (left, right, featureIdx, threshold) per node, children > 0 are node indices,
+//   <= 0 are -leafIndex into leafValues -- the convention HostNode::left/right already use;
+//   features[featureIdx] = up to 3 rects "x y w h weight" (+ <tilted>).
+// Stage thresholds are stored as in the old files (the -0.0001f bias of tempcv.cpp:419 is applied
+// by build_hidden), so an old-format file and its converted copy give identical detections.
+int read_new_cascade(const Elem &node, HostCascade &c) {
+    const Elem *st = node.child("stageType"), *ft = node.child("featureType");
+    auto word = [](const Elem *e) { auto t = e ? split_ws(e->text) : std::vector<std::string>(); return t.size() == 1 ? t[0] : std::string(); };
+    if (word(st) != "BOOST") FMT_FAIL("stageType must be BOOST (found '%s')", word(st).c_str());
+    if (word(ft) != "HAAR")
+        FMT_FAIL("featureType '%s' is not supported: this path evaluates Haar features only (LBP / HOG cascades need another evaluator)",
+                 word(ft).c_str());
+    if (!scalar_int(node.child("width"), c.win_w) || c.win_w <= 0) FMT_FAIL("Invalid width node: width must be positive integer");
+    if (!scalar_int(node.child("height"), c.win_h) || c.win_h <= 0) FMT_FAIL("Invalid height node: height must be positive integer");
+    const Elem *features = node.child("features");
+    if (!features || features->kids.empty()) FMT_FAIL("Invalid features node");
+    struct Feat { int rect[3][4]; float weight[3]; int n, tilted; };
+    std::vector<Feat> feats(features->kids.size());
+    for (size_t fi = 0; fi < feats.size(); fi++) {
+        const Elem &fe = *features->kids[fi];
+        Feat &F = feats[fi];
+        memset(&F, 0, sizeof F);
+        const Elem *rects = fe.child("rects");
+        if (!rects || rects->kids.size() < 1 || rects->kids.size() > 3)
+            FMT_FAIL("Rects node is not a valid sequence. (feature %zu)", fi);
+        F.n = (int)rects->kids.size();
+        for (int l = 0; l < F.n; l++) {
+            auto t = split_ws(rects->kids[l]->text);
+            if (t.size() != 5) FMT_FAIL("Rect %d is not a valid sequence. (feature %zu)", l, fi);
+            for (int q = 0; q < 4; q++) {
+                if (!tok_is_int(t[q])) FMT_FAIL("rect coordinates must be integer. (feature %zu, rect %d)", fi, l);
+                F.rect[l][q] = atoi(t[q].c_str());
+            }
+            if (F.rect[l][0] < 0 || F.rect[l][1] < 0 || F.rect[l][2] <= 0 || F.rect[l][3] <= 0)
+                FMT_FAIL("rect must have non-negative origin and positive size. (feature %zu, rect %d)", fi, l);
+            if (!tok_real(t[4], F.weight[l])) FMT_FAIL("weight must be real number. (feature %zu, rect %d)", fi, l);
+        }
+        const Elem *tl = fe.child("tilted");
+        if (tl && !scalar_int(tl, F.tilted)) FMT_FAIL("tilted must be 0 or 1. (feature %zu)", fi);
+    }
+    const Elem *stages = node.child("stages");
+    if (!stages || stages->kids.empty()) FMT_FAIL("Invalid stages node");
+    const int n = (int)stages->kids.size();
+    for (int i = 0; i < n; i++) {
+        const Elem &stage = *stages->kids[i];
+        const Elem *weak = stage.child("weakClassifiers");
+        if (!weak || weak->kids.empty()) FMT_FAIL("weakClassifiers node is not a valid sequence. (stage %d)", i);
+        c.st_ntrees.push_back((int)weak->kids.size());
+        for (int j = 0; j < (int)weak->kids.size(); j++) {
+            const Elem &tree = *weak->kids[j];
+            auto in = tree.child("internalNodes") ? split_ws(tree.child("internalNodes")->text) : std::vector<std::string>();
+            auto lv = tree.child("leafValues") ? split_ws(tree.child("leafValues")->text) : std::vector<std::string>();
+            if (in.empty() || in.size() % 4 != 0)
+                FMT_FAIL("internalNodes must hold (left, right, feature, threshold) quadruples. (stage %d, tree %d)", i, j);
+            const int count = (int)in.size() / 4;
+            if ((int)lv.size() != count + 1)
+                FMT_FAIL("Tree structure is broken: %zu leaf values for %d nodes. (stage %d, tree %d)", lv.size(), count, i, j);
+            c.tr_nnodes.push_back(count);
+            for (int k = 0; k < count; k++) {
+                HostNode hn;
+                memset(&hn, 0, sizeof hn);
+                if (!tok_is_int(in[4 * k]) || !tok_is_int(in[4 * k + 1]) || !tok_is_int(in[4 * k + 2]))
+                    FMT_FAIL("node links and feature index must be integer. (stage %d, tree %d, node %d)", i, j, k);
+                hn.left = atoi(in[4 * k].c_str());
+                hn.right = atoi(in[4 * k + 1].c_str());
+                const int fi = atoi(in[4 * k + 2].c_str());
+                for (int side = 0; side < 2; side++) {
+                    const int v = side ? hn.right : hn.left;
+                    if (v > 0 ? (v <= k || v >= count) : -v > count)
+                        FMT_FAIL("%s node must be valid node number. (stage %d, tree %d, node %d)", side ? "right" : "left", i, j, k);
+                }
+                if (fi < 0 || fi >= (int)feats.size())
+                    FMT_FAIL("feature index %d outside 0..%zu. (stage %d, tree %d, node %d)", fi, feats.size() - 1, i, j, k);
+                if (!tok_real(in[4 * k + 3], hn.threshold))
+                    FMT_FAIL("threshold must be real number. (stage %d, tree %d, node %d)", i, j, k);
+                const Feat &F = feats[fi];
+                hn.tilted = F.tilted != 0;
+                for (int l = 0; l < F.n; l++) {
+                    if (F.rect[l][0] + F.rect[l][2] > c.win_w || F.rect[l][1] + F.rect[l][3] > c.win_h)
+                        FMT_FAIL("rect %d of feature %d does not fit the %dx%d window. (stage %d, tree %d, node %d)", l, fi,
+                                 c.win_w, c.win_h, i, j, k);
+                    for (int q = 0; q < 4; q++) hn.rect[l][q] = F.rect[l][q];
+                    hn.weight[l] = F.weight[l];
+                }
+                c.nodes.push_back(hn);
+            }
+            for (auto &t : lv) {
+                float v;
+                if (!tok_real(t, v)) FMT_FAIL("leaf value must be real number. (stage %d, tree %d)", i, j);
+                c.alpha.push_back(v);
+            }
+        }
+        float thr;
+        const Elem *te = stage.child("stageThreshold");
+        auto tt = te ? split_ws(te->text) : std::vector<std::string>();
+        if (tt.size() != 1 || !tok_real(tt[0], thr)) FMT_FAIL("stage threshold must be real number. (stage %d)", i);
+        c.st_thr.push_back(thr);
+        c.st_parent.push_back(i - 1);   // linear cascade
+        c.st_next.push_back(-1);
+    }
+    c.st_child.assign(n, -1);
+    for (int i = 0; i + 1 < n; i++) c.st_child[i] = i + 1;
+    return 0;
+}
+
 }  // namespace
 
 int load_cascade_xml(const char *path, HostCascade &out) {
@@ -297,13 +407,16 @@ int load_cascade_xml(const char *path, HostCascade &out) {
     Parser ps{buf.data() + start, buf.data() + buf.size(), {}};
     Elem root;
     if (!ps.element(root, 0)) FMT_FAIL("'%s': XML error: %s", path, ps.err.c_str());
-    const Elem *node = nullptr;
-    for (auto &k : root.kids)
-        if (k->type_id == "opencv-haar-classifier") { node = k.get(); break; }
-    if (!node) FMT_FAIL("'%s': no node of type opencv-haar-classifier (new-format cascades are not supported)", path);
+    const Elem *node = nullptr, *node_new = nullptr;
+    for (auto &k : root.kids) {
+        if (k->type_id == "opencv-haar-classifier" && !node) node = k.get();
+        if (k->type_id == "opencv-cascade-classifier" && !node_new) node_new = k.get();
+    }
+    if (!node && !node_new)
+        FMT_FAIL("'%s': no node of type opencv-haar-classifier or opencv-cascade-classifier", path);
     out = HostCascade();
-    out.name = node->name;
-    int rc = read_cascade(*node, out);
+    out.name = (node ? node : node_new)->name;
+    int rc = node ? read_cascade(*node, out) : read_new_cascade(*node_new, out);
     if (rc) return rc;
     return build_hidden(out);
 }

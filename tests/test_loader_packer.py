@@ -109,9 +109,101 @@ def test_missing_and_foreign_files():
         clfd.Cascade("/nonexistent/haarcascade.xml")
     assert e.value.status == -4
     f = tempfile.NamedTemporaryFile("w", suffix=".xml", delete=False)
-    f.write("<?xml version='1.0'?><opencv_storage><cascade type_id=\"opencv-cascade-classifier\"></cascade></opencv_storage>")
+    f.write("<?xml version='1.0'?><opencv_storage><cascade type_id=\"opencv-ml-svm\"></cascade></opencv_storage>")
     f.close()
     with pytest.raises(clfd.ClfdError) as e:
         clfd.Cascade(f.name)
     assert "opencv-haar-classifier" in str(e.value)
+    open(f.name, "w").write("<?xml version='1.0'?><opencv_storage><cascade type_id=\"opencv-cascade-classifier\"></cascade></opencv_storage>")
+    with pytest.raises(clfd.ClfdError) as e:   # new format, but empty
+        clfd.Cascade(f.name)
+    assert "stageType" in str(e.value)
     os.unlink(f.name)
+
+
+def _write_new_format(arrays, win, path, tilted_tag=True):
+    """old-format arrays -> an 'opencv-cascade-classifier' (HAAR, BOOST) file, the way OpenCV's
+    own converter lays it out: one feature per node, internalNodes quadruples, leafValues."""
+    a = arrays
+    out = ["<?xml version=\"1.0\"?>", "<opencv_storage>", "<cascade type_id=\"opencv-cascade-classifier\"><stageType>BOOST</stageType>",
+           "  <featureType>HAAR</featureType>", f"  <height>{win[1]}</height>", f"  <width>{win[0]}</width>",
+           f"  <stageNum>{len(a['st_ntrees'])}</stageNum>", "  <stages>"]
+    t = n = al = 0
+    feats = []
+    for s, nt in enumerate(a["st_ntrees"]):
+        out += ["    <_>", f"      <maxWeakCount>{nt}</maxWeakCount>",
+                f"      <stageThreshold>{float(a['st_thr'][s])!r}</stageThreshold>", "      <weakClassifiers>"]
+        for _ in range(nt):
+            cnt = int(a["tr_nnodes"][t])
+            quad = []
+            for k in range(cnt):
+                quad.append(f"{int(a['nd_left'][n])} {int(a['nd_right'][n])} {len(feats)} {float(a['nd_thr'][n])!r}")
+                feats.append(n)
+                n += 1
+            leaves = " ".join(repr(float(v)) for v in a["alpha"][al:al + cnt + 1])
+            al += cnt + 1
+            out += ["        <_>", "          <internalNodes>", "            " + " ".join(quad) + "</internalNodes>",
+                    "          <leafValues>", "            " + leaves + "</leafValues></_>"]
+            t += 1
+        out += ["      </weakClassifiers></_>"]
+    out += ["  </stages>", "  <features>"]
+    rect = np.asarray(a["nd_rect"]).reshape(-1, 3, 4)
+    wt = np.asarray(a["nd_weight"]).reshape(-1, 3)
+    for n in feats:
+        out += ["    <_>", "      <rects>"]
+        for k in range(3):
+            if rect[n, k, 2] == 0 or rect[n, k, 3] == 0:
+                continue
+            x, y, w, h = (int(v) for v in rect[n, k])
+            out += ["        <_>", f"          {x} {y} {w} {h} {float(wt[n, k])!r}</_>"]
+        out[-1] += "</rects>"
+        if a["nd_tilted"][n] and tilted_tag:
+            out += ["      <tilted>1</tilted>"]
+        out[-1] += "</_>"
+    out += ["  </features></cascade>", "</opencv_storage>", ""]
+    open(path, "w").write("\n".join(out))
+
+
+@pytest.mark.parametrize("name", ["frontalface_alt", "frontalface_alt2", "fullbody"])
+def test_new_format_cascade_equals_old_format(name, tmp_path):
+    """the 'opencv-cascade-classifier' (HAAR) on-disk format carries the same
+    content; the reader must produce the same arrays, hidden cascade and packing as the old file."""
+    old = clfd.Cascade(cascade_path(name))
+    p = str(tmp_path / f"new_{name}.xml")
+    _write_new_format(old.arrays(), (old.info.win_w, old.info.win_h), p)
+    new = clfd.Cascade(p)
+    a, b = old.arrays(), new.arrays()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    for x, y in zip(old.hidden(), new.hidden()):
+        assert np.array_equal(x, y)
+    for f in ("n_stages", "n_trees", "n_nodes", "is_tree", "is_stump_based", "has_tilted", "dense_stages", "dense_stumps"):
+        assert getattr(old.info, f) == getattr(new.info, f), f
+
+
+def test_new_format_rejects_lbp_and_broken_trees(tmp_path):
+    old = clfd.Cascade(cascade_path("eye"))
+    p = str(tmp_path / "x.xml")
+    _write_new_format(old.arrays(), (20, 20), p)
+    text = open(p).read()
+    for bad, msg in [(text.replace("<featureType>HAAR", "<featureType>LBP"), "LBP"),
+                     (text.replace("<stageType>BOOST", "<stageType>TREE"), "stageType"),
+                     (text.replace("</leafValues>", " 0.5</leafValues>", 1), "leaf values"),
+                     (text.replace("<width>20</width>", "<width>10</width>"), "does not fit")]:
+        q = str(tmp_path / "bad.xml")
+        open(q, "w").write(bad)
+        with pytest.raises(clfd.ClfdError) as e:
+            clfd.Cascade(q)
+        assert msg in str(e.value)
+
+
+def test_new_format_files_shipped_with_cv2_if_present():
+    cv2 = pytest.importorskip("cv2")
+    import os
+    d = getattr(getattr(cv2, "data", None), "haarcascades", None)
+    if not d or not os.path.exists(os.path.join(d, "haarcascade_eye.xml")):
+        pytest.skip("cv2 ships no cascade data here")
+    for name in ("eye", "frontalface_default", "profileface"):
+        old, new = clfd.Cascade(cascade_path(name)), clfd.Cascade(os.path.join(d, f"haarcascade_{name}.xml"))
+        a, b = old.arrays(), new.arrays()
+        assert all(np.array_equal(a[k], b[k]) for k in a)
