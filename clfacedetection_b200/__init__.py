@@ -161,11 +161,13 @@ class Detector:
 
     def __init__(self, ctx: Context, cascades, width: int, height: int, *, max_batch: int = 1,
                  scale_factor: float = 1.1, min_size=(0, 0), max_size=(0, 0), want_codes: bool = False,
-                 max_rects: int = 0):
+                 max_rects: int = 0, scale_cascade: bool = False):
+        """scale_cascade: CLFD_MODE_SCALE_CASCADE (one integral image, scaled features: what the
+        cvHaarDetectObjects call of main.cpp:145 computes) instead of the image pyramid"""
         self.ctx = ctx
         self.cascades = list(cascades) if isinstance(cascades, (list, tuple)) else [cascades]
         cfg = abi.DetectorConfig(width, height, max_batch, scale_factor, min_size[0], min_size[1],
-                                 max_size[0], max_size[1], int(want_codes), max_rects)
+                                 max_size[0], max_size[1], int(want_codes), max_rects, int(scale_cascade))
         self.cfg = cfg
         arr = (C.c_void_p * len(self.cascades))(*[c._h for c in self.cascades])
         self._h = C.c_void_p()

@@ -33,7 +33,7 @@ class DetectorConfig(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("max_batch", C.c_int),
                 ("scale_factor", C.c_double), ("min_w", C.c_int), ("min_h", C.c_int),
                 ("max_w", C.c_int), ("max_h", C.c_int), ("want_codes", C.c_int),
-                ("max_rects", C.c_int64)]
+                ("max_rects", C.c_int64), ("mode", C.c_int)]
 
 
 class Rect(C.Structure):

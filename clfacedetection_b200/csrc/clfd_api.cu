@@ -236,6 +236,11 @@ struct CascadePlan {
     DevBuf<DeepNode> d_nodes;
     DevBuf<int> d_tree_first;
     DevBuf<float> d_alpha;
+    // scale-cascade mode
+    std::vector<ScLevel> sc_levels;
+    DevBuf<ScLevel> d_sc_levels;
+    DevBuf<ScNode> d_sc_nodes;
+    int sc_rows = 0;
     DevBuf<TailStump> d_tail[2];   // warp-per-window tail records of the tile kernel, [ystep-1]
     DenseParams dense[2];          // the cascade's parameter blobs with this detector's tail pointers
     DevBuf<int16_t> d_codes;
@@ -580,10 +585,9 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
     int max_w = cfg->max_w, max_h = cfg->max_h;
     if (max_h == 0 || max_w == 0) { max_h = H; max_w = W; }   // tempcv.cpp:1230-1234
 
-    // level loop, all cascades in lock step over the shared factor sequence
+    if (cfg->mode != CLFD_MODE_SCALE_IMAGE && cfg->mode != CLFD_MODE_SCALE_CASCADE) INVALID("unknown mode %d", cfg->mode);
+    const bool scale_cascade = cfg->mode == CLFD_MODE_SCALE_CASCADE;
     std::vector<std::pair<int, int>> sizes;          // union pyramid
-    std::map<int, int> pyr_index;                    // factor index -> pyramid level
-    std::vector<bool> done(n_cascades, false);
     bool any_tilted = false;
     for (int ci = 0; ci < n_cascades; ci++) {
         if (!cascades[ci]) INVALID("cascade %d is NULL", ci);
@@ -591,6 +595,49 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
         det->cas.back()->cascade = cascades[ci];
         any_tilted |= cascades[ci]->host.has_tilted;
     }
+    if (scale_cascade) {
+        // one "pyramid level": the frame itself (a same-size INTER_LINEAR resize is the identity)
+        sizes.push_back({W, H});
+        const int pitch = (int)round_up(W + 1, 8);
+        for (int ci = 0; ci < n_cascades; ci++) {
+            CascadePlan &cp = *det->cas[ci];
+            const HostCascade &hc = cascades[ci]->host;
+            int n_factors = 0;   // tempcv.cpp:1344-1350
+            double factor = 1;
+            for (; factor * hc.win_w < W - 10 && factor * hc.win_h < H - 10; factor *= cfg->scale_factor) n_factors++;
+            factor = 1;
+            for (; n_factors-- > 0; factor *= cfg->scale_factor) {   // tempcv.cpp:1361-1380
+                const double ystep = std::max(2., factor);
+                const int win_w = cv_round(hc.win_w * factor), win_h = cv_round(hc.win_h * factor);
+                const int endX = cv_round((W - win_w) / ystep), endY = cv_round((H - win_h) / ystep);
+                if (win_w < cfg->min_w || win_h < cfg->min_h) continue;
+                if (endX <= 0 || endY <= 0) continue;
+                if (cp.sc_levels.size() >= 255) INVALID("more than 255 scales");
+                ScLevel L;
+                memset(&L, 0, sizeof L);
+                L.factor = factor; L.ystep = ystep; L.win_w = win_w; L.win_h = win_h; L.nx = endX; L.ny = endY;
+                L.node_base = (int)(cp.sc_levels.size() * hc.n_nodes());
+                L.row_base = cp.sc_rows; L.win_base = cp.windows_per_frame;
+                cp.sc_rows += endY;
+                cp.windows_per_frame += (long long)endX * endY;
+                cp.sc_levels.push_back(L);
+                clfd_level pl;
+                pl.factor = factor; pl.img_w = W; pl.img_h = H; pl.win_w = win_w; pl.win_h = win_h;
+                pl.ystep = 0; pl.nx = endX; pl.ny = endY; pl.win_base = L.win_base;
+                cp.pub_levels.push_back(pl);
+            }
+            std::vector<ScNode> nodes(cp.sc_levels.size() * (size_t)hc.n_nodes());
+            for (size_t li = 0; li < cp.sc_levels.size(); li++)
+                pack_sc_level(hc, cp.sc_levels[li].factor, pitch, cp.sc_levels[li], nodes.data() + li * hc.n_nodes());
+            int rc2;
+            if ((rc2 = cp.d_sc_levels.upload(cp.sc_levels, ctx->stream)) || (rc2 = cp.d_sc_nodes.upload(nodes, ctx->stream))) return rc2;
+            CK(cudaStreamSynchronize(ctx->stream));   // `nodes` goes out of scope
+            cp.bytes_cascade += (int64_t)(W + 1) * (H + 1) * (4 + 8 + (hc.has_tilted ? 4 : 0)) + nodes.size() * sizeof(ScNode);
+        }
+    } else {
+    // level loop, all cascades in lock step over the shared factor sequence
+    std::map<int, int> pyr_index;                    // factor index -> pyramid level
+    std::vector<bool> done(n_cascades, false);
     double factor = 1;
     for (int k = 0;; k++, factor *= cfg->scale_factor) {
         bool all_done = true;
@@ -630,6 +677,7 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
         }
         if (all_done) break;
     }
+    }
     cudaStream_t s = ctx->stream;
     int rc = 0;
     if (!sizes.empty() && (rc = det->pyr.build(W, H, sizes, cfg->max_batch, any_tilted, s))) return rc;
@@ -649,12 +697,12 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
             cp.dense[yi].tail = cp.d_tail[yi].p;
         }
         if ((rc = cp.d_counters.alloc(4 * kSlots))) return rc;
-        if (cfg->want_codes && (rc = cp.d_codes.alloc((size_t)std::max<long long>(cp.windows_per_frame, 1) * cfg->max_batch)))
+        if ((cfg->want_codes || scale_cascade) && (rc = cp.d_codes.alloc((size_t)std::max<long long>(cp.windows_per_frame, 1) * cfg->max_batch)))
             return rc;
         max_wpf = std::max(max_wpf, cp.windows_per_frame);
         cp.bytes_cascade += cp.cascade->packed.deep_nodes.size() * sizeof(DeepNode);
     }
-    det->queue_cap = (unsigned long long)std::max<long long>(max_wpf, 1) * cfg->max_batch;
+    det->queue_cap = scale_cascade ? 1 : (unsigned long long)std::max<long long>(max_wpf, 1) * cfg->max_batch;   // (no queue in scale-cascade mode)
     det->rect_cap = cfg->max_rects > 0 ? (unsigned long long)cfg->max_rects : (1ull << 20);
     if ((rc = det->queue.alloc(det->queue_cap)) || (rc = det->rects.alloc(det->rect_cap))) return rc;
     CK(cudaMallocHost((void **)&det->h_rects, det->rect_cap * sizeof(DevRect)));
@@ -746,6 +794,28 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
             a.deep.has_tilted = cp.cascade->host.has_tilted;
             a.deep.win_w = cp.cascade->host.win_w; a.deep.win_h = cp.cascade->host.win_h;
             a.deep.inv_area = pk.dense[0].inv_area;
+            if (det->cfg.mode == CLFD_MODE_SCALE_CASCADE) {
+                ScArgs sa;
+                memset(&sa, 0, sizeof sa);
+                const PyrLevel &L0 = det->pyr.levels[0];
+                sa.sum = a.sum + L0.sum_off; sa.sq = a.sq + L0.sum_off; sa.tilted = a.tilted ? a.tilted + L0.sum_off : nullptr;
+                sa.sum_frame_stride = a.sum_frame_stride;
+                sa.pitch = L0.sum_pitch; sa.W = det->cfg.width; sa.H = det->cfg.height;
+                sa.levels = cp.d_sc_levels.p; sa.nodes = cp.d_sc_nodes.p;
+                sa.n_levels = (int)cp.sc_levels.size(); sa.rows_per_frame = cp.sc_rows; sa.n_frames = n_frames;
+                sa.cascade_index = ci; sa.frame_base = frame_base; sa.windows_per_frame = cp.windows_per_frame;
+                sa.codes = cp.d_codes.p + (size_t)frame_base * cp.windows_per_frame;
+                sa.rects = a.rects; sa.rect_cap = a.rect_cap; sa.counters = a.counters; sa.deep = a.deep;
+                if (ev && ci == 0) CK(cudaEventRecord(ev[5], s));
+                CK(launch_sc(sa, s));
+                launches += 2;
+                if (ev && ci == 0) { CK(cudaEventRecord(ev[6], s)); CK(cudaEventRecord(ev[7], s)); }
+                if (ci + 1 < (int)det->cas.size())
+                    CK(cudaMemcpyAsync(det->cas[ci + 1]->d_counters.p + 4 * slot, cp.d_counters.p + 4 * slot, sizeof(unsigned long long),
+                                       cudaMemcpyDeviceToDevice, s));
+                ci++;
+                continue;
+            }
             if (ev && ci == 0) CK(cudaEventRecord(ev[5], s));
             if (pk.dense[0].tail_stages > 0) {
                 // ystep-2 levels (de-interleaved tile layout) and ystep-1 levels (natural layout)
@@ -966,7 +1036,7 @@ int clfd_detect(clfd_detector *det, const uint8_t *frames_host, int n_frames, si
 
 int clfd_detector_get_codes(clfd_detector *det, int cascade, int16_t *codes, int64_t cap) {
     if (!det || !codes || cascade < 0 || cascade >= (int)det->cas.size()) INVALID("bad argument");
-    if (!det->cfg.want_codes) INVALID("detector was created without want_codes");
+    if (!det->cfg.want_codes && det->cfg.mode != CLFD_MODE_SCALE_CASCADE) INVALID("detector was created without want_codes");
     CK(cudaSetDevice(det->ctx->device));
     CascadePlan &cp = *det->cas[cascade];
     const int64_t n = cp.windows_per_frame * det->last_frames;

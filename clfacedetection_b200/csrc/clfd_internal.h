@@ -162,6 +162,27 @@ struct CasLevel {
     double factor;
 };
 
+// Scale-cascade mode (REF-SC, tempcv.cpp:1330-1456): one full-frame integral image, the
+// FEATURES scaled per factor (cvSetImagesForHaarClassifierCascade, tempcv.cpp:549-768).
+struct alignas(16) ScNode {   // 80 B: one tree node with its rects scaled for one factor
+    int off[12];            // element offsets dy*pitch + dx of p0..p3 of rect 0,1,2 in the frame's integral
+    float w[3];
+    float thr;
+    int left, right;        // >0 node index in tree, <=0 leaf -idx
+    int flags;              // bit0 tilted, bits 8.. nrects
+    int pad;
+};
+struct ScLevel {          // one scale
+    double factor, ystep, inv_area;
+    int win_w, win_h, nx, ny;   // nx, ny = endX, endY of the invoker's grid
+    int eq_off[4];              // equRect corners as element offsets
+    int node_base;              // first ScNode of this scale
+    int row_base;               // first grid row of this scale among all rows of a frame
+    long long win_base;         // first window of this scale among all windows of a frame
+};
+constexpr int kScCodeSkipped = -32768;   // grid position the skip rule never evaluates (tempcv.cpp:1161)
+constexpr int kScCodeOutside = -32767;   // window rejected by the bounds check (tempcv.cpp:817-820, result -1)
+
 struct QueueItem {        // survivor handed to the deep kernel
     uint32_t key;           // frame << 16 | cas_level << 8 | next_stage
     uint32_t xy;            // y << 16 | x   (window origin, pixels of the level)

@@ -15,6 +15,9 @@ struct PackedCascade {
 };
 
 void pack_cascade(const HostCascade &c, PackedCascade &out);
+// cvSetImagesForHaarClassifierCascade(scale) (tempcv.cpp:549-768) for one factor of the scale-cascade
+// mode: fills L.inv_area / L.eq_off and n_nodes() ScNodes at `out` (pitch = elements per integral row)
+void pack_sc_level(const HostCascade &c, double factor, int pitch, ScLevel &L, ScNode *out);
 const char *get_error();
 
 int dense_tile_stride(int win_w, int ystep);  // ints per smem tile row (ystep * stride = 8 mod 32)

@@ -185,6 +185,50 @@ int dense_tile_stride(int win_w, int ystep) {
     return s;
 }
 
+static inline int cv_round_d(double v) { return (int)lrint(v); }   // cvRound: round half to even
+
+void pack_sc_level(const HostCascade &c, double scale, int pitch, ScLevel &L, ScNode *out) {
+    // tempcv.cpp:614-618
+    const int ex = cv_round_d(scale), ey = ex;
+    const int ew = cv_round_d((c.win_w - 2) * scale), eh = cv_round_d((c.win_h - 2) * scale);
+    const double weight_scale = 1. / (ew * eh);
+    L.inv_area = weight_scale;
+    L.eq_off[0] = ey * pitch + ex; L.eq_off[1] = ey * pitch + ex + ew;
+    L.eq_off[2] = (ey + eh) * pitch + ex; L.eq_off[3] = (ey + eh) * pitch + ex + ew;
+    for (int n = 0; n < c.n_nodes(); n++) {   // tempcv.cpp:636-760; the flagx / flagy branch is dead (kx, ky >= 1)
+        const HostNode &nd = c.nodes[n];
+        ScNode &d = out[n];
+        memset(&d, 0, sizeof d);
+        const int nr = c.hid_nrects[n];
+        double sum0 = 0, area0 = 0;
+        const double correction_ratio = weight_scale * (!nd.tilted ? 1 : 0.5);   // :733
+        for (int k = 0; k < nr; k++) {
+            const int tx = cv_round_d(nd.rect[k][0] * scale), tw = cv_round_d(nd.rect[k][2] * scale);   // :704-716
+            const int ty = cv_round_d(nd.rect[k][1] * scale), th = cv_round_d(nd.rect[k][3] * scale);
+            int dy[4], dx[4];
+            if (!nd.tilted) {   // :738-741
+                dy[0] = ty;      dx[0] = tx;
+                dy[1] = ty;      dx[1] = tx + tw;
+                dy[2] = ty + th; dx[2] = tx;
+                dy[3] = ty + th; dx[3] = tx + tw;
+            } else {            // :745-749
+                dy[2] = ty + tw;      dx[2] = tx + tw;
+                dy[3] = ty + tw + th; dx[3] = tx + tw - th;
+                dy[0] = ty;           dx[0] = tx;
+                dy[1] = ty + th;      dx[1] = tx - th;
+            }
+            for (int q = 0; q < 4; q++) d.off[k * 4 + q] = dy[q] * pitch + dx[q];
+            d.w[k] = (float)(nd.weight[k] * correction_ratio);   // :752
+            if (k == 0) area0 = tw * th;
+            else sum0 += d.w[k] * tw * th;   // float*int*int evaluated in float, :757
+        }
+        d.w[0] = (float)(-sum0 / area0);   // :760
+        d.thr = nd.threshold;
+        d.left = nd.left; d.right = nd.right;
+        d.flags = (nd.tilted ? 1 : 0) | (nr << 8);
+    }
+}
+
 void pack_cascade(const HostCascade &c, PackedCascade &out) {
     const int S = c.n_stages(), T = c.n_trees(), N = c.n_nodes();
     out.deep_stages.resize(S);

@@ -60,4 +60,21 @@ cudaError_t launch_cascade_deep(const CascadeArgs &a, int n_sms, cudaStream_t st
 
 size_t dense_smem_bytes(const DenseParams &P);
 
+// ---- scale-cascade mode (kernels_sc.cu) -----------------------------------------------
+struct ScArgs {
+    const int32_t *sum; const unsigned long long *sq; const int32_t *tilted;   // full-frame integrals (level 0)
+    size_t sum_frame_stride;
+    int pitch, W, H;                // elements per integral row, frame size
+    const ScLevel *levels;          // device
+    const ScNode *nodes;            // device, n_levels x n_nodes
+    int n_levels, rows_per_frame, n_frames, cascade_index, frame_base;
+    long long windows_per_frame;
+    int16_t *codes;                 // device, [n_frames][windows_per_frame] (always present in this mode)
+    DevRect *rects; unsigned long long rect_cap;
+    unsigned long long *counters;   // [0] rects [2] rect overflow
+    DeepCascadeDev deep;            // stages / tree_first_node / alpha (scale independent)
+};
+// every grid position of every scale (k_sc_eval), then the invoker's skip rule + rect emission (k_sc_rows)
+cudaError_t launch_sc(const ScArgs &a, cudaStream_t stream);
+
 }  // namespace clfd

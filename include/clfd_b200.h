@@ -138,7 +138,21 @@ typedef struct clfd_detector_config {
     int max_w, max_h;         /* maximum window (0 = image size, clod.cpp:394-397) */
     int want_codes;           /* keep per-window exit codes (parity tests) */
     int64_t max_rects;        /* device rect capacity per call (0 = default) */
+    int mode;                 /* CLFD_MODE_SCALE_IMAGE (0, default) or CLFD_MODE_SCALE_CASCADE */
 } clfd_detector_config;
+/* CLFD_MODE_SCALE_IMAGE  : image pyramid, cascade at scale 1 -- the CV_HAAR_SCALE_IMAGE path the
+ *                          north star names (tempcv.cpp:1257-1329).
+ * CLFD_MODE_SCALE_CASCADE: ONE integral image, features scaled per factor, window step
+ *                          max(2, factor) and the skip-after-stage-0-reject rule -- what the
+ *                          cvHaarDetectObjects call of main.cpp:145 (flags 0) computes
+ *                          (tempcv.cpp:1330-1456, 1132-1175) and the formulation of clod's own
+ *                          runStage (clod.cpp:1176-1336).  max_w / max_h are ignored (the
+ *                          reference's scale loop has no upper limit but the image).  Exit codes
+ *                          additionally use -32768 (position skipped by the rule) and -32767
+ *                          (window rejected by the bounds check).  clfd_level.ystep is 0: the step
+ *                          is max(2, factor); window (ix, iy) sits at cvRound(ix*step), cvRound(iy*step). */
+#define CLFD_MODE_SCALE_IMAGE 0
+#define CLFD_MODE_SCALE_CASCADE 1
 
 typedef struct clfd_rect {
     int32_t x, y, w, h;   /* CvRect of the accepted window (tempcv.cpp:1099-1100) */

@@ -68,6 +68,12 @@ def lib():
         L.vjo_detect.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_double,
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int64,
                                  C.POINTER(C.c_int16), C.POINTER(C.c_uint8), C.POINTER(_Stats), C.c_int]
+        L.vjo_plan_sc.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                  C.POINTER(_Level), C.c_int]
+        L.vjo_detect_sc.restype = C.c_int64
+        L.vjo_detect_sc.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_double,
+                                    C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int16),
+                                    C.POINTER(_Stats), C.c_int]
         L.vjo_eval_level.restype = C.c_int64
         L.vjo_eval_level.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.POINTER(C.c_int16), C.POINTER(C.c_uint8), C.POINTER(_Stats), C.c_int]
@@ -102,6 +108,9 @@ class Stats:
 def _stats(s: _Stats) -> Stats:
     return Stats(s.windows, s.weak_evals, s.node_evals, s.accepted, s.near_stage_thr,
                  list(s.stage_reach))
+
+
+CODE_SKIPPED, CODE_OUTSIDE = -32768, -32767
 
 
 class Cascade:
@@ -170,6 +179,33 @@ class Cascade:
                 break
             cap = int(n)
         return rects[:n].copy(), codes, near, _stats(st), levels
+
+    def detect_sc(self, img: np.ndarray, scale_factor: float, min_size=(0, 0), want_codes: bool = True,
+                  n_threads: int = 0):
+        """REF-SC (scale-cascade, tempcv.cpp:1330-1456) detection of one gray frame
+        -> (rects[n,4], codes, Stats, levels); codes use CODE_SKIPPED / CODE_OUTSIDE."""
+        img = np.ascontiguousarray(img, np.uint8)
+        H, W = img.shape
+        buf = (_Level * 256)()
+        nl = lib().vjo_plan_sc(W, H, self.flat.win_w, self.flat.win_h, scale_factor, min_size[0], min_size[1], buf, 256)
+        if nl < 0:
+            raise ValueError(lib().vjo_last_error().decode())
+        levels = [Level(b.factor, b.img_w, b.img_h, b.win_w, b.win_h, b.ystep, b.nx, b.ny) for b in buf[:nl]]
+        nwin = sum(l.nx * l.ny for l in levels)
+        codes = np.zeros(nwin, np.int16) if want_codes else None
+        cap = 1 << 16
+        st = _Stats()
+        while True:
+            rects = np.zeros((cap, 4), np.int32)
+            n = lib().vjo_detect_sc(self._h, _p(img, C.c_uint8), W, H, img.strides[0], scale_factor,
+                                    min_size[0], min_size[1], _p(rects, C.c_int32), cap, _p(codes, C.c_int16),
+                                    C.byref(st), n_threads)
+            if n < 0:
+                raise ValueError(lib().vjo_last_error().decode())
+            if n <= cap:
+                break
+            cap = int(n)
+        return rects[:n].copy(), codes, _stats(st), levels
 
     def eval_level(self, img: np.ndarray, ystep: int, n_threads: int = 0):
         """All grid windows of one image evaluated as a single level (no resize)."""

@@ -671,6 +671,154 @@ int64_t vjo_detect(const vjo_cascade *c, const uint8_t *img, int W, int H, int s
 }
 
 /* ------------------------------------------------------------------------------------
+ * REF-SC: the scale-cascade path of cvHaarDetectObjectsForROC (tempcv.cpp:1330-1456 with
+ * flags = 0: no Canny pruning, no biggest-object search), i.e. what main.cpp:145 runs:
+ * ONE integral image of the full frame, the FEATURES scaled per factor by
+ * cvSetImagesForHaarClassifierCascade (tempcv.cpp:549-768), windows on the grid of
+ * HaarDetectObjects_ScaleCascade_Invoker (tempcv.cpp:1132-1175) including its skip rule:
+ * after a window whose cvRunHaarClassifierCascade result is 0 the next x position is
+ * skipped (result 0 = rejected by stage 0 of a linear cascade, tempcv.cpp:946 "-i", or ANY
+ * rejection of a stage-tree cascade, tempcv.cpp:857).
+ * ---------------------------------------------------------------------------------- */
+int vjo_plan_sc(int W, int H, int w0, int h0, double scale_factor, int min_w, int min_h,
+                vjo_level *levels, int max_levels)
+{
+    if (!(scale_factor > 1)) { FAIL("scale factor must be > 1"); return -1; }
+    int n_factors = 0, n = 0;
+    double factor;
+    for (factor = 1; factor * w0 < W - 10 && factor * h0 < H - 10; factor *= scale_factor) n_factors++; /* :1344-1350 */
+    factor = 1;
+    for (; n_factors-- > 0; factor *= scale_factor) { /* :1361 */
+        const double ystep = factor > 2. ? factor : 2.; /* :1365 */
+        const int win_w = cv_round(w0 * factor), win_h = cv_round(h0 * factor);
+        const int endX = cv_round((W - win_w) / ystep), endY = cv_round((H - win_h) / ystep); /* :1371-1372 */
+        if (win_w < min_w || win_h < min_h) continue; /* :1374-1379 */
+        if (n >= max_levels) { FAIL("too many scales"); return -1; }
+        vjo_level *L = &levels[n++];
+        L->factor = factor; L->img_w = W; L->img_h = H; L->win_w = win_w; L->win_h = win_h;
+        L->ystep = 0; /* the step is max(2, factor), a double */
+        L->nx = endX > 0 ? endX : 0; L->ny = endY > 0 ? endY : 0;
+    }
+    return n;
+}
+
+/* cvSetImagesForHaarClassifierCascade(scale) on a copy of the nodes (tempcv.cpp:614-618,636-760) */
+static void sc_set_scale(const vjo_cascade *c, double scale, int step, node_t *lvl, double *inv_area, int eq_off[4])
+{
+    const int ex = cv_round(scale), ey = ex; /* :614 */
+    const int ew = cv_round((c->win_w - 2) * scale), eh = cv_round((c->win_h - 2) * scale);
+    const double weight_scale = 1. / (ew * eh);
+    *inv_area = weight_scale;
+    eq_off[0] = ey * step + ex; eq_off[1] = ey * step + ex + ew;
+    eq_off[2] = (ey + eh) * step + ex; eq_off[3] = (ey + eh) * step + ex + ew;
+    memcpy(lvl, c->nodes, sizeof(node_t) * c->n_nodes);
+    for (int n = 0; n < c->n_nodes; n++) {
+        node_t *nd = &lvl[n];
+        double sum0 = 0, area0 = 0;
+        for (int k = 0; k < nd->nrects; k++) { /* kx, ky >= 1 (checked at creation): the flagx/flagy branch is dead */
+            rect_t tr;
+            tr.x = cv_round(nd->r[k].x * scale); tr.w = cv_round(nd->r[k].w * scale);
+            tr.y = cv_round(nd->r[k].y * scale); tr.h = cv_round(nd->r[k].h * scale);
+            const double correction_ratio = weight_scale * (!nd->tilted ? 1 : 0.5);
+            int dy[4], dx[4];
+            if (!nd->tilted) {
+                dy[0] = tr.y;        dx[0] = tr.x;
+                dy[1] = tr.y;        dx[1] = tr.x + tr.w;
+                dy[2] = tr.y + tr.h; dx[2] = tr.x;
+                dy[3] = tr.y + tr.h; dx[3] = tr.x + tr.w;
+            } else {
+                dy[2] = tr.y + tr.w;        dx[2] = tr.x + tr.w;
+                dy[3] = tr.y + tr.w + tr.h; dx[3] = tr.x + tr.w - tr.h;
+                dy[0] = tr.y;               dx[0] = tr.x;
+                dy[1] = tr.y + tr.h;        dx[1] = tr.x - tr.h;
+            }
+            for (int q = 0; q < 4; q++) nd->off[k][q] = dy[q] * step + dx[q];
+            nd->weight[k] = (float)(nd->xml_weight[k] * correction_ratio);
+            if (k == 0) area0 = tr.w * tr.h;
+            else sum0 += nd->weight[k] * tr.w * tr.h;
+        }
+        nd->weight[0] = (float)(-sum0 / area0);
+    }
+}
+
+int64_t vjo_detect_sc(const vjo_cascade *c, const uint8_t *img, int W, int H, int stride,
+                      double scale_factor, int min_w, int min_h,
+                      int32_t *rects, int64_t cap, int16_t *codes, vjo_stats *stats, int n_threads)
+{
+    vjo_level lv[256];
+    const int nl = vjo_plan_sc(W, H, c->win_w, c->win_h, scale_factor, min_w, min_h, lv, 256);
+    if (nl < 0) return -1;
+    vjo_stats total; memset(&total, 0, sizeof total);
+    const size_t n1 = (size_t)(W + 1) * (H + 1);
+    int32_t *sum = (int32_t *)malloc(n1 * sizeof(int32_t));
+    double *sq = (double *)malloc(n1 * sizeof(double));
+    int32_t *tl = c->has_tilted ? (int32_t *)malloc(n1 * sizeof(int32_t)) : NULL;
+    node_t *lvl = (node_t *)malloc(sizeof(node_t) * c->n_nodes);
+    vjo_integral(img, W, H, stride, sum, sq, tl); /* :1335 */
+    const level_img im = { sum, tl, sq, W + 1 };
+    int64_t n_out = 0; size_t woff = 0;
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+#else
+    n_threads = 1;
+#endif
+    for (int l = 0; l < nl; l++) {
+        const vjo_level *L = &lv[l];
+        const size_t nwin = (size_t)L->nx * L->ny;
+        if (nwin == 0) continue;
+        const double ystep = L->factor > 2. ? L->factor : 2.;
+        vjo_cascade cs = *c; /* shallow copy: only inv_window_area differs per scale */
+        int eq_off[4];
+        sc_set_scale(c, L->factor, im.step, lvl, &cs.inv_window_area, eq_off);
+        int16_t *lc = codes ? codes + woff : (int16_t *)malloc(nwin * sizeof(int16_t));
+#pragma omp parallel num_threads(n_threads)
+        {
+            vjo_stats local; memset(&local, 0, sizeof local);
+#pragma omp for schedule(dynamic, 4)
+            for (int iy = 0; iy < L->ny; iy++) { /* :1139-1165 */
+                const int y = cv_round(iy * ystep);
+                int ixstep = 1;
+                for (int ix = 0; ix < L->nx; ix++) lc[(size_t)iy * L->nx + ix] = VJO_CODE_SKIPPED;
+                for (int ix = 0; ix < L->nx; ix += ixstep) {
+                    const int x = cv_round(ix * ystep);
+                    int code, result;
+                    if (x < 0 || y < 0 || x + L->win_w >= W + 1 || y + L->win_h >= H + 1) { /* :817-820: returns -1 */
+                        code = VJO_CODE_OUTSIDE; result = -1;
+                    } else {
+                        int nf = 0;
+                        code = run_window(&cs, lvl, &im, x, y, eq_off, &nf, &local);
+                        if (c->is_tree) result = code & 1;               /* 0 on any rejection, :857 */
+                        else result = code == c->count ? 1 : -code;      /* -i, :946,966 */
+                    }
+                    lc[(size_t)iy * L->nx + ix] = (int16_t)code;
+                    ixstep = result != 0 ? 1 : 2; /* :1161 */
+                }
+            }
+#pragma omp critical
+            stats_add(&total, &local);
+        }
+        for (int iy = 0; iy < L->ny; iy++)
+            for (int ix = 0; ix < L->nx; ix++) {
+                const int code = lc[(size_t)iy * L->nx + ix];
+                if (code >= 0 && code_accepts(c, code)) {
+                    if (rects && n_out < cap) { /* :1159-1160 */
+                        rects[n_out * 4 + 0] = cv_round(ix * ystep);
+                        rects[n_out * 4 + 1] = cv_round(iy * ystep);
+                        rects[n_out * 4 + 2] = L->win_w;
+                        rects[n_out * 4 + 3] = L->win_h;
+                    }
+                    n_out++;
+                }
+            }
+        if (!codes) free(lc);
+        woff += nwin;
+    }
+    free(sum); free(sq); free(tl); free(lvl);
+    if (stats) *stats = total;
+    return n_out;
+}
+
+/* ------------------------------------------------------------------------------------
  * AgroupRectangles (tempcv.cpp:130-243); cv::partition is external OpenCV (call site
  * tempcv.cpp:160): connected components of the similarity graph, classes numbered in
  * order of their first member.

@@ -109,6 +109,20 @@ int64_t vjo_eval_level(const vjo_cascade *c, const uint8_t *img, int w, int h, i
                        int ystep, int16_t *codes, uint8_t *near, vjo_stats *stats,
                        int n_threads);
 
+/* REF-SC: the scale-cascade path (tempcv.cpp:1330-1456, flags = 0; what main.cpp:145 runs):
+ * one integral image, features scaled per factor (tempcv.cpp:549-768), grid and skip rule of
+ * HaarDetectObjects_ScaleCascade_Invoker (tempcv.cpp:1132-1175).  vjo_plan_sc fills one
+ * vjo_level per evaluated scale (img_w/h = frame size, ystep = 0: the step is max(2, factor),
+ * nx/ny = endX/endY).  codes: as vjo_detect, plus VJO_CODE_SKIPPED for grid positions the skip
+ * rule never evaluates and VJO_CODE_OUTSIDE for windows the bounds check rejects (result -1). */
+#define VJO_CODE_SKIPPED (-32768)
+#define VJO_CODE_OUTSIDE (-32767)
+int vjo_plan_sc(int W, int H, int w0, int h0, double scale_factor, int min_w, int min_h,
+                vjo_level *levels, int max_levels);
+int64_t vjo_detect_sc(const vjo_cascade *c, const uint8_t *img, int W, int H, int stride,
+                      double scale_factor, int min_w, int min_h,
+                      int32_t *rects, int64_t cap, int16_t *codes, vjo_stats *stats, int n_threads);
+
 /* AgroupRectangles(rectList, weights, groupThreshold, eps) (tempcv.cpp:130-243).
  * rects in/out [n][4]; weights out [n]; returns the new count. */
 int vjo_group_rectangles(int32_t *rects, int n, int group_threshold, double eps,

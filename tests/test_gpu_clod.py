@@ -238,3 +238,42 @@ def test_submit_collect_pipeline_keeps_batches_apart(gpu_ctx):
         det.submit(pinned[2])    # two already in flight
     det.collect(); det.collect()
     det.close()
+
+
+@pytest.mark.parametrize("name,sf,shape", [("frontalface_alt", 1.2, (640, 480)), ("frontalface_alt2", 1.3, (500, 380)),
+                                           ("frontalface_alt_tree", 1.25, (480, 360)), ("fullbody", 1.2, (400, 420))])
+def test_scale_cascade_mode_equals_ref_sc_oracle(gpu_ctx, name, sf, shape):
+    """CLFD_MODE_SCALE_CASCADE: one integral image, features scaled per factor,
+    step max(2, factor) and the skip rule of HaarDetectObjects_ScaleCascade_Invoker -- exit codes
+    (including skipped / out-of-bounds markers) and the rect set identical to the REF-SC oracle."""
+    W, H = shape
+    frames = np.stack([octave_frame(W, H, 21), uniform_frame(W, H, 22), np.full((H, W), 255, np.uint8)])
+    cas = clfd.Cascade(cascade_path(name))
+    det = clfd.Detector(gpu_ctx, cas, W, H, max_batch=3, scale_factor=sf, scale_cascade=True)
+    res = det.detect(frames)
+    codes = det.codes(0, 3)
+    oc = oracle_cascade(name)
+    for f in range(3):
+        rects, ocodes, st, levels = oc.detect_sc(frames[f], sf)
+        assert [(l.nx, l.ny, l.win_w, l.win_h) for l in levels] == [(l.nx, l.ny, l.win_w, l.win_h) for l in det.levels()]
+        assert len(ocodes) == det.windows_per_frame()
+        bad = np.flatnonzero(codes[f] != ocodes)
+        assert bad.size == 0, f"{name} frame {f}: {bad.size} codes differ, first {bad[:5]} gpu {codes[f][bad[:5]]} oracle {ocodes[bad[:5]]}"
+        assert np.array_equal(res.frame_rects(f), _sorted(rects))
+    assert (codes == -32768).any()   # the skip rule fired
+    det.close()
+
+
+def test_scale_cascade_mode_min_size_and_batch_ranges(gpu_ctx, monkeypatch):
+    monkeypatch.setenv("CLFD_DETECT_CHUNKS", "2")
+    frames = np.stack([octave_frame(480, 360, i) for i in range(8)])
+    cas = clfd.Cascade(cascade_path("frontalface_alt"))
+    det = clfd.Detector(gpu_ctx, cas, 480, 360, max_batch=8, scale_factor=1.3, min_size=(40, 40), scale_cascade=True)
+    res = det.detect(frames)
+    oc = oracle_cascade("frontalface_alt")
+    for f in (0, 5, 7):
+        rects, ocodes, _, levels = oc.detect_sc(frames[f], 1.3, (40, 40))
+        assert np.array_equal(det.codes(0, 8)[f], ocodes)
+        assert np.array_equal(res.frame_rects(f), _sorted(rects))
+        assert all(l.win_w >= 40 for l in det.levels())
+    det.close()
