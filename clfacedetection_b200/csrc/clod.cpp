@@ -15,16 +15,17 @@
 namespace {
 
 struct DetKey {
-    const clfd_cascade* cascade; int w, h, min_w, min_h, max_w, max_h; double sf;
+    const clfd_cascade* cascade; int w, h, min_w, min_h, max_w, max_h; double sf; int mode;
     bool operator<(const DetKey& o) const {
-        return std::tie(cascade, w, h, min_w, min_h, max_w, max_h, sf) <
-               std::tie(o.cascade, o.w, o.h, o.min_w, o.min_h, o.max_w, o.max_h, o.sf);
+        return std::tie(cascade, w, h, min_w, min_h, max_w, max_h, sf, mode) <
+               std::tie(o.cascade, o.w, o.h, o.min_w, o.min_h, o.max_w, o.max_h, o.sf, o.mode);
     }
 };
 
 struct ClodState {
     clfd_context* ctx = nullptr;
     double scale_factor = 1.1;                       // clod.cpp:1349
+    int mode = CLFD_MODE_SCALE_IMAGE;
     std::map<DetKey, clfd_detector*> detectors;      // plans are cached per (cascade, shape, limits)
     std::vector<clfd_rect> rects;
     std::vector<unsigned char> gray;
@@ -80,6 +81,10 @@ void clodSetScaleFactor(CLODEnvironmentData* data, double scale_factor) {
     state(data)->scale_factor = scale_factor;
 }
 
+void clodSetDetectionMode(CLODEnvironmentData* data, int scale_cascade) {
+    state(data)->mode = scale_cascade ? CLFD_MODE_SCALE_CASCADE : CLFD_MODE_SCALE_IMAGE;
+}
+
 CLODDetectObjectsResult clodDetectObjects(const IplImage* image, const CvHaarClassifierCascade* cascade,
                                           const CLODEnvironmentData* data, const CvSize min_window_size,
                                           const CvSize max_window_size, const cl_uint min_neighbors,
@@ -99,12 +104,13 @@ CLODDetectObjectsResult clodDetectObjects(const IplImage* image, const CvHaarCla
     }
 
     DetKey key{cas, W, H, min_window_size.width, min_window_size.height, max_window_size.width, max_window_size.height,
-               s->scale_factor};
+               s->scale_factor, s->mode};
     clfd_detector*& det = s->detectors[key];
     if (!det) {
         clfd_detector_config cfg;
         memset(&cfg, 0, sizeof cfg);
         cfg.width = W; cfg.height = H; cfg.max_batch = 1; cfg.scale_factor = s->scale_factor;
+        cfg.mode = s->mode;
         cfg.min_w = key.min_w; cfg.min_h = key.min_h; cfg.max_w = key.max_w; cfg.max_h = key.max_h;   // 0 = unlimited (clod.cpp:394-397)
         CHECK(clfd_detector_create(s->ctx, &cas, 1, &cfg, &det));
     }

@@ -290,8 +290,12 @@ void cvIntegral(const CvArr* image, CvArr* sum, CvArr* sqsum, CvArr* tilted) {
     if (tilted) store(tilted, 2);
 }
 
+// flags & CV_HAAR_SCALE_IMAGE: image pyramid (tempcv.cpp:1257-1329); otherwise -- as in main.cpp:145,
+// which passes 0 -- the scale-cascade path (tempcv.cpp:1330-1456).  Canny pruning / biggest-object
+// / rough-search flags are not implemented (not on the hot path) and abort loudly.
 CvSeq* cvHaarDetectObjects(const CvArr* image, CvHaarClassifierCascade* cascade, CvMemStorage*, double scale_factor,
-                           int min_neighbors, int, CvSize min_size, CvSize max_size) {
+                           int min_neighbors, int flags, CvSize min_size, CvSize max_size) {
+    if (flags & ~CV_HAAR_SCALE_IMAGE) { fprintf(stderr, "cvHaarDetectObjects: unsupported flags 0x%x\n", flags); abort(); }
     const View s = view_of(image);
     clfd_context* ctx = cvShimContext(0);
     std::vector<unsigned char> gray;
@@ -307,6 +311,7 @@ CvSeq* cvHaarDetectObjects(const CvArr* image, CvHaarClassifierCascade* cascade,
     memset(&cfg, 0, sizeof cfg);
     cfg.width = s.w; cfg.height = s.h; cfg.max_batch = 1; cfg.scale_factor = scale_factor;
     cfg.min_w = min_size.width; cfg.min_h = min_size.height; cfg.max_w = max_size.width; cfg.max_h = max_size.height;
+    cfg.mode = (flags & CV_HAAR_SCALE_IMAGE) ? CLFD_MODE_SCALE_IMAGE : CLFD_MODE_SCALE_CASCADE;
     clfd_detector* det = nullptr;
     CHECK(clfd_detector_create(ctx, &cas, 1, &cfg, &det));
     std::vector<clfd_rect> rects(1 << 20);

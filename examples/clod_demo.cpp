@@ -1,6 +1,6 @@
 // clod_demo.cpp -- minimal client of the reference-facing C++ API (include/clif.h, clod.h):
 // what a user of the reference's clod library writes, minus the highgui windows.
-//   clod_demo <cascade.xml> <image.pgm|-> <scale_factor> <min_neighbors> [min_w min_h]
+//   clod_demo <cascade.xml> <image.pgm|-> <scale_factor> <min_neighbors> [min_w min_h [scale_cascade]]
 // Prints one "x y w h weight" line per detection and a summary of clifIntegral.
 #include <cstdio>
 #include <cstdlib>
@@ -19,6 +19,7 @@ int main(int argc, char** argv) {
     CvSize isz = cvSize(frame->width, frame->height);
     clodInitBuffers(data, &isz);
     clodSetScaleFactor(data, atof(argv[3]));
+    if (argc > 7) clodSetDetectionMode(data, atoi(argv[7]));   // 1: scaled features on one integral image (main.cpp:145's semantics)
 
     CLIFIntegralResult r = clifIntegral(frame, data->clif, CL_TRUE);
     const int W1 = frame->width + 1;

@@ -10,8 +10,8 @@
  * and ignored, exactly like the reference's OpenCL branch ignores `flags`
  * (clod.cpp:1355-1356); there is no CPU path to fall back to.
  *
- * Additive API (not in the reference): clodSetScaleFactor.  The reference hard-codes 1.1
- * (clod.cpp:831,1184,1349), which stays the default.
+ * Additive API (not in the reference): clodSetScaleFactor (the reference hard-codes 1.1,
+ * clod.cpp:831,1184,1349, which stays the default) and clodSetDetectionMode.
  */
 #ifndef CLFD_B200_CLOD_H
 #define CLFD_B200_CLOD_H
@@ -81,5 +81,10 @@ CLODDetectObjectsResult clodDetectObjects(const IplImage* image, const CvHaarCla
 
 /* additive: pyramid scale factor (> 1) used by subsequent clodDetectObjects calls */
 void clodSetScaleFactor(CLODEnvironmentData* data, double scale_factor);
+/* additive: 0 (default) = image pyramid (CV_HAAR_SCALE_IMAGE, tempcv.cpp:1257-1329);
+ * 1 = scaled features on one integral image, the semantics of the cvHaarDetectObjects call the
+ * reference's main.cpp:145 compares against (tempcv.cpp:1330-1456) and the formulation of the
+ * reference's own clodDetectObjects (clod.cpp:1176-1336). */
+void clodSetDetectionMode(CLODEnvironmentData* data, int scale_cascade);
 
 #endif

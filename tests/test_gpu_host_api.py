@@ -47,6 +47,23 @@ def test_clod_demo_matches_oracle(tmp_path, min_neighbors):
         assert np.array_equal(key(got), key(rects))
 
 
+def test_clod_demo_scale_cascade_mode_matches_ref_sc(tmp_path):
+    """clodSetDetectionMode(data, 1): the semantics of the cvHaarDetectObjects call of main.cpp:145."""
+    from clfacedetection_b200.frames import octave_frame
+    img = octave_frame(640, 480, 3)
+    pgm = str(tmp_path / "frame.pgm")
+    _write_pgm(pgm, img)
+    out = subprocess.run([os.path.join(ROOT, "examples", "clod_demo"), cascade_path("frontalface_alt"), pgm, "1.2", "0", "0", "0", "1"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    n = int(lines[1].split()[1])
+    got = np.array([[int(v) for v in ln.split()[:4]] for ln in lines[2:2 + n]], np.int32).reshape(-1, 4)
+    rects, _, _, _ = oracle_cascade("frontalface_alt").detect_sc(img, 1.2)
+    key = lambda r: r[np.lexsort((r[:, 0], r[:, 1], r[:, 2]))] if len(r) else r
+    assert len(rects) > 0 and np.array_equal(key(got), key(rects))
+
+
 def test_reference_main_runs_unchanged():
     exe = os.path.join(ROOT, "tests", "_build", "ref_main")
     if not os.path.exists(exe):
