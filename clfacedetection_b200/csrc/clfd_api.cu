@@ -245,6 +245,9 @@ struct CascadePlan {
     DenseParams dense[2];          // the cascade's parameter blobs with this detector's tail pointers
     DevBuf<int16_t> d_codes;
     DevBuf<unsigned long long> d_counters;
+    DevBuf<unsigned long long> d_count_b;   // second-queue counter, one per slot
+    int mid_begin = 0, mid_end = 0;         // stages of the thread-per-window mid kernel (equal: none)
+    std::vector<int> mid_cuts;              // pass boundaries: mid_begin = cuts[0] < ... < cuts.back() = mid_end
     unsigned long long h_counters[4] = {0, 0, 0, 0};
 };
 
@@ -257,7 +260,7 @@ struct clfd_detector {
     clfd_detector_config cfg;
     PyramidPlan pyr;
     std::vector<std::unique_ptr<CascadePlan>> cas;
-    DevBuf<QueueItem> queue;
+    DevBuf<QueueItem> queue, queue_b;
     DevBuf<DevRect> rects;
     DevBuf<uint8_t> dev_frames[kSlots];   // staging for host input (clfd_detect / clfd_detect_submit)
     DevBuf<DevRect> rects2;               // rect buffer of slot 1 (slot 0 uses `rects`)
@@ -684,6 +687,7 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
     else if (sizes.empty()) { det->pyr.W = W; det->pyr.H = H; det->pyr.max_batch = cfg->max_batch; }
 
     long long max_wpf = 0;
+    bool need_queue_b = false;
     for (auto &cpp : det->cas) {
         CascadePlan &cp = *cpp;
         const PackedCascade &pk = cp.cascade->packed;
@@ -696,7 +700,24 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
             if (!pk.tail[yi].empty() && (rc = cp.d_tail[yi].upload(pk.tail[yi], s))) return rc;
             cp.dense[yi].tail = cp.d_tail[yi].p;
         }
-        if ((rc = cp.d_counters.alloc(4 * kSlots))) return rc;
+        if ((rc = cp.d_counters.alloc(4 * kSlots)) || (rc = cp.d_count_b.alloc(kSlots))) return rc;
+        // mid kernel: the stages right after the tile prefix of a LINEAR cascade whose trees the tile
+        // kernel cannot take, while they are too small for a warp per window (< 24 trees), at most 8
+        if (!scale_cascade && !cp.cascade->host.is_tree && pk.dense[0].tail_stages < pk.dense[0].total_stages) {
+            const HostCascade &hc = cp.cascade->host;
+            cp.mid_begin = cp.mid_end = pk.dense[0].tail_stages;
+            while (cp.mid_end < hc.n_stages() && cp.mid_end - cp.mid_begin < 8 && hc.st_ntrees[cp.mid_end] < 24) cp.mid_end++;
+            if (getenv("CLFD_NO_MID")) cp.mid_end = cp.mid_begin;
+            need_queue_b |= cp.mid_end > cp.mid_begin;
+            // passes: the first ends once it holds >= 10 trees, the later ones >= 30 (lanes are
+            // re-compacted between passes)
+            cp.mid_cuts.assign(1, cp.mid_begin);
+            int acc = 0;
+            for (int st = cp.mid_begin; st < cp.mid_end; st++) {
+                acc += hc.st_ntrees[st];
+                if (acc >= (cp.mid_cuts.size() == 1 ? 10 : 30) || st + 1 == cp.mid_end) { cp.mid_cuts.push_back(st + 1); acc = 0; }
+            }
+        }
         if ((cfg->want_codes || scale_cascade) && (rc = cp.d_codes.alloc((size_t)std::max<long long>(cp.windows_per_frame, 1) * cfg->max_batch)))
             return rc;
         max_wpf = std::max(max_wpf, cp.windows_per_frame);
@@ -705,6 +726,7 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
     det->queue_cap = scale_cascade ? 1 : (unsigned long long)std::max<long long>(max_wpf, 1) * cfg->max_batch;   // (no queue in scale-cascade mode)
     det->rect_cap = cfg->max_rects > 0 ? (unsigned long long)cfg->max_rects : (1ull << 20);
     if ((rc = det->queue.alloc(det->queue_cap)) || (rc = det->rects.alloc(det->rect_cap))) return rc;
+    if (need_queue_b && (rc = det->queue_b.alloc(det->queue_cap))) return rc;
     CK(cudaMallocHost((void **)&det->h_rects, det->rect_cap * sizeof(DevRect)));
     CK(cudaMallocHost((void **)&det->h_counters, kSlots * 4 * 16 * sizeof(unsigned long long)));
     CK(cudaStreamSynchronize(s));
@@ -768,6 +790,7 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
     for (auto &cpp : det->cas) {
         if (first) CK(cudaMemsetAsync(cpp->d_counters.p + 4 * slot, 0, 4 * sizeof(unsigned long long), s));
         else CK(cudaMemsetAsync(cpp->d_counters.p + 4 * slot + 1, 0, sizeof(unsigned long long), s));   // the queue is per range
+        CK(cudaMemsetAsync(cpp->d_count_b.p + slot, 0, sizeof(unsigned long long), s));
     }
     int ci = 0;
     for (auto &cpp : det->cas) {
@@ -794,6 +817,8 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
             a.deep.has_tilted = cp.cascade->host.has_tilted;
             a.deep.win_w = cp.cascade->host.win_w; a.deep.win_h = cp.cascade->host.win_h;
             a.deep.inv_area = pk.dense[0].inv_area;
+            a.deep.mid_begin = cp.mid_begin; a.deep.mid_end = cp.mid_end;
+            a.deep_in = a.queue; a.deep_count = a.counters + 1;
             if (det->cfg.mode == CLFD_MODE_SCALE_CASCADE) {
                 ScArgs sa;
                 memset(&sa, 0, sizeof sa);
@@ -824,6 +849,8 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
                     CK(launch_cascade_tiles(cp.dense[0], a, cp.n_tiles_y2, cp.n_tiles - cp.n_tiles_y2, s));
                     launches++;
                 }
+            } else if (cp.mid_end > cp.mid_begin) {
+                // no tile prefix: the first mid pass walks the window grid itself
             } else {
                 CK(launch_enqueue_all(a, s));
                 launches++;
@@ -831,7 +858,28 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
             if (ev && ci == 0) CK(cudaEventRecord(ev[6], s));
             // cascades the tile kernel finishes itself (tail_stages == total_stages) never fill the queue
             const bool tiles_finish = pk.dense[0].tail_stages > 0 && pk.dense[0].tail_stages == pk.dense[0].total_stages;
-            if (!tiles_finish) { CK(launch_cascade_deep(a, ctx->n_sms, s)); launches++; }
+            if (!tiles_finish) {
+                if (cp.mid_end > cp.mid_begin) {
+                    // ping-pong between the tile queue (counters[1]) and queue_b (count_b)
+                    QueueItem *qs[2] = {det->queue.p, det->queue_b.p};
+                    unsigned long long *cs[2] = {a.counters + 1, cp.d_count_b.p + slot};
+                    int in = pk.dense[0].tail_stages > 0 ? 0 : -1;   // -1: the grid
+                    for (size_t k = 0; k + 1 < cp.mid_cuts.size(); k++) {
+                        const int out = in == 0 ? 1 : 0;
+                        if (k > 0 || in == 0) { /* the output queue may hold an older pass: start it empty */
+                            if (!(k == 0)) CK(cudaMemsetAsync(cs[out], 0, sizeof(unsigned long long), s));
+                        }
+                        a.mid_in = in < 0 ? nullptr : qs[in]; a.mid_in_count = in < 0 ? nullptr : cs[in];
+                        a.mid_out = qs[out]; a.mid_out_count = cs[out];
+                        a.deep.mid_begin = cp.mid_cuts[k]; a.deep.mid_end = cp.mid_cuts[k + 1];
+                        CK(launch_cascade_mid(a, ctx->n_sms, s));
+                        launches++;
+                        in = out;
+                    }
+                    a.deep_in = qs[in]; a.deep_count = cs[in];
+                }
+                if (cp.mid_end < pk.dense[0].total_stages) { CK(launch_cascade_deep(a, ctx->n_sms, s)); launches++; }
+            }
             if (ev && ci == 0) CK(cudaEventRecord(ev[7], s));
         }
         // all cascades append to one rect buffer: carry the rect count over

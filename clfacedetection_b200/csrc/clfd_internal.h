@@ -134,6 +134,7 @@ struct DeepCascadeDev {
     const DeepNode *nodes;
     const float *alpha;
     int n_stages, is_tree, has_tilted, win_w, win_h;
+    int mid_begin, mid_end;      // stages the thread-per-window mid kernel evaluates (equal: none)
     double inv_area;
 };
 

@@ -45,7 +45,11 @@ struct CascadeArgs {
     int frame_base;                 // added to the frame index of emitted rects (ranges of a batch)
     long long windows_per_frame;
     int16_t *codes;                 // device, [n_frames][windows_per_frame] or NULL
-    QueueItem *queue; unsigned long long queue_cap;
+    QueueItem *queue; unsigned long long queue_cap;   // written by the tile kernel / k_enqueue_all, counted in counters[1]
+    // mid kernel pass: input queue (NULL = every grid window) -> output queue
+    const QueueItem *mid_in; const unsigned long long *mid_in_count;
+    QueueItem *mid_out; unsigned long long *mid_out_count;
+    const QueueItem *deep_in; const unsigned long long *deep_count;   // what the deep kernel reads
     DevRect *rects; unsigned long long rect_cap;
     unsigned long long *counters;   // [0] rects  [1] queue items  [2] rect overflow [3] queue overflow
     DeepCascadeDev deep;
@@ -55,6 +59,8 @@ struct CascadeArgs {
 cudaError_t launch_cascade_tiles(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, cudaStream_t stream);
 // fill the queue with every window (cascades without a dense prefix)
 cudaError_t launch_enqueue_all(const CascadeArgs &a, cudaStream_t stream);
+// thread-per-window evaluation of stages [deep.mid_begin, deep.mid_end) (generic trees), survivors -> queue_b
+cudaError_t launch_cascade_mid(const CascadeArgs &a, int n_sms, cudaStream_t stream);
 // warp-per-window evaluation of the queue
 cudaError_t launch_cascade_deep(const CascadeArgs &a, int n_sms, cudaStream_t stream);
 

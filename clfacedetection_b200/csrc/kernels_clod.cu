@@ -671,16 +671,149 @@ __device__ __forceinline__ int rect_sum_g(const int32_t *__restrict__ base, int 
     return __ldg(base + o0) - __ldg(base + o1) - __ldg(base + o2) + __ldg(base + o3);
 }
 
+// One tree of the generic cascade for one window: icvEvalHidHaarClassifier (tempcv.cpp:771-792) and
+// the stump fast paths (tempcv.cpp:872-930).  Returns the leaf value.
+__device__ __forceinline__ float deep_eval_tree(const DeepCascadeDev &D, int tree, const int32_t *__restrict__ sum,
+                                                const int32_t *__restrict__ til, int pitch, double sigma, bool dbl) {
+    const int n0 = __ldg(D.tree_first_node + tree);
+    int idx = 0;
+    do {
+        const uint4 *nd = reinterpret_cast<const uint4 *>(D.nodes + n0 + idx);
+        const uint4 c0 = __ldg(nd), c1 = __ldg(nd + 1), c2 = __ldg(nd + 2);
+        const int flags = __ldg(reinterpret_cast<const int *>(nd + 3));
+        // c0 = dx[0..11], dy[0..3]; c1 = dy[4..11], w0, w1; c2 = w2, thr, left, right
+        const int32_t *__restrict__ base = (flags & 1) ? til : sum;
+        const int r0 = rect_sum_g(base, pitch, c0.x, c0.w);
+        const int r1 = rect_sum_g(base, pitch, c0.y, c1.x);
+        const float w0 = __uint_as_float(c1.z), w1 = __uint_as_float(c1.w);
+        const float thr = __uint_as_float(c2.y);
+        const double t = __dmul_rn((double)thr, sigma);
+        double sv;
+        if (dbl) {
+            sv = __fma_rn((double)r1, (double)w1, __dmul_rn((double)r0, (double)w0));
+        } else {
+            sv = __dadd_rn((double)__fmul_rn(__int2float_rn(r0), w0), (double)__fmul_rn(__int2float_rn(r1), w1));
+            if ((flags >> 8) == 3) {
+                const int r2 = rect_sum_g(base, pitch, c0.z, c1.y);
+                sv = __dadd_rn(sv, (double)__fmul_rn(__int2float_rn(r2), __uint_as_float(c2.x)));
+            }
+        }
+        idx = sv < t ? (int)c2.z : (int)c2.w;
+    } while (idx > 0);
+    return __ldg(D.alpha + n0 + tree - idx);
+}
+
+// ------------------------------------------------------------------------------------
+// mid kernel: one THREAD per window for the stages [mid_begin, mid_end) of a linear cascade
+// whose trees the tile kernel cannot evaluate (multi-node trees, tilted features).  Those
+// stages have few trees (3, 9, 14, ... in frontalface_alt2), so a warp per window would idle
+// most lanes, and they still see most windows.  Input: every grid window (cascades without a
+// tile prefix) or the tile kernel's queue; survivors go to the second queue for the deep kernel.
+// Lanes hold consecutive windows, so the corner loads of a warp fall into a few cache lines.
+// Run in a few passes of two or three stages each, ping-ponging between the two queues, so
+// the lanes are re-compacted while the survivor count still drops fast.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_cascade_mid(const __grid_constant__ CascadeArgs a) {
+    const DeepCascadeDev &D = a.deep;
+    const int lane = threadIdx.x & 31;
+    const bool from_grid = a.mid_in == nullptr;
+    ull n = from_grid ? (ull)a.windows_per_frame * a.n_frames : *a.mid_in_count;
+    if (!from_grid && n > a.queue_cap) n = a.queue_cap;
+    const ull stride = (ull)gridDim.x * 128;
+    // whole warps iterate together (ballots below)
+    for (ull base_item = ((ull)blockIdx.x * 128 + threadIdx.x) - lane; base_item < n; base_item += stride) {
+        const ull item = base_item + lane;
+        const bool valid = item < n;
+        int frame = 0, cl = 0, x = 0, y = 0;
+        if (valid) {
+            if (from_grid) {
+                frame = (int)(item / (ull)a.windows_per_frame);
+                const long long w = (long long)(item - (ull)frame * a.windows_per_frame);
+                int lo = 0, hi = a.n_cas_levels - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (__ldg(&a.cas_levels[mid].win_base) <= w) lo = mid; else hi = mid - 1;
+                }
+                cl = lo;
+                const int nx = __ldg(&a.cas_levels[lo].nx), ystep = __ldg(&a.cas_levels[lo].ystep);
+                const int local = (int)(w - __ldg(&a.cas_levels[lo].win_base));
+                const int iy = local / nx;
+                x = (local - iy * nx) * ystep; y = iy * ystep;
+            } else {
+                const QueueItem q = a.mid_in[item];
+                frame = q.key >> 16; cl = (q.key >> 8) & 255;
+                x = q.xy & 0xffff; y = q.xy >> 16;
+            }
+        }
+        bool alive = valid;
+        int stage = D.mid_begin;
+        const CasLevel CL = a.cas_levels[cl];
+        if (valid) {
+            const PyrLevel L = a.levels[CL.pyr_level];
+            const int pitch = L.sum_pitch;
+            const size_t off = (size_t)frame * a.sum_frame_stride + L.sum_off + (size_t)y * pitch + x;
+            const int32_t *__restrict__ sum = a.sum + off;
+            const int32_t *__restrict__ til = a.tilted ? a.tilted + off : sum;
+            const ull *__restrict__ sq = a.sq + off;
+            const int eq_w = D.win_w - 2, eq_h = D.win_h - 2;
+            const int g0 = pitch + 1, g1 = g0 + eq_w, g2 = (1 + eq_h) * pitch + 1, g3 = g2 + eq_w;
+            const int s4 = __ldg(sum + g0) - __ldg(sum + g1) - __ldg(sum + g2) + __ldg(sum + g3);
+            const ull q4 = __ldg(sq + g0) - __ldg(sq + g1) - __ldg(sq + g2) + __ldg(sq + g3);
+            const double sigma = window_sigma(s4, q4, D.inv_area);
+            for (; stage < D.mid_end; stage++) {
+                const DeepStage st = D.stages[stage];
+                const bool dbl = st.flags & 1;
+                double S = 0.0;
+                for (int j = 0; j < st.ntrees; j++)
+                    S = __dadd_rn(S, (double)deep_eval_tree(D, st.first_tree + j, sum, til, pitch, sigma, dbl));
+                if (S < (double)st.thr) { alive = false; break; }
+            }
+        }
+        if (valid && !alive && a.codes)
+            a.codes[(size_t)frame * a.windows_per_frame + CL.win_base + (size_t)(y / CL.ystep) * CL.nx + x / CL.ystep] = (int16_t)stage;
+        const bool accepted = alive && D.mid_end >= D.n_stages;
+        if (accepted) {
+            emit_rect(a, CL, frame, x, y);
+            if (a.codes)
+                a.codes[(size_t)frame * a.windows_per_frame + CL.win_base + (size_t)(y / CL.ystep) * CL.nx + x / CL.ystep] = (int16_t)D.n_stages;
+        }
+        const bool pass_on = alive && !accepted;
+        const unsigned m = __ballot_sync(0xffffffffu, pass_on);
+        if (m) {
+            ull qb = 0;
+            if (lane == 0) qb = atomicAdd(a.mid_out_count, (ull)__popc(m));
+            qb = __shfl_sync(0xffffffffu, qb, 0);
+            if (pass_on) {
+                const ull slot = qb + __popc(m & ((1u << lane) - 1u));
+                if (slot < a.queue_cap) {
+                    QueueItem it;
+                    it.key = ((uint32_t)frame << 16) | ((uint32_t)cl << 8) | (uint32_t)D.mid_end;
+                    it.xy = ((uint32_t)y << 16) | (uint32_t)x;
+                    a.mid_out[slot] = it;
+                } else {
+                    atomicAdd(a.counters + 3, 1ull);
+                }
+            }
+        }
+    }
+}
+
+cudaError_t launch_cascade_mid(const CascadeArgs &a, int n_sms, cudaStream_t stream) {
+    if (a.n_frames == 0) return cudaSuccess;
+    k_cascade_mid<<<n_sms * 16, 128, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(kDeepThreads) k_cascade_deep(const __grid_constant__ CascadeArgs a) {
     const int lane = threadIdx.x & 31;
     const ull warp0 = ((ull)blockIdx.x * kDeepThreads + threadIdx.x) >> 5;
     const ull nwarps = ((ull)gridDim.x * kDeepThreads) >> 5;
-    ull n = a.counters[1];
+    ull n = *a.deep_count;
     if (n > a.queue_cap) n = a.queue_cap;
     const DeepCascadeDev &D = a.deep;
 
     for (ull item = warp0; item < n; item += nwarps) {
-        const QueueItem q = a.queue[item];
+        const QueueItem q = a.deep_in[item];
         const int frame = q.key >> 16, cl = (q.key >> 8) & 255, stage0 = q.key & 255;
         const int x = q.xy & 0xffff, y = q.xy >> 16;
         const CasLevel CL = a.cas_levels[cl];
@@ -706,35 +839,7 @@ __global__ void __launch_bounds__(kDeepThreads) k_cascade_deep(const __grid_cons
             for (int j0 = 0; j0 < st.ntrees; j0 += 32) {
                 const int j = j0 + lane;
                 float av = 0.f;
-                if (j < st.ntrees) {
-                    const int tree = st.first_tree + j;
-                    const int n0 = __ldg(D.tree_first_node + tree);
-                    int idx = 0;
-                    do {
-                        const uint4 *nd = reinterpret_cast<const uint4 *>(D.nodes + n0 + idx);
-                        const uint4 c0 = __ldg(nd), c1 = __ldg(nd + 1), c2 = __ldg(nd + 2);
-                        const int flags = __ldg(reinterpret_cast<const int *>(nd + 3));
-                        // c0 = dx[0..11], dy[0..3]; c1 = dy[4..11], w0, w1; c2 = w2, thr, left, right
-                        const int32_t *__restrict__ base = (flags & 1) ? til : sum;
-                        const int r0 = rect_sum_g(base, pitch, c0.x, c0.w);
-                        const int r1 = rect_sum_g(base, pitch, c0.y, c1.x);
-                        const float w0 = __uint_as_float(c1.z), w1 = __uint_as_float(c1.w);
-                        const float thr = __uint_as_float(c2.y);
-                        const double t = __dmul_rn((double)thr, sigma);
-                        double sv;
-                        if (dbl) {
-                            sv = __fma_rn((double)r1, (double)w1, __dmul_rn((double)r0, (double)w0));
-                        } else {
-                            sv = __dadd_rn((double)__fmul_rn(__int2float_rn(r0), w0), (double)__fmul_rn(__int2float_rn(r1), w1));
-                            if ((flags >> 8) == 3) {
-                                const int r2 = rect_sum_g(base, pitch, c0.z, c1.y);
-                                sv = __dadd_rn(sv, (double)__fmul_rn(__int2float_rn(r2), __uint_as_float(c2.x)));
-                            }
-                        }
-                        idx = sv < t ? (int)c2.z : (int)c2.w;
-                    } while (idx > 0);
-                    av = __ldg(D.alpha + n0 + tree - idx);
-                }
+                if (j < st.ntrees) av = deep_eval_tree(D, st.first_tree + j, sum, til, pitch, sigma, dbl);
                 if (order_free) {
                     part = __dadd_rn(part, (double)av);
                 } else {
