@@ -723,10 +723,10 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
         max_wpf = std::max(max_wpf, cp.windows_per_frame);
         cp.bytes_cascade += cp.cascade->packed.deep_nodes.size() * sizeof(DeepNode);
     }
-    det->queue_cap = scale_cascade ? 1 : (unsigned long long)std::max<long long>(max_wpf, 1) * cfg->max_batch;   // (no queue in scale-cascade mode)
+    det->queue_cap = (unsigned long long)std::max<long long>(max_wpf, 1) * cfg->max_batch;
     det->rect_cap = cfg->max_rects > 0 ? (unsigned long long)cfg->max_rects : (1ull << 20);
     if ((rc = det->queue.alloc(det->queue_cap)) || (rc = det->rects.alloc(det->rect_cap))) return rc;
-    if (need_queue_b && (rc = det->queue_b.alloc(det->queue_cap))) return rc;
+    if ((need_queue_b || scale_cascade) && (rc = det->queue_b.alloc(det->queue_cap))) return rc;
     CK(cudaMallocHost((void **)&det->h_rects, det->rect_cap * sizeof(DevRect)));
     CK(cudaMallocHost((void **)&det->h_counters, kSlots * 4 * 16 * sizeof(unsigned long long)));
     CK(cudaStreamSynchronize(s));
@@ -832,8 +832,38 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
                 sa.codes = cp.d_codes.p + (size_t)frame_base * cp.windows_per_frame;
                 sa.rects = a.rects; sa.rect_cap = a.rect_cap; sa.counters = a.counters; sa.deep = a.deep;
                 if (ev && ci == 0) CK(cudaEventRecord(ev[5], s));
-                CK(launch_sc(sa, s));
-                launches += 2;
+                // passes over growing stage ranges (cumulative trees >= 10, 40, 150, rest), survivors
+                // re-compacted through the two queues in between; a stage tree runs as one pass
+                {
+                    const HostCascade &hc = cp.cascade->host;
+                    std::vector<int> cuts(1, 0);
+                    if (hc.is_tree || getenv("CLFD_SC_ONE_PASS")) cuts.push_back(hc.n_stages());
+                    else {
+                        static const int limit[3] = {10, 40, 150};
+                        int acc = 0;
+                        for (int st = 0; st < hc.n_stages(); st++) {
+                            acc += hc.st_ntrees[st];
+                            if (cuts.size() <= 3 && acc >= limit[cuts.size() - 1] && st + 1 < hc.n_stages()) { cuts.push_back(st + 1); acc = 0; }
+                        }
+                        cuts.push_back(hc.n_stages());
+                    }
+                    QueueItem *qs[2] = {det->queue.p, det->queue_b.p};
+                    unsigned long long *cs[2] = {a.counters + 1, cp.d_count_b.p + slot};
+                    sa.queue_cap = det->queue_cap;
+                    int in = -1;
+                    for (size_t k = 0; k + 1 < cuts.size(); k++) {
+                        const int out = in == 0 ? 1 : 0;
+                        if (k >= 2) CK(cudaMemsetAsync(cs[out], 0, sizeof(unsigned long long), s));   // holds an older pass
+                        sa.stage_begin = cuts[k]; sa.stage_end = cuts[k + 1];
+                        sa.in = in < 0 ? nullptr : qs[in]; sa.in_count = in < 0 ? nullptr : cs[in];
+                        sa.out = qs[out]; sa.out_count = cs[out];
+                        CK(launch_sc_eval(sa, ctx->n_sms, s));
+                        launches++;
+                        in = out;
+                    }
+                }
+                CK(launch_sc_rows(sa, s));
+                launches++;
                 if (ev && ci == 0) { CK(cudaEventRecord(ev[6], s)); CK(cudaEventRecord(ev[7], s)); }
                 if (ci + 1 < (int)det->cas.size())
                     CK(cudaMemcpyAsync(det->cas[ci + 1]->d_counters.p + 4 * slot, cp.d_counters.p + 4 * slot, sizeof(unsigned long long),

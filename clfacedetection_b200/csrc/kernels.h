@@ -77,10 +77,18 @@ struct ScArgs {
     long long windows_per_frame;
     int16_t *codes;                 // device, [n_frames][windows_per_frame] (always present in this mode)
     DevRect *rects; unsigned long long rect_cap;
-    unsigned long long *counters;   // [0] rects [2] rect overflow
+    unsigned long long *counters;   // [0] rects [2] rect overflow [3] queue overflow
     DeepCascadeDev deep;            // stages / tree_first_node / alpha (scale independent)
+    // one evaluation pass: stages [stage_begin, stage_end) of the positions in `in` (NULL = every grid
+    // position); survivors of a non-final pass go to `out`
+    int stage_begin, stage_end;
+    const QueueItem *in; const unsigned long long *in_count;
+    QueueItem *out; unsigned long long *out_count;
+    unsigned long long queue_cap;
 };
-// every grid position of every scale (k_sc_eval), then the invoker's skip rule + rect emission (k_sc_rows)
-cudaError_t launch_sc(const ScArgs &a, cudaStream_t stream);
+// one evaluation pass over the grid / a survivor queue (k_sc_eval)
+cudaError_t launch_sc_eval(const ScArgs &a, int n_sms, cudaStream_t stream);
+// the invoker's skip rule + rect emission over the finished exit codes (k_sc_rows)
+cudaError_t launch_sc_rows(const ScArgs &a, cudaStream_t stream);
 
 }  // namespace clfd

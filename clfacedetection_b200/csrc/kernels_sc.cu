@@ -8,7 +8,9 @@
 //
 //   k_sc_eval : one thread per grid position (scale, iy, ix), lanes = consecutive ix, so the
 //       32 corner loads of a warp are 32 * ystep * 4 bytes apart at most (a few cache lines);
-//       the integral image of a frame (8-25 MB) lives in L2.  Every position is evaluated --
+//       the integral image of a frame (8-25 MB) lives in L2.  Linear cascades run in a few
+//       passes over growing stage ranges with the survivors re-compacted through a queue in
+//       between (thread per survivor), so lanes stay busy.  Every position is evaluated --
 //       the reference's skip rule makes the set of evaluated windows depend on the RESULTS of
 //       their left neighbours, so it is applied afterwards:
 //   k_sc_rows : one thread per grid row walks its exit codes left to right with the invoker's
@@ -64,72 +66,106 @@ __device__ __forceinline__ float sc_eval_tree(const ScNode *__restrict__ nodes, 
     return __ldg(alpha_tree - idx);
 }
 
+// One pass: stages [a.stage_begin, a.stage_end) for every grid position (a.in == NULL) or for the
+// survivors of the previous pass (queue items: key = frame, xy = position index).  A window
+// rejected here gets its exit code; survivors of a pass that is not the last go to a.out.
+// Stage-tree cascades run as ONE pass (their walk is not a linear stage sequence).
 __global__ void __launch_bounds__(128) k_sc_eval(const __grid_constant__ ScArgs a) {
-    const long long w = (long long)blockIdx.x * 128 + threadIdx.x;
-    const int frame = blockIdx.y;
-    if (w >= a.windows_per_frame) return;
-    int lo = 0, hi = a.n_levels - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (__ldg(&a.levels[mid].win_base) <= w) lo = mid; else hi = mid - 1;
-    }
-    const ScLevel L = a.levels[lo];
-    const int local = (int)(w - L.win_base);
-    const int iy = local / L.nx, ix = local - iy * L.nx;
-    const int x = __double2int_rn(__dmul_rn((double)ix, L.ystep));   // cvRound(ix*ystep), tempcv.cpp:1144
-    const int y = __double2int_rn(__dmul_rn((double)iy, L.ystep));   // cvRound(iy*ystep), tempcv.cpp:1141
-    int16_t *code_out = a.codes + (size_t)frame * a.windows_per_frame + w;
-    if (x < 0 || y < 0 || x + L.win_w >= a.W + 1 || y + L.win_h >= a.H + 1) {   // tempcv.cpp:817-820
-        *code_out = (int16_t)kScCodeOutside;
-        return;
-    }
-    const size_t off = (size_t)frame * a.sum_frame_stride + (size_t)y * a.pitch + x;
-    const int32_t *__restrict__ sum = a.sum + off;
-    const int32_t *__restrict__ til = a.tilted ? a.tilted + off : sum;
-    const ull *__restrict__ sq = a.sq + off;
-    const int s4 = __ldg(sum + L.eq_off[0]) - __ldg(sum + L.eq_off[1]) - __ldg(sum + L.eq_off[2]) + __ldg(sum + L.eq_off[3]);
-    const ull q4 = __ldg(sq + L.eq_off[0]) - __ldg(sq + L.eq_off[1]) - __ldg(sq + L.eq_off[2]) + __ldg(sq + L.eq_off[3]);
-    const double sigma = sc_sigma(s4, q4, L.inv_area);
-    const ScNode *__restrict__ nodes = a.nodes + L.node_base;
     const DeepCascadeDev &D = a.deep;
-
-    int code;
-    if (D.is_tree) {   // tempcv.cpp:834-861
-        int ptr = 0, last = 0, accepted = 0;
-        for (;;) {
-            const DeepStage st = D.stages[ptr];
-            last = ptr;
-            double S = 0.0;
-            for (int j = 0; j < st.ntrees; j++) {
-                const int tree = st.first_tree + j, n0 = __ldg(D.tree_first_node + tree);
-                S = __dadd_rn(S, (double)sc_eval_tree(nodes, n0, D.alpha + n0 + tree, sum, til, sigma, false));
+    const int lane = threadIdx.x & 31;
+    const bool from_grid = a.in == nullptr;
+    ull n = from_grid ? (ull)a.windows_per_frame * a.n_frames : *a.in_count;
+    if (!from_grid && n > a.queue_cap) n = a.queue_cap;
+    const bool last_pass = a.stage_end >= D.n_stages;
+    const ull stride = (ull)gridDim.x * 128;
+    for (ull base_item = ((ull)blockIdx.x * 128 + threadIdx.x) - lane; base_item < n; base_item += stride) {
+        const ull item = base_item + lane;
+        const bool valid = item < n;
+        int frame = 0;
+        long long w = 0;
+        if (valid) {
+            if (from_grid) { frame = (int)(item / (ull)a.windows_per_frame); w = (long long)(item - (ull)frame * a.windows_per_frame); }
+            else { const QueueItem q = a.in[item]; frame = (int)q.key; w = (long long)q.xy; }
+        }
+        bool pass_on = false;
+        if (valid) {
+            int lo = 0, hi = a.n_levels - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (__ldg(&a.levels[mid].win_base) <= w) lo = mid; else hi = mid - 1;
             }
-            if (S >= (double)st.thr) {
-                ptr = st.child;
-                if (ptr < 0) { accepted = 1; break; }
+            const ScLevel L = a.levels[lo];
+            const int local = (int)(w - L.win_base);
+            const int iy = local / L.nx, ix = local - iy * L.nx;
+            const int x = __double2int_rn(__dmul_rn((double)ix, L.ystep));   // cvRound(ix*ystep), tempcv.cpp:1144
+            const int y = __double2int_rn(__dmul_rn((double)iy, L.ystep));   // cvRound(iy*ystep), tempcv.cpp:1141
+            int16_t *code_out = a.codes + (size_t)frame * a.windows_per_frame + w;
+            if (x < 0 || y < 0 || x + L.win_w >= a.W + 1 || y + L.win_h >= a.H + 1) {   // tempcv.cpp:817-820
+                *code_out = (int16_t)kScCodeOutside;
             } else {
-                int p = ptr;
-                while (p >= 0 && __ldg(&D.stages[p].next) < 0) p = __ldg(&D.stages[p].parent);
-                if (p < 0) break;
-                ptr = __ldg(&D.stages[p].next);
+                const size_t off = (size_t)frame * a.sum_frame_stride + (size_t)y * a.pitch + x;
+                const int32_t *__restrict__ sum = a.sum + off;
+                const int32_t *__restrict__ til = a.tilted ? a.tilted + off : sum;
+                const ull *__restrict__ sq = a.sq + off;
+                const int s4 = __ldg(sum + L.eq_off[0]) - __ldg(sum + L.eq_off[1]) - __ldg(sum + L.eq_off[2]) + __ldg(sum + L.eq_off[3]);
+                const ull q4 = __ldg(sq + L.eq_off[0]) - __ldg(sq + L.eq_off[1]) - __ldg(sq + L.eq_off[2]) + __ldg(sq + L.eq_off[3]);
+                const double sigma = sc_sigma(s4, q4, L.inv_area);
+                const ScNode *__restrict__ nodes = a.nodes + L.node_base;
+                if (D.is_tree) {   // tempcv.cpp:834-861
+                    int ptr = 0, last = 0, accepted = 0;
+                    for (;;) {
+                        const DeepStage st = D.stages[ptr];
+                        last = ptr;
+                        double S = 0.0;
+                        for (int j = 0; j < st.ntrees; j++) {
+                            const int tree = st.first_tree + j, n0 = __ldg(D.tree_first_node + tree);
+                            S = __dadd_rn(S, (double)sc_eval_tree(nodes, n0, D.alpha + n0 + tree, sum, til, sigma, false));
+                        }
+                        if (S >= (double)st.thr) {
+                            ptr = st.child;
+                            if (ptr < 0) { accepted = 1; break; }
+                        } else {
+                            int p = ptr;
+                            while (p >= 0 && __ldg(&D.stages[p].next) < 0) p = __ldg(&D.stages[p].parent);
+                            if (p < 0) break;
+                            ptr = __ldg(&D.stages[p].next);
+                        }
+                    }
+                    *code_out = (int16_t)(2 * last + accepted);
+                } else {           // tempcv.cpp:862-966
+                    int i = a.stage_begin;
+                    for (; i < a.stage_end; i++) {
+                        const DeepStage st = D.stages[i];
+                        const bool dbl = st.flags & 1;
+                        double S = 0.0;
+                        for (int j = 0; j < st.ntrees; j++) {
+                            const int tree = st.first_tree + j, n0 = __ldg(D.tree_first_node + tree);
+                            S = __dadd_rn(S, (double)sc_eval_tree(nodes, n0, D.alpha + n0 + tree, sum, til, sigma, dbl));
+                        }
+                        if (S < (double)st.thr) break;
+                    }
+                    if (i < a.stage_end || last_pass) *code_out = (int16_t)i;   // rejected at i, or accepted (i == n_stages)
+                    else pass_on = true;
+                }
             }
         }
-        code = 2 * last + accepted;
-    } else {           // tempcv.cpp:862-966
-        int i = 0;
-        for (; i < D.n_stages; i++) {
-            const DeepStage st = D.stages[i];
-            const bool dbl = st.flags & 1;
-            double S = 0.0;
-            for (int j = 0; j < st.ntrees; j++) {
-                const int tree = st.first_tree + j, n0 = __ldg(D.tree_first_node + tree);
-                S = __dadd_rn(S, (double)sc_eval_tree(nodes, n0, D.alpha + n0 + tree, sum, til, sigma, dbl));
+        const unsigned m = __ballot_sync(0xffffffffu, pass_on);
+        if (m) {
+            ull qb = 0;
+            if (lane == 0) qb = atomicAdd(a.out_count, (ull)__popc(m));
+            qb = __shfl_sync(0xffffffffu, qb, 0);
+            if (pass_on) {
+                const ull slot = qb + __popc(m & ((1u << lane) - 1u));
+                if (slot < a.queue_cap) {
+                    QueueItem it;
+                    it.key = (uint32_t)frame; it.xy = (uint32_t)w;
+                    a.out[slot] = it;
+                } else {
+                    atomicAdd(a.counters + 3, 1ull);
+                }
             }
-            if (S < (double)st.thr) break;
         }
-        code = i;
     }
-    *code_out = (int16_t)code;
 }
 
 __global__ void __launch_bounds__(128) k_sc_rows(const __grid_constant__ ScArgs a) {
@@ -173,11 +209,14 @@ __global__ void __launch_bounds__(128) k_sc_rows(const __grid_constant__ ScArgs 
     }
 }
 
-cudaError_t launch_sc(const ScArgs &a, cudaStream_t stream) {
+cudaError_t launch_sc_eval(const ScArgs &a, int n_sms, cudaStream_t stream) {
     if (a.windows_per_frame == 0 || a.n_frames == 0) return cudaSuccess;
-    k_sc_eval<<<dim3((unsigned)((a.windows_per_frame + 127) / 128), a.n_frames), 128, 0, stream>>>(a);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    k_sc_eval<<<n_sms * 16, 128, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sc_rows(const ScArgs &a, cudaStream_t stream) {
+    if (a.windows_per_frame == 0 || a.n_frames == 0) return cudaSuccess;
     k_sc_rows<<<dim3((unsigned)((a.rows_per_frame + 127) / 128), a.n_frames), 128, 0, stream>>>(a);
     return cudaGetLastError();
 }
