@@ -5,6 +5,7 @@ needs cv2 4.x for the OpenCV pins and the oracle for the detection fixtures).
   * opencv_pins.npz : cv2.resize(INTER_LINEAR), cv2.integral3 and cv2.groupRectangles outputs
     on small fixed-seed inputs -- the external (OpenCV) arithmetic the reference calls at
     tempcv.cpp:1301-1302,160 pinned independently of our own restatement.
+  * refsc.npz : REF-SC (scale-cascade mode) oracle outputs for four cascade kinds, same layout.
   * refsi_<cascade>.npz : REF-SI oracle outputs (raw rects, exit-code histogram, CRC of the
     exit-code map, stats) for two 320x240 frames per cascade -- regression pins for the oracle
     and golden vectors for the CUDA path.
@@ -58,6 +59,19 @@ def main():
             out[f"levels_{fi}"] = np.array([[l.img_w, l.img_h, l.win_w, l.win_h, l.ystep, l.nx, l.ny] for l in levels], np.int32)
         np.savez_compressed(os.path.join(HERE, f"refsi_{name}.npz"), **out)
         print(name, {k: out[k].tolist() for k in ("stats_0", "stats_1")})
+
+    # REF-SC (scale-cascade path, tempcv.cpp:1330-1456): one file for four cascade kinds
+    out = {}
+    for name in ("frontalface_alt", "frontalface_alt2", "frontalface_alt_tree", "fullbody"):
+        cas = oracle.Cascade(os.path.join(ROOT, "data", "haarcascades", f"haarcascade_{name}.xml"))
+        for fi, frame in enumerate([octave_frame(320, 240, 21), uniform_frame(320, 240, 22)]):
+            r, codes, st, levels = cas.detect_sc(frame, 1.2)
+            out[f"{name}_rects_{fi}"] = r
+            out[f"{name}_crc_{fi}"] = np.array([zlib.crc32(codes.tobytes())], np.uint32)
+            out[f"{name}_stats_{fi}"] = np.array([st.windows, st.weak_evals, st.accepted, int((codes == -32768).sum()),
+                                                  int((codes == -32767).sum())], np.int64)
+            out[f"{name}_levels_{fi}"] = np.array([[l.win_w, l.win_h, l.nx, l.ny] for l in levels], np.int32)
+    np.savez_compressed(os.path.join(HERE, "refsc.npz"), **out)
 
 
 if __name__ == "__main__":

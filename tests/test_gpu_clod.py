@@ -277,3 +277,19 @@ def test_scale_cascade_mode_min_size_and_batch_ranges(gpu_ctx, monkeypatch):
         assert np.array_equal(res.frame_rects(f), _sorted(rects))
         assert all(l.win_w >= 40 for l in det.levels())
     det.close()
+
+
+def test_scale_cascade_mode_golden_fixture(gpu_ctx):
+    """committed REF-SC vectors (tests/golden/refsc.npz) against the CUDA path"""
+    import os, zlib
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "refsc.npz"))
+    for name in ("frontalface_alt", "fullbody"):
+        cas = clfd.Cascade(cascade_path(name))
+        det = clfd.Detector(gpu_ctx, cas, 320, 240, max_batch=2, scale_factor=1.2, scale_cascade=True)
+        frames = np.stack([octave_frame(320, 240, 21), uniform_frame(320, 240, 22)])
+        res = det.detect(frames)
+        codes = det.codes(0, 2)
+        for fi in range(2):
+            assert zlib.crc32(codes[fi].tobytes()) == int(g[f"{name}_crc_{fi}"][0])
+            assert np.array_equal(res.frame_rects(fi), _sorted(g[f"{name}_rects_{fi}"]))
+        det.close()

@@ -146,3 +146,116 @@ def test_independent_python_restatement_of_the_evaluator():
                     break
                 depth += 1
             assert depth == codes[iy, ix], (ix, iy)
+
+
+SC_CASCADES = ["frontalface_alt", "frontalface_alt2", "frontalface_alt_tree", "fullbody"]
+
+
+@pytest.mark.parametrize("name", SC_CASCADES)
+def test_golden_refsc_detection(name):
+    """REF-SC (scale-cascade path, tempcv.cpp:1330-1456) regression pins."""
+    g = np.load(os.path.join(GOLD, "refsc.npz"))
+    cas = oracle_cascade(name)
+    for fi, frame in enumerate([octave_frame(320, 240, 21), uniform_frame(320, 240, 22)]):
+        r, codes, st, levels = cas.detect_sc(frame, 1.2)
+        assert np.array_equal(r, g[f"{name}_rects_{fi}"])
+        assert zlib.crc32(codes.tobytes()) == int(g[f"{name}_crc_{fi}"][0])
+        assert [st.windows, st.weak_evals, st.accepted, int((codes == -32768).sum()), int((codes == -32767).sum())] == \
+            g[f"{name}_stats_{fi}"].tolist()
+        assert [[l.win_w, l.win_h, l.nx, l.ny] for l in levels] == g[f"{name}_levels_{fi}"].tolist()
+
+
+def test_refsc_grid_and_skip_rule_invariants():
+    """Structure of the scale-cascade path: the scale loop of tempcv.cpp:1344-1380, the grid of the
+    invoker (endX/endY = cvRound((size - win) / step), step = max(2, factor)) and its skip rule: a
+    position is skipped iff its left neighbour was evaluated and returned 0."""
+    cas = oracle_cascade("frontalface_alt")
+    W, H, sf = 400, 300, 1.25
+    frame = octave_frame(W, H, 31)
+    rects, codes, st, levels = cas.detect_sc(frame, sf)
+    f, n = 1.0, 0
+    while f * 20 < W - 10 and f * 20 < H - 10:
+        f *= sf
+        n += 1
+    assert len(levels) == n
+    off = 0
+    n_eval = 0
+    for l in levels:
+        step = max(2.0, l.factor)
+        assert (l.win_w, l.win_h) == (int(np.rint(20 * l.factor)), int(np.rint(20 * l.factor)))
+        assert l.nx == int(np.rint((W - l.win_w) / step)) and l.ny == int(np.rint((H - l.win_h) / step))
+        c = codes[off:off + l.nx * l.ny].reshape(l.ny, l.nx)
+        off += l.nx * l.ny
+        assert (c[:, 0] != -32768).all()                       # a row always starts evaluated
+        skipped = c == -32768
+        left_zero = np.zeros_like(skipped)
+        left_zero[:, 1:] = c[:, :-1] == 0                      # linear cascade: result 0 == rejected by stage 0
+        assert (skipped <= left_zero).all()                    # only after a stage-0 reject
+        assert not (skipped[:, 1:] & skipped[:, :-1]).any()    # never two in a row
+        # an evaluated stage-0 reject is ALWAYS followed by a skipped position
+        ev_zero = (c == 0)
+        assert (skipped[:, 1:] == ev_zero[:, :-1]).all()
+        n_eval += int((c >= 0).sum())
+        acc = np.argwhere(c == 22)
+        for iy, ix in acc:
+            assert [int(np.rint(ix * step)), int(np.rint(iy * step)), l.win_w, l.win_h] in rects.tolist()
+    assert n_eval == st.windows and len(rects) == int((codes == 22).sum())
+
+
+def test_refsc_python_restatement_of_feature_scaling():
+    """cvSetImagesForHaarClassifierCascade(scale) (tempcv.cpp:614-618,704-760) restated in numpy for
+    one window of one scale and compared with the oracle's exit code at that position."""
+    cas = oracle_cascade("frontalface_alt")
+    f = cas.flat
+    W, H, sf = 200, 160, 1.3
+    frame = octave_frame(W, H, 41)
+    rects, codes, st, levels = cas.detect_sc(frame, sf)
+    s, q, _ = oracle.integral(frame)
+    rnd = lambda v: int(np.rint(v))
+    first = np.concatenate([[0], np.cumsum(f.st_ntrees)])
+    off = 0
+    checked = 0
+    for l in levels:
+        step = max(2.0, l.factor)
+        ex = rnd(l.factor); ew, eh = rnd(18 * l.factor), rnd(18 * l.factor)
+        inv = 1.0 / (ew * eh)
+        c = codes[off:off + l.nx * l.ny].reshape(l.ny, l.nx)
+        off += l.nx * l.ny
+        for iy, ix in [(0, 0), (l.ny // 2, l.nx // 3), (l.ny - 1, l.nx - 1)]:
+            if c[iy, ix] < 0:
+                continue
+            x, y = rnd(ix * step), rnd(iy * step)
+            box = lambda A, x0, y0, w, h: float(A[y0 + h, x0 + w]) - float(A[y0 + h, x0]) - float(A[y0, x0 + w]) + float(A[y0, x0])
+            mean = box(s, x + ex, y + ex, ew, eh) * inv
+            var = box(q, x + ex, y + ex, ew, eh) * inv - mean * mean
+            sigma = np.sqrt(var) if var >= 0 else 1.0
+            code = 22
+            for st_i in range(22):
+                ssum = 0.0
+                for t in range(first[st_i], first[st_i + 1]):
+                    wts, area0, sum0, vals = [], 0, 0.0, []
+                    nr = 3 if (abs(f.nd_weight[t, 2]) > 0 and f.nd_rect[t, 2, 2] and f.nd_rect[t, 2, 3]) else 2
+                    for k in range(nr):
+                        rx, ry, rw, rh = (rnd(v * l.factor) for v in f.nd_rect[t, k])
+                        wk = np.float32(float(f.nd_weight[t, k]) * inv)
+                        if k == 0:
+                            area0 = rw * rh
+                        else:
+                            sum0 += float(np.float32(np.float32(wk * np.float32(rw)) * np.float32(rh)))
+                        wts.append(wk)
+                        vals.append(box(s, x + rx, y + ry, rw, rh))
+                    wts[0] = np.float32(-sum0 / area0)
+                    two = all(not (abs(f.nd_weight[u, 2]) > 0 and f.nd_rect[u, 2, 2]) for u in range(first[st_i], first[st_i + 1]))
+                    if two:
+                        sv = vals[1] * float(wts[1]) + vals[0] * float(wts[0])
+                    else:
+                        sv = float(np.float32(np.float32(vals[0]) * wts[0])) + float(np.float32(np.float32(vals[1]) * wts[1]))
+                        if nr == 3:
+                            sv += float(np.float32(np.float32(vals[2]) * wts[2]))
+                    ssum += float(f.alpha[2 * t + (1 if sv >= float(f.nd_thr[t]) * sigma else 0)])
+                if ssum < float(np.float32(f.st_thr[st_i] - np.float32(0.0001))):
+                    code = st_i
+                    break
+            assert code == c[iy, ix], (l.factor, ix, iy, code, c[iy, ix])
+            checked += 1
+    assert checked >= 20
