@@ -58,9 +58,9 @@ int build_hidden(HostCascade &c);
 // ------------------------------------------------------------------------------------
 // Tile geometry of the smem-tile ("dense") cascade kernel: TW x TH windows per CTA.
 constexpr int kTileW = 64;
-constexpr int kTileH = 16;
+constexpr int kTileH = 32;
 constexpr int kTileWindows = kTileW * kTileH;
-constexpr int kDenseThreads = 128;
+constexpr int kDenseThreads = 256;
 constexpr int kDenseWarps = kDenseThreads / 32;
 constexpr int kDenseSlots = kTileWindows / kDenseThreads;   // windows per thread (8)
 constexpr int kDenseChunk = 4;                               // windows a thread carries through a stage at once

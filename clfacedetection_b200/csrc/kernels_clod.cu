@@ -5,7 +5,7 @@
 // grid of HaarDetectObjects_ScaleImage_Invoker (tempcv.cpp:1011-1103).
 //
 // One or two kernels per cascade per batch, no host round trip in between:
-//   k_cascade_tiles : one CTA per 64x16-window tile of one level of one frame.  The int32
+//   k_cascade_tiles : one CTA per 64x32-window tile of one level of one frame.  The int32
 //       integral tile is staged into shared memory (TMA bulk row copies, cp.async.bulk +
 //       mbarrier, on ystep-1 levels), sigma is computed once per window in FP64, and the
 //       cascade is evaluated in two phases: fixed geometry (thread per window column, no
@@ -90,7 +90,7 @@ __device__ __forceinline__ void emit_rect(const CascadeArgs &a, const CasLevel &
 // ------------------------------------------------------------------------------------
 // dense tile kernel
 //
-// One CTA (128 threads) per 64x16-window tile.  Shared memory:
+// One CTA (256 threads) per 64x32-window tile.  Shared memory:
 //   tile    int32 [rows][S]   ystep-1 levels: natural layout, staged by TMA bulk row copies;
 //                             ystep-2 levels: even columns in [0,S/2), odd columns in [S/2,S)
 //                             of each row (LDG.128 + 2 x STS.64).  In both layouts a window's
@@ -98,13 +98,13 @@ __device__ __forceinline__ void emit_rect(const CascadeArgs &a, const CasLevel &
 //                             bank class is (wx + 8*wy) mod 32: the 32 lanes of a warp with
 //                             consecutive wx never conflict, and neither do compacted rows
 //                             whose windows have distinct classes.
-//   sgf     float [1024]      per-window sigma rounded to FP32 for the phase-1 filter (the FP64
+//   sgf     float [2048]      per-window sigma rounded to FP32 for the phase-1 filter (the FP64
 //                             value is recomputed where exact arithmetic needs it)
-//   list    u16 [1024]        survivors (phase 1 output; per-warp segments compacted in place in phase 2)
+//   list    u16 [2048]        survivors (phase 1 output; per-warp segments compacted in place in phase 2)
 //   scr     384 B per warp    re-packing scratch of phase 2
 //
 // Phase 1, "fixed geometry" (stages 0 .. n_fixed-1, where most windows are still alive):
-//   thread t owns the column of 8 windows (wx = t & 63, wy = (t >> 6) + 2k).  Their tile
+//   thread t owns the column of 8 windows (wx = t & 63, wy = (t >> 6) + 4k).  Their tile
 //   addresses differ by a compile-time constant, so a corner address is computed ONCE per
 //   stump and the 4 windows of a chunk are read with immediate offsets (LDS [R + k*ROWSTEP]):
 //   no per-window address arithmetic, no compaction traffic, conflict-free banks.  Stumps
