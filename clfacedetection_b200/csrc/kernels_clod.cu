@@ -322,7 +322,7 @@ __device__ __forceinline__ bool stage_verdict(const DenseParams &P, const DenseC
 }
 
 // ROWSTEP_T: compile-time byte distance between a thread's consecutive windows in phase 1
-// (= 2 window rows), or 0 to use the runtime value (generic window sizes).
+// (= kDenseThreads / kTileW window rows), or 0 to use the runtime value (generic window sizes).
 template <int ROWSTEP_T>
 __global__ void __launch_bounds__(kDenseThreads)
 k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ CascadeArgs a, const int tile0) {
@@ -394,7 +394,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     const float inf = __int_as_float(0x7f800000);
 
     // ---- phase 1: sigma, then the fixed-geometry stages ----
-    constexpr int kRowsPerSlot = kDenseThreads / kTileW;   // window rows between a thread's slots (2)
+    constexpr int kRowsPerSlot = kDenseThreads / kTileW;   // window rows between a thread's slots (4)
     const int wx = tid & (kTileW - 1), wy0 = tid / kTileW;
     uint32_t alive = 0;   // bit k: window (wx, wy0 + 2k) still alive
 #pragma unroll
