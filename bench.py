@@ -35,7 +35,8 @@ sys.path.insert(0, ROOT)
 W, H = 1920, 1080
 CASCADE = "frontalface_alt"
 SCALE = 1.2
-XML = os.path.join(ROOT, "data", "haarcascades", f"haarcascade_{CASCADE}.xml")
+MIN_SIZE = (0, 0)
+XML = [os.path.join(ROOT, "data", "haarcascades", f"haarcascade_{CASCADE}.xml")]
 KERNEL_NAMES = ["resize_colsum", "colscan", "integral_rows", "tilted", "cascade_tiles", "cascade_deep"]
 
 
@@ -114,13 +115,14 @@ def cpu_reference(frames: np.ndarray, threads: int):
     """The reference's CPU path (REF-SI restatement = oracle port) on `frames`; returns
     (seconds, windows, rects)."""
     import oracle
-    cas = oracle.Cascade(XML)
+    cascades = [oracle.Cascade(x) for x in XML]
     t0 = time.perf_counter()
     windows = rects = 0
     for f in frames:
-        r, _, _, st, _ = cas.detect(f, SCALE, want_codes=False, n_threads=threads)
-        windows += st.windows
-        rects += len(r)
+        for cas in cascades:
+            r, _, _, st, _ = cas.detect(f, SCALE, MIN_SIZE, want_codes=False, n_threads=threads)
+            windows += st.windows
+            rects += len(r)
     return time.perf_counter() - t0, windows, rects
 
 
@@ -141,7 +143,7 @@ def run_reference(args):
         win_total += w
     fps = per_step * args.steps / t_total
     line = {
-        "impl": "reference", "metric": "frames_per_sec_1080p", "value": fps, "unit": "frames/s",
+        "impl": "reference", "metric": "frames_per_sec_1080p" if (W, H) == (1920, 1080) else f"frames_per_sec_{W}x{H}", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"haarcascade_{CASCADE} {W}x{H} scale {SCALE}, {per_step} octave-noise frames per step "
@@ -157,7 +159,7 @@ def run_reference(args):
 
 
 def main():
-    global CASCADE, XML
+    global CASCADE, XML, W, H, SCALE, MIN_SIZE
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -170,11 +172,17 @@ def main():
     ap.add_argument("--mode", default="pyramid", choices=["pyramid", "scale-cascade"],
                     help="pyramid = CV_HAAR_SCALE_IMAGE semantics (the metric); scale-cascade = scaled features on one "
                          "integral image (SURVEY 8-f row 3), an extra measurement, not the headline")
+    ap.add_argument("--size", default=f"{W}x{H}", help="frame shape WxH (default: the metric's 1920x1080)")
+    ap.add_argument("--scale", type=float, default=SCALE, help="pyramid scale factor (default: the metric's 1.2)")
+    ap.add_argument("--min-size", default="0x0", help="minimum window WxH")
     ap.add_argument("--cascade", default=CASCADE, help="stock cascade name (default: the metric's frontalface_alt; "
-                    "frontalface_default is BASELINE.json configs[1])")
+                    "frontalface_default is BASELINE.json configs[1]); a comma list shares one pyramid (configs[2], [3])")
     args = ap.parse_args()
     CASCADE = args.cascade
-    XML = os.path.join(ROOT, "data", "haarcascades", f"haarcascade_{CASCADE}.xml")
+    XML = [os.path.join(ROOT, "data", "haarcascades", f"haarcascade_{c}.xml") for c in CASCADE.split(",")]
+    W, H = (int(v) for v in args.size.lower().split("x"))
+    SCALE = args.scale
+    MIN_SIZE = tuple(int(v) for v in args.min_size.lower().split("x"))
     if args.impl == "reference":
         return run_reference(args)
 
@@ -203,9 +211,10 @@ def main():
     dev = host.cuda()
 
     ctx = clfd.Context(local_rank)
-    cas = clfd.Cascade(XML)
-    det = clfd.Detector(ctx, cas, W, H, max_batch=B, scale_factor=SCALE, scale_cascade=args.mode == "scale-cascade")
-    wpf = det.windows_per_frame()
+    cas = [clfd.Cascade(x) for x in XML]
+    det = clfd.Detector(ctx, cas, W, H, max_batch=B, scale_factor=SCALE, min_size=MIN_SIZE,
+                        scale_cascade=args.mode == "scale-cascade")
+    wpf = sum(det.windows_per_frame(i) for i in range(len(cas)))
     stream = torch.cuda.current_stream().cuda_stream
 
     def barrier():
@@ -327,13 +336,15 @@ def main():
                 "l1_data_pipe": {"pct_of_peak": kernels[dom].get("ncu_l1_data_pipe_pct"),
                                  "source": ncu["source"] if ncu else None}}
         line = {
-            "metric": "frames_per_sec_1080p", "value": round(fps, 2), "unit": "frames/s", "n_gpus": world,
+            "metric": "frames_per_sec_1080p" if (W, H) == (1920, 1080) else f"frames_per_sec_{W}x{H}", "value": round(fps, 2), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"haarcascade_{CASCADE} {W}x{H} scale {SCALE}, batch {B} octave-noise frames per GPU per step"
+                                   + (f", min window {MIN_SIZE[0]}x{MIN_SIZE[1]}" if MIN_SIZE != (0, 0) else "")
                                    + (" [scale-cascade mode]" if args.mode == "scale-cascade" else ""),
                        "frames_per_step_per_gpu": B, "windows_per_frame": wpf, "levels": len(det.levels()),
-                       "l2": "inputs and intermediates (132 MB frames, 5.6 GB integrals per batch) exceed the 126 MB L2"},
+                       "l2": f"inputs and intermediates ({B * W * H / 1e6:.0f} MB frames, {stats['bytes_integral'] * B / 1e9:.1f} GB integrals "
+                             "per batch) exceed the 126 MB L2; no flush needed"},
             "windows_per_sec": round(fps * wpf, 1),
             "wall_s": round(wall, 4),
             "rects_per_step": total_rects,
