@@ -86,7 +86,8 @@ struct DenseStage {
                              // bit2 alpha sum exact in any order (HostCascade::order_free)
     uint32_t tail_first;     // index of the stage's first stump in the global TailStump array
     float sum_eps;           // bound on the error of an FP32 sum of the stage's alphas in any order
-    uint32_t pad;
+    uint32_t n_shared;       // parameter-resident copy only: the first n_shared stumps of the stage are two-rect
+                             // stumps whose rects share two corners, stored in six-offset form (see haar_pack.cpp)
 };
 // Two blobs per cascade: [0] for ystep-1 levels (natural tile layout, addr = y*S + x) and
 // [1] for ystep-2 levels (columns de-interleaved: addr = y*S + (x&1)*S/2 + (x>>1)), so that in

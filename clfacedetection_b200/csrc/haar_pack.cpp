@@ -337,11 +337,39 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
             const double e = (double)c.st_ntrees[i] * ldexp(1.0, -23) * abs_sum;
             ds.sum_eps = std::isfinite(e) ? (float)(e * 1.0000002) + FLT_MIN : INFINITY;
         }
-        // parameter-resident copy of the leading stages that fit the kernel-parameter budget
+        // parameter-resident copy of the leading stages that fit the kernel-parameter budget.  Inside a
+        // stage the copy is REORDERED (the FP32 filters do not depend on the order; the exact fallback
+        // reads the global records, which stay in tree order): first the two-rect stumps whose rects have
+        // two corners in common -- the usual edge feature, a rectangle and one of its halves -- in a
+        // six-offset form E0,E1,F0,F1,G0,G1 with rect0 = (E0-E1)+(F0-F1), rect1 = (E0-E1)+(G0-G1): six
+        // corner loads instead of eight.  With p0,p3 entering a rect sum with + and p1,p2 with -, the
+        // common pair can only be (p0,p2), (p3,p1), (p0,p1) or (p3,p2).
+        const bool share_corners = !getenv("CLFD_NO_SHARED_CORNERS");   // test hook
         int ns = 0, nstump = 0;
         while (ns < elig && nstump + c.st_ntrees[ns] <= kMaxDenseStumps) {
             P.stage[ns].first = (uint16_t)nstump;
-            for (int t = c.st_first_tree[ns]; t < c.st_first_tree[ns + 1]; t++) P.stump[nstump++] = out.tail[yi][t];
+            std::vector<DenseStump> six, rest;
+            for (int t = c.st_first_tree[ns]; t < c.st_first_tree[ns + 1]; t++) {
+                DenseStump st = out.tail[yi][t];
+                bool shared = false;
+                if (share_corners && c.hid_nrects[c.tr_first_node[t]] == 2) {
+                    const uint32_t *A = st.off, *B = st.off + 4;
+                    static const int pairs[4][2] = {{0, 2}, {3, 1}, {0, 1}, {3, 2}};   // (plus, minus) corner
+                    for (const auto &pr : pairs) {
+                        const int pl = pr[0], mi = pr[1];
+                        if (A[pl] != B[pl] || A[mi] != B[mi]) continue;
+                        const int opl = pl == 0 ? 3 : 0, omi = mi == 1 ? 2 : 1;   // the other plus / minus corner
+                        const uint32_t o[6] = {A[pl], A[mi], A[opl], A[omi], B[opl], B[omi]};
+                        for (int q = 0; q < 12; q++) st.off[q] = q < 6 ? o[q] : 0;
+                        shared = true;
+                        break;
+                    }
+                }
+                (shared ? six : rest).push_back(st);
+            }
+            P.stage[ns].n_shared = (uint32_t)six.size();
+            for (const auto &st : six) P.stump[nstump++] = st;
+            for (const auto &st : rest) P.stump[nstump++] = st;
             ns++;
         }
         P.n_stages = ns;

@@ -245,14 +245,22 @@ __device__ __noinline__ bool dense_stage_exact(const DenseParams &P, const Dense
 // plus the cancellation terms), S[k] adds the selected alpha in FP32.
 //   FIXED = true : window k lives at base[0] + k*ROWSTEP (compile-time) -> immediate offsets
 //   FIXED = false: window k lives at base[k]
-template <int KK, int K, bool FIXED, int ROWSTEP>
+template <int KK, int K, bool FIXED, int ROWSTEP, bool SHARED>
 __device__ __forceinline__ void stump_filter_window(const StumpRegs &q, bool dbl, bool three, float eps, const uint32_t (&c)[12],
                                                     const uint32_t (&base)[K], const float (&sg)[K], float (&S)[K], bool (&near)[K]) {
     const float eps4 = eps * 0.25f;
     constexpr int IMM = KK * ROWSTEP;
     const uint32_t b = base[FIXED ? 0 : KK];
     int r0, r1;
-    if (FIXED) {   // LDS [corner of window 0 + immediate]
+    if (SHARED) {   // two rects with two common corners, six offsets (haar_pack.cpp)
+        int e, f, g;
+        if (FIXED) {
+            e = lds32i<IMM>(c[0]) - lds32i<IMM>(c[1]); f = lds32i<IMM>(c[2]) - lds32i<IMM>(c[3]); g = lds32i<IMM>(c[4]) - lds32i<IMM>(c[5]);
+        } else {
+            e = lds32(b + q.o[0]) - lds32(b + q.o[1]); f = lds32(b + q.o[2]) - lds32(b + q.o[3]); g = lds32(b + q.o[4]) - lds32(b + q.o[5]);
+        }
+        r0 = e + f; r1 = e + g;
+    } else if (FIXED) {   // LDS [corner of window 0 + immediate]
         r0 = lds32i<IMM>(c[0]) - lds32i<IMM>(c[1]) - lds32i<IMM>(c[2]) + lds32i<IMM>(c[3]);
         r1 = lds32i<IMM>(c[4]) - lds32i<IMM>(c[5]) - lds32i<IMM>(c[6]) + lds32i<IMM>(c[7]);
     } else {
@@ -264,7 +272,7 @@ __device__ __forceinline__ void stump_filter_window(const StumpRegs &q, bool dbl
     const float t32 = __fmul_rn(q.thr, sg[KK]);
     float m = __fmul_rn(fabsf(t32), eps);
     if (dbl) m = __fadd_rn(m, __fmul_rn(__fadd_rn(fabsf(p0), fabsf(p1)), eps4));   // the reference adds EXACT products: fp32 product errors do not cancel
-    if (three) {
+    if (!SHARED && three) {
         int r2;
         if (FIXED) r2 = lds32i<IMM>(c[8]) - lds32i<IMM>(c[9]) - lds32i<IMM>(c[10]) + lds32i<IMM>(c[11]);
         else r2 = lds32(b + q.o[8]) - lds32(b + q.o[9]) - lds32(b + q.o[10]) + lds32(b + q.o[11]);
@@ -276,20 +284,20 @@ __device__ __forceinline__ void stump_filter_window(const StumpRegs &q, bool dbl
     S[KK] = __fadd_rn(S[KK], d >= 0.f ? q.a1 : q.a0);
 }
 
-template <int K, bool FIXED, int ROWSTEP>
+template <int K, bool FIXED, int ROWSTEP, bool SHARED>
 __device__ __forceinline__ void stump_filter(const StumpRegs &q, bool dbl, bool any3, float eps, const uint32_t (&base)[K],
                                              const float (&sg)[K], float (&S)[K], bool (&near)[K]) {
     static_assert(K >= 1 && K <= 4, "1..4 windows per thread");
-    const bool three = any3 && q.o[11] != 0u;   // warp-uniform per stump
+    const bool three = !SHARED && any3 && q.o[11] != 0u;   // warp-uniform per stump
     uint32_t c[12];
     if (FIXED) {   // corner addresses of window 0, shared by all K windows
 #pragma unroll
-        for (int i = 0; i < 12; i++) c[i] = base[0] + q.o[i];
+        for (int i = 0; i < (SHARED ? 6 : 12); i++) c[i] = base[0] + q.o[i];
     }
-    stump_filter_window<0, K, FIXED, ROWSTEP>(q, dbl, three, eps, c, base, sg, S, near);
-    if (K > 1) stump_filter_window<(K > 1 ? 1 : 0), K, FIXED, ROWSTEP>(q, dbl, three, eps, c, base, sg, S, near);
-    if (K > 2) stump_filter_window<(K > 2 ? 2 : 0), K, FIXED, ROWSTEP>(q, dbl, three, eps, c, base, sg, S, near);
-    if (K > 3) stump_filter_window<(K > 3 ? 3 : 0), K, FIXED, ROWSTEP>(q, dbl, three, eps, c, base, sg, S, near);
+    stump_filter_window<0, K, FIXED, ROWSTEP, SHARED>(q, dbl, three, eps, c, base, sg, S, near);
+    if (K > 1) stump_filter_window<(K > 1 ? 1 : 0), K, FIXED, ROWSTEP, SHARED>(q, dbl, three, eps, c, base, sg, S, near);
+    if (K > 2) stump_filter_window<(K > 2 ? 2 : 0), K, FIXED, ROWSTEP, SHARED>(q, dbl, three, eps, c, base, sg, S, near);
+    if (K > 3) stump_filter_window<(K > 3 ? 3 : 0), K, FIXED, ROWSTEP, SHARED>(q, dbl, three, eps, c, base, sg, S, near);
 }
 
 // Stumps grp, grp + G, ... of stage s for K windows of this lane.  Stumps come from the
@@ -301,14 +309,16 @@ __device__ __forceinline__ void stage_filter(const DenseParams &P, int s, int gr
     const uint32_t flags = P.stage[s].flags;
     const bool dbl = flags & 1u, any3 = flags & 2u;
     const float eps = P.filter_eps;
-    if (s < P.n_stages && G == 1) {   // all lanes on the same stump: constant bank
-        const int first = P.stage[s].first;
+    if (s < P.n_stages && G == 1) {   // all lanes on the same stump: constant bank (reordered copy: six-load stumps first)
+        const int first = P.stage[s].first, n6 = (int)P.stage[s].n_shared;
 #pragma unroll 1
-        for (int j = grp; j < count; j += G) stump_filter<K, FIXED, ROWSTEP>(stump_from_param(P.stump[first + j]), dbl, any3, eps, base, sg, S, near);
+        for (int j = 0; j < n6; j++) stump_filter<K, FIXED, ROWSTEP, true>(stump_from_param(P.stump[first + j]), dbl, false, eps, base, sg, S, near);
+#pragma unroll 1
+        for (int j = n6; j < count; j++) stump_filter<K, FIXED, ROWSTEP, false>(stump_from_param(P.stump[first + j]), dbl, any3, eps, base, sg, S, near);
     } else {
         const DenseStump *__restrict__ rec = P.tail + P.stage[s].tail_first;
 #pragma unroll 1
-        for (int j = grp; j < count; j += G) stump_filter<K, FIXED, ROWSTEP>(stump_from_global(rec + j, any3), dbl, any3, eps, base, sg, S, near);
+        for (int j = grp; j < count; j += G) stump_filter<K, FIXED, ROWSTEP, false>(stump_from_global(rec + j, any3), dbl, any3, eps, base, sg, S, near);
     }
 }
 
