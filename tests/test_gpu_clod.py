@@ -293,3 +293,45 @@ def test_scale_cascade_mode_golden_fixture(gpu_ctx):
             assert zlib.crc32(codes[fi].tobytes()) == int(g[f"{name}_crc_{fi}"][0])
             assert np.array_equal(res.frame_rects(fi), _sorted(g[f"{name}_rects_{fi}"]))
         det.close()
+
+
+def test_empty_ragged_and_odd_inputs(gpu_ctx):
+    """Frames too small for any window (no level at all), row strides larger than the width and not
+    16-byte multiples, a 1-frame batch in a detector planned for more, and both modes."""
+    import torch
+    cas = clfd.Cascade(cascade_path("frontalface_alt"))
+    # (i) smaller than the window: zero levels, zero rects, no launch failure
+    for sc in (False, True):
+        det = clfd.Detector(gpu_ctx, cas, 19, 18, scale_factor=1.2, scale_cascade=sc, want_codes=True)
+        assert det.windows_per_frame() == 0 and len(det.levels()) == 0
+        res = det.detect(np.zeros((1, 18, 19), np.uint8))
+        assert len(res.rects) == 0
+        det.close()
+    # (ii) ragged rows: width 301 inside a 333-byte pitch, frame pitch with slack, device and host input
+    W, H = 301, 233
+    frame = octave_frame(W, H, 51)
+    oc = oracle_cascade("frontalface_alt")
+    want, ocodes, _, _, _ = oc.detect(frame, 1.2)
+    want_sc, ocodes_sc, _, _ = oc.detect_sc(frame, 1.2)
+    buf = np.full((3, H + 5, 333), 77, np.uint8)
+    buf[:, :H, :W] = frame
+    view = buf[:, :H, :W]                      # strides (frame 338*333... , row 333)
+    for sc, w, c in ((False, want, ocodes), (True, want_sc, ocodes_sc)):
+        det = clfd.Detector(gpu_ctx, cas, W, H, max_batch=4, scale_factor=1.2, scale_cascade=sc, want_codes=True)
+        cnt = clfd.abi.C.c_int64()
+        clfd.abi.check(clfd.abi.lib().clfd_detect(det._h, view.ctypes.data, 3, view.strides[0], view.strides[1],
+                                                   det._rects.ctypes.data_as(clfd.abi.C.POINTER(clfd.abi.Rect)), det._rect_cap,
+                                                   clfd.abi.C.byref(cnt)))
+        res = clfd.DetectResult(det._rects[:cnt.value].copy(), det.stats())
+        codes = det.codes(0, 3)
+        for f in range(3):
+            assert np.array_equal(codes[f], c)
+            assert np.array_equal(res.frame_rects(f), _sorted(w))
+        # the same ragged layout already on the device, through enqueue / fetch
+        t = torch.from_numpy(buf).cuda()
+        torch.cuda.synchronize()
+        det.enqueue(t, 3, t.stride(0), t.stride(1), torch.cuda.current_stream().cuda_stream)
+        res2 = det.fetch(torch.cuda.current_stream().cuda_stream)
+        for f in range(3):
+            assert np.array_equal(res2.frame_rects(f), _sorted(w))
+        det.close()
