@@ -1,7 +1,7 @@
 #!/bin/bash
 # Runs the five BASELINE.json configurations on one B200 and prints one line each
 # (value = device-resident frames/s, e2e = host frames in / rects out, cpu = REF-SI oracle on the host cores).
-# usage: ./tools_configs.sh > gpurun_out/configs.jsonl
+# usage: ./tools/configs.sh > gpurun_out/configs.jsonl
 run() { python bench.py --steps "$1" --warmup 3 "${@:2}" 2>/dev/null | python -c "
 import sys, json
 d = json.loads(sys.stdin.read())
