@@ -142,6 +142,16 @@ def run_reference(args):
         t_total += t
         win_total += w
     fps = per_step * args.steps / t_total
+    # for the record: the scale-cascade formulation (REF-SC: what main.cpp:145 runs and the shape of
+    # clod's own CPU variants, clod.cpp:1339-1500) on the same frames, one pass
+    import oracle
+    t0 = time.perf_counter()
+    sc_windows = 0
+    for f in frames:
+        for x in XML:
+            _, _, st, _ = oracle.Cascade(x).detect_sc(f, SCALE, MIN_SIZE, want_codes=False, n_threads=cores)
+            sc_windows += st.windows
+    sc_fps = per_step / (time.perf_counter() - t0)
     line = {
         "impl": "reference", "metric": "frames_per_sec_1080p" if (W, H) == (1920, 1080) else f"frames_per_sec_{W}x{H}", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
@@ -150,7 +160,8 @@ def run_reference(args):
                                "(bounded sample of the 64-frame GPU batch)", "frames_per_step": per_step},
         "windows_per_sec": win_total / t_total,
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{per_step} frames/step x {args.steps} steps, OpenMP over window rows"},
+                         "sample": f"{per_step} frames/step x {args.steps} steps, OpenMP over window rows",
+                         "scale_cascade_formulation_value": sc_fps, "scale_cascade_windows_per_frame": sc_windows // per_step},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
