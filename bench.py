@@ -345,8 +345,17 @@ def main():
                         "step / their CUDA-event time; traffic = ncu DRAM bytes of the same two launches scaled to this "
                         "batch.  The kernel is NOT HBM-bound: it saturates the SM's L1 data pipe (shared-memory corner "
                         "loads, one 128-B wavefront per clock per SM), see l1_data_pipe and DESIGN.md",
-                "l1_data_pipe": {"pct_of_peak": kernels[dom].get("ncu_l1_data_pipe_pct"),
+                "l1_data_pipe": {"ncu_pct_of_peak": kernels[dom].get("ncu_l1_data_pipe_pct"),
                                  "source": ncu["source"] if ncu else None}}
+        wf = ncu["kernels"][dom].get("l1_wavefronts_per_frame") if ncu and dom in ncu["kernels"] else None
+        if wf and clocks.get("sm_mhz"):
+            # live: the capture's wavefront count per frame x this run's frames / this run's kernel time,
+            # against one 128-byte wavefront per clock per SM at the SM clock sampled during the run
+            n_sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+            peak_wf = n_sms * clocks["sm_mhz"] * 1e6
+            ach_wf = wf * B / (kernel_ms[KERNEL_NAMES.index(dom)] * 1e-3)
+            roof["l1_data_pipe"].update({"achieved": round(ach_wf / 1e9, 1), "peak": round(peak_wf / 1e9, 1),
+                                         "unit": "G wavefronts/s", "frac": round(ach_wf / peak_wf, 4)})
         line = {
             "metric": "frames_per_sec_1080p" if (W, H) == (1920, 1080) else f"frames_per_sec_{W}x{H}", "value": round(fps, 2), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4),
