@@ -832,20 +832,26 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
                 sa.codes = cp.d_codes.p + (size_t)frame_base * cp.windows_per_frame;
                 sa.rects = a.rects; sa.rect_cap = a.rect_cap; sa.counters = a.counters; sa.deep = a.deep;
                 if (ev && ci == 0) CK(cudaEventRecord(ev[5], s));
-                // passes over growing stage ranges (cumulative trees >= 10, 40, 150, rest), survivors
+                // passes over growing stage ranges (cumulative trees >= 10, 40, 90, 160, ... per pass), survivors
                 // re-compacted through the two queues in between; a stage tree runs as one pass
                 {
                     const HostCascade &hc = cp.cascade->host;
                     std::vector<int> cuts(1, 0);
+                    int deep_from = hc.n_stages();   // first stage of the final warp-per-survivor pass
                     if (hc.is_tree || getenv("CLFD_SC_ONE_PASS")) cuts.push_back(hc.n_stages());
                     else {
-                        static const int limit[3] = {10, 40, 150};
+                        static const int limit[7] = {10, 40, 90, 160, 300, 500, 800};
                         int acc = 0;
+                        int deep_min = 50;
+                        if (const char *e = getenv("CLFD_SC_DEEP_MIN")) deep_min = atoi(e);
                         for (int st = 0; st < hc.n_stages(); st++) {
+                            // stages of >= 32 trees fill a warp's lanes: from the first one on (after at
+                            // least one thread pass) the survivors are finished one warp per position
+                            if (st > 0 && hc.st_ntrees[st] >= deep_min) { deep_from = st; break; }
                             acc += hc.st_ntrees[st];
-                            if (cuts.size() <= 3 && acc >= limit[cuts.size() - 1] && st + 1 < hc.n_stages()) { cuts.push_back(st + 1); acc = 0; }
+                            if (cuts.size() <= 7 && acc >= limit[cuts.size() - 1] && st + 1 < hc.n_stages()) { cuts.push_back(st + 1); acc = 0; }
                         }
-                        cuts.push_back(hc.n_stages());
+                        if (cuts.back() != deep_from) cuts.push_back(deep_from);
                     }
                     QueueItem *qs[2] = {det->queue.p, det->queue_b.p};
                     unsigned long long *cs[2] = {a.counters + 1, cp.d_count_b.p + slot};
@@ -860,6 +866,12 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
                         CK(launch_sc_eval(sa, ctx->n_sms, s));
                         launches++;
                         in = out;
+                    }
+                    if (deep_from < hc.n_stages()) {
+                        sa.stage_begin = deep_from; sa.stage_end = hc.n_stages();
+                        sa.in = qs[in]; sa.in_count = cs[in];
+                        CK(launch_sc_deep(sa, ctx->n_sms, s));
+                        launches++;
                     }
                 }
                 CK(launch_sc_rows(sa, s));

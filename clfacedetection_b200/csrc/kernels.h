@@ -88,6 +88,8 @@ struct ScArgs {
 };
 // one evaluation pass over the grid / a survivor queue (k_sc_eval)
 cudaError_t launch_sc_eval(const ScArgs &a, int n_sms, cudaStream_t stream);
+// final pass, warp per survivor: stages [stage_begin, n_stages) of a linear cascade (k_sc_deep)
+cudaError_t launch_sc_deep(const ScArgs &a, int n_sms, cudaStream_t stream);
 // the invoker's skip rule + rect emission over the finished exit codes (k_sc_rows)
 cudaError_t launch_sc_rows(const ScArgs &a, cudaStream_t stream);
 

@@ -10,7 +10,8 @@
 //       32 corner loads of a warp are 32 * ystep * 4 bytes apart at most (a few cache lines);
 //       the integral image of a frame (8-25 MB) lives in L2.  Linear cascades run in a few
 //       passes over growing stage ranges with the survivors re-compacted through a queue in
-//       between (thread per survivor), so lanes stay busy.  Every position is evaluated --
+//       between (thread per survivor), so lanes stay busy; the large late stages (>= 32 trees) run
+//       one warp per survivor, lanes over trees (k_sc_deep).  Every position is evaluated --
 //       the reference's skip rule makes the set of evaluated windows depend on the RESULTS of
 //       their left neighbours, so it is applied afterwards:
 //   k_sc_rows : one thread per grid row walks its exit codes left to right with the invoker's
@@ -168,6 +169,69 @@ __global__ void __launch_bounds__(128) k_sc_eval(const __grid_constant__ ScArgs 
     }
 }
 
+// Final pass for the large stages (>= 32 trees): one WARP per surviving position, lanes stride over
+// the trees of a stage, from a.stage_begin to the end of a LINEAR cascade.  The stage sum is reduced
+// with shuffles when the packer proved it exact in any order (DeepStage flags bit1), otherwise the
+// lanes' leaf values are added in tree order.
+__global__ void __launch_bounds__(256) k_sc_deep(const __grid_constant__ ScArgs a) {
+    const DeepCascadeDev &D = a.deep;
+    const int lane = threadIdx.x & 31;
+    const ull warp0 = ((ull)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const ull nwarps = ((ull)gridDim.x * 256) >> 5;
+    ull n = *a.in_count;
+    if (n > a.queue_cap) n = a.queue_cap;
+    for (ull item = warp0; item < n; item += nwarps) {
+        const QueueItem q = a.in[item];
+        const int frame = (int)q.key;
+        const long long w = (long long)q.xy;
+        int lo = 0, hi = a.n_levels - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (__ldg(&a.levels[mid].win_base) <= w) lo = mid; else hi = mid - 1;
+        }
+        const ScLevel L = a.levels[lo];
+        const int local = (int)(w - L.win_base);
+        const int iy = local / L.nx, ix = local - iy * L.nx;
+        const int x = __double2int_rn(__dmul_rn((double)ix, L.ystep));
+        const int y = __double2int_rn(__dmul_rn((double)iy, L.ystep));
+        const size_t off = (size_t)frame * a.sum_frame_stride + (size_t)y * a.pitch + x;   // in bounds: checked by the first pass
+        const int32_t *__restrict__ sum = a.sum + off;
+        const int32_t *__restrict__ til = a.tilted ? a.tilted + off : sum;
+        const ull *__restrict__ sq = a.sq + off;
+        const int s4 = __ldg(sum + L.eq_off[0]) - __ldg(sum + L.eq_off[1]) - __ldg(sum + L.eq_off[2]) + __ldg(sum + L.eq_off[3]);
+        const ull q4 = __ldg(sq + L.eq_off[0]) - __ldg(sq + L.eq_off[1]) - __ldg(sq + L.eq_off[2]) + __ldg(sq + L.eq_off[3]);
+        const double sigma = sc_sigma(s4, q4, L.inv_area);
+        const ScNode *__restrict__ nodes = a.nodes + L.node_base;
+        int i = a.stage_begin;
+        for (; i < D.n_stages; i++) {
+            const DeepStage st = D.stages[i];
+            const bool dbl = st.flags & 1, order_free = st.flags & 2;
+            double S = 0.0, part = 0.0;
+            for (int j0 = 0; j0 < st.ntrees; j0 += 32) {
+                const int j = j0 + lane;
+                float av = 0.f;
+                if (j < st.ntrees) {
+                    const int tree = st.first_tree + j, n0 = __ldg(D.tree_first_node + tree);
+                    av = sc_eval_tree(nodes, n0, D.alpha + n0 + tree, sum, til, sigma, dbl);
+                }
+                if (order_free) {
+                    part = __dadd_rn(part, (double)av);
+                } else {
+                    const int cnt = min(32, st.ntrees - j0);
+                    for (int k = 0; k < cnt; k++) S = __dadd_rn(S, (double)__shfl_sync(0xffffffffu, av, k));
+                }
+            }
+            if (order_free) {
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) part = __dadd_rn(part, __shfl_xor_sync(0xffffffffu, part, d));
+                S = part;
+            }
+            if (S < (double)st.thr) break;
+        }
+        if (lane == 0) a.codes[(size_t)frame * a.windows_per_frame + w] = (int16_t)i;   // rejected at i, or n_stages = accepted
+    }
+}
+
 __global__ void __launch_bounds__(128) k_sc_rows(const __grid_constant__ ScArgs a) {
     const int row = blockIdx.x * 128 + threadIdx.x;
     const int frame = blockIdx.y;
@@ -212,6 +276,12 @@ __global__ void __launch_bounds__(128) k_sc_rows(const __grid_constant__ ScArgs 
 cudaError_t launch_sc_eval(const ScArgs &a, int n_sms, cudaStream_t stream) {
     if (a.windows_per_frame == 0 || a.n_frames == 0) return cudaSuccess;
     k_sc_eval<<<n_sms * 16, 128, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sc_deep(const ScArgs &a, int n_sms, cudaStream_t stream) {
+    if (a.windows_per_frame == 0 || a.n_frames == 0) return cudaSuccess;
+    k_sc_deep<<<n_sms * 8, 256, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
