@@ -104,6 +104,7 @@ def lib() -> C.CDLL:
                               C.POINTER(C.c_int64)]
     L.clfd_group_batch.argtypes = [C.POINTER(Rect), C.c_int64, C.c_int, C.c_double, C.c_int, C.POINTER(Rect),
                                    C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int64)]
+    L.clfd_detect_image.argtypes = [vp, u8p, C.c_int, C.c_int, C.POINTER(Rect), C.c_int64, C.POINTER(C.c_int64)]
     L.clfd_detect_submit.argtypes = [vp, u8p, C.c_int, C.c_size_t, C.c_int]
     L.clfd_detect_collect.argtypes = [vp, C.POINTER(Rect), C.c_int64, C.POINTER(C.c_int64)]
     L.clfd_detector_get_codes.argtypes = [vp, C.c_int, C.POINTER(C.c_int16), C.c_int64]

@@ -264,6 +264,7 @@ struct clfd_detector {
     DevBuf<DevRect> rects;
     DevBuf<uint8_t> dev_frames[kSlots];   // staging for host input (clfd_detect / clfd_detect_submit)
     DevBuf<DevRect> rects2;               // rect buffer of slot 1 (slot 0 uses `rects`)
+    DevBuf<uint8_t> dev_bgr;              // interleaved colour input of clfd_detect_image
     DevRect *h_rects = nullptr;           // pinned, kSlots x rect_cap... slot 1 holds kEagerRects only
     DevRect *h_rects1 = nullptr;
     unsigned long long *h_counters = nullptr;  // pinned, kSlots x (4 per cascade, 16 cascades)
@@ -1122,6 +1123,29 @@ int clfd_detect(clfd_detector *det, const uint8_t *frames_host, int n_frames, si
     int rc = clfd_detect_submit(det, frames_host, n_frames, frame_stride, row_stride);
     if (rc) return rc;
     return clfd_detect_collect(det, rects, cap, n_rects);
+}
+
+// One interleaved 8-bit image (1, 3 = BGR or 4 = BGRA channels) from the host: the colour
+// conversion runs on the device and feeds the detector directly (no gray round trip).
+int clfd_detect_image(clfd_detector *det, const uint8_t *img_host, int channels, int stride, clfd_rect *rects, int64_t cap,
+                      int64_t *n_rects) {
+    if (!det || !img_host) INVALID("NULL argument");
+    const int W = det->cfg.width, H = det->cfg.height;
+    if (channels == 1) return clfd_detect(det, img_host, 1, (size_t)stride * H, stride, rects, cap, n_rects);
+    if (channels != 3 && channels != 4) INVALID("channels must be 1, 3 or 4");
+    if (stride < W * channels) INVALID("row stride %d smaller than %d pixels of %d channels", stride, W, channels);
+    if (det->n_submitted != det->n_collected) INVALID("clfd_detect_image while submitted batches are in flight");
+    clfd_context *ctx = det->ctx;
+    CK(cudaSetDevice(ctx->device));
+    const size_t dstride = round_up(W, 16), dframe = dstride * H;
+    int rc;
+    if (!det->dev_frames[0].p && (rc = det->dev_frames[0].alloc(dframe * det->cfg.max_batch + 64))) return rc;
+    if (det->dev_bgr.n < (size_t)stride * H && (rc = det->dev_bgr.alloc((size_t)stride * H))) return rc;
+    CK(cudaMemcpyAsync(det->dev_bgr.p, img_host, (size_t)stride * H, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_bgr_to_gray(det->dev_bgr.p, W, H, stride, channels, det->dev_frames[0].p, (int)dstride, ctx->stream));
+    ctx->launches++;
+    if ((rc = clfd_detector_enqueue(det, det->dev_frames[0].p, 1, dframe, (int)dstride, nullptr))) return rc;
+    return clfd_detector_fetch(det, rects, cap, n_rects, nullptr);
 }
 
 int clfd_detector_get_codes(clfd_detector *det, int cascade, int16_t *codes, int64_t cap) {

@@ -93,16 +93,6 @@ CLODDetectObjectsResult clodDetectObjects(const IplImage* image, const CvHaarCla
     const clfd_cascade* cas = cvShimCascadeHandle(cascade);
     const int W = image->width, H = image->height;
 
-    const unsigned char* pix = (const unsigned char*)image->imageData;
-    int step = image->widthStep;
-    if (image->nChannels != 1) {   // the reference's setupImage always converted BGR (clod.cpp:360-369)
-        s->gray.resize((size_t)W * H);
-        CHECK(clfd_bgr_to_gray(s->ctx, (const uint8_t*)image->imageData, W, H, image->widthStep, image->nChannels, 0,
-                               s->gray.data(), W, 0));
-        pix = s->gray.data();
-        step = W;
-    }
-
     DetKey key{cas, W, H, min_window_size.width, min_window_size.height, max_window_size.width, max_window_size.height,
                s->scale_factor, s->mode};
     clfd_detector*& det = s->detectors[key];
@@ -116,7 +106,10 @@ CLODDetectObjectsResult clodDetectObjects(const IplImage* image, const CvHaarCla
     }
     if (s->rects.empty()) s->rects.resize(1 << 20);
     int64_t n = 0;
-    CHECK(clfd_detect(det, pix, 1, (size_t)step * H, step, s->rects.data(), (int64_t)s->rects.size(), &n));
+    // the reference's setupImage always converted from BGR (clod.cpp:360-369); here 1, 3 or 4 channels,
+    // converted on the device on the way in
+    CHECK(clfd_detect_image(det, (const uint8_t*)image->imageData, image->nChannels, image->widthStep, s->rects.data(),
+                            (int64_t)s->rects.size(), &n));
 
     std::vector<int32_t> r4((size_t)n * 4), weights(n > 0 ? n : 1, 0);
     for (int64_t i = 0; i < n; i++) {

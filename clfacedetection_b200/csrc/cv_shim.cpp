@@ -6,6 +6,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "clfd_b200.h"
@@ -298,26 +299,23 @@ CvSeq* cvHaarDetectObjects(const CvArr* image, CvHaarClassifierCascade* cascade,
     if (flags & ~CV_HAAR_SCALE_IMAGE) { fprintf(stderr, "cvHaarDetectObjects: unsupported flags 0x%x\n", flags); abort(); }
     const View s = view_of(image);
     clfd_context* ctx = cvShimContext(0);
-    std::vector<unsigned char> gray;
-    const unsigned char* pix = s.data;
-    int step = s.step;
-    if (s.channels != 1) {
-        gray.resize((size_t)s.w * s.h);
-        CHECK(clfd_bgr_to_gray(ctx, s.data, s.w, s.h, s.step, s.channels, 0, gray.data(), s.w, 0));
-        pix = gray.data(); step = s.w;
-    }
     const clfd_cascade* cas = cvShimCascadeHandle(cascade);
-    clfd_detector_config cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.width = s.w; cfg.height = s.h; cfg.max_batch = 1; cfg.scale_factor = scale_factor;
-    cfg.min_w = min_size.width; cfg.min_h = min_size.height; cfg.max_w = max_size.width; cfg.max_h = max_size.height;
-    cfg.mode = (flags & CV_HAAR_SCALE_IMAGE) ? CLFD_MODE_SCALE_IMAGE : CLFD_MODE_SCALE_CASCADE;
-    clfd_detector* det = nullptr;
-    CHECK(clfd_detector_create(ctx, &cas, 1, &cfg, &det));
-    std::vector<clfd_rect> rects(1 << 20);
+    // detector plans are cached per (cascade, shape, parameters): OpenCV keeps its hidden cascade too
+    const int mode = (flags & CV_HAAR_SCALE_IMAGE) ? CLFD_MODE_SCALE_IMAGE : CLFD_MODE_SCALE_CASCADE;
+    typedef std::tuple<const clfd_cascade*, int, int, double, int, int, int, int, int> Key;
+    static std::map<Key, clfd_detector*> cache;
+    clfd_detector*& det = cache[Key(cas, s.w, s.h, scale_factor, min_size.width, min_size.height, max_size.width, max_size.height, mode)];
+    if (!det) {
+        clfd_detector_config cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.width = s.w; cfg.height = s.h; cfg.max_batch = 1; cfg.scale_factor = scale_factor;
+        cfg.min_w = min_size.width; cfg.min_h = min_size.height; cfg.max_w = max_size.width; cfg.max_h = max_size.height;
+        cfg.mode = mode;
+        CHECK(clfd_detector_create(ctx, &cas, 1, &cfg, &det));
+    }
+    static std::vector<clfd_rect> rects(1 << 20);
     int64_t n = 0;
-    CHECK(clfd_detect(det, pix, 1, (size_t)step * s.h, step, rects.data(), (int64_t)rects.size(), &n));
-    clfd_detector_destroy(det);
+    CHECK(clfd_detect_image(det, s.data, s.channels, s.step, rects.data(), (int64_t)rects.size(), &n));
     std::vector<int32_t> r4((size_t)n * 4), w(n > 0 ? n : 1, 0);
     for (int64_t i = 0; i < n; i++) { r4[4 * i] = rects[i].x; r4[4 * i + 1] = rects[i].y; r4[4 * i + 2] = rects[i].w; r4[4 * i + 3] = rects[i].h; }
     int m = (int)n;

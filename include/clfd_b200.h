@@ -195,6 +195,12 @@ CLFD_API int clfd_detector_fetch(clfd_detector *det, clfd_rect *rects, int64_t c
 CLFD_API int clfd_detect(clfd_detector *det, const uint8_t *frames_host, int n_frames,
                          size_t frame_stride, int row_stride, clfd_rect *rects, int64_t cap,
                          int64_t *n_rects);
+/* One interleaved image (channels 1, or 3 / 4 = BGR / BGRA as in IplImage) from the host: the
+ * colour conversion of clifGrayscale (clif.cpp:241-271) runs on the device and feeds the detector
+ * directly.  This is the whole of clodDetectObjects' device work for one frame (its setupImage,
+ * clod.cpp:360-369, converts every input from BGR). */
+CLFD_API int clfd_detect_image(clfd_detector *det, const uint8_t *img_host, int channels, int stride,
+                               clfd_rect *rects, int64_t cap, int64_t *n_rects);
 /* The same, split in two so that batches overlap: _submit copies batch i+1 (pinned host
  * memory, copy stream) while batch i still computes, _collect waits for the OLDEST submitted
  * batch and hands out its rects.  At most 2 batches in flight.  The reference has no such
