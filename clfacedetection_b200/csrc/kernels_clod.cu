@@ -101,22 +101,23 @@ __device__ __forceinline__ void emit_rect(const CascadeArgs &a, const CasLevel &
 //   sgf     float [2048]      per-window sigma rounded to FP32 for the phase-1 filter (the FP64
 //                             value is recomputed where exact arithmetic needs it)
 //   list    u16 [2048]        survivors (phase 1 output; per-warp segments compacted in place in phase 2)
-//   scr     384 B per warp    re-packing scratch of phase 2
 //
 // Phase 1, "fixed geometry" (stages 0 .. n_fixed-1, where most windows are still alive):
 //   thread t owns the column of 8 windows (wx = t & 63, wy = (t >> 6) + 4k).  Their tile
 //   addresses differ by a compile-time constant, so a corner address is computed ONCE per
 //   stump and the 4 windows of a chunk are read with immediate offsets (LDS [R + k*ROWSTEP]):
 //   no per-window address arithmetic, no compaction traffic, conflict-free banks.  Stumps
-//   come from the constant bank (the packed cascade is a kernel parameter).  An FP32 filter
+//   come from the constant bank (the packed cascade is a kernel parameter), a stage's two-rect
+//   stumps with two common corners first, in their six-load form.  An FP32 filter
 //   decides each stump; whenever |s32 - t32| is inside a guard band (2^-20 |t32| plus the
 //   cancellation terms) the window's whole stage is redone by dense_stage_exact(), which
 //   reproduces the reference's C expressions bit for bit.  Outside the band both agree by the
 //   error analysis in DESIGN.md, so results are identical to the all-FP64 evaluation (tests
 //   also run with force_exact = 1 and compare).
+// Hand-over: the survivors are counting-sorted by bank class and dealt to the eight warps.
 // Phase 2, warp-autonomous (all remaining stages the tile kernel knows; see the kernel body):
 //   stump-based upright cascades are finished here; the others hand the survivors of their
-//   eligible prefix to the queue of k_cascade_deep.
+//   eligible prefix to the queue of k_cascade_mid / k_cascade_deep.
 // ------------------------------------------------------------------------------------
 // Tile accesses use 32-bit shared-window addresses and explicit ld.shared (a generic pointer
 // would make the compiler rebuild the shared window base inside every loop).
