@@ -107,6 +107,9 @@ struct DenseParams {
     int tail_stages;    // leading stages the tile kernel evaluates (upright stumps, linear): == total_stages
                         // when it finishes the cascade itself, otherwise survivors go to the deep kernel
     int g1_min;         // phase 2: more than this many windows in a warp -> thread per window (G = 1), max 16
+    int tilted_tile;    // the cascade has tilted features: a second smem tile holds the tilted integral, right
+                        // behind the first (tilted nodes' offsets already point into it)
+    int pad1;
     double inv_area;
     const TailStump *tail;   // device, layout of this blob's ystep (patched in by the detector)
     DenseStage stage[kMaxDenseStages];

@@ -282,7 +282,10 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
         if (const char *e = getenv("CLFD_FORCE_EXACT")) P.force_exact = atoi(e) != 0;   // test hook: bypass the FP32 filters
         P.inv_area = 1. / ((c.win_w - 2) * (c.win_h - 2));
         const size_t tile_bytes = (size_t)dense_tile_rows(c.win_h, ystep) * P.tile_stride * 4;
-        const bool dense_ok = tile_bytes <= 65536 && c.win_w <= 255 && c.win_h <= 255;
+        // a cascade with tilted features keeps a second tile (the tilted integral) behind the first
+        const size_t tilt_base = (tile_bytes + 127) & ~(size_t)127;
+        P.tilted_tile = c.has_tilted && !getenv("CLFD_NO_TILTED_TILE") ? 1 : 0;
+        const bool dense_ok = tile_bytes <= 65536 && (!P.tilted_tile || 2 * tilt_base <= 160 * 1024) && c.win_w <= 255 && c.win_h <= 255;
         int elig = 0;
         while (dense_ok && elig < S && elig < kMaxDenseStages) {
             if (c.is_tree && (c.st_next[elig] != -1 || c.st_parent[elig] != elig - 1 ||
@@ -290,7 +293,7 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
                 break;
             bool ok = true;
             for (int t = c.st_first_tree[elig]; t < c.st_first_tree[elig + 1] && ok; t++)
-                ok = c.tr_nnodes[t] == 1 && !c.nodes[c.tr_first_node[t]].tilted;
+                ok = c.tr_nnodes[t] == 1 && (P.tilted_tile || !c.nodes[c.tr_first_node[t]].tilted);
             if (!ok) break;
             elig++;
         }
@@ -318,7 +321,7 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
                 for (int k = 0; k < c.hid_nrects[n]; k++) {
                     int dx[4], dy[4];
                     corner_coords(nd, k, dx, dy);
-                    for (int q = 0; q < 4; q++) ts.off[k * 4 + q] = tile_offset(dy[q], dx[q]);
+                    for (int q = 0; q < 4; q++) ts.off[k * 4 + q] = tile_offset(dy[q], dx[q]) + (nd.tilted ? (uint32_t)tilt_base : 0u);
                     ts.w[k] = c.hid_weight[(size_t)n * 3 + k];
                 }
                 ts.thr = nd.threshold;

@@ -144,6 +144,7 @@ __host__ __device__ inline DenseSmemPlan dense_smem_plan(const DenseParams &P) {
     const size_t rows = (size_t)(kTileH - 1) * P.ystep + P.win_h + 1;
     p.tile = 0;
     p.sgf = (rows * P.tile_stride * 4 + 127) & ~(size_t)127;
+    if (P.tilted_tile) p.sgf *= 2;   // second tile: the tilted integral (same geometry)
     p.list = p.sgf + kTileWindows * sizeof(float);
     p.ctl = p.list + kTileWindows * sizeof(uint16_t);
     p.bar = p.ctl + kCtlInts * sizeof(int);
@@ -375,19 +376,26 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
 
     // ---- stage the integral tile ----
     for (int i = tid; i < kCtlInts; i += kDenseThreads) ctl[i] = 0;
+    const int n_tiles_smem = P.tilted_tile ? 2 : 1;
+    const size_t tile2_off = ((size_t)((kTileH - 1) * ystep + P.win_h + 1) * S * 4 + 127) & ~(size_t)127;
+    const int32_t *__restrict__ gtil = a.tilted ? a.tilted + frame_off + (size_t)py0 * L.sum_pitch + px0 : gsum;
     if (ystep == 1) {   // natural layout: one TMA bulk copy per row
         if (tid == 0) mbar_init(bar, 1);
         __syncthreads();
-        if (tid == 0) mbar_expect_tx(bar, (uint32_t)(rows * cols * 4));
-        for (int r = tid; r < rows; r += kDenseThreads)
-            tma_bulk_g2s(tile + (size_t)r * S * 4, gsum + (size_t)r * L.sum_pitch, (uint32_t)(cols * 4), bar);
+        if (tid == 0) mbar_expect_tx(bar, (uint32_t)(rows * cols * 4 * n_tiles_smem));
+        for (int r = tid; r < rows * n_tiles_smem; r += kDenseThreads) {
+            const int t2 = r >= rows, rr = t2 ? r - rows : r;
+            tma_bulk_g2s(tile + (t2 ? tile2_off : 0) + (size_t)rr * S * 4, (t2 ? gtil : gsum) + (size_t)rr * L.sum_pitch,
+                         (uint32_t)(cols * 4), bar);
+        }
         mbar_wait(bar, 0);
     } else {            // de-interleave columns: x -> (x&1)*S/2 + (x>>1)
         const int c4 = cols >> 2, total = rows * c4;
-        for (int i = tid; i < total; i += kDenseThreads) {
-            const int r = i / c4, cq = i - r * c4;
-            const int4 v = __ldg(reinterpret_cast<const int4 *>(gsum + (size_t)r * L.sum_pitch) + cq);
-            int *row = reinterpret_cast<int *>(tile) + r * S;
+        for (int i = tid; i < total * n_tiles_smem; i += kDenseThreads) {
+            const int t2 = i >= total, ii = t2 ? i - total : i;
+            const int r = ii / c4, cq = ii - r * c4;
+            const int4 v = __ldg(reinterpret_cast<const int4 *>((t2 ? gtil : gsum) + (size_t)r * L.sum_pitch) + cq);
+            int *row = reinterpret_cast<int *>(tile + (t2 ? tile2_off : 0)) + r * S;
             *reinterpret_cast<int2 *>(row + 2 * cq) = make_int2(v.x, v.z);
             *reinterpret_cast<int2 *>(row + (S >> 1) + 2 * cq) = make_int2(v.y, v.w);
         }
