@@ -242,6 +242,7 @@ struct CascadePlan {
     DevBuf<ScNode> d_sc_nodes;
     int sc_rows = 0;
     DevBuf<TailStump> d_tail[2];   // warp-per-window tail records of the tile kernel, [ystep-1]
+    DevBuf<DenseStage> d_stage_tab[2];   // stage trees: stage table in execution order
     DenseParams dense[2];          // the cascade's parameter blobs with this detector's tail pointers
     DevBuf<int16_t> d_codes;
     DevBuf<unsigned long long> d_counters;
@@ -421,7 +422,7 @@ int clfd_cascade_get_info(const clfd_cascade *c, clfd_cascade_info *info) {
     }
     for (int v : h.st_ntrees) info->max_trees_per_stage = std::max(info->max_trees_per_stage, v);
     for (int v : h.tr_nnodes) info->max_nodes_per_tree = std::max(info->max_nodes_per_tree, v);
-    info->dense_stages = c->packed.dense[0].tail_stages;
+    info->dense_stages = c->packed.dense[0].exec_stages;
     info->dense_stumps = c->packed.dense_stumps;
     for (int v : h.order_free) info->order_free_stages += v;
     info->packed_bytes = (int)(c->packed.deep_stages.size() * sizeof(DeepStage) + c->packed.deep_nodes.size() * sizeof(DeepNode) +
@@ -700,6 +701,8 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
             cp.dense[yi] = pk.dense[yi];
             if (!pk.tail[yi].empty() && (rc = cp.d_tail[yi].upload(pk.tail[yi], s))) return rc;
             cp.dense[yi].tail = cp.d_tail[yi].p;
+            if (!pk.stage_tab[yi].empty() && (rc = cp.d_stage_tab[yi].upload(pk.stage_tab[yi], s))) return rc;
+            cp.dense[yi].stage_g = cp.d_stage_tab[yi].p;
         }
         if ((rc = cp.d_counters.alloc(4 * kSlots)) || (rc = cp.d_count_b.alloc(kSlots))) return rc;
         // mid kernel: the stages right after the tile prefix of a LINEAR cascade whose trees the tile
@@ -900,7 +903,7 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
             }
             if (ev && ci == 0) CK(cudaEventRecord(ev[6], s));
             // cascades the tile kernel finishes itself (tail_stages == total_stages) never fill the queue
-            const bool tiles_finish = pk.dense[0].tail_stages > 0 && pk.dense[0].tail_stages == pk.dense[0].total_stages;
+            const bool tiles_finish = pk.dense[0].tail_stages > 0 && pk.dense[0].exec_stages == pk.dense[0].total_stages;
             if (!tiles_finish) {
                 if (cp.mid_end > cp.mid_begin) {
                     // ping-pong between the tile queue (counters[1]) and queue_b (count_b)

@@ -79,11 +79,14 @@ struct DenseStump {
     float pad[2];
 };
 typedef DenseStump TailStump;
+constexpr uint32_t kRouteAccept = 255, kRouteReject = 254;
 struct DenseStage {
     uint16_t first, count;   // first: index into DenseParams::stump (stages < n_stages only)
     float thr;               // biased threshold
     uint32_t flags;          // bit0 double-product stage (two_rects fast path), bit1 any 3-rect stump,
-                             // bit2 alpha sum exact in any order (HostCascade::order_free)
+                             // bit2 alpha sum exact in any order (HostCascade::order_free);
+                             // stage trees (stage_g): bits 8-15 the stage's index in the file, bits 16-23 / 24-31 the
+                             // execution position a window goes to when it passes / fails (kRouteAccept, kRouteReject)
     uint32_t tail_first;     // index of the stage's first stump in the global TailStump array
     float sum_eps;           // bound on the error of an FP32 sum of the stage's alphas in any order
     uint32_t n_shared;       // parameter-resident copy only: the first n_shared stumps of the stage are two-rect
@@ -109,9 +112,11 @@ struct DenseParams {
     int g1_min;         // phase 2: more than this many windows in a warp -> thread per window (G = 1), max 16
     int tilted_tile;    // the cascade has tilted features: a second smem tile holds the tilted integral, right
                         // behind the first (tilted nodes' offsets already point into it)
-    int pad1;
+    int exec_stages;    // == tail_stages, or for a stage tree the tile kernel walks itself: all stages, in
+                        // execution order (stage_g; the first tail_stages of them are the linear prefix)
     double inv_area;
     const TailStump *tail;   // device, layout of this blob's ystep (patched in by the detector)
+    const struct DenseStage *stage_g;   // device: stage table in execution order (stage trees only)
     DenseStage stage[kMaxDenseStages];
     DenseStump stump[kMaxDenseStumps];
 };

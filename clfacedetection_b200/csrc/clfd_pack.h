@@ -8,6 +8,7 @@ struct PackedCascade {
     DenseParams dense[2];              // kernel-parameter blobs of the smem-tile kernel: [ystep-1]
     int dense_stumps = 0;              // stumps in the stages the tile kernel evaluates
     std::vector<TailStump> tail[2];    // stumps of the tile-evaluated stages in tile-offset form, [ystep-1]
+    std::vector<DenseStage> stage_tab[2];   // stage trees the tile kernel walks: all stages in execution order
     std::vector<DeepStage> deep_stages;  // global-memory blob of the deep kernel
     std::vector<DeepNode> deep_nodes;
     std::vector<int> tree_first_node;

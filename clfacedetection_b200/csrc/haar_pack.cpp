@@ -286,37 +286,73 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
         const size_t tilt_base = (tile_bytes + 127) & ~(size_t)127;
         P.tilted_tile = c.has_tilted && !getenv("CLFD_NO_TILTED_TILE") ? 1 : 0;
         const bool dense_ok = tile_bytes <= 65536 && (!P.tilted_tile || 2 * tilt_base <= 160 * 1024) && c.win_w <= 255 && c.win_h <= 255;
-        int elig = 0;
+        auto stage_ok = [&](int i) {   // one-node trees, tilted only with the second tile
+            for (int t = c.st_first_tree[i]; t < c.st_first_tree[i + 1]; t++)
+                if (c.tr_nnodes[t] != 1 || (!P.tilted_tile && c.nodes[c.tr_first_node[t]].tilted)) return false;
+            return true;
+        };
+        int elig = 0;   // the linear prefix
         while (dense_ok && elig < S && elig < kMaxDenseStages) {
             if (c.is_tree && (c.st_next[elig] != -1 || c.st_parent[elig] != elig - 1 ||
                               (elig > 0 && c.st_child[elig - 1] != elig)))
                 break;
-            bool ok = true;
-            for (int t = c.st_first_tree[elig]; t < c.st_first_tree[elig + 1] && ok; t++)
-                ok = c.tr_nnodes[t] == 1 && (P.tilted_tile || !c.nodes[c.tr_first_node[t]].tilted);
-            if (!ok) break;
+            if (!stage_ok(elig)) break;
             elig++;
         }
+        // A stage tree of stumps is walked by the tile kernel itself (tempcv.cpp:834-861): the stages in
+        // depth-first preorder (a stage, its child subtree, then its `next` alternative) -- both the
+        // stage a passing window goes to (child) and the one a failing window goes to (the `next` of the
+        // nearest ancestor-or-self that has one) lie later in that order, so one sweep over the order
+        // with a per-window target position evaluates every window's path.
+        std::vector<int> order;
+        if (c.is_tree && dense_ok && elig > 0 && elig < S && S < (int)kRouteReject && !getenv("CLFD_NO_TREE_TILES")) {
+            std::vector<int> stack{0};
+            std::vector<char> seen(S, 0);
+            bool ok = true;
+            while (!stack.empty() && ok) {
+                const int i = stack.back();
+                stack.pop_back();
+                ok = !seen[i] && stage_ok(i);
+                seen[i] = 1;
+                order.push_back(i);
+                if (c.st_next[i] >= 0) stack.push_back(c.st_next[i]);
+                if (c.st_child[i] >= 0) stack.push_back(c.st_child[i]);
+            }
+            if (!ok || (int)order.size() != S) order.clear();
+            for (int e = 0; e < elig && !order.empty(); e++) if (order[e] != e) order.clear();
+        }
+        const bool walk_tree = !order.empty();
+        if (!walk_tree) { order.resize(elig); for (int e = 0; e < elig; e++) order[e] = e; }
+        const int E = (int)order.size();
+        std::vector<int> pos(S, -1);
+        for (int e = 0; e < E; e++) pos[order[e]] = e;
         P.tail_stages = elig;
+        P.exec_stages = E;
         P.g1_min = 16;
         if (const char *e = getenv("CLFD_G1_MIN")) P.g1_min = std::max(1, std::min(16, atoi(e)));
-        const int n_elig_stumps = c.st_first_tree[elig];
+        int n_elig_stumps = 0;
+        for (int e = 0; e < E; e++) n_elig_stumps += c.st_ntrees[order[e]];
         out.dense_stumps = n_elig_stumps;
         out.tail[yi].assign(n_elig_stumps, TailStump());
+        out.stage_tab[yi].assign(walk_tree ? E : 0, DenseStage());
         auto tile_offset = [&](int dy, int dx) {
             const int word = ystep == 1 ? dy * P.tile_stride + dx
                                         : dy * P.tile_stride + (dx & 1) * (P.tile_stride / 2) + (dx >> 1);
             return (uint32_t)(word * 4);
         };
-        for (int i = 0; i < elig; i++) {
-            DenseStage &ds = P.stage[i];
+        int tail_at = 0;   // records in execution order (== tree order for the linear prefix)
+        for (int e = 0; e < E; e++) {
+            const int i = order[e];
+            DenseStage ds;
+            memset(&ds, 0, sizeof ds);
             bool any3 = false;
             double abs_sum = 0;
+            ds.tail_first = (uint32_t)tail_at;
             for (int t = c.st_first_tree[i]; t < c.st_first_tree[i + 1]; t++) {
                 const int n = c.tr_first_node[t];
                 const HostNode &nd = c.nodes[n];
                 any3 |= c.hid_nrects[n] == 3;
-                TailStump &ts = out.tail[yi][t];
+                TailStump &ts = out.tail[yi][tail_at++];
                 memset(&ts, 0, sizeof ts);
                 for (int k = 0; k < c.hid_nrects[n]; k++) {
                     int dx[4], dy[4];
@@ -335,10 +371,18 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
             // double products only on the reference's stump fast path (tempcv.cpp:862,872)
             ds.flags = ((!c.is_tree && c.is_stump_based && c.two_rects[i]) ? 1u : 0u) | (any3 ? 2u : 0u) |
                        (c.order_free[i] ? 4u : 0u);
-            ds.tail_first = (uint32_t)c.st_first_tree[i];
             // FP32 summation of n alphas in any order: |error| <= (n-1) 2^-24 sum|alpha|; 2x slack
-            const double e = (double)c.st_ntrees[i] * ldexp(1.0, -23) * abs_sum;
-            ds.sum_eps = std::isfinite(e) ? (float)(e * 1.0000002) + FLT_MIN : INFINITY;
+            const double er = (double)c.st_ntrees[i] * ldexp(1.0, -23) * abs_sum;
+            ds.sum_eps = std::isfinite(er) ? (float)(er * 1.0000002) + FLT_MIN : INFINITY;
+            if (walk_tree) {
+                const uint32_t pass = c.st_child[i] >= 0 ? (uint32_t)pos[c.st_child[i]] : kRouteAccept;
+                int p = i;
+                while (p >= 0 && c.st_next[p] < 0) p = c.st_parent[p];   // tempcv.cpp:853-855
+                const uint32_t fail = p >= 0 ? (uint32_t)pos[c.st_next[p]] : kRouteReject;
+                ds.flags |= ((uint32_t)i << 8) | (pass << 16) | (fail << 24);
+                out.stage_tab[yi][e] = ds;
+            }
+            if (e < elig) P.stage[e] = ds;
         }
         // parameter-resident copy of the leading stages that fit the kernel-parameter budget.  Inside a
         // stage the copy is REORDERED (the FP32 filters do not depend on the order; the exact fallback

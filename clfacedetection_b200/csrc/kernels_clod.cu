@@ -134,7 +134,7 @@ __device__ __forceinline__ int lds32i(uint32_t addr) {
 }
 
 struct DenseSmemPlan {
-    size_t tile, sgf, list, ctl, bar, total;
+    size_t tile, sgf, list, ctl, bar, act, tgt, total;
 };
 // control block (ints): [0..31] survivors of phase 1 per bank class, [32..63] their exclusive prefix,
 // [64] total
@@ -148,7 +148,11 @@ __host__ __device__ inline DenseSmemPlan dense_smem_plan(const DenseParams &P) {
     p.list = p.sgf + kTileWindows * sizeof(float);
     p.ctl = p.list + kTileWindows * sizeof(uint16_t);
     p.bar = p.ctl + kCtlInts * sizeof(int);
-    p.total = p.bar + 16;
+    p.act = p.tgt = p.total = p.bar + 16;
+    if (P.exec_stages > P.tail_stages) {   // stage tree: the windows of the current stage, every window's target position
+        p.tgt = p.act + kTileWindows * sizeof(uint16_t);
+        p.total = p.tgt + kTileWindows;
+    }
     return p;
 }
 size_t dense_smem_bytes(const DenseParams &P) { return dense_smem_plan(P).total; }
@@ -215,12 +219,11 @@ __device__ __forceinline__ StumpRegs stump_from_global(const DenseStump *__restr
 }
 
 // Exact evaluation of one stage for one window: the reference's arithmetic, stumps in tree order.
-__device__ __noinline__ bool dense_stage_exact(const DenseParams &P, const DenseCtx &c, int s, int wid) {
+__device__ __noinline__ bool dense_stage_exact(const DenseParams &P, const DenseCtx &c, uint32_t tail_first, int count, bool dbl,
+                                               float sthr, int wid) {
     const uint32_t base = dense_base(c, wid);
     const double sigma = dense_sigma(P, c, wid);
-    const int count = P.stage[s].count;
-    const bool dbl = P.stage[s].flags & 1u;
-    const DenseStump *rec = P.tail + P.stage[s].tail_first;
+    const DenseStump *rec = P.tail + tail_first;
     double S = 0.0;
     for (int j = 0; j < count; j++) {
         const StumpRegs q = stump_from_global(rec + j, true);
@@ -239,7 +242,7 @@ __device__ __noinline__ bool dense_stage_exact(const DenseParams &P, const Dense
         }
         S = __dadd_rn(S, (double)(sum >= t ? q.a1 : q.a0));
     }
-    return S >= (double)P.stage[s].thr;
+    return S >= (double)sthr;
 }
 
 // FP32 filter: one stump for K windows of this thread.  The stump decision sign(s - t) is taken
@@ -302,23 +305,23 @@ __device__ __forceinline__ void stump_filter(const StumpRegs &q, bool dbl, bool 
     if (K > 3) stump_filter_window<(K > 3 ? 3 : 0), K, FIXED, ROWSTEP, SHARED>(q, dbl, three, eps, c, base, sg, S, near);
 }
 
-// Stumps grp, grp + G, ... of stage s for K windows of this lane.  Stumps come from the
-// constant bank when the stage is parameter resident, else from global memory.
+// Stumps grp, grp + G, ... of stage st for K windows of this lane.  Stumps come from the
+// constant bank when the stage is parameter resident (`resident`), else from global memory.
 template <int K, bool FIXED, int ROWSTEP>
-__device__ __forceinline__ void stage_filter(const DenseParams &P, int s, int grp, int G, const uint32_t (&base)[K],
-                                             const float (&sg)[K], float (&S)[K], bool (&near)[K]) {
-    const int count = P.stage[s].count;
-    const uint32_t flags = P.stage[s].flags;
+__device__ __forceinline__ void stage_filter(const DenseParams &P, const DenseStage &st, bool resident, int grp, int G,
+                                             const uint32_t (&base)[K], const float (&sg)[K], float (&S)[K], bool (&near)[K]) {
+    const int count = st.count;
+    const uint32_t flags = st.flags;
     const bool dbl = flags & 1u, any3 = flags & 2u;
     const float eps = P.filter_eps;
-    if (s < P.n_stages && G == 1) {   // all lanes on the same stump: constant bank (reordered copy: six-load stumps first)
-        const int first = P.stage[s].first, n6 = (int)P.stage[s].n_shared;
+    if (resident && G == 1) {   // all lanes on the same stump: constant bank (reordered copy: six-load stumps first)
+        const int first = st.first, n6 = (int)st.n_shared;
 #pragma unroll 1
         for (int j = 0; j < n6; j++) stump_filter<K, FIXED, ROWSTEP, true>(stump_from_param(P.stump[first + j]), dbl, false, eps, base, sg, S, near);
 #pragma unroll 1
         for (int j = n6; j < count; j++) stump_filter<K, FIXED, ROWSTEP, false>(stump_from_param(P.stump[first + j]), dbl, any3, eps, base, sg, S, near);
     } else {
-        const DenseStump *__restrict__ rec = P.tail + P.stage[s].tail_first;
+        const DenseStump *__restrict__ rec = P.tail + st.tail_first;
 #pragma unroll 1
         for (int j = grp; j < count; j += G) stump_filter<K, FIXED, ROWSTEP, false>(stump_from_global(rec + j, any3), dbl, any3, eps, base, sg, S, near);
     }
@@ -327,15 +330,16 @@ __device__ __forceinline__ void stage_filter(const DenseParams &P, int s, int gr
 // Stage verdict of one window from its FP32 stage sum.  |S32 - S| <= sum_eps for any summation
 // order, so outside that band (and with no stump inside its own band) the FP32 verdict is the
 // reference's; inside, the stage is redone exactly.
-__device__ __forceinline__ bool stage_verdict(const DenseParams &P, const DenseCtx &c, int s, float sthr, float seps, int wid,
-                                              float S, bool near) {
-    if (near || !(fabsf(__fadd_rn(S, -sthr)) > seps)) return dense_stage_exact(P, c, s, wid);
+__device__ __forceinline__ bool stage_verdict(const DenseParams &P, const DenseCtx &c, const DenseStage &st, float sthr, float seps,
+                                              int wid, float S, bool near) {
+    if (near || !(fabsf(__fadd_rn(S, -sthr)) > seps)) return dense_stage_exact(P, c, st.tail_first, st.count, st.flags & 1u, st.thr, wid);
     return S >= sthr;
 }
 
 // ROWSTEP_T: compile-time byte distance between a thread's consecutive windows in phase 1
 // (= kDenseThreads / kTileW window rows), or 0 to use the runtime value (generic window sizes).
-template <int ROWSTEP_T>
+// TREE: the cascade is a stage tree the kernel walks itself (DenseParams::exec_stages > tail_stages).
+template <int ROWSTEP_T, bool TREE>
 __global__ void __launch_bounds__(kDenseThreads)
 k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ CascadeArgs a, const int tile0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -447,13 +451,13 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
                 Ssum[k] = 0.f;
                 near[k] = false;
             }
-            if (ROWSTEP_T) stage_filter<kDenseChunk, true, ROWSTEP_T>(P, s, 0, 1, base, sg, Ssum, near);
-            else stage_filter<kDenseChunk, false, 0>(P, s, 0, 1, base, sg, Ssum, near);
+            if (ROWSTEP_T) stage_filter<kDenseChunk, true, ROWSTEP_T>(P, P.stage[s], true, 0, 1, base, sg, Ssum, near);
+            else stage_filter<kDenseChunk, false, 0>(P, P.stage[s], true, 0, 1, base, sg, Ssum, near);
 #pragma unroll
             for (int k = 0; k < kDenseChunk; k++) {
                 if (!((m4 >> k) & 1u)) continue;
                 const int wid = (wy0 + (k0 + k) * kRowsPerSlot) * kTileW + wx;
-                if (!stage_verdict(P, c, s, sthr, seps, wid, Ssum[k], near[k])) {
+                if (!stage_verdict(P, c, P.stage[s], sthr, seps, wid, Ssum[k], near[k])) {
                     alive &= ~(1u << (k0 + k));
                     if (c.codes) dense_write_code(c, wid, s * c.code_mul);
                 }
@@ -523,7 +527,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
         // append the survivors among this pass's windows at cur[n_next..]: always at or below the
         // positions the pass has already read (in-place compaction)
         auto keep = [&](bool valid, int wid, float Ssum, bool near) {
-            const bool pass = valid && stage_verdict(P, c, s, sthr, seps, wid, Ssum, near);
+            const bool pass = valid && stage_verdict(P, c, P.stage[s], sthr, seps, wid, Ssum, near);
             const unsigned m = __ballot_sync(0xffffffffu, pass);
             if (pass) cur[n_next + __popc(m & ((1u << lane) - 1u))] = (uint16_t)wid;
             n_next += __popc(m);
@@ -542,7 +546,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
                     const float sg[2] = {sgf[wid0], sgf[wid1]};
                     float Ssum[2] = {0.f, 0.f};
                     bool near[2] = {false, false};
-                    stage_filter<2, false, 0>(P, s, 0, 1, base, sg, Ssum, near);
+                    stage_filter<2, false, 0>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near);
                     keep(v0, wid0, Ssum[0], near[0]);
                     keep(v1, wid1, Ssum[1], near[1]);
                 } else {           // one row
@@ -553,7 +557,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
                     const float sg[1] = {sgf[wid0]};
                     float Ssum[1] = {0.f};
                     bool near[1] = {false};
-                    stage_filter<1, false, 0>(P, s, 0, 1, base, sg, Ssum, near);
+                    stage_filter<1, false, 0>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near);
                     keep(v0, wid0, Ssum[0], near[0]);
                 }
             }
@@ -568,7 +572,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
             const float sg[1] = {sgf[wid0]};
             float Ssum[1] = {0.f};
             bool near[1] = {false};
-            if (valid) stage_filter<1, false, 0>(P, s, grp, G, base, sg, Ssum, near);
+            if (valid) stage_filter<1, false, 0>(P, P.stage[s], s < P.n_stages, grp, G, base, sg, Ssum, near);
             float acc = Ssum[0];
             unsigned nr = near[0];
             for (int d = 1 << lw; d < 32; d <<= 1) {
@@ -580,6 +584,103 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
         __syncwarp();
         n = n_next;
         dealt = false;   // the compacted list is contiguous: rows of 32, the last one partial
+    }
+    if (TREE) {
+        // ---- stage tree (tempcv.cpp:834-861): the remaining stages in execution order (depth-first
+        //      preorder, haar_pack.cpp).  tgt[w] = the position window w waits for; at position e the
+        //      warp splits its list into the windows whose turn it is (-> act) and the rest (stay in
+        //      cur), evaluates act like a linear stage, and routes every window by the verdict:
+        //      to a later position (back into cur), to a detection, or out. ----
+        if (n == 0) return;
+        uint16_t *act = reinterpret_cast<uint16_t *>(smem_raw + plan.act) + warp * kSeg;
+        unsigned char *tgt = smem_raw + plan.tgt;
+        const int e0 = s;
+        for (int e = e0; e < P.exec_stages && n > 0; e++) {
+            int n_wait = 0, n_act = 0;
+            const int R = (n + 31) >> 5;
+            for (int r = 0; r < R; r++) {
+                const int c0 = dealt ? (n - r + R - 1) / R : min(32, n - 32 * r);
+                const bool v = lane < c0;
+                const int wid = cur[32 * r + (v ? lane : 0)];
+                __syncwarp();
+                const bool turn = v && (e == e0 || tgt[wid] == e);
+                const unsigned mt = __ballot_sync(0xffffffffu, turn), mw = __ballot_sync(0xffffffffu, v && !turn);
+                const unsigned below = (1u << lane) - 1u;
+                if (turn) act[n_act + __popc(mt & below)] = (uint16_t)wid;
+                else if (v) cur[n_wait + __popc(mw & below)] = (uint16_t)wid;
+                n_act += __popc(mt);
+                n_wait += __popc(mw);
+            }
+            __syncwarp();
+            dealt = false;
+            n = n_wait;
+            if (n_act == 0) continue;
+            const DenseStage st = P.stage_g[e];
+            const float sthr = st.thr, seps = P.force_exact ? inf : st.sum_eps;
+            const int orig = (st.flags >> 8) & 255;
+            const uint32_t to_pass = (st.flags >> 16) & 255u, to_fail = st.flags >> 24;
+            auto route = [&](bool valid, int wid, float Ssum, bool near) {
+                uint32_t to = kRouteReject;
+                bool pass = false;
+                if (valid) {
+                    pass = stage_verdict(P, c, st, sthr, seps, wid, Ssum, near);
+                    to = pass ? to_pass : to_fail;
+                }
+                const bool on = valid && to < kRouteReject;
+                const unsigned m = __ballot_sync(0xffffffffu, on);
+                if (on) {
+                    cur[n + __popc(m & ((1u << lane) - 1u))] = (uint16_t)wid;
+                    tgt[wid] = (unsigned char)to;
+                } else if (valid) {
+                    if (to == kRouteAccept) emit_rect(a, CL, frame, px0 + (wid & (kTileW - 1)) * ystep, py0 + (wid / kTileW) * ystep);
+                    if (c.codes) dense_write_code(c, wid, 2 * orig + (pass ? 1 : 0));
+                }
+                n += __popc(m);
+            };
+            if (n_act > P.g1_min) {
+                const int Ra = (n_act + 31) >> 5;
+                for (int r = 0; r < Ra; r += 2) {
+                    const bool v0 = 32 * r + lane < n_act, v1 = 32 * r + 32 + lane < n_act;
+                    const int wid0 = act[v0 ? 32 * r + lane : 0], wid1 = act[v1 ? 32 * r + 32 + lane : 0];
+                    if (r + 1 < Ra) {
+                        const uint32_t base[2] = {dense_base(c, wid0), dense_base(c, wid1)};
+                        const float sg[2] = {sgf[wid0], sgf[wid1]};
+                        float Ssum[2] = {0.f, 0.f};
+                        bool near[2] = {false, false};
+                        stage_filter<2, false, 0>(P, st, false, 0, 1, base, sg, Ssum, near);
+                        route(v0, wid0, Ssum[0], near[0]);
+                        route(v1, wid1, Ssum[1], near[1]);
+                    } else {
+                        const uint32_t base[1] = {dense_base(c, wid0)};
+                        const float sg[1] = {sgf[wid0]};
+                        float Ssum[1] = {0.f};
+                        bool near[1] = {false};
+                        stage_filter<1, false, 0>(P, st, false, 0, 1, base, sg, Ssum, near);
+                        route(v0, wid0, Ssum[0], near[0]);
+                    }
+                }
+            } else {
+                int lw = 4;
+                while (lw > 0 && (1 << (lw - 1)) >= n_act) lw--;
+                const int slot = lane & ((1 << lw) - 1), grp = lane >> lw, G = 32 >> lw;
+                const bool valid = slot < n_act;
+                const int wid0 = act[valid ? slot : 0];
+                const uint32_t base[1] = {dense_base(c, wid0)};
+                const float sg[1] = {sgf[wid0]};
+                float Ssum[1] = {0.f};
+                bool near[1] = {false};
+                if (valid) stage_filter<1, false, 0>(P, st, false, grp, G, base, sg, Ssum, near);
+                float acc = Ssum[0];
+                unsigned nr = near[0];
+                for (int d = 1 << lw; d < 32; d <<= 1) {
+                    acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, d));
+                    nr |= __shfl_xor_sync(0xffffffffu, nr, d);
+                }
+                route(lane < n_act, wid0, acc, nr != 0);
+            }
+            __syncwarp();
+        }
+        return;
     }
     // ---- survivors: detections, or (cascades with a deep tail) queue items ----
     if (n == 0) return;
@@ -609,18 +710,6 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     }
 }
 
-template <int ROWSTEP_T>
-static cudaError_t launch_tiles_t(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, size_t smem, cudaStream_t stream) {
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_cascade_tiles<ROWSTEP_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
-    k_cascade_tiles<ROWSTEP_T><<<dim3(n_tiles, a.n_frames), kDenseThreads, smem, stream>>>(P, a, tile0);
-    return cudaGetLastError();
-}
-
 // row steps of the stock window sizes (bytes between a thread's consecutive phase-1 windows)
 constexpr int dense_stride_ce(int win_w, int ystep) {
     int cols = ((kTileW - 1) * ystep + win_w + 1 + 3) & ~3;
@@ -630,6 +719,26 @@ constexpr int dense_stride_ce(int win_w, int ystep) {
     return s;
 }
 constexpr int dense_rowstep_ce(int win_w, int ystep) { return (kDenseThreads / kTileW) * ystep * dense_stride_ce(win_w, ystep) * 4; }
+
+template <int ROWSTEP_T, bool TREE>
+static cudaError_t launch_tiles_tt(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, size_t smem, cudaStream_t stream) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_cascade_tiles<ROWSTEP_T, TREE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    k_cascade_tiles<ROWSTEP_T, TREE><<<dim3(n_tiles, a.n_frames), kDenseThreads, smem, stream>>>(P, a, tile0);
+    return cudaGetLastError();
+}
+template <int ROWSTEP_T>
+static cudaError_t launch_tiles_t(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, size_t smem, cudaStream_t stream) {
+    if (P.exec_stages > P.tail_stages) {   // stage tree: 20-pixel windows get the immediate-offset code, the rest the generic one
+        if (ROWSTEP_T == dense_rowstep_ce(24, 2)) return launch_tiles_tt<0, true>(P, a, tile0, n_tiles, smem, stream);
+        return launch_tiles_tt<ROWSTEP_T == dense_rowstep_ce(24, 2) ? 0 : ROWSTEP_T, true>(P, a, tile0, n_tiles, smem, stream);
+    }
+    return launch_tiles_tt<ROWSTEP_T, false>(P, a, tile0, n_tiles, smem, stream);
+}
 
 cudaError_t launch_cascade_tiles(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, cudaStream_t stream) {
     if (n_tiles <= 0 || a.n_frames == 0) return cudaSuccess;

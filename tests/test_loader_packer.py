@@ -62,7 +62,7 @@ def test_from_arrays_round_trip_and_child_links():
     child = a["st_child"]
     # SURVEY Appendix B topology: 0-4 linear, stage 4 -> child 5 (next 6); odd chain ends at 39
     assert child[:5].tolist() == [1, 2, 3, 4, 5] and a["st_next"][5] == 6 and child[39] == -1
-    assert c.info.dense_stages == 5   # only the unconditional linear prefix can be tile-evaluated
+    assert c.info.dense_stages == 47  # a stage tree of stumps is walked by the tile kernel (5 linear stages + 42 routed)
 
 
 def test_dense_prefix_rules():
