@@ -71,15 +71,19 @@ constexpr int kMaxDenseStages = 32;    // stages the tile kernel can evaluate (a
 // resident (constant bank: a warp whose lanes all evaluate the same stump reads it with LDC,
 // off the L1 data pipe the corner loads saturate); every tile-evaluated stump also has a copy
 // in global memory (lanes on different stumps, stages beyond the parameter budget).
-struct DenseStump {
+struct alignas(16) DenseStump {
     uint32_t off[12];  // BYTE offsets into the smem tile: p0..p3 of rect 0,1,2 (rect 2: zeros if absent)
     float w[3];        // hidden weights (w[2] = 0 if absent)
     float thr;
-    float a0, a1;      // alpha[0] (sum < t), alpha[1] (sum >= t)
-    float pad[2];
+    float a0, a1;      // alpha[0] (sum < t), alpha[1] (sum >= t); 0 where that branch leads to another node
+    uint32_t meta;     // multi-node trees: node index in its tree | node to go to if sum < t << 8 | if sum >= t << 16
+                       // (kNodeLeaf: a leaf, the tree is done); padding records have index kNodePad
+    float pad;
 };
 typedef DenseStump TailStump;
 constexpr uint32_t kRouteAccept = 255, kRouteReject = 254;
+constexpr uint32_t kNodeLeaf = 255, kNodePad = 254;
+constexpr int kMaxTreeNodes = 4;   // trees the tile kernel evaluates have at most this many nodes
 struct DenseStage {
     uint16_t first, count;   // first: index into DenseParams::stump (stages < n_stages only)
     float thr;               // biased threshold
@@ -114,6 +118,8 @@ struct DenseParams {
                         // behind the first (tilted nodes' offsets already point into it)
     int exec_stages;    // == tail_stages, or for a stage tree the tile kernel walks itself: all stages, in
                         // execution order (stage_g; the first tail_stages of them are the linear prefix)
+    int npt;            // records per tree: 1 = stumps; 2..4 = multi-node trees, every tree padded to npt node records
+    int pad2;
     double inv_area;
     const TailStump *tail;   // device, layout of this blob's ystep (patched in by the detector)
     const struct DenseStage *stage_g;   // device: stage table in execution order (stage trees only)

@@ -286,9 +286,23 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
         const size_t tilt_base = (tile_bytes + 127) & ~(size_t)127;
         P.tilted_tile = c.has_tilted && !getenv("CLFD_NO_TILTED_TILE") ? 1 : 0;
         const bool dense_ok = tile_bytes <= 65536 && (!P.tilted_tile || 2 * tilt_base <= 160 * 1024) && c.win_w <= 255 && c.win_h <= 255;
-        auto stage_ok = [&](int i) {   // one-node trees, tilted only with the second tile
-            for (int t = c.st_first_tree[i]; t < c.st_first_tree[i + 1]; t++)
-                if (c.tr_nnodes[t] != 1 || (!P.tilted_tile && c.nodes[c.tr_first_node[t]].tilted)) return false;
+        // multi-node trees (<= kMaxTreeNodes nodes, children after their parent) are evaluated node by node
+        // with a per-window "node I am at" state; every tree is padded to npt = the cascade's largest tree
+        int npt = 1;
+        for (int t = 0; t < T; t++) npt = std::max(npt, c.tr_nnodes[t]);
+        if (getenv("CLFD_NO_NODE_TILES") && npt > 1) npt = kMaxTreeNodes + 1;   // test hook: leave trees to the mid / deep kernels
+        P.npt = npt <= kMaxTreeNodes ? npt : 1;
+        auto stage_ok = [&](int i) {   // tilted only with the second tile
+            for (int t = c.st_first_tree[i]; t < c.st_first_tree[i + 1]; t++) {
+                if (c.tr_nnodes[t] > P.npt) return false;
+                for (int j = 0; j < c.tr_nnodes[t]; j++) {
+                    const HostNode &nd = c.nodes[c.tr_first_node[t] + j];
+                    if (!P.tilted_tile && nd.tilted) return false;
+                    if ((nd.left > 0 && (nd.left <= j || nd.left >= c.tr_nnodes[t])) ||
+                        (nd.right > 0 && (nd.right <= j || nd.right >= c.tr_nnodes[t])))
+                        return false;
+                }
+            }
             return true;
         };
         int elig = 0;   // the linear prefix
@@ -305,7 +319,7 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
         // nearest ancestor-or-self that has one) lie later in that order, so one sweep over the order
         // with a per-window target position evaluates every window's path.
         std::vector<int> order;
-        if (c.is_tree && dense_ok && elig > 0 && elig < S && S < (int)kRouteReject && !getenv("CLFD_NO_TREE_TILES")) {
+        if (c.is_tree && P.npt == 1 && dense_ok && elig > 0 && elig < S && S < (int)kRouteReject && !getenv("CLFD_NO_TREE_TILES")) {
             std::vector<int> stack{0};
             std::vector<char> seen(S, 0);
             bool ok = true;
@@ -331,7 +345,7 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
         P.g1_min = 16;
         if (const char *e = getenv("CLFD_G1_MIN")) P.g1_min = std::max(1, std::min(16, atoi(e)));
         int n_elig_stumps = 0;
-        for (int e = 0; e < E; e++) n_elig_stumps += c.st_ntrees[order[e]];
+        for (int e = 0; e < E; e++) n_elig_stumps += c.st_ntrees[order[e]] * P.npt;
         out.dense_stumps = n_elig_stumps;
         out.tail[yi].assign(n_elig_stumps, TailStump());
         out.stage_tab[yi].assign(walk_tree ? E : 0, DenseStage());
@@ -349,30 +363,37 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
             double abs_sum = 0;
             ds.tail_first = (uint32_t)tail_at;
             for (int t = c.st_first_tree[i]; t < c.st_first_tree[i + 1]; t++) {
-                const int n = c.tr_first_node[t];
-                const HostNode &nd = c.nodes[n];
-                any3 |= c.hid_nrects[n] == 3;
-                TailStump &ts = out.tail[yi][tail_at++];
-                memset(&ts, 0, sizeof ts);
-                for (int k = 0; k < c.hid_nrects[n]; k++) {
-                    int dx[4], dy[4];
-                    corner_coords(nd, k, dx, dy);
-                    for (int q = 0; q < 4; q++) ts.off[k * 4 + q] = tile_offset(dy[q], dx[q]) + (nd.tilted ? (uint32_t)tilt_base : 0u);
-                    ts.w[k] = c.hid_weight[(size_t)n * 3 + k];
-                }
-                ts.thr = nd.threshold;
                 const int a = c.tr_first_node[t] + t;            // alpha base of tree t
-                ts.a0 = c.alpha[a + (-nd.left)];                 // sum <  t -> left  (tempcv.cpp:788)
-                ts.a1 = c.alpha[a + (-nd.right)];                // sum >= t -> right
-                abs_sum += fmax(fabs((double)ts.a0), fabs((double)ts.a1));
+                double amax = 0;
+                for (int j = 0; j < P.npt; j++) {
+                    TailStump &ts = out.tail[yi][tail_at++];
+                    memset(&ts, 0, sizeof ts);
+                    if (j >= c.tr_nnodes[t]) { ts.meta = kNodePad | (kNodeLeaf << 8) | (kNodeLeaf << 16); continue; }
+                    const int n = c.tr_first_node[t] + j;
+                    const HostNode &nd = c.nodes[n];
+                    any3 |= c.hid_nrects[n] == 3;
+                    for (int k = 0; k < c.hid_nrects[n]; k++) {
+                        int dx[4], dy[4];
+                        corner_coords(nd, k, dx, dy);
+                        for (int q = 0; q < 4; q++) ts.off[k * 4 + q] = tile_offset(dy[q], dx[q]) + (nd.tilted ? (uint32_t)tilt_base : 0u);
+                        ts.w[k] = c.hid_weight[(size_t)n * 3 + k];
+                    }
+                    ts.thr = nd.threshold;
+                    ts.a0 = nd.left <= 0 ? c.alpha[a + (-nd.left)] : 0.f;     // sum <  t -> left  (tempcv.cpp:788)
+                    ts.a1 = nd.right <= 0 ? c.alpha[a + (-nd.right)] : 0.f;   // sum >= t -> right
+                    ts.meta = (uint32_t)j | ((nd.left > 0 ? (uint32_t)nd.left : kNodeLeaf) << 8) |
+                              ((nd.right > 0 ? (uint32_t)nd.right : kNodeLeaf) << 16);
+                    amax = fmax(amax, fmax(fabs((double)ts.a0), fabs((double)ts.a1)));
+                }
+                abs_sum += amax;
             }
-            ds.first = 0; ds.count = (uint16_t)c.st_ntrees[i];
+            ds.first = 0; ds.count = (uint16_t)(c.st_ntrees[i] * P.npt);   // records
             ds.thr = c.hid_thr[i];
             // double products only on the reference's stump fast path (tempcv.cpp:862,872)
             ds.flags = ((!c.is_tree && c.is_stump_based && c.two_rects[i]) ? 1u : 0u) | (any3 ? 2u : 0u) |
                        (c.order_free[i] ? 4u : 0u);
             // FP32 summation of n alphas in any order: |error| <= (n-1) 2^-24 sum|alpha|; 2x slack
-            const double er = (double)c.st_ntrees[i] * ldexp(1.0, -23) * abs_sum;
+            const double er = (double)(c.st_ntrees[i] * P.npt) * ldexp(1.0, -23) * abs_sum;
             ds.sum_eps = std::isfinite(er) ? (float)(er * 1.0000002) + FLT_MIN : INFINITY;
             if (walk_tree) {
                 const uint32_t pass = c.st_child[i] >= 0 ? (uint32_t)pos[c.st_child[i]] : kRouteAccept;
@@ -393,13 +414,13 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
         // common pair can only be (p0,p2), (p3,p1), (p0,p1) or (p3,p2).
         const bool share_corners = !getenv("CLFD_NO_SHARED_CORNERS");   // test hook
         int ns = 0, nstump = 0;
-        while (ns < elig && nstump + c.st_ntrees[ns] <= kMaxDenseStumps) {
+        while (ns < elig && nstump + c.st_ntrees[ns] * P.npt <= kMaxDenseStumps) {
             P.stage[ns].first = (uint16_t)nstump;
             std::vector<DenseStump> six, rest;
-            for (int t = c.st_first_tree[ns]; t < c.st_first_tree[ns + 1]; t++) {
+            for (int t = c.st_first_tree[ns] * P.npt; t < c.st_first_tree[ns + 1] * P.npt; t++) {
                 DenseStump st = out.tail[yi][t];
                 bool shared = false;
-                if (share_corners && c.hid_nrects[c.tr_first_node[t]] == 2) {
+                if (share_corners && P.npt == 1 && c.hid_nrects[c.tr_first_node[t]] == 2) {   // (multi-node trees keep their order)
                     const uint32_t *A = st.off, *B = st.off + 4;
                     static const int pairs[4][2] = {{0, 2}, {3, 1}, {0, 1}, {3, 2}};   // (plus, minus) corner
                     for (const auto &pr : pairs) {

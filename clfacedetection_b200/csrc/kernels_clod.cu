@@ -196,12 +196,13 @@ __device__ __forceinline__ double dense_sigma(const DenseParams &P, const DenseC
 struct StumpRegs {
     uint32_t o[12];
     float w0, w1, w2, thr, a0, a1;
+    uint32_t meta;
 };
 __device__ __forceinline__ StumpRegs stump_from_param(const DenseStump &q) {   // constant bank (LDC)
     StumpRegs r;
 #pragma unroll
     for (int i = 0; i < 12; i++) r.o[i] = q.off[i];
-    r.w0 = q.w[0]; r.w1 = q.w[1]; r.w2 = q.w[2]; r.thr = q.thr; r.a0 = q.a0; r.a1 = q.a1;
+    r.w0 = q.w[0]; r.w1 = q.w[1]; r.w2 = q.w[2]; r.thr = q.thr; r.a0 = q.a0; r.a1 = q.a1; r.meta = q.meta;
     return r;
 }
 __device__ __forceinline__ StumpRegs stump_from_global(const DenseStump *__restrict__ p, bool any3) {   // 4-5 x LDG.128
@@ -214,19 +215,25 @@ __device__ __forceinline__ StumpRegs stump_from_global(const DenseStump *__restr
     r.o[4] = q1.x; r.o[5] = q1.y; r.o[6] = q1.z; r.o[7] = q1.w;
     r.o[8] = q2.x; r.o[9] = q2.y; r.o[10] = q2.z; r.o[11] = q2.w;
     r.w0 = __uint_as_float(q3.x); r.w1 = __uint_as_float(q3.y); r.w2 = __uint_as_float(q3.z); r.thr = __uint_as_float(q3.w);
-    r.a0 = __uint_as_float(q4.x); r.a1 = __uint_as_float(q4.y);
+    r.a0 = __uint_as_float(q4.x); r.a1 = __uint_as_float(q4.y); r.meta = q4.z;
     return r;
 }
 
 // Exact evaluation of one stage for one window: the reference's arithmetic, stumps in tree order.
+template <bool NODES>
 __device__ __noinline__ bool dense_stage_exact(const DenseParams &P, const DenseCtx &c, uint32_t tail_first, int count, bool dbl,
                                                float sthr, int wid) {
     const uint32_t base = dense_base(c, wid);
     const double sigma = dense_sigma(P, c, wid);
     const DenseStump *rec = P.tail + tail_first;
     double S = 0.0;
+    uint32_t at = 0;   // multi-node trees: the node this window is at (icvEvalHidHaarClassifier, tempcv.cpp:771-792)
     for (int j = 0; j < count; j++) {
         const StumpRegs q = stump_from_global(rec + j, true);
+        if (NODES) {
+            if ((q.meta & 255u) == 0u) at = 0;
+            if ((q.meta & 255u) != at) continue;
+        }
         const int r0 = lds32(base + q.o[0]) - lds32(base + q.o[1]) - lds32(base + q.o[2]) + lds32(base + q.o[3]);
         const int r1 = lds32(base + q.o[4]) - lds32(base + q.o[5]) - lds32(base + q.o[6]) + lds32(base + q.o[7]);
         const double t = __dmul_rn((double)q.thr, sigma);
@@ -240,6 +247,10 @@ __device__ __noinline__ bool dense_stage_exact(const DenseParams &P, const Dense
                 sum = __dadd_rn(sum, (double)__fmul_rn(__int2float_rn(r2), q.w2));
             }
         }
+        if (NODES) {
+            at = ((sum >= t ? q.meta >> 16 : q.meta >> 8)) & 255u;
+            if (at != kNodeLeaf) continue;   // on to a child node: nothing to add yet
+        }
         S = __dadd_rn(S, (double)(sum >= t ? q.a1 : q.a0));
     }
     return S >= (double)sthr;
@@ -250,9 +261,12 @@ __device__ __noinline__ bool dense_stage_exact(const DenseParams &P, const Dense
 // plus the cancellation terms), S[k] adds the selected alpha in FP32.
 //   FIXED = true : window k lives at base[0] + k*ROWSTEP (compile-time) -> immediate offsets
 //   FIXED = false: window k lives at base[k]
-template <int KK, int K, bool FIXED, int ROWSTEP, bool SHARED>
+//   NODES = true : multi-node trees; at[k] = the node window k is at, a record only counts for the
+//                  windows that are at its node (the others still load its corners: uniform code)
+template <int KK, int K, bool FIXED, int ROWSTEP, bool SHARED, bool NODES>
 __device__ __forceinline__ void stump_filter_window(const StumpRegs &q, bool dbl, bool three, float eps, const uint32_t (&c)[12],
-                                                    const uint32_t (&base)[K], const float (&sg)[K], float (&S)[K], bool (&near)[K]) {
+                                                    const uint32_t (&base)[K], const float (&sg)[K], float (&S)[K], bool (&near)[K],
+                                                    uint32_t (&at)[K]) {
     const float eps4 = eps * 0.25f;
     constexpr int IMM = KK * ROWSTEP;
     const uint32_t b = base[FIXED ? 0 : KK];
@@ -285,13 +299,20 @@ __device__ __forceinline__ void stump_filter_window(const StumpRegs &q, bool dbl
         s32 = __fadd_rn(s32, __fmul_rn(__int2float_rn(r2), q.w2));
     }
     const float d = __fadd_rn(s32, -t32);
-    near[KK] = near[KK] || (fabsf(d) <= m);
-    S[KK] = __fadd_rn(S[KK], d >= 0.f ? q.a1 : q.a0);
+    if (NODES) {
+        const bool on = at[KK] == (q.meta & 255u);
+        near[KK] = near[KK] || (on && fabsf(d) <= m);
+        S[KK] = __fadd_rn(S[KK], on ? (d >= 0.f ? q.a1 : q.a0) : 0.f);   // a branch to another node carries 0
+        at[KK] = on ? ((d >= 0.f ? q.meta >> 16 : q.meta >> 8) & 255u) : at[KK];
+    } else {
+        near[KK] = near[KK] || (fabsf(d) <= m);
+        S[KK] = __fadd_rn(S[KK], d >= 0.f ? q.a1 : q.a0);
+    }
 }
 
-template <int K, bool FIXED, int ROWSTEP, bool SHARED>
+template <int K, bool FIXED, int ROWSTEP, bool SHARED, bool NODES>
 __device__ __forceinline__ void stump_filter(const StumpRegs &q, bool dbl, bool any3, float eps, const uint32_t (&base)[K],
-                                             const float (&sg)[K], float (&S)[K], bool (&near)[K]) {
+                                             const float (&sg)[K], float (&S)[K], bool (&near)[K], uint32_t (&at)[K]) {
     static_assert(K >= 1 && K <= 4, "1..4 windows per thread");
     const bool three = !SHARED && any3 && q.o[11] != 0u;   // warp-uniform per stump
     uint32_t c[12];
@@ -299,17 +320,24 @@ __device__ __forceinline__ void stump_filter(const StumpRegs &q, bool dbl, bool 
 #pragma unroll
         for (int i = 0; i < (SHARED ? 6 : 12); i++) c[i] = base[0] + q.o[i];
     }
-    stump_filter_window<0, K, FIXED, ROWSTEP, SHARED>(q, dbl, three, eps, c, base, sg, S, near);
-    if (K > 1) stump_filter_window<(K > 1 ? 1 : 0), K, FIXED, ROWSTEP, SHARED>(q, dbl, three, eps, c, base, sg, S, near);
-    if (K > 2) stump_filter_window<(K > 2 ? 2 : 0), K, FIXED, ROWSTEP, SHARED>(q, dbl, three, eps, c, base, sg, S, near);
-    if (K > 3) stump_filter_window<(K > 3 ? 3 : 0), K, FIXED, ROWSTEP, SHARED>(q, dbl, three, eps, c, base, sg, S, near);
+    if (NODES && (q.meta & 255u) == 0u) {   // a tree's root: every window starts over
+#pragma unroll
+        for (int k = 0; k < K; k++) at[k] = 0u;
+    }
+    stump_filter_window<0, K, FIXED, ROWSTEP, SHARED, NODES>(q, dbl, three, eps, c, base, sg, S, near, at);
+    if (K > 1) stump_filter_window<(K > 1 ? 1 : 0), K, FIXED, ROWSTEP, SHARED, NODES>(q, dbl, three, eps, c, base, sg, S, near, at);
+    if (K > 2) stump_filter_window<(K > 2 ? 2 : 0), K, FIXED, ROWSTEP, SHARED, NODES>(q, dbl, three, eps, c, base, sg, S, near, at);
+    if (K > 3) stump_filter_window<(K > 3 ? 3 : 0), K, FIXED, ROWSTEP, SHARED, NODES>(q, dbl, three, eps, c, base, sg, S, near, at);
 }
 
 // Stumps grp, grp + G, ... of stage st for K windows of this lane.  Stumps come from the
 // constant bank when the stage is parameter resident (`resident`), else from global memory.
-template <int K, bool FIXED, int ROWSTEP>
+template <int K, bool FIXED, int ROWSTEP, bool NODES>
 __device__ __forceinline__ void stage_filter(const DenseParams &P, const DenseStage &st, bool resident, int grp, int G,
                                              const uint32_t (&base)[K], const float (&sg)[K], float (&S)[K], bool (&near)[K]) {
+    uint32_t at[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) at[k] = 0u;
     const int count = st.count;
     const uint32_t flags = st.flags;
     const bool dbl = flags & 1u, any3 = flags & 2u;
@@ -317,29 +345,40 @@ __device__ __forceinline__ void stage_filter(const DenseParams &P, const DenseSt
     if (resident && G == 1) {   // all lanes on the same stump: constant bank (reordered copy: six-load stumps first)
         const int first = st.first, n6 = (int)st.n_shared;
 #pragma unroll 1
-        for (int j = 0; j < n6; j++) stump_filter<K, FIXED, ROWSTEP, true>(stump_from_param(P.stump[first + j]), dbl, false, eps, base, sg, S, near);
+        for (int j = 0; j < n6; j++) stump_filter<K, FIXED, ROWSTEP, true, false>(stump_from_param(P.stump[first + j]), dbl, false, eps, base, sg, S, near, at);
 #pragma unroll 1
-        for (int j = n6; j < count; j++) stump_filter<K, FIXED, ROWSTEP, false>(stump_from_param(P.stump[first + j]), dbl, any3, eps, base, sg, S, near);
+        for (int j = n6; j < count; j++) stump_filter<K, FIXED, ROWSTEP, false, NODES>(stump_from_param(P.stump[first + j]), dbl, any3, eps, base, sg, S, near, at);
     } else {
         const DenseStump *__restrict__ rec = P.tail + st.tail_first;
+        if (NODES) {   // the groups split the stage by whole trees
+            const int npt = P.npt;
 #pragma unroll 1
-        for (int j = grp; j < count; j += G) stump_filter<K, FIXED, ROWSTEP, false>(stump_from_global(rec + j, any3), dbl, any3, eps, base, sg, S, near);
+            for (int j = grp * npt; j < count; j += G * npt)
+#pragma unroll 1
+                for (int i = 0; i < npt; i++)
+                    stump_filter<K, FIXED, ROWSTEP, false, true>(stump_from_global(rec + j + i, any3), dbl, any3, eps, base, sg, S, near, at);
+        } else {
+#pragma unroll 1
+            for (int j = grp; j < count; j += G) stump_filter<K, FIXED, ROWSTEP, false, false>(stump_from_global(rec + j, any3), dbl, any3, eps, base, sg, S, near, at);
+        }
     }
 }
 
 // Stage verdict of one window from its FP32 stage sum.  |S32 - S| <= sum_eps for any summation
 // order, so outside that band (and with no stump inside its own band) the FP32 verdict is the
 // reference's; inside, the stage is redone exactly.
+template <bool NODES>
 __device__ __forceinline__ bool stage_verdict(const DenseParams &P, const DenseCtx &c, const DenseStage &st, float sthr, float seps,
                                               int wid, float S, bool near) {
-    if (near || !(fabsf(__fadd_rn(S, -sthr)) > seps)) return dense_stage_exact(P, c, st.tail_first, st.count, st.flags & 1u, st.thr, wid);
+    if (near || !(fabsf(__fadd_rn(S, -sthr)) > seps)) return dense_stage_exact<NODES>(P, c, st.tail_first, st.count, st.flags & 1u, st.thr, wid);
     return S >= sthr;
 }
 
 // ROWSTEP_T: compile-time byte distance between a thread's consecutive windows in phase 1
 // (= kDenseThreads / kTileW window rows), or 0 to use the runtime value (generic window sizes).
 // TREE: the cascade is a stage tree the kernel walks itself (DenseParams::exec_stages > tail_stages).
-template <int ROWSTEP_T, bool TREE>
+// NODES: multi-node trees (DenseParams::npt > 1).
+template <int ROWSTEP_T, bool TREE, bool NODES>
 __global__ void __launch_bounds__(kDenseThreads)
 k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ CascadeArgs a, const int tile0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -451,13 +490,13 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
                 Ssum[k] = 0.f;
                 near[k] = false;
             }
-            if (ROWSTEP_T) stage_filter<kDenseChunk, true, ROWSTEP_T>(P, P.stage[s], true, 0, 1, base, sg, Ssum, near);
-            else stage_filter<kDenseChunk, false, 0>(P, P.stage[s], true, 0, 1, base, sg, Ssum, near);
+            if (ROWSTEP_T) stage_filter<kDenseChunk, true, ROWSTEP_T, NODES>(P, P.stage[s], true, 0, 1, base, sg, Ssum, near);
+            else stage_filter<kDenseChunk, false, 0, NODES>(P, P.stage[s], true, 0, 1, base, sg, Ssum, near);
 #pragma unroll
             for (int k = 0; k < kDenseChunk; k++) {
                 if (!((m4 >> k) & 1u)) continue;
                 const int wid = (wy0 + (k0 + k) * kRowsPerSlot) * kTileW + wx;
-                if (!stage_verdict(P, c, P.stage[s], sthr, seps, wid, Ssum[k], near[k])) {
+                if (!stage_verdict<NODES>(P, c, P.stage[s], sthr, seps, wid, Ssum[k], near[k])) {
                     alive &= ~(1u << (k0 + k));
                     if (c.codes) dense_write_code(c, wid, s * c.code_mul);
                 }
@@ -527,7 +566,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
         // append the survivors among this pass's windows at cur[n_next..]: always at or below the
         // positions the pass has already read (in-place compaction)
         auto keep = [&](bool valid, int wid, float Ssum, bool near) {
-            const bool pass = valid && stage_verdict(P, c, P.stage[s], sthr, seps, wid, Ssum, near);
+            const bool pass = valid && stage_verdict<NODES>(P, c, P.stage[s], sthr, seps, wid, Ssum, near);
             const unsigned m = __ballot_sync(0xffffffffu, pass);
             if (pass) cur[n_next + __popc(m & ((1u << lane) - 1u))] = (uint16_t)wid;
             n_next += __popc(m);
@@ -546,7 +585,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
                     const float sg[2] = {sgf[wid0], sgf[wid1]};
                     float Ssum[2] = {0.f, 0.f};
                     bool near[2] = {false, false};
-                    stage_filter<2, false, 0>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near);
+                    stage_filter<2, false, 0, NODES>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near);
                     keep(v0, wid0, Ssum[0], near[0]);
                     keep(v1, wid1, Ssum[1], near[1]);
                 } else {           // one row
@@ -557,7 +596,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
                     const float sg[1] = {sgf[wid0]};
                     float Ssum[1] = {0.f};
                     bool near[1] = {false};
-                    stage_filter<1, false, 0>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near);
+                    stage_filter<1, false, 0, NODES>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near);
                     keep(v0, wid0, Ssum[0], near[0]);
                 }
             }
@@ -572,7 +611,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
             const float sg[1] = {sgf[wid0]};
             float Ssum[1] = {0.f};
             bool near[1] = {false};
-            if (valid) stage_filter<1, false, 0>(P, P.stage[s], s < P.n_stages, grp, G, base, sg, Ssum, near);
+            if (valid) stage_filter<1, false, 0, NODES>(P, P.stage[s], s < P.n_stages, grp, G, base, sg, Ssum, near);
             float acc = Ssum[0];
             unsigned nr = near[0];
             for (int d = 1 << lw; d < 32; d <<= 1) {
@@ -623,7 +662,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
                 uint32_t to = kRouteReject;
                 bool pass = false;
                 if (valid) {
-                    pass = stage_verdict(P, c, st, sthr, seps, wid, Ssum, near);
+                    pass = stage_verdict<NODES>(P, c, st, sthr, seps, wid, Ssum, near);
                     to = pass ? to_pass : to_fail;
                 }
                 const bool on = valid && to < kRouteReject;
@@ -647,7 +686,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
                         const float sg[2] = {sgf[wid0], sgf[wid1]};
                         float Ssum[2] = {0.f, 0.f};
                         bool near[2] = {false, false};
-                        stage_filter<2, false, 0>(P, st, false, 0, 1, base, sg, Ssum, near);
+                        stage_filter<2, false, 0, NODES>(P, st, false, 0, 1, base, sg, Ssum, near);
                         route(v0, wid0, Ssum[0], near[0]);
                         route(v1, wid1, Ssum[1], near[1]);
                     } else {
@@ -655,7 +694,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
                         const float sg[1] = {sgf[wid0]};
                         float Ssum[1] = {0.f};
                         bool near[1] = {false};
-                        stage_filter<1, false, 0>(P, st, false, 0, 1, base, sg, Ssum, near);
+                        stage_filter<1, false, 0, NODES>(P, st, false, 0, 1, base, sg, Ssum, near);
                         route(v0, wid0, Ssum[0], near[0]);
                     }
                 }
@@ -669,7 +708,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
                 const float sg[1] = {sgf[wid0]};
                 float Ssum[1] = {0.f};
                 bool near[1] = {false};
-                if (valid) stage_filter<1, false, 0>(P, st, false, grp, G, base, sg, Ssum, near);
+                if (valid) stage_filter<1, false, 0, NODES>(P, st, false, grp, G, base, sg, Ssum, near);
                 float acc = Ssum[0];
                 unsigned nr = near[0];
                 for (int d = 1 << lw; d < 32; d <<= 1) {
@@ -720,24 +759,24 @@ constexpr int dense_stride_ce(int win_w, int ystep) {
 }
 constexpr int dense_rowstep_ce(int win_w, int ystep) { return (kDenseThreads / kTileW) * ystep * dense_stride_ce(win_w, ystep) * 4; }
 
-template <int ROWSTEP_T, bool TREE>
+template <int ROWSTEP_T, bool TREE, bool NODES>
 static cudaError_t launch_tiles_tt(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, size_t smem, cudaStream_t stream) {
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_cascade_tiles<ROWSTEP_T, TREE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_cascade_tiles<ROWSTEP_T, TREE, NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    k_cascade_tiles<ROWSTEP_T, TREE><<<dim3(n_tiles, a.n_frames), kDenseThreads, smem, stream>>>(P, a, tile0);
+    k_cascade_tiles<ROWSTEP_T, TREE, NODES><<<dim3(n_tiles, a.n_frames), kDenseThreads, smem, stream>>>(P, a, tile0);
     return cudaGetLastError();
 }
 template <int ROWSTEP_T>
 static cudaError_t launch_tiles_t(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, size_t smem, cudaStream_t stream) {
-    if (P.exec_stages > P.tail_stages) {   // stage tree: 20-pixel windows get the immediate-offset code, the rest the generic one
-        if (ROWSTEP_T == dense_rowstep_ce(24, 2)) return launch_tiles_tt<0, true>(P, a, tile0, n_tiles, smem, stream);
-        return launch_tiles_tt<ROWSTEP_T == dense_rowstep_ce(24, 2) ? 0 : ROWSTEP_T, true>(P, a, tile0, n_tiles, smem, stream);
-    }
-    return launch_tiles_tt<ROWSTEP_T, false>(P, a, tile0, n_tiles, smem, stream);
+    // stage trees and multi-node trees: 20-pixel windows get the immediate-offset code, the rest the generic one
+    constexpr int R = ROWSTEP_T == dense_rowstep_ce(24, 2) ? 0 : ROWSTEP_T;
+    if (P.exec_stages > P.tail_stages) return launch_tiles_tt<R, true, false>(P, a, tile0, n_tiles, smem, stream);
+    if (P.npt > 1) return launch_tiles_tt<R, false, true>(P, a, tile0, n_tiles, smem, stream);
+    return launch_tiles_tt<ROWSTEP_T, false, false>(P, a, tile0, n_tiles, smem, stream);
 }
 
 cudaError_t launch_cascade_tiles(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, cudaStream_t stream) {

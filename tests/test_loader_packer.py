@@ -67,10 +67,10 @@ def test_from_arrays_round_trip_and_child_links():
 
 def test_dense_prefix_rules():
     assert clfd.Cascade(cascade_path("frontalface_alt")).info.dense_stages >= 8
-    assert clfd.Cascade(cascade_path("frontalface_alt2")).info.dense_stages == 0     # multi-node trees
+    assert clfd.Cascade(cascade_path("frontalface_alt2")).info.dense_stages == 20    # 2-node trees: per-window node state
     assert clfd.Cascade(cascade_path("fullbody")).info.dense_stages == 30            # tilted stumps: second smem tile
     assert clfd.Cascade(cascade_path("mcs_nose")).info.dense_stages == 20
-    assert clfd.Cascade(cascade_path("eye_tree_eyeglasses")).info.dense_stages == 0  # multi-node trees
+    assert clfd.Cascade(cascade_path("eye_tree_eyeglasses")).info.dense_stages == 30  # 3-node trees + tilted
 
 
 def _mutate(name, old, new, count=1):
