@@ -117,7 +117,7 @@ def test_any_split_between_fixed_and_compacted_stages(gpu_ctx, monkeypatch, nf):
 
 def test_other_window_shapes_use_the_generic_tile_kernel(gpu_ctx):
     # lowerbody-like shapes are not shipped here; fullbody (14x28) exercises the non-templated
-    # row step of the tile kernel for its two dense stages, then the deep kernel with tilted features
+    # row step of the tile kernel, with tilted features (second tile)
     _compare(gpu_ctx, ["fullbody"], np.stack([octave_frame(700, 500, 6)]), 1.25)
 
 
@@ -210,6 +210,83 @@ def test_synthetic_cascade_order_sensitive_sums(gpu_ctx, big):
         assert np.array_equal(det.codes(0, 2)[f], ocodes)
         assert np.array_equal(res.frame_rects(f), _sorted(rects))
     det.close()
+
+
+def _mixed_tree_cascade(stage_trees=(5, 9, 14, 20, 40, 60)):
+    """Trees of 1, 2, 3 and 4 nodes (cyclically; the 4-node shape has a leaf, a chain and a fork)
+    assembled from frontalface_alt's features, every stage threshold at the middle of its leaf
+    values: the tile kernel pads every tree to 4 node records and tracks the node a window is at."""
+    from oracle.cascade_xml import FlatCascade, load_cascade_xml
+    f = load_cascade_xml(cascade_path("frontalface_alt"))
+    shapes = {1: [(0, -1)], 2: [(1, 0), (-1, -2)], 3: [(1, 2), (0, -1), (-2, -3)],
+              4: [(0, 1), (2, 3), (-1, -2), (-3, -4)]}   # (left, right): > 0 node, <= 0 leaf -idx
+    nn, left, right, alpha, thr = [], [], [], [], []
+    feat = 0
+    for nt in stage_trees:
+        mid = 0.0
+        for t in range(nt):
+            k = 1 + (len(nn) % 4)
+            nn.append(k)
+            for (l, r) in shapes[k]:
+                left.append(l); right.append(r)
+            leaves = [f.alpha[2 * (feat + i // 2) + (i & 1)] for i in range(k + 1)]
+            alpha += leaves
+            mid += float(np.mean(leaves))
+            feat += k
+        thr.append(mid - 0.05)
+    N, S = feat, len(stage_trees)
+    c = np.ascontiguousarray
+    return FlatCascade(name="mixed-trees", win_w=f.win_w, win_h=f.win_h, st_ntrees=np.array(stage_trees, np.int32),
+                       st_thr=np.array(thr, np.float32), st_parent=np.arange(-1, S - 1, dtype=np.int32),
+                       st_next=np.full(S, -1, np.int32), tr_nnodes=np.array(nn, np.int32),
+                       nd_tilted=c(f.nd_tilted[:N], np.int32), nd_rect=c(f.nd_rect[:N], np.int32),
+                       nd_weight=c(f.nd_weight[:N], np.float32), nd_thr=c(f.nd_thr[:N], np.float32),
+                       nd_left=np.array(left, np.int32), nd_right=np.array(right, np.int32), alpha=np.array(alpha, np.float32))
+
+
+@pytest.mark.parametrize("hook", [None, "CLFD_FORCE_EXACT", "CLFD_NO_NODE_TILES"])
+def test_synthetic_cascade_mixed_tree_shapes(gpu_ctx, monkeypatch, hook):
+    import oracle
+    if hook:
+        monkeypatch.setenv(hook, "1")
+    flat = _mixed_tree_cascade()
+    cas = clfd.Cascade(flat=flat)
+    assert cas.info.max_nodes_per_tree == 4 and not cas.info.is_stump_based
+    assert cas.info.dense_stages == (0 if hook == "CLFD_NO_NODE_TILES" else cas.info.n_stages)
+    oc = oracle.Cascade(flat)
+    det = clfd.Detector(gpu_ctx, cas, 640, 480, max_batch=2, scale_factor=1.2, want_codes=True)
+    frames = np.stack([octave_frame(640, 480, 12), uniform_frame(640, 480, 12)])
+    res = det.detect(frames)
+    seen = set()
+    for f in range(2):
+        rects, ocodes, _, _, _ = oc.detect(frames[f], 1.2)
+        assert np.array_equal(det.codes(0, 2)[f], ocodes)
+        assert np.array_equal(res.frame_rects(f), _sorted(rects))
+        seen |= set(np.unique(ocodes).tolist())
+    assert len(seen) >= 5, seen   # the thresholds really split the windows over the stages
+    det.close()
+
+
+@pytest.mark.parametrize("hook,names", [("CLFD_NO_NODE_TILES", ["frontalface_alt2", "eye_tree_eyeglasses"]),
+                                        ("CLFD_NO_TREE_TILES", ["frontalface_alt_tree"]),
+                                        ("CLFD_NO_TILTED_TILE", ["fullbody", "mcs_nose"])])
+def test_generic_kernels_behind_the_tile_kernel(gpu_ctx, monkeypatch, hook, names):
+    """The stock cascades all finish inside the tile kernel; the hooks switch its tree / stage-tree /
+    tilted support off so that the mid and deep kernels (cascades with larger trees) stay covered."""
+    monkeypatch.setenv(hook, "1")
+    assert clfd.Cascade(cascade_path(names[0])).info.dense_stages < clfd.Cascade(cascade_path(names[0])).info.n_stages
+    _compare(gpu_ctx, names, np.stack([octave_frame(480, 360, 5)]), 1.2)
+
+
+@pytest.mark.parametrize("env", [{"CLFD_FORCE_EXACT": "1"}, {"CLFD_N_FIXED": "0"}, {"CLFD_N_FIXED": "5"}, {"CLFD_G1_MIN": "1"}])
+def test_tile_kernel_variants_under_every_split(gpu_ctx, monkeypatch, env):
+    """stage tree / multi-node / tilted variants of the tile kernel: all-FP64 evaluation, no fixed
+    stages (the stage-tree walk starts from a dealt list when the linear prefix is all fixed:
+    N_FIXED=5), thread-per-window only."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    _compare(gpu_ctx, ["frontalface_alt_tree", "frontalface_alt2", "eye_tree_eyeglasses", "fullbody"],
+             np.stack([octave_frame(400, 300, 8)]), 1.2)
 
 
 def test_submit_collect_pipeline_keeps_batches_apart(gpu_ctx):
