@@ -12,7 +12,9 @@
  * restatement of tempcv.cpp (C expression types kept as written).  The pieces that
  * live in OpenCV (resize, integral, tilted integral, groupRectangles) ARE pinned,
  * bit-for-bit, against cv2 4.13 in tests/test_oracle_pins.py and by the committed
- * fixtures under tests/golden/.
+ * fixtures under tests/golden/.  The evaluator has a SOFT pin there too: at the unscaled
+ * pyramid level its raw candidates equal those of OpenCV 4.13's own CascadeClassifier (an
+ * independent implementation) for the upright cascades; see DESIGN.md section 2.
  *
  * All file:line citations are relative to /root/reference/CLFaceDetection/.
  */
