@@ -88,6 +88,16 @@ void vjo_cascade_free(vjo_cascade *c)
     free(c->stage); free(c->trees); free(c->nodes); free(c->alphas); free(c);
 }
 
+/* The reference halves the weights of tilted features (tempcv.cpp:733).  OpenCV 4.x's evaluator
+ * does not; the soft pin against cv2.CascadeClassifier (tests/test_oracle_pins.py) sets
+ * VJO_TEST_TILTED_CORRECTION=1 to compare the tilted GEOMETRY with that implementation.
+ * Never set outside that test. */
+static double tilted_correction(void)
+{
+    const char *e = getenv("VJO_TEST_TILTED_CORRECTION");
+    return e ? atof(e) : 0.5;
+}
+
 vjo_cascade *vjo_cascade_create(int win_w, int win_h, int n_stages,
                                 const int *st_ntrees, const float *st_thr,
                                 const int *st_parent, const int *st_next,
@@ -214,7 +224,7 @@ vjo_cascade *vjo_cascade_create(int win_w, int win_h, int n_stages,
                 rect_t tr;
                 tr.x = cv_round(nd->r[k].x * scale); tr.w = cv_round(nd->r[k].w * scale);
                 tr.y = cv_round(nd->r[k].y * scale); tr.h = cv_round(nd->r[k].h * scale);
-                double correction_ratio = weight_scale * (!nd->tilted ? 1 : 0.5); /* :733 */
+                double correction_ratio = weight_scale * (!nd->tilted ? 1 : tilted_correction()); /* :733 */
                 if (!nd->tilted) { /* :738-741 */
                     nd->dy[k][0] = tr.y;        nd->dx[k][0] = tr.x;
                     nd->dy[k][1] = tr.y;        nd->dx[k][1] = tr.x + tr.w;

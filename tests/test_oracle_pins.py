@@ -293,3 +293,34 @@ def test_evaluator_agrees_with_opencv4_cascade_classifier():
         pooled[0] += both
         pooled[1] += either
     assert pooled[0] >= 0.75 * pooled[1], pooled
+
+
+def test_tilted_geometry_and_trees_agree_with_opencv4(monkeypatch):
+    """The tilted cascades differ from OpenCV 4.x in ONE documented constant: the reference halves
+    the weights of tilted features (tempcv.cpp:733), the 4.x evaluator does not.  With that
+    correction switched off in the oracle (test knob), its level-0 candidates must again be
+    cv2's: this pins the tilted integral, the tilted corner geometry (tempcv.cpp:745-749) and the
+    multi-node tree walk (eye_tree_eyeglasses: 3-node trees) against an independent implementation."""
+    g = np.load(os.path.join(GOLD, "cv2_detector_soft_pin.npz"))
+    frames = [(960, 540, 0), (960, 540, 7), (1280, 720, 3), (800, 600, 5)]
+    monkeypatch.setenv("VJO_TEST_TILTED_CORRECTION", "1")
+    for name, min0 in [("mcs_nose", 100), ("eye_tree_eyeglasses", 100), ("fullbody", 1)]:
+        cas = oracle.Cascade(cascade_path(name))   # not the cached one: built under the knob
+        win = oracle.load_cascade_xml(cascade_path(name)).win_w
+        both = either = both0 = either0 = 0
+        for fi, (w, h, seed) in enumerate(frames):
+            mine = {tuple(r) for r in np.asarray(cas.detect(octave_frame(w, h, seed), 1.2)[0]).reshape(-1, 4).tolist()}
+            theirs = {tuple(r) for r in g[f"{name}_{fi}"].tolist()}
+            both += len(mine & theirs)
+            either += len(mine | theirs)
+            both0 += len({r for r in mine & theirs if r[2] == win})
+            either0 += len({r for r in mine | theirs if r[2] == win})
+        assert either0 >= min0 and both0 >= 0.95 * either0, (name, both0, either0)   # float-vs-double decisions at a threshold
+        if either >= 30:
+            assert both >= 0.8 * either, (name, both, either)
+    monkeypatch.delenv("VJO_TEST_TILTED_CORRECTION")
+    # and with the reference's 0.5 in place the same comparison must FAIL clearly (the knob does something)
+    cas = oracle_cascade("mcs_nose")
+    mine = {tuple(r) for r in np.asarray(cas.detect(octave_frame(960, 540, 0), 1.2)[0]).reshape(-1, 4).tolist()}
+    theirs = {tuple(r) for r in g["mcs_nose_0"].tolist()}
+    assert len(mine & theirs) < 0.6 * len(mine | theirs)
