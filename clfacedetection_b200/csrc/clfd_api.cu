@@ -667,7 +667,8 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
             memset(&CL, 0, sizeof CL);
             CL.pyr_level = pyr_index[k];
             CL.nx = nx; CL.ny = ny; CL.ystep = ystep; CL.win_w = win_w; CL.win_h = win_h;
-            CL.tiles_x = (nx + kTileW - 1) / kTileW; CL.tiles_y = (ny + kTileH - 1) / kTileH;
+            const int tile_h = cp.cascade->packed.dense[ystep - 1].tile_h > 0 ? cp.cascade->packed.dense[ystep - 1].tile_h : kTileH;
+            CL.tiles_x = (nx + kTileW - 1) / kTileW; CL.tiles_y = (ny + tile_h - 1) / tile_h;
             CL.tile_base = cp.n_tiles; CL.win_base = cp.windows_per_frame; CL.factor = factor;
             cp.n_tiles += CL.tiles_x * CL.tiles_y;
             if (ystep == 2) cp.n_tiles_y2 = cp.n_tiles;

@@ -59,6 +59,7 @@ int build_hidden(HostCascade &c);
 // Tile geometry of the smem-tile ("dense") cascade kernel: TW x TH windows per CTA.
 constexpr int kTileW = 64;
 constexpr int kTileH = 32;
+constexpr int kTileHSmall = 16;
 constexpr int kTileWindows = kTileW * kTileH;
 constexpr int kDenseThreads = 256;
 constexpr int kDenseWarps = kDenseThreads / 32;
@@ -119,7 +120,7 @@ struct DenseParams {
     int exec_stages;    // == tail_stages, or for a stage tree the tile kernel walks itself: all stages, in
                         // execution order (stage_g; the first tail_stages of them are the linear prefix)
     int npt;            // records per tree: 1 = stumps; 2..4 = multi-node trees, every tree padded to npt node records
-    int pad2;
+    int tile_h;         // window rows per tile: kTileH, or kTileHSmall where two tiles (tilted) would leave one CTA per SM
     double inv_area;
     const TailStump *tail;   // device, layout of this blob's ystep (patched in by the detector)
     const struct DenseStage *stage_g;   // device: stage table in execution order (stage trees only)

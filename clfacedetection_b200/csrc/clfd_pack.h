@@ -22,7 +22,7 @@ void pack_sc_level(const HostCascade &c, double factor, int pitch, ScLevel &L, S
 const char *get_error();
 
 int dense_tile_stride(int win_w, int ystep);  // ints per smem tile row (ystep * stride = 8 mod 32)
-int dense_tile_rows(int win_h, int ystep);    // integral rows a tile needs
+int dense_tile_rows(int win_h, int ystep, int tile_h);    // integral rows a tile needs
 int dense_tile_cols(int win_w, int ystep);    // integral columns a tile needs (multiple of 4)
 
 }  // namespace clfd

@@ -172,7 +172,7 @@ static void corner_coords(const HostNode &nd, int k, int dx[4], int dy[4]) {
 }
 
 int dense_tile_cols(int win_w, int ystep) { return ((kTileW - 1) * ystep + win_w + 1 + 3) & ~3; }
-int dense_tile_rows(int win_h, int ystep) { return (kTileH - 1) * ystep + win_h + 1; }
+int dense_tile_rows(int win_h, int ystep, int tile_h) { return (tile_h - 1) * ystep + win_h + 1; }
 int dense_tile_stride(int win_w, int ystep) {
     // ystep 1: natural layout, stride >= cols.  ystep 2: even columns in the first half of a
     // row, odd columns in the second half, stride/2 >= cols/2.  In both the word distance
@@ -281,10 +281,14 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
         P.filter_eps = 9.5367431640625e-07f;  // 2^-20
         if (const char *e = getenv("CLFD_FORCE_EXACT")) P.force_exact = atoi(e) != 0;   // test hook: bypass the FP32 filters
         P.inv_area = 1. / ((c.win_w - 2) * (c.win_h - 2));
-        const size_t tile_bytes = (size_t)dense_tile_rows(c.win_h, ystep) * P.tile_stride * 4;
-        // a cascade with tilted features keeps a second tile (the tilted integral) behind the first
-        const size_t tilt_base = (tile_bytes + 127) & ~(size_t)127;
+        // a cascade with tilted features keeps a second tile (the tilted integral) behind the first; on
+        // ystep-2 levels (more integral rows per tile) the tiles are half as high then, or the two tiles
+        // leave room for only one or two CTAs per SM
         P.tilted_tile = c.has_tilted && !getenv("CLFD_NO_TILTED_TILE") ? 1 : 0;
+        P.tile_h = kTileH;
+        if (P.tilted_tile && ystep == 2 && !c.is_tree && !getenv("CLFD_NO_SMALL_TILES")) P.tile_h = kTileHSmall;
+        const size_t tile_bytes = (size_t)dense_tile_rows(c.win_h, ystep, P.tile_h) * P.tile_stride * 4;
+        const size_t tilt_base = (tile_bytes + 127) & ~(size_t)127;
         const bool dense_ok = tile_bytes <= 65536 && (!P.tilted_tile || 2 * tilt_base <= 160 * 1024) && c.win_w <= 255 && c.win_h <= 255;
         // multi-node trees (<= kMaxTreeNodes nodes, children after their parent) are evaluated node by node
         // with a per-window "node I am at" state; every tree is padded to npt = the cascade's largest tree

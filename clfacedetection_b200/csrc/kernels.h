@@ -1,6 +1,8 @@
 // kernels.h -- launchers of the sm_100a kernels (kernels_*.cu).  Every launcher enqueues
 // on `stream` and returns the cudaError_t of the launch.
 #pragma once
+#include <atomic>
+#include <mutex>
 #include <cuda_runtime.h>
 
 #include "clfd_internal.h"
@@ -27,6 +29,28 @@ struct PyramidArgs {
     const int4 *tilted_items; int n_tilted_items;      // (level, -, -, -)
     int max_level_w;
 };
+
+// Raises a kernel's dynamic shared-memory limit when a launch needs more than any earlier one on
+// the CURRENT device (the attribute is per device; several host threads may launch at once).
+struct SmemLimitCache {
+    std::atomic<size_t> configured[64];
+    std::mutex lock;
+    SmemLimitCache() { for (auto &c : configured) c.store(0); }
+    template <typename Kernel>
+    cudaError_t ensure(Kernel kernel, size_t smem) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        std::atomic<size_t> &c = configured[dev & 63];
+        if (smem <= c.load(std::memory_order_acquire)) return cudaSuccess;
+        std::lock_guard<std::mutex> g(lock);
+        if (smem <= c.load(std::memory_order_relaxed)) return cudaSuccess;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) c.store(smem, std::memory_order_release);
+        return e;
+    }
+};
+
 cudaError_t launch_resize_colsum(const PyramidArgs &a, cudaStream_t stream);
 cudaError_t launch_colscan(const PyramidArgs &a, cudaStream_t stream);
 cudaError_t launch_integral_rows(const PyramidArgs &a, cudaStream_t stream, int *n_launches);

@@ -289,11 +289,9 @@ cudaError_t launch_tilted(const PyramidArgs &a, cudaStream_t stream) {
     if (a.n_tilted_items == 0 || a.n_frames == 0 || !a.tilted) return cudaSuccess;
     if (a.max_level_w > kTiltedThreads * kTiltedMaxCols) return cudaErrorInvalidValue;
     const size_t smem = (size_t)4 * (a.max_level_w + 2) * sizeof(int32_t);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_tilted, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
+    static SmemLimitCache limit;
+    if (smem > 48 * 1024) {
+        if (cudaError_t e = limit.ensure(k_tilted, smem)) return e;
     }
     k_tilted<<<dim3(a.n_tilted_items, a.n_frames), kTiltedThreads, smem, stream>>>(a);
     return cudaGetLastError();

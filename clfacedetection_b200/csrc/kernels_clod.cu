@@ -141,17 +141,17 @@ struct DenseSmemPlan {
 constexpr int kCtlCount = 0, kCtlPrefix = 32, kCtlAlive = 64, kCtlInts = 72;
 __host__ __device__ inline DenseSmemPlan dense_smem_plan(const DenseParams &P) {
     DenseSmemPlan p;
-    const size_t rows = (size_t)(kTileH - 1) * P.ystep + P.win_h + 1;
+    const size_t rows = (size_t)(P.tile_h - 1) * P.ystep + P.win_h + 1, windows = (size_t)kTileW * P.tile_h;
     p.tile = 0;
     p.sgf = (rows * P.tile_stride * 4 + 127) & ~(size_t)127;
     if (P.tilted_tile) p.sgf *= 2;   // second tile: the tilted integral (same geometry)
-    p.list = p.sgf + kTileWindows * sizeof(float);
-    p.ctl = p.list + kTileWindows * sizeof(uint16_t);
+    p.list = p.sgf + windows * sizeof(float);
+    p.ctl = p.list + windows * sizeof(uint16_t);
     p.bar = p.ctl + kCtlInts * sizeof(int);
     p.act = p.tgt = p.total = p.bar + 16;
     if (P.exec_stages > P.tail_stages) {   // stage tree: the windows of the current stage, every window's target position
-        p.tgt = p.act + kTileWindows * sizeof(uint16_t);
-        p.total = p.tgt + kTileWindows;
+        p.tgt = p.act + windows * sizeof(uint16_t);
+        p.total = p.tgt + windows;
     }
     return p;
 }
@@ -164,7 +164,7 @@ struct DenseCtx {
     int sq_pitch;     // elements
     int row_mul;      // bytes between window rows in the tile
     int ystep, S;
-    int tx, ty, nx;
+    int tx, wy_tile, nx;   // tile column; first window row of the tile
     int code_mul;
 };
 
@@ -176,7 +176,7 @@ __device__ __forceinline__ uint32_t dense_tile_off(const DenseCtx &c, int y, int
 }
 __device__ __forceinline__ void dense_write_code(const DenseCtx &c, int wid, int code) {
     const int wx = wid & (kTileW - 1), wy = wid / kTileW;
-    c.codes[(size_t)(c.ty * kTileH + wy) * c.nx + c.tx * kTileW + wx] = (int16_t)code;
+    c.codes[(size_t)(c.wy_tile + wy) * c.nx + c.tx * kTileW + wx] = (int16_t)code;
 }
 
 // FP64 sigma of window `wid` (tempcv.cpp:824-832): int32 corners from the tile, uint64 from global
@@ -378,8 +378,9 @@ __device__ __forceinline__ bool stage_verdict(const DenseParams &P, const DenseC
 // (= kDenseThreads / kTileW window rows), or 0 to use the runtime value (generic window sizes).
 // TREE: the cascade is a stage tree the kernel walks itself (DenseParams::exec_stages > tail_stages).
 // NODES: multi-node trees (DenseParams::npt > 1).
-template <int ROWSTEP_T, bool TREE, bool NODES>
-__global__ void __launch_bounds__(kDenseThreads)
+// TILE_H: window rows per tile (== DenseParams::tile_h).
+template <int ROWSTEP_T, bool TREE, bool NODES, int TILE_H>
+__global__ void __launch_bounds__(kDenseThreads)   // (no min-blocks argument: even "1" lets ptxas take 88 registers and costs a CTA per SM)
 k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ CascadeArgs a, const int tile0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const DenseSmemPlan plan = dense_smem_plan(P);
@@ -407,9 +408,11 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     const int local = tile_id - CL.tile_base;
     const int tx = local % CL.tiles_x, ty = local / CL.tiles_x;
     const int ystep = P.ystep;   // == CL.ystep by construction of the launch
-    const int px0 = tx * kTileW * ystep, py0 = ty * kTileH * ystep;   // tile origin in the integral image
-    const int n_wx = min(kTileW, CL.nx - tx * kTileW), n_wy = min(kTileH, CL.ny - ty * kTileH);
-    const int rows = min((kTileH - 1) * ystep + P.win_h + 1, L.h + 1 - py0);
+    constexpr int kTileWindows = kTileW * TILE_H, kDenseSlots = kTileWindows / kDenseThreads;   // (shadow the 32-row constants)
+    static_assert(kDenseSlots % kDenseChunk == 0, "tile height must be a multiple of 16");
+    const int px0 = tx * kTileW * ystep, py0 = ty * TILE_H * ystep;   // tile origin in the integral image
+    const int n_wx = min(kTileW, CL.nx - tx * kTileW), n_wy = min(TILE_H, CL.ny - ty * TILE_H);
+    const int rows = min((TILE_H - 1) * ystep + P.win_h + 1, L.h + 1 - py0);
     const int cols = ((kTileW - 1) * ystep + P.win_w + 1 + 3) & ~3;
     const int S = P.tile_stride;
 
@@ -420,7 +423,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     // ---- stage the integral tile ----
     for (int i = tid; i < kCtlInts; i += kDenseThreads) ctl[i] = 0;
     const int n_tiles_smem = P.tilted_tile ? 2 : 1;
-    const size_t tile2_off = ((size_t)((kTileH - 1) * ystep + P.win_h + 1) * S * 4 + 127) & ~(size_t)127;
+    const size_t tile2_off = ((size_t)((TILE_H - 1) * ystep + P.win_h + 1) * S * 4 + 127) & ~(size_t)127;
     const int32_t *__restrict__ gtil = a.tilted ? a.tilted + frame_off + (size_t)py0 * L.sum_pitch + px0 : gsum;
     if (ystep == 1) {   // natural layout: one TMA bulk copy per row
         if (tid == 0) mbar_init(bar, 1);
@@ -451,7 +454,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     c.sq_pitch = L.sum_pitch;
     c.row_mul = ystep * S * 4;
     c.ystep = ystep; c.S = S;
-    c.tx = tx; c.ty = ty; c.nx = CL.nx;
+    c.tx = tx; c.wy_tile = ty * TILE_H; c.nx = CL.nx;
     c.code_mul = P.is_tree ? 2 : 1;
     const float inf = __int_as_float(0x7f800000);
 
@@ -759,15 +762,11 @@ constexpr int dense_stride_ce(int win_w, int ystep) {
 }
 constexpr int dense_rowstep_ce(int win_w, int ystep) { return (kDenseThreads / kTileW) * ystep * dense_stride_ce(win_w, ystep) * 4; }
 
-template <int ROWSTEP_T, bool TREE, bool NODES>
+template <int ROWSTEP_T, bool TREE, bool NODES, int TILE_H = kTileH>
 static cudaError_t launch_tiles_tt(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, size_t smem, cudaStream_t stream) {
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_cascade_tiles<ROWSTEP_T, TREE, NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
-    k_cascade_tiles<ROWSTEP_T, TREE, NODES><<<dim3(n_tiles, a.n_frames), kDenseThreads, smem, stream>>>(P, a, tile0);
+    static SmemLimitCache limit;
+    if (cudaError_t e = limit.ensure(k_cascade_tiles<ROWSTEP_T, TREE, NODES, TILE_H>, smem)) return e;
+    k_cascade_tiles<ROWSTEP_T, TREE, NODES, TILE_H><<<dim3(n_tiles, a.n_frames), kDenseThreads, smem, stream>>>(P, a, tile0);
     return cudaGetLastError();
 }
 template <int ROWSTEP_T>
@@ -775,6 +774,11 @@ static cudaError_t launch_tiles_t(const DenseParams &P, const CascadeArgs &a, in
     // stage trees and multi-node trees: 20-pixel windows get the immediate-offset code, the rest the generic one
     constexpr int R = ROWSTEP_T == dense_rowstep_ce(24, 2) ? 0 : ROWSTEP_T;
     if (P.exec_stages > P.tail_stages) return launch_tiles_tt<R, true, false>(P, a, tile0, n_tiles, smem, stream);
+    if (P.tile_h == kTileHSmall) {   // tilted cascades on ystep-2 levels
+        if (P.npt > 1) return launch_tiles_tt<R, false, true, kTileHSmall>(P, a, tile0, n_tiles, smem, stream);
+        return launch_tiles_tt<R, false, false, kTileHSmall>(P, a, tile0, n_tiles, smem, stream);
+    }
+    if (P.tile_h != kTileH) return cudaErrorInvalidValue;
     if (P.npt > 1) return launch_tiles_tt<R, false, true>(P, a, tile0, n_tiles, smem, stream);
     return launch_tiles_tt<ROWSTEP_T, false, false>(P, a, tile0, n_tiles, smem, stream);
 }
