@@ -15,7 +15,8 @@ import numpy as np
 from . import abi
 from .abi import ClfdError  # noqa: F401
 
-__all__ = ["Context", "Cascade", "Detector", "group_rectangles", "ClfdError", "DetectResult"]
+__all__ = ["Context", "Cascade", "Detector", "group_rectangles", "group_rectangles_roc", "group_batch", "ClfdError",
+           "DetectResult"]
 
 
 def _ptr(a):
@@ -263,6 +264,25 @@ class Detector:
         abi.check(abi.lib().clfd_detector_get_codes(self._h, cascade, out.ctypes.data_as(C.POINTER(C.c_int16)), out.size))
         return out
 
+    def reject_levels(self, cascade: int = 0):
+        """Reject-level / ROC output of the last blocking detect (cvHaarDetectObjectsForROC with
+        outputRejectLevels, tempcv.cpp:1084-1094) -> (rects RECT_DTYPE, levels int32, stage sums
+        float64) in the reference's scan order.  Needs want_codes=True."""
+        cap = 1 << 12
+        while True:
+            r = np.zeros(cap, RECT_DTYPE)
+            lv = np.zeros(cap, np.int32)
+            wt = np.zeros(cap, np.float64)
+            n = C.c_int64()
+            rc = abi.lib().clfd_detector_reject_levels(self._h, cascade, r.ctypes.data_as(C.POINTER(abi.Rect)),
+                                                       lv.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                       wt.ctypes.data_as(C.POINTER(C.c_double)), cap, C.byref(n))
+            if rc == -5 and n.value > cap:   # CLFD_ERR_CAPACITY: n holds the count
+                cap = int(n.value)
+                continue
+            abi.check(rc)
+            return r[:n.value].copy(), lv[:n.value].copy(), wt[:n.value].copy()
+
     def read_level(self, level: int, frame: int = 0, cascade: int = 0, tilted: bool = False):
         lv = self.levels(cascade)[level]
         w, h = lv.img_w, lv.img_h
@@ -282,6 +302,21 @@ def group_rectangles(rects: np.ndarray, group_threshold: int, eps: float = 0.2):
     abi.check(abi.lib().clfd_group_rectangles(r.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n), group_threshold,
                                               eps, w.ctypes.data_as(C.POINTER(C.c_int32))))
     return r[:n.value].copy(), w[:n.value].copy()
+
+
+def group_rectangles_roc(rects: np.ndarray, reject_levels: np.ndarray, level_weights: np.ndarray,
+                         group_threshold: int, eps: float = 0.2):
+    """AgroupRectangles, ROC variant (tempcv.cpp:255-258) -> (rects[m,4], levels[m], stage sums[m])"""
+    r = np.ascontiguousarray(rects, np.int32).reshape(-1, 4).copy()
+    lv = np.ascontiguousarray(reject_levels, np.int32).copy()
+    wt = np.ascontiguousarray(level_weights, np.float64).copy()
+    n = C.c_int(len(r))
+    if len(r) == 0:
+        return r, lv, wt
+    abi.check(abi.lib().clfd_group_rectangles_roc(r.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n), group_threshold, eps,
+                                                  lv.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                  wt.ctypes.data_as(C.POINTER(C.c_double))))
+    return r[:n.value].copy(), lv[:n.value].copy(), wt[:n.value].copy()
 
 
 def group_batch(rects: np.ndarray, group_threshold: int, eps: float = 0.2, n_threads: int = 0):

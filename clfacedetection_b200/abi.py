@@ -113,6 +113,10 @@ def lib() -> C.CDLL:
     L.clfd_detector_set_profiling.argtypes = [vp, C.c_int]
     L.clfd_detector_get_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.clfd_group_rectangles.argtypes = [C.POINTER(C.c_int32), ip, C.c_int, C.c_double, C.POINTER(C.c_int32)]
+    L.clfd_group_rectangles_roc.argtypes = [C.POINTER(C.c_int32), ip, C.c_int, C.c_double, C.POINTER(C.c_int32),
+                                            C.POINTER(C.c_double)]
+    L.clfd_detector_reject_levels.argtypes = [vp, C.c_int, C.POINTER(Rect), C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                                              C.c_int64, C.POINTER(C.c_int64)]
     _lib = L
     return L
 

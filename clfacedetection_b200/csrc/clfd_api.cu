@@ -266,6 +266,8 @@ struct clfd_detector {
     DevBuf<uint8_t> dev_frames[kSlots];   // staging for host input (clfd_detect / clfd_detect_submit)
     DevBuf<DevRect> rects2;               // rect buffer of slot 1 (slot 0 uses `rects`)
     DevBuf<uint8_t> dev_bgr;              // interleaved colour input of clfd_detect_image
+    DevBuf<RocItem> roc;                  // candidates of clfd_detector_reject_levels
+    DevBuf<unsigned long long> roc_count;
     DevRect *h_rects = nullptr;           // pinned, kSlots x rect_cap... slot 1 holds kEagerRects only
     DevRect *h_rects1 = nullptr;
     unsigned long long *h_counters = nullptr;  // pinned, kSlots x (4 per cascade, 16 cascades)
@@ -1161,6 +1163,61 @@ int clfd_detector_get_codes(clfd_detector *det, int cascade, int16_t *codes, int
     if (n > cap) { set_error("codes buffer too small: need %lld", (long long)n); return CLFD_ERR_CAPACITY; }
     CK(cudaDeviceSynchronize());
     if (n > 0) CK(cudaMemcpy(codes, cp.d_codes.p, n * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// Reject levels of the last batch (tempcv.cpp:1084-1094): a pass over the exit codes, see k_roc_collect.
+int clfd_detector_reject_levels(clfd_detector *det, int cascade, clfd_rect *rects, int32_t *reject_levels,
+                                double *level_weights, int64_t cap, int64_t *n_out) {
+    if (!det || !n_out || cascade < 0 || cascade >= (int)det->cas.size() || cap < 0 ||
+        (cap > 0 && (!rects || !reject_levels || !level_weights)))
+        INVALID("bad argument");
+    *n_out = 0;
+    if (det->cfg.mode == CLFD_MODE_SCALE_CASCADE) INVALID("reject levels are defined on the image-pyramid path only (tempcv.cpp:1084)");
+    if (!det->cfg.want_codes) INVALID("detector was created without want_codes");
+    if (det->n_submitted != det->n_collected) INVALID("clfd_detector_reject_levels while submitted batches are in flight");
+    CascadePlan &cp = *det->cas[cascade];
+    if (det->last_frames == 0 || cp.windows_per_frame == 0) return 0;
+    clfd_context *ctx = det->ctx;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    const unsigned long long roc_cap = 1ull << 20;
+    if (!det->roc.p && ((rc = det->roc.alloc(roc_cap)) || (rc = det->roc_count.alloc(1)))) return rc;
+    CascadeArgs a;
+    memset(&a, 0, sizeof a);
+    a.sum = det->pyr.sum.p; a.sq = det->pyr.sq.p;
+    a.tilted = det->pyr.want_tilted ? det->pyr.tilted.p : nullptr;
+    a.sum_frame_stride = det->pyr.sum_frame_stride;
+    a.levels = det->pyr.d_levels.p; a.cas_levels = cp.d_levels.p;
+    a.n_cas_levels = (int)cp.levels.size(); a.n_frames = det->last_frames;
+    a.cascade_index = cascade; a.windows_per_frame = cp.windows_per_frame;
+    a.codes = cp.d_codes.p;
+    a.deep.stages = cp.d_stages.p; a.deep.tree_first_node = cp.d_tree_first.p;
+    a.deep.nodes = cp.d_nodes.p; a.deep.alpha = cp.d_alpha.p;
+    a.deep.n_stages = cp.cascade->host.n_stages(); a.deep.is_tree = cp.cascade->host.is_tree;
+    a.deep.has_tilted = cp.cascade->host.has_tilted;
+    a.deep.win_w = cp.cascade->host.win_w; a.deep.win_h = cp.cascade->host.win_h;
+    a.deep.inv_area = cp.cascade->packed.dense[0].inv_area;
+    CK(cudaMemsetAsync(det->roc_count.p, 0, sizeof(unsigned long long), ctx->stream));
+    CK(launch_roc_collect(a, det->roc.p, roc_cap, det->roc_count.p, ctx->stream));
+    ctx->launches++;
+    unsigned long long n = 0;
+    CK(cudaMemcpyAsync(&n, det->roc_count.p, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n > roc_cap) { set_error("more than %llu reject-level candidates", roc_cap); return CLFD_ERR_CAPACITY; }
+    *n_out = (int64_t)n;
+    if ((int64_t)n > cap) { set_error("reject-level buffers too small: need %llu", n); return CLFD_ERR_CAPACITY; }
+    std::vector<RocItem> items(n);
+    if (n) CK(cudaMemcpy(items.data(), det->roc.p, n * sizeof(RocItem), cudaMemcpyDeviceToHost));
+    std::sort(items.begin(), items.end(), [](const RocItem &p, const RocItem &q) {   // the reference's scan order
+        return p.r.frame != q.r.frame ? p.r.frame < q.r.frame : p.win < q.win;
+    });
+    for (size_t i = 0; i < items.size(); i++) {
+        const DevRect &r = items[i].r;
+        rects[i].x = r.x; rects[i].y = r.y; rects[i].w = r.w; rects[i].h = r.h; rects[i].frame = r.frame; rects[i].cascade = r.cascade;
+        reject_levels[i] = items[i].level;
+        level_weights[i] = items[i].weight;
+    }
     return 0;
 }
 

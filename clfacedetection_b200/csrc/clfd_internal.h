@@ -208,5 +208,12 @@ struct QueueItem {        // survivor handed to the deep kernel
 struct DevRect {
     int x, y, w, h, frame, cascade;
 };
+// one candidate of the reject-level (ROC) output; `win` = window index in the frame: the scan order
+struct RocItem {
+    DevRect r;
+    int level, pad;
+    long long win;
+    double weight;
+};
 
 }  // namespace clfd

@@ -4,6 +4,7 @@
 // OpenCV, call site tempcv.cpp:160) = connected components of the similarity relation,
 // classes numbered by their first member.  Replaces the reference's own filterResult
 // (clod.cpp:282-357), which is defective.
+#include <cfloat>
 #include <climits>
 #include <cstdlib>
 #include <cstring>
@@ -41,8 +42,9 @@ inline int trunc_sat(float v) { return v > (float)INT_MAX ? INT_MAX : (int)v; }
 
 }  // namespace
 
-extern "C" int clfd_group_rectangles(int32_t *rects_xywh, int *n_io, int group_threshold, double eps,
-                                     int32_t *weights) {
+// weights: out = neighbour counts; with level_weights (the ROC variant, tempcv.cpp:255-258) weights carries
+// the reject levels in and the winning level of each kept class out
+static int group_impl(int32_t *rects_xywh, int *n_io, int group_threshold, double eps, int32_t *weights, double *level_weights) {
     if (!rects_xywh || !n_io || *n_io < 0) { clfd::set_error("bad argument"); return CLFD_ERR_INVALID; }
     const int n = *n_io;
     if (group_threshold <= 0 || n == 0) {  // tempcv.cpp:147-157
@@ -66,6 +68,15 @@ extern "C" int clfd_group_rectangles(int32_t *rects_xywh, int *n_io, int group_t
         acc[c * 4 + 0] += in[i].x; acc[c * 4 + 1] += in[i].y; acc[c * 4 + 2] += in[i].w; acc[c * 4 + 3] += in[i].h;
         count[c]++;
     }
+    std::vector<int> rej_level(nclasses, 0);
+    std::vector<double> rej_weight(nclasses, DBL_MIN);   // :165 (DBL_MIN, not -DBL_MAX, as written there)
+    if (level_weights && weights) {   // :176-189: highest level of the class, largest stage sum at that level
+        for (int i = 0; i < n; i++) {
+            const int c = label[ds.find(i)];
+            if (weights[i] > rej_level[c]) { rej_level[c] = weights[i]; rej_weight[c] = level_weights[i]; }
+            else if (weights[i] == rej_level[c] && level_weights[i] > rej_weight[c]) rej_weight[c] = level_weights[i];
+        }
+    }
     std::vector<R4> mean(nclasses);
     for (int c = 0; c < nclasses; c++) {  // :191-199: float reciprocal, truncation
         const float s = 1.f / count[c];
@@ -75,9 +86,10 @@ extern "C" int clfd_group_rectangles(int32_t *rects_xywh, int *n_io, int group_t
     int out = 0;
     std::vector<R4> kept;
     std::vector<int> kept_w;
+    std::vector<double> kept_lw;
     for (int i = 0; i < nclasses; i++) {  // :207-242
         const R4 r1 = mean[i];
-        const int n1 = count[i];
+        const int n1 = level_weights ? rej_level[i] : count[i];   // :210
         if (n1 <= group_threshold) continue;
         bool nested = false;
         for (int j = 0; j < nclasses && !nested; j++) {
@@ -88,12 +100,24 @@ extern "C" int clfd_group_rectangles(int32_t *rects_xywh, int *n_io, int group_t
             nested = r1.x >= r2.x - dx && r1.y >= r2.y - dy && r1.x + r1.w <= r2.x + r2.w + dx &&
                      r1.y + r1.h <= r2.y + r2.h + dy && (n2 > std::max(3, n1) || n1 < 3);
         }
-        if (!nested) { kept.push_back(r1); kept_w.push_back(n1); out++; }
+        if (!nested) { kept.push_back(r1); kept_w.push_back(n1); kept_lw.push_back(rej_weight[i]); out++; }
     }
     memcpy(rects_xywh, kept.data(), (size_t)out * sizeof(R4));
     if (weights) memcpy(weights, kept_w.data(), (size_t)out * sizeof(int));
+    if (level_weights) memcpy(level_weights, kept_lw.data(), (size_t)out * sizeof(double));
     *n_io = out;
     return 0;
+}
+
+extern "C" int clfd_group_rectangles(int32_t *rects_xywh, int *n_io, int group_threshold, double eps,
+                                     int32_t *weights) {
+    return group_impl(rects_xywh, n_io, group_threshold, eps, weights, nullptr);
+}
+
+extern "C" int clfd_group_rectangles_roc(int32_t *rects_xywh, int *n_io, int group_threshold, double eps,
+                                         int32_t *reject_levels, double *level_weights) {
+    if (!reject_levels || !level_weights) { clfd::set_error("bad argument"); return CLFD_ERR_INVALID; }
+    return group_impl(rects_xywh, n_io, group_threshold, eps, reject_levels, level_weights);
 }
 
 // Batch form: the raw rects of a whole batch, as clfd_detect / _collect return

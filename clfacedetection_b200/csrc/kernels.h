@@ -86,6 +86,9 @@ cudaError_t launch_enqueue_all(const CascadeArgs &a, cudaStream_t stream);
 // thread-per-window evaluation of stages [deep.mid_begin, deep.mid_end) (generic trees), survivors -> queue_b
 cudaError_t launch_cascade_mid(const CascadeArgs &a, int n_sms, cudaStream_t stream);
 // warp-per-window evaluation of the queue
+// reject-level output: scans the exit codes of n_frames frames, appends the candidates of
+// tempcv.cpp:1084-1094 (count at counter[0]) with the exact stage sum of their last stage
+cudaError_t launch_roc_collect(const CascadeArgs &a, RocItem *out, unsigned long long cap, unsigned long long *counter, cudaStream_t stream);
 cudaError_t launch_cascade_deep(const CascadeArgs &a, int n_sms, cudaStream_t stream);
 
 size_t dense_smem_bytes(const DenseParams &P);

@@ -1049,6 +1049,65 @@ __global__ void __launch_bounds__(kDeepThreads) k_cascade_deep(const __grid_cons
     }
 }
 
+// ------------------------------------------------------------------------------------
+// reject levels (cvHaarDetectObjectsForROC with outputRejectLevels, tempcv.cpp:1084-1094):
+// a pass over the exit codes.  Thread per window; the rare candidates redo the last stage
+// they evaluated with the generic node records, in the reference's order, to get its sum.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_roc_collect(const CascadeArgs a, RocItem *__restrict__ out, const ull cap, ull *counter) {
+    const long long w = (long long)blockIdx.x * 256 + threadIdx.x;
+    const int frame = blockIdx.y;
+    if (w >= a.windows_per_frame) return;
+    const DeepCascadeDev &D = a.deep;
+    const int code = a.codes[(size_t)frame * a.windows_per_frame + w];
+    int level, last;
+    if (D.is_tree) {   // result 0 for every rejection: count + 0 < 4 never holds
+        if (!(code & 1)) return;
+        level = D.n_stages; last = code >> 1;
+    } else {           // result -i for a rejection by stage i, -count when accepted
+        if (D.n_stages - code >= 4) return;
+        level = code; last = code == D.n_stages ? D.n_stages - 1 : code;
+    }
+    int lo = 0, hi = a.n_cas_levels - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&a.cas_levels[mid].win_base) <= w) lo = mid; else hi = mid - 1;
+    }
+    const CasLevel CL = a.cas_levels[lo];
+    const PyrLevel L = a.levels[CL.pyr_level];
+    const int local = (int)(w - CL.win_base);
+    const int iy = local / CL.nx, ix = local - iy * CL.nx;
+    const int x = ix * CL.ystep, y = iy * CL.ystep;
+    const int pitch = L.sum_pitch;
+    const size_t off = (size_t)frame * a.sum_frame_stride + L.sum_off + (size_t)y * pitch + x;
+    const int32_t *__restrict__ sum = a.sum + off;
+    const int32_t *__restrict__ til = a.tilted ? a.tilted + off : sum;
+    const ull *__restrict__ sq = a.sq + off;
+    const int eq_w = D.win_w - 2, eq_h = D.win_h - 2;
+    const int g0 = pitch + 1, g1 = g0 + eq_w, g2 = (1 + eq_h) * pitch + 1, g3 = g2 + eq_w;
+    const int s4 = __ldg(sum + g0) - __ldg(sum + g1) - __ldg(sum + g2) + __ldg(sum + g3);
+    const ull q4 = __ldg(sq + g0) - __ldg(sq + g1) - __ldg(sq + g2) + __ldg(sq + g3);
+    const double sigma = window_sigma(s4, q4, D.inv_area);
+    const DeepStage st = D.stages[last];
+    double S = 0.0;
+    for (int j = 0; j < st.ntrees; j++)
+        S = __dadd_rn(S, (double)deep_eval_tree(D, st.first_tree + j, sum, til, pitch, sigma, st.flags & 1));
+    const ull slot = atomicAdd(counter, 1ull);
+    if (slot >= cap) return;
+    RocItem it;
+    it.r.x = __double2int_rn(__dmul_rn((double)x, CL.factor));
+    it.r.y = __double2int_rn(__dmul_rn((double)y, CL.factor));
+    it.r.w = CL.win_w; it.r.h = CL.win_h; it.r.frame = a.frame_base + frame; it.r.cascade = a.cascade_index;
+    it.level = level; it.pad = 0; it.win = w; it.weight = S;
+    out[slot] = it;
+}
+
+cudaError_t launch_roc_collect(const CascadeArgs &a, RocItem *out, unsigned long long cap, unsigned long long *counter, cudaStream_t stream) {
+    if (a.windows_per_frame == 0 || a.n_frames == 0) return cudaSuccess;
+    k_roc_collect<<<dim3((unsigned)((a.windows_per_frame + 255) / 256), a.n_frames), 256, 0, stream>>>(a, out, cap, counter);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_cascade_deep(const CascadeArgs &a, int n_sms, cudaStream_t stream) {
     if (a.n_frames == 0) return cudaSuccess;
     k_cascade_deep<<<n_sms * 8, kDeepThreads, 0, stream>>>(a);

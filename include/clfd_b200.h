@@ -219,6 +219,17 @@ CLFD_API int clfd_detector_get_codes(clfd_detector *det, int cascade, int16_t *c
 CLFD_API int clfd_detector_read_level(clfd_detector *det, int cascade, int level, int frame,
                                       uint8_t *pyr, int32_t *sum, uint64_t *sqsum,
                                       int32_t *tilted);
+/* Reject-level / ROC output of the last batch: what cvHaarDetectObjectsForROC
+ * returns with outputRejectLevels = true on the image-pyramid path (tempcv.cpp:1084-1094): the
+ * accepted windows (level = number of stages) AND the windows rejected by one of the last three
+ * stages (level = index of that stage; a stage-tree cascade reports accepted windows only, its
+ * evaluator returns 0 for every rejection), each with the stage sum of the last stage it
+ * evaluated (double, the reference's summation order).  Needs want_codes = 1 and a completed
+ * blocking clfd_detect / clfd_detect_image; candidates come back in the reference's scan order
+ * (frame, level, y, x).  Not available in scale-cascade mode. */
+CLFD_API int clfd_detector_reject_levels(clfd_detector *det, int cascade, clfd_rect *rects,
+                                         int32_t *reject_levels, double *level_weights, int64_t cap,
+                                         int64_t *n_out);
 CLFD_API int clfd_detector_get_stats(clfd_detector *det, clfd_run_stats *stats);
 /* Per-kernel device time (ms) of the last enqueue measured with CUDA events:
  * [0] resize+colsum [1] colscan [2] integral rows [3] tilted [4] cascade tile kernel
@@ -231,6 +242,12 @@ CLFD_API int clfd_detector_get_kernel_ms(clfd_detector *det, float ms[8]);
  * call site 1462-1472).  rects in/out as x,y,w,h quadruples; returns new count in *n. */
 CLFD_API int clfd_group_rectangles(int32_t *rects_xywh, int *n, int group_threshold, double eps,
                                    int32_t *weights);
+
+/* The ROC variant (tempcv.cpp:255-258, used after outputRejectLevels detection): reject_levels /
+ * level_weights per rect in; per kept class out: its highest level and the largest stage sum
+ * seen at that level.  A class is kept when that LEVEL exceeds group_threshold (tempcv.cpp:210). */
+CLFD_API int clfd_group_rectangles_roc(int32_t *rects_xywh, int *n, int group_threshold, double eps,
+                                       int32_t *reject_levels, double *level_weights);
 
 /* The same for the raw rects of a whole batch (as clfd_detect / clfd_detect_collect return
  * them): grouped per (frame, cascade) on n_threads host threads (0 = all).  Run it for batch i

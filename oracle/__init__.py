@@ -68,6 +68,13 @@ def lib():
         L.vjo_detect.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_double,
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int64,
                                  C.POINTER(C.c_int16), C.POINTER(C.c_uint8), C.POINTER(_Stats), C.c_int]
+        L.vjo_detect_roc.restype = C.c_int64
+        L.vjo_detect_roc.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_double,
+                                     C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_int16), C.POINTER(C.c_uint8),
+                                     C.POINTER(_Stats), C.c_int]
+        L.vjo_group_rectangles_roc.argtypes = [C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_double,
+                                               C.POINTER(C.c_int32), C.POINTER(C.c_double)]
         L.vjo_plan_sc.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                   C.POINTER(_Level), C.c_int]
         L.vjo_detect_sc.restype = C.c_int64
@@ -180,6 +187,28 @@ class Cascade:
             cap = int(n)
         return rects[:n].copy(), codes, near, _stats(st), levels
 
+    def detect_roc(self, img: np.ndarray, scale_factor: float, min_size=(0, 0), max_size=(0, 0), n_threads: int = 0):
+        """REF-SI with outputRejectLevels (tempcv.cpp:1084-1094) -> (rects[n,4], reject_levels[n],
+        level_weights[n]) in the reference's scan order."""
+        img = np.ascontiguousarray(img, np.uint8)
+        H, W = img.shape
+        cap = 1 << 16
+        st = _Stats()
+        while True:
+            rects = np.zeros((cap, 4), np.int32)
+            lv = np.zeros(cap, np.int32)
+            wt = np.zeros(cap, np.float64)
+            n = lib().vjo_detect_roc(self._h, _p(img, C.c_uint8), W, H, img.strides[0], scale_factor,
+                                     min_size[0], min_size[1], max_size[0], max_size[1],
+                                     _p(rects, C.c_int32), _p(lv, C.c_int32), _p(wt, C.c_double), cap,
+                                     None, None, C.byref(st), n_threads)
+            if n < 0:
+                raise ValueError(lib().vjo_last_error().decode())
+            if n <= cap:
+                break
+            cap = int(n)
+        return rects[:n].copy(), lv[:n].copy(), wt[:n].copy()
+
     def detect_sc(self, img: np.ndarray, scale_factor: float, min_size=(0, 0), want_codes: bool = True,
                   n_threads: int = 0):
         """REF-SC (scale-cascade, tempcv.cpp:1330-1456) detection of one gray frame
@@ -259,3 +288,15 @@ def group_rectangles(rects: np.ndarray, group_threshold: int, eps: float = 0.2):
     w = np.zeros(max(len(r), 1), np.int32)
     m = lib().vjo_group_rectangles(_p(r, C.c_int32), len(r), group_threshold, eps, _p(w, C.c_int32))
     return r[:m].copy(), w[:m].copy()
+
+
+def group_rectangles_roc(rects: np.ndarray, reject_levels: np.ndarray, level_weights: np.ndarray,
+                         group_threshold: int, eps: float = 0.2):
+    """AgroupRectangles, ROC variant (tempcv.cpp:255-258) -> (rects[m,4], levels[m], weights[m])"""
+    r = np.ascontiguousarray(rects, np.int32).reshape(-1, 4).copy()
+    lv = np.ascontiguousarray(reject_levels, np.int32).copy()
+    wt = np.ascontiguousarray(level_weights, np.float64).copy()
+    if len(r) == 0:
+        return r, lv, wt
+    m = lib().vjo_group_rectangles_roc(_p(r, C.c_int32), len(r), group_threshold, eps, _p(lv, C.c_int32), _p(wt, C.c_double))
+    return r[:m].copy(), lv[:m].copy(), wt[:m].copy()

@@ -462,8 +462,9 @@ static inline double eval_tree(const tree_t *tr, const node_t *nodes_base, const
 
 /* returns the parity code (see vj_oracle.h) */
 static int run_window(const vjo_cascade *c, const node_t *lvl_nodes, const level_img *im,
-                      int x, int y, int eq_off[4], int *near_flag, vjo_stats *st)
+                      int x, int y, int eq_off[4], int *near_flag, vjo_stats *st, double *last_sum)
 {
+    double last_stage_sum = 0.0; /* the stage_sum cvRunHaarClassifierCascadeSum hands back (tempcv.cpp:797) */
     int p_offset = y * im->step + x;
     int near = 0;
     /* variance normalisation, tempcv.cpp:822-832 */
@@ -493,6 +494,7 @@ static int run_window(const vjo_cascade *c, const node_t *lvl_nodes, const level
             for (int j = 0; j < s->count; j++)
                 stage_sum += eval_tree(&s->tree[j], c->nodes, lvl_nodes, im, vnf, p_offset, &nodes);
             weak += s->count;
+            last_stage_sum = stage_sum;
             NEAR_CHECK(stage_sum, s->threshold);
             if (stage_sum >= s->threshold) {
                 ptr = s->child;
@@ -536,6 +538,7 @@ static int run_window(const vjo_cascade *c, const node_t *lvl_nodes, const level
                 }
             }
             weak += s->count; nodes += s->count;
+            last_stage_sum = stage_sum;
             NEAR_CHECK(stage_sum, s->threshold);
             if (stage_sum < s->threshold) break; /* return -i, :946 */
         }
@@ -550,12 +553,14 @@ static int run_window(const vjo_cascade *c, const node_t *lvl_nodes, const level
             for (int j = 0; j < s->count; j++)
                 stage_sum += eval_tree(&s->tree[j], c->nodes, lvl_nodes, im, vnf, p_offset, &nodes);
             weak += s->count;
+            last_stage_sum = stage_sum;
             NEAR_CHECK(stage_sum, s->threshold);
             if (stage_sum < s->threshold) break;
         }
         code = i;
         if (i == c->count) st->accepted++;
     }
+    if (last_sum) *last_sum = last_stage_sum;
     st->windows++;
     st->weak_evals += weak;
     st->node_evals += nodes;
@@ -573,7 +578,7 @@ static void stats_add(vjo_stats *a, const vjo_stats *b)
 
 /* evaluate the ystep grid of one level given its integral images */
 static void eval_grid(const vjo_cascade *c, const level_img *im, int lw, int lh, int ystep,
-                      int nx, int ny, int16_t *codes, uint8_t *near, vjo_stats *stats, int n_threads)
+                      int nx, int ny, int16_t *codes, uint8_t *near, vjo_stats *stats, int n_threads, double *last_sums)
 {
     (void)lw; (void)lh;
     /* resolve corner offsets for this level's row step (the reference stores pointers,
@@ -599,7 +604,8 @@ static void eval_grid(const vjo_cascade *c, const level_img *im, int lw, int lh,
         for (int iy = 0; iy < ny; iy++) {
             for (int ix = 0; ix < nx; ix++) {
                 int nf = 0;
-                int code = run_window(c, lvl, im, ix * ystep, iy * ystep, eq_off, &nf, &local);
+                int code = run_window(c, lvl, im, ix * ystep, iy * ystep, eq_off, &nf, &local,
+                                      last_sums ? last_sums + (size_t)iy * nx + ix : NULL);
                 if (codes) codes[(size_t)iy * nx + ix] = (int16_t)code;
                 if (near) near[(size_t)iy * nx + ix] = (uint8_t)nf;
                 else (void)nf;
@@ -629,7 +635,7 @@ int64_t vjo_eval_level(const vjo_cascade *c, const uint8_t *img, int w, int h, i
     int32_t *tl = c->has_tilted ? (int32_t *)malloc(n1 * sizeof(int32_t)) : NULL;
     vjo_integral(img, w, h, stride, sum, sq, tl);
     level_img im = { sum, tl, sq, w + 1 };
-    eval_grid(c, &im, w, h, ystep, nx, ny, codes, near, &local, n_threads);
+    eval_grid(c, &im, w, h, ystep, nx, ny, codes, near, &local, n_threads, NULL);
     free(sum); free(sq); free(tl);
     if (stats) *stats = local;
     return local.accepted;
@@ -639,6 +645,18 @@ int64_t vjo_detect(const vjo_cascade *c, const uint8_t *img, int W, int H, int s
                    double scale_factor, int min_w, int min_h, int max_w, int max_h,
                    int32_t *rects, int64_t cap, int16_t *codes, uint8_t *near,
                    vjo_stats *stats, int n_threads)
+{
+    return vjo_detect_roc(c, img, W, H, stride, scale_factor, min_w, min_h, max_w, max_h, rects, NULL, NULL, cap,
+                          codes, near, stats, n_threads);
+}
+
+/* cvHaarDetectObjectsForROC with outputRejectLevels (tempcv.cpp:1084-1094): besides the accepted
+ * windows (level = stage count) also the windows rejected by one of the last three stages, each
+ * with the stage sum of the last stage it evaluated.  reject_levels == NULL: plain detection. */
+int64_t vjo_detect_roc(const vjo_cascade *c, const uint8_t *img, int W, int H, int stride,
+                       double scale_factor, int min_w, int min_h, int max_w, int max_h,
+                       int32_t *rects, int32_t *reject_levels, double *level_weights, int64_t cap,
+                       int16_t *codes, uint8_t *near, vjo_stats *stats, int n_threads)
 {
     vjo_level lv[256];
     int nl = vjo_plan_levels(W, H, c->win_w, c->win_h, scale_factor, min_w, min_h, max_w, max_h, lv, 256);
@@ -659,20 +677,33 @@ int64_t vjo_detect(const vjo_cascade *c, const uint8_t *img, int W, int H, int s
         vjo_integral(small, L->img_w, L->img_h, L->img_w, sum, sq, tl);
         level_img im = { sum, tl, sq, L->img_w + 1 };
         int16_t *lc = codes ? codes + woff : (int16_t *)malloc(nwin * sizeof(int16_t));
+        double *ls = reject_levels ? (double *)malloc(nwin * sizeof(double)) : NULL;
         eval_grid(c, &im, L->img_w, L->img_h, L->ystep, L->nx, L->ny, lc, near ? near + woff : NULL,
-                  &total, n_threads);
+                  &total, n_threads, ls);
         for (int iy = 0; iy < L->ny; iy++)
-            for (int ix = 0; ix < L->nx; ix++)
-                if (code_accepts(c, lc[(size_t)iy * L->nx + ix])) {
+            for (int ix = 0; ix < L->nx; ix++) {
+                const int code = lc[(size_t)iy * L->nx + ix];
+                int take = code_accepts(c, code), level = c->count;
+                if (reject_levels) { /* tempcv.cpp:1084-1094 */
+                    /* result: 1 accepted; linear cascade -i for a rejection by stage i; stage tree 0 */
+                    int result = take ? 1 : (c->is_tree ? 0 : -code);
+                    if (result == 1) result = -1 * c->count;
+                    take = c->count + result < 4;
+                    level = -result;
+                }
+                if (take) {
                     if (rects && n_out < cap) { /* tempcv.cpp:1099-1100 */
                         rects[n_out * 4 + 0] = cv_round(ix * L->ystep * L->factor);
                         rects[n_out * 4 + 1] = cv_round(iy * L->ystep * L->factor);
                         rects[n_out * 4 + 2] = L->win_w;
                         rects[n_out * 4 + 3] = L->win_h;
+                        if (reject_levels) { reject_levels[n_out] = level; level_weights[n_out] = ls[(size_t)iy * L->nx + ix]; }
                     }
                     n_out++;
                 }
+            }
         if (!codes) free(lc);
+        free(ls);
         woff += nwin;
     }
     free(small); free(sum); free(sq); free(tl);
@@ -796,7 +827,7 @@ int64_t vjo_detect_sc(const vjo_cascade *c, const uint8_t *img, int W, int H, in
                         code = VJO_CODE_OUTSIDE; result = -1;
                     } else {
                         int nf = 0;
-                        code = run_window(&cs, lvl, &im, x, y, eq_off, &nf, &local);
+                        code = run_window(&cs, lvl, &im, x, y, eq_off, &nf, &local, NULL);
                         if (c->is_tree) result = code & 1;               /* 0 on any rejection, :857 */
                         else result = code == c->count ? 1 : -code;      /* -i, :946,966 */
                     }
@@ -847,7 +878,9 @@ static int uf_find(int *parent, int i)
     return i;
 }
 
-int vjo_group_rectangles(int32_t *rects, int n, int group_threshold, double eps, int32_t *weights)
+/* AgroupRectangles (tempcv.cpp:145-243).  level_weights != NULL: the ROC variant (:255-258) -- `weights`
+ * then carries the reject levels in and the winning level per class out */
+static int group_impl(int32_t *rects, int n, int group_threshold, double eps, int32_t *weights, double *level_weights)
 {
     if (group_threshold <= 0 || n == 0) { /* tempcv.cpp:147-157 */
         if (weights) for (int i = 0; i < n; i++) weights[i] = 1;
@@ -875,6 +908,15 @@ int vjo_group_rectangles(int32_t *rects, int n, int group_threshold, double eps,
         for (int k = 0; k < 4; k++) rr[cl * 4 + k] += rects[i * 4 + k];
         rw[cl]++;
     }
+    int *rej = (int *)calloc(nclasses, sizeof(int));
+    double *rejw = (double *)malloc(sizeof(double) * (nclasses ? nclasses : 1));
+    for (int i = 0; i < nclasses; i++) rejw[i] = DBL_MIN; /* :165 */
+    if (level_weights && weights) /* :176-189 */
+        for (int i = 0; i < n; i++) {
+            int cl = labels[i];
+            if (weights[i] > rej[cl]) { rej[cl] = weights[i]; rejw[cl] = level_weights[i]; }
+            else if (weights[i] == rej[cl] && level_weights[i] > rejw[cl]) rejw[cl] = level_weights[i];
+        }
     for (int i = 0; i < nclasses; i++) { /* :191-199 */
         float s = 1.f / rw[i];
         for (int k = 0; k < 4; k++) {
@@ -885,7 +927,7 @@ int vjo_group_rectangles(int32_t *rects, int n, int group_threshold, double eps,
     int out = 0;
     for (int i = 0; i < nclasses; i++) { /* :207-242 */
         const int32_t *r1 = rr + 4 * i;
-        int n1 = rw[i], j;
+        int n1 = level_weights ? rej[i] : rw[i], j; /* :210 */
         if (n1 <= group_threshold) continue;
         for (j = 0; j < nclasses; j++) {
             int n2 = rw[j];
@@ -900,9 +942,21 @@ int vjo_group_rectangles(int32_t *rects, int n, int group_threshold, double eps,
         if (j == nclasses) {
             memcpy(rects + 4 * out, r1, 4 * sizeof(int32_t));
             if (weights) weights[out] = n1;
+            if (level_weights) level_weights[out] = rejw[i];
             out++;
         }
     }
-    free(parent); free(labels); free(cls_of_root); free(rr); free(rw);
+    free(parent); free(labels); free(cls_of_root); free(rr); free(rw); free(rej); free(rejw);
     return out;
+}
+
+int vjo_group_rectangles(int32_t *rects, int n, int group_threshold, double eps, int32_t *weights)
+{
+    return group_impl(rects, n, group_threshold, eps, weights, NULL);
+}
+
+int vjo_group_rectangles_roc(int32_t *rects, int n, int group_threshold, double eps, int32_t *reject_levels,
+                             double *level_weights)
+{
+    return group_impl(rects, n, group_threshold, eps, reject_levels, level_weights);
 }

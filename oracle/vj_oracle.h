@@ -105,6 +105,15 @@ int64_t vjo_detect(const vjo_cascade *c, const uint8_t *img, int W, int H, int s
                    int32_t *rects, int64_t cap, int16_t *codes, uint8_t *near,
                    vjo_stats *stats, int n_threads);
 
+/* cvHaarDetectObjectsForROC with outputRejectLevels = true (tempcv.cpp:1084-1094), REF-SI path:
+ * accepted windows (level = number of stages) and windows rejected by one of the last three
+ * stages (level = that stage's index), level_weights = the stage sum of the last evaluated
+ * stage.  reject_levels / level_weights hold `cap` entries like rects. */
+int64_t vjo_detect_roc(const vjo_cascade *c, const uint8_t *img, int W, int H, int stride,
+                       double scale_factor, int min_w, int min_h, int max_w, int max_h,
+                       int32_t *rects, int32_t *reject_levels, double *level_weights, int64_t cap,
+                       int16_t *codes, uint8_t *near, vjo_stats *stats, int n_threads);
+
 /* Evaluate every grid window of ONE level whose image is given directly (no resize):
  * used by unit tests of the evaluator. */
 int64_t vjo_eval_level(const vjo_cascade *c, const uint8_t *img, int w, int h, int stride,
@@ -129,6 +138,10 @@ int64_t vjo_detect_sc(const vjo_cascade *c, const uint8_t *img, int W, int H, in
  * rects in/out [n][4]; weights out [n]; returns the new count. */
 int vjo_group_rectangles(int32_t *rects, int n, int group_threshold, double eps,
                          int32_t *weights);
+/* the ROC variant (tempcv.cpp:255-258): reject_levels / level_weights in (per rect) and out (per
+ * kept class: the highest level in the class and the largest stage sum seen at that level) */
+int vjo_group_rectangles_roc(int32_t *rects, int n, int group_threshold, double eps, int32_t *reject_levels,
+                             double *level_weights);
 
 #ifdef __cplusplus
 }

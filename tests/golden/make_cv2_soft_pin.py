@@ -36,6 +36,11 @@ def main():
             r = cc.detectMultiScale(octave_frame(w, h, seed), scaleFactor=1.2, minNeighbors=0)
             out[f"{name}_{fi}"] = np.asarray(r, np.int32).reshape(-1, 4)
             print(name, fi, len(out[f"{name}_{fi}"]))
+            # accepted windows with the stage sum of the last stage (levelWeights of detectMultiScale3)
+            r3, l3, w3 = cc.detectMultiScale3(octave_frame(w, h, seed), scaleFactor=1.2, minNeighbors=0, outputRejectLevels=True)
+            out[f"{name}_{fi}_roc_rects"] = np.asarray(r3, np.int32).reshape(-1, 4)
+            out[f"{name}_{fi}_roc_levels"] = np.asarray(l3, np.int32).reshape(-1)
+            out[f"{name}_{fi}_roc_weights"] = np.asarray(w3, np.float64).reshape(-1)
     np.savez_compressed(os.path.join(HERE, "cv2_detector_soft_pin.npz"), **out)
 
 

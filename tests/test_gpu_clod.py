@@ -289,6 +289,53 @@ def test_tile_kernel_variants_under_every_split(gpu_ctx, monkeypatch, env):
              np.stack([octave_frame(400, 300, 8)]), 1.2)
 
 
+@pytest.mark.parametrize("name", ["frontalface_alt", "eye", "frontalface_alt2", "frontalface_alt_tree", "fullbody", "mcs_nose"])
+def test_reject_levels_equal_oracle(gpu_ctx, name):
+    """cvHaarDetectObjectsForROC with outputRejectLevels (tempcv.cpp:1084-1094).
+    Candidates, their order, reject levels and the FP64 stage sums must equal the oracle's bit for bit."""
+    frames = np.stack([octave_frame(640, 480, 7), uniform_frame(640, 480, 8), octave_frame(640, 480, 9)])
+    cas = clfd.Cascade(cascade_path(name))
+    det = clfd.Detector(gpu_ctx, cas, 640, 480, max_batch=3, scale_factor=1.2, want_codes=True)
+    det.detect(frames)
+    r, lv, wt = det.reject_levels()
+    oc = oracle_cascade(name)
+    at = 0
+    total = 0
+    for f in range(3):
+        orr, olv, owt = oc.detect_roc(frames[f], 1.2)
+        n = len(orr)
+        mine = r[at:at + n]
+        assert np.all(mine["frame"] == f) and (at + n == len(r) or r[at + n]["frame"] > f)
+        assert np.array_equal(np.stack([mine["x"], mine["y"], mine["w"], mine["h"]], 1).reshape(-1, 4), orr.reshape(-1, 4))
+        assert np.array_equal(lv[at:at + n], olv)
+        assert wt[at:at + n].tobytes() == owt.tobytes()
+        at += n
+        total += n
+    assert at == len(r)
+    if name in ("frontalface_alt", "eye", "mcs_nose"):
+        assert total > 10 and len(np.unique(lv)) >= 2   # rejected-late windows are really there
+    det.close()
+
+
+def test_reject_levels_errors(gpu_ctx):
+    cas = clfd.Cascade(cascade_path("frontalface_alt"))
+    frame = np.stack([octave_frame(320, 240, 1)])
+    det = clfd.Detector(gpu_ctx, cas, 320, 240, max_batch=1, scale_factor=1.2)
+    det.detect(frame)
+    with pytest.raises(clfd.ClfdError, match="want_codes"):
+        det.reject_levels()
+    det.close()
+    det = clfd.Detector(gpu_ctx, cas, 320, 240, max_batch=1, scale_factor=1.2, scale_cascade=True)
+    det.detect(frame)
+    with pytest.raises(clfd.ClfdError, match="image-pyramid"):
+        det.reject_levels()
+    det.close()
+    det = clfd.Detector(gpu_ctx, cas, 320, 240, max_batch=1, scale_factor=1.2, want_codes=True)
+    r, lv, wt = det.reject_levels()   # nothing detected yet
+    assert len(r) == 0
+    det.close()
+
+
 def test_submit_collect_pipeline_keeps_batches_apart(gpu_ctx):
     """clfd_detect_submit / _collect: two batches in flight (the copy of batch i+1 overlaps the
     kernels of batch i).  Results must come back in submission order and equal the blocking call."""

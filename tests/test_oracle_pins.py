@@ -324,3 +324,59 @@ def test_tilted_geometry_and_trees_agree_with_opencv4(monkeypatch):
     mine = {tuple(r) for r in np.asarray(cas.detect(octave_frame(960, 540, 0), 1.2)[0]).reshape(-1, 4).tolist()}
     theirs = {tuple(r) for r in g["mcs_nose_0"].tolist()}
     assert len(mine & theirs) < 0.6 * len(mine | theirs)
+
+
+def test_reject_levels_oracle_properties_and_opencv4_stage_sums():
+    """cvHaarDetectObjectsForROC with outputRejectLevels (tempcv.cpp:1084-1094) in the oracle:
+    the accepted candidates are exactly detect()'s rects; a window rejected by stage i carries a
+    stage sum below that stage's threshold, an accepted one a sum at or above the last threshold;
+    and for windows OpenCV 4's detectMultiScale3 also accepts at the unscaled level, its
+    levelWeights (the same last-stage sum, computed by an independent implementation) are
+    bit-equal to the oracle's."""
+    g = np.load(os.path.join(GOLD, "cv2_detector_soft_pin.npz"))
+    frames = [(960, 540, 0), (960, 540, 7), (1280, 720, 3), (800, 600, 5)]
+    for name, min_equal in [("frontalface_alt", 10), ("eye", 800), ("frontalface_default", 40), ("frontalface_alt2", 10)]:
+        cas = oracle_cascade(name)
+        flat = oracle.load_cascade_xml(cascade_path(name))
+        thr = cas.hidden()[2]
+        n_stages = len(flat.st_ntrees)
+        equal = 0
+        for fi, (w, h, seed) in enumerate(frames):
+            img = octave_frame(w, h, seed)
+            r, lv, wt = cas.detect_roc(img, 1.2)
+            assert np.array_equal(r[lv == n_stages], cas.detect(img, 1.2, want_codes=False)[0])
+            assert lv.min(initial=n_stages) >= n_stages - 3 and lv.max(initial=0) <= n_stages
+            rej = lv < n_stages
+            assert np.all(wt[rej] < thr[lv[rej]].astype(np.float64))
+            assert np.all(wt[~rej] >= np.float64(thr[n_stages - 1]))
+            mine = {tuple(a): x for a, l, x in zip(r.tolist(), lv.tolist(), wt.tolist()) if l == n_stages and a[2] == flat.win_w}
+            for a, l, x in zip(g[f"{name}_{fi}_roc_rects"].tolist(), g[f"{name}_{fi}_roc_levels"].tolist(),
+                               g[f"{name}_{fi}_roc_weights"].tolist()):
+                if tuple(a) in mine:
+                    assert l == n_stages and x == mine[tuple(a)], (name, a, x, mine[tuple(a)])
+                    equal += 1
+        assert equal >= min_equal, (name, equal)
+
+
+def test_roc_grouping_product_equals_oracle():
+    """AgroupRectangles ROC variant (tempcv.cpp:255-258, 176-189, 210): host code of the product
+    against the oracle's restatement, on real candidates and on random clusters."""
+    import clfacedetection_b200 as clfd
+    cas = oracle_cascade("eye")
+    r, lv, wt = cas.detect_roc(octave_frame(640, 480, 7), 1.2)
+    rng = np.random.default_rng(3)
+    base = rng.integers(0, 300, size=(6, 2))
+    pick = rng.integers(0, 6, size=80)
+    rr = np.array([[base[p][0] + rng.integers(-5, 6), base[p][1] + rng.integers(-5, 6), 40 + rng.integers(-3, 4),
+                    40 + rng.integers(-3, 4)] for p in pick], np.int32)
+    cases = [(r, lv, wt), (rr, rng.integers(18, 23, size=80).astype(np.int32), rng.normal(size=80)),
+             (rr[:0], lv[:0], wt[:0])]
+    for rects, levels, weights in cases:
+        for thr in (0, 1, 2, 19, 21, 30):
+            a = oracle.group_rectangles_roc(rects, levels, weights, thr)
+            b = clfd.group_rectangles_roc(rects, levels, weights, thr)
+            assert all(np.array_equal(x, y) for x, y in zip(a, b)), thr
+    # a class keeps its highest level and, at that level, the largest stage sum
+    a = oracle.group_rectangles_roc(np.array([[10, 10, 40, 40]] * 4, np.int32), np.array([20, 22, 22, 21], np.int32),
+                                    np.array([5.0, 1.0, 3.0, 9.0]), 2)
+    assert a[1].tolist() == [22] and a[2].tolist() == [3.0]
