@@ -241,6 +241,11 @@ struct CascadePlan {
     DevBuf<ScLevel> d_sc_levels;
     DevBuf<ScNode> d_sc_nodes;
     int sc_rows = 0;
+    // scales with window step 2 run through the tile kernel (pack_sc_dense): one blob + launch per scale
+    struct ScTile { DenseParams P; DevBuf<TailStump> tail; DevBuf<DenseStage> stage_tab; int tile_base = 0, n_tiles = 0; };
+    std::vector<std::unique_ptr<ScTile>> sc_tiles;
+    DevBuf<CasLevel> d_sc_tile_levels;
+    long long sc_tile_windows = 0;   // grid positions [0, sc_tile_windows) of a frame belong to those scales
     DevBuf<TailStump> d_tail[2];   // warp-per-window tail records of the tile kernel, [ystep-1]
     DevBuf<DenseStage> d_stage_tab[2];   // stage trees: stage table in execution order
     DenseParams dense[2];          // the cascade's parameter blobs with this detector's tail pointers
@@ -639,6 +644,36 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
             int rc2;
             if ((rc2 = cp.d_sc_levels.upload(cp.sc_levels, ctx->stream)) || (rc2 = cp.d_sc_nodes.upload(nodes, ctx->stream))) return rc2;
             CK(cudaStreamSynchronize(ctx->stream));   // `nodes` goes out of scope
+            // the leading scales whose window step is exactly 2 (factor <= 2): tile kernel
+            if (!getenv("CLFD_SC_NO_TILES")) {
+                std::vector<CasLevel> tl;
+                int tile_base = 0;
+                for (size_t li = 0; li < cp.sc_levels.size(); li++) {
+                    const ScLevel &L = cp.sc_levels[li];
+                    if (L.ystep != 2.0 || L.win_base != cp.sc_tile_windows) break;
+                    std::unique_ptr<CascadePlan::ScTile> t(new CascadePlan::ScTile);
+                    std::vector<TailStump> tail;
+                    std::vector<DenseStage> stab;
+                    if (!pack_sc_dense(hc, L.factor, t->P, tail, stab)) break;
+                    if ((rc2 = t->tail.upload(tail, ctx->stream)) || (!stab.empty() && (rc2 = t->stage_tab.upload(stab, ctx->stream)))) return rc2;
+                    CK(cudaStreamSynchronize(ctx->stream));
+                    t->P.tail = t->tail.p; t->P.stage_g = t->stage_tab.p;
+                    CasLevel CL;
+                    memset(&CL, 0, sizeof CL);
+                    CL.pyr_level = 0; CL.nx = L.nx; CL.ny = L.ny; CL.ystep = 2; CL.win_w = L.win_w; CL.win_h = L.win_h;
+                    CL.tiles_x = (L.nx + kTileW - 1) / kTileW; CL.tiles_y = (L.ny + t->P.tile_h - 1) / t->P.tile_h;
+                    CL.tile_base = tile_base; CL.win_base = L.win_base; CL.factor = L.factor;
+                    t->tile_base = tile_base; t->n_tiles = CL.tiles_x * CL.tiles_y;
+                    tile_base += t->n_tiles;
+                    tl.push_back(CL);
+                    cp.sc_tiles.push_back(std::move(t));
+                    cp.sc_tile_windows = L.win_base + (long long)L.nx * L.ny;
+                }
+                if (!tl.empty()) {
+                    if ((rc2 = cp.d_sc_tile_levels.upload(tl, ctx->stream))) return rc2;
+                    CK(cudaStreamSynchronize(ctx->stream));
+                }
+            }
             cp.bytes_cascade += (int64_t)(W + 1) * (H + 1) * (4 + 8 + (hc.has_tilted ? 4 : 0)) + nodes.size() * sizeof(ScNode);
         }
     } else {
@@ -839,6 +874,17 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
                 sa.codes = cp.d_codes.p + (size_t)frame_base * cp.windows_per_frame;
                 sa.rects = a.rects; sa.rect_cap = a.rect_cap; sa.counters = a.counters; sa.deep = a.deep;
                 if (ev && ci == 0) CK(cudaEventRecord(ev[5], s));
+                // scales with window step 2: the tile kernel, one launch per scale, exit codes only
+                if (!cp.sc_tiles.empty()) {
+                    CascadeArgs ta = a;
+                    ta.cas_levels = cp.d_sc_tile_levels.p; ta.n_cas_levels = (int)cp.sc_tiles.size();
+                    ta.codes = sa.codes; ta.rects = nullptr; ta.rect_cap = 0;
+                    for (auto &t : cp.sc_tiles) {
+                        CK(launch_cascade_tiles(t->P, ta, t->tile_base, t->n_tiles, s));
+                        launches++;
+                    }
+                    sa.first_window = cp.sc_tile_windows;
+                }
                 // passes over growing stage ranges (cumulative trees >= 10, 40, 90, 160, ... per pass), survivors
                 // re-compacted through the two queues in between; a stage tree runs as one pass
                 {

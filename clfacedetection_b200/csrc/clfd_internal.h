@@ -121,6 +121,7 @@ struct DenseParams {
                         // execution order (stage_g; the first tail_stages of them are the linear prefix)
     int npt;            // records per tree: 1 = stumps; 2..4 = multi-node trees, every tree padded to npt node records
     int tile_h;         // window rows per tile: kTileH, or kTileHSmall where two tiles (tilted) would leave one CTA per SM
+    int eq_x, eq_y, eq_w, eq_h;   // the variance rectangle inside the window (tempcv.cpp:614-616): (1, 1, w-2, h-2) at scale 1
     double inv_area;
     const TailStump *tail;   // device, layout of this blob's ystep (patched in by the detector)
     const struct DenseStage *stage_g;   // device: stage table in execution order (stage trees only)

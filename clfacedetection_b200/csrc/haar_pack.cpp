@@ -229,6 +229,194 @@ void pack_sc_level(const HostCascade &c, double scale, int pitch, ScLevel &L, Sc
     }
 }
 
+// Tile-kernel blobs.  `elig` = leading stages the tile kernel can evaluate: one-node upright
+// trees, and in a stage tree only the unconditional linear prefix (stage i the single child
+// of stage i-1 with no `next` alternative).  Every eligible stump gets a TailStump record
+// (global memory, warp-autonomous phase); the stumps of the first n_fixed stages are also
+// parameter resident (DenseStump, fixed-geometry phase).
+static void pack_dense_one(const HostCascade &c, int ystep, DenseParams &P, std::vector<TailStump> &tail,
+                           std::vector<DenseStage> &stage_tab, int &dense_stumps) {
+    const int S = c.n_stages(), T = c.n_trees();
+    memset(&P, 0, sizeof P);
+    P.total_stages = S;
+    P.win_w = c.win_w; P.win_h = c.win_h;
+    P.tile_stride = dense_tile_stride(c.win_w, ystep);
+    P.is_tree = c.is_tree ? 1 : 0;
+    P.ystep = ystep;
+    P.filter_eps = 9.5367431640625e-07f;  // 2^-20
+    if (const char *e = getenv("CLFD_FORCE_EXACT")) P.force_exact = atoi(e) != 0;   // test hook: bypass the FP32 filters
+    P.inv_area = 1. / ((c.win_w - 2) * (c.win_h - 2));
+    P.eq_x = 1; P.eq_y = 1; P.eq_w = c.win_w - 2; P.eq_h = c.win_h - 2;   // equRect at scale 1 (tempcv.cpp:614-616)
+    // a cascade with tilted features keeps a second tile (the tilted integral) behind the first; on
+    // ystep-2 levels (more integral rows per tile) the tiles are half as high then, or the two tiles
+    // leave room for only one or two CTAs per SM
+    P.tilted_tile = c.has_tilted && !getenv("CLFD_NO_TILTED_TILE") ? 1 : 0;
+    P.tile_h = kTileH;
+    if (P.tilted_tile && ystep == 2 && !c.is_tree && !getenv("CLFD_NO_SMALL_TILES")) P.tile_h = kTileHSmall;
+    const size_t tile_bytes = (size_t)dense_tile_rows(c.win_h, ystep, P.tile_h) * P.tile_stride * 4;
+    const size_t tilt_base = (tile_bytes + 127) & ~(size_t)127;
+    const bool dense_ok = tile_bytes <= 65536 && (!P.tilted_tile || 2 * tilt_base <= 160 * 1024) && c.win_w <= 255 && c.win_h <= 255;
+    // multi-node trees (<= kMaxTreeNodes nodes, children after their parent) are evaluated node by node
+    // with a per-window "node I am at" state; every tree is padded to npt = the cascade's largest tree
+    int npt = 1;
+    for (int t = 0; t < T; t++) npt = std::max(npt, c.tr_nnodes[t]);
+    if (getenv("CLFD_NO_NODE_TILES") && npt > 1) npt = kMaxTreeNodes + 1;   // test hook: leave trees to the mid / deep kernels
+    P.npt = npt <= kMaxTreeNodes ? npt : 1;
+    auto stage_ok = [&](int i) {   // tilted only with the second tile
+        for (int t = c.st_first_tree[i]; t < c.st_first_tree[i + 1]; t++) {
+            if (c.tr_nnodes[t] > P.npt) return false;
+            for (int j = 0; j < c.tr_nnodes[t]; j++) {
+                const HostNode &nd = c.nodes[c.tr_first_node[t] + j];
+                if (!P.tilted_tile && nd.tilted) return false;
+                if ((nd.left > 0 && (nd.left <= j || nd.left >= c.tr_nnodes[t])) ||
+                    (nd.right > 0 && (nd.right <= j || nd.right >= c.tr_nnodes[t])))
+                    return false;
+            }
+        }
+        return true;
+    };
+    int elig = 0;   // the linear prefix
+    while (dense_ok && elig < S && elig < kMaxDenseStages) {
+        if (c.is_tree && (c.st_next[elig] != -1 || c.st_parent[elig] != elig - 1 ||
+                          (elig > 0 && c.st_child[elig - 1] != elig)))
+            break;
+        if (!stage_ok(elig)) break;
+        elig++;
+    }
+    // A stage tree of stumps is walked by the tile kernel itself (tempcv.cpp:834-861): the stages in
+    // depth-first preorder (a stage, its child subtree, then its `next` alternative) -- both the
+    // stage a passing window goes to (child) and the one a failing window goes to (the `next` of the
+    // nearest ancestor-or-self that has one) lie later in that order, so one sweep over the order
+    // with a per-window target position evaluates every window's path.
+    std::vector<int> order;
+    if (c.is_tree && P.npt == 1 && dense_ok && elig > 0 && elig < S && S < (int)kRouteReject && !getenv("CLFD_NO_TREE_TILES")) {
+        std::vector<int> stack{0};
+        std::vector<char> seen(S, 0);
+        bool ok = true;
+        while (!stack.empty() && ok) {
+            const int i = stack.back();
+            stack.pop_back();
+            ok = !seen[i] && stage_ok(i);
+            seen[i] = 1;
+            order.push_back(i);
+            if (c.st_next[i] >= 0) stack.push_back(c.st_next[i]);
+            if (c.st_child[i] >= 0) stack.push_back(c.st_child[i]);
+        }
+        if (!ok || (int)order.size() != S) order.clear();
+        for (int e = 0; e < elig && !order.empty(); e++) if (order[e] != e) order.clear();
+    }
+    const bool walk_tree = !order.empty();
+    if (!walk_tree) { order.resize(elig); for (int e = 0; e < elig; e++) order[e] = e; }
+    const int E = (int)order.size();
+    std::vector<int> pos(S, -1);
+    for (int e = 0; e < E; e++) pos[order[e]] = e;
+    P.tail_stages = elig;
+    P.exec_stages = E;
+    P.g1_min = 16;
+    if (const char *e = getenv("CLFD_G1_MIN")) P.g1_min = std::max(1, std::min(16, atoi(e)));
+    int n_elig_stumps = 0;
+    for (int e = 0; e < E; e++) n_elig_stumps += c.st_ntrees[order[e]] * P.npt;
+    dense_stumps = n_elig_stumps;
+    tail.assign(n_elig_stumps, TailStump());
+    stage_tab.assign(walk_tree ? E : 0, DenseStage());
+    auto tile_offset = [&](int dy, int dx) {
+        const int word = ystep == 1 ? dy * P.tile_stride + dx
+                                    : dy * P.tile_stride + (dx & 1) * (P.tile_stride / 2) + (dx >> 1);
+        return (uint32_t)(word * 4);
+    };
+    int tail_at = 0;   // records in execution order (== tree order for the linear prefix)
+    for (int e = 0; e < E; e++) {
+        const int i = order[e];
+        DenseStage ds;
+        memset(&ds, 0, sizeof ds);
+        bool any3 = false;
+        double abs_sum = 0;
+        ds.tail_first = (uint32_t)tail_at;
+        for (int t = c.st_first_tree[i]; t < c.st_first_tree[i + 1]; t++) {
+            const int a = c.tr_first_node[t] + t;            // alpha base of tree t
+            double amax = 0;
+            for (int j = 0; j < P.npt; j++) {
+                TailStump &ts = tail[tail_at++];
+                memset(&ts, 0, sizeof ts);
+                if (j >= c.tr_nnodes[t]) { ts.meta = kNodePad | (kNodeLeaf << 8) | (kNodeLeaf << 16); continue; }
+                const int n = c.tr_first_node[t] + j;
+                const HostNode &nd = c.nodes[n];
+                any3 |= c.hid_nrects[n] == 3;
+                for (int k = 0; k < c.hid_nrects[n]; k++) {
+                    int dx[4], dy[4];
+                    corner_coords(nd, k, dx, dy);
+                    for (int q = 0; q < 4; q++) ts.off[k * 4 + q] = tile_offset(dy[q], dx[q]) + (nd.tilted ? (uint32_t)tilt_base : 0u);
+                    ts.w[k] = c.hid_weight[(size_t)n * 3 + k];
+                }
+                ts.thr = nd.threshold;
+                ts.a0 = nd.left <= 0 ? c.alpha[a + (-nd.left)] : 0.f;     // sum <  t -> left  (tempcv.cpp:788)
+                ts.a1 = nd.right <= 0 ? c.alpha[a + (-nd.right)] : 0.f;   // sum >= t -> right
+                ts.meta = (uint32_t)j | ((nd.left > 0 ? (uint32_t)nd.left : kNodeLeaf) << 8) |
+                          ((nd.right > 0 ? (uint32_t)nd.right : kNodeLeaf) << 16);
+                amax = fmax(amax, fmax(fabs((double)ts.a0), fabs((double)ts.a1)));
+            }
+            abs_sum += amax;
+        }
+        ds.first = 0; ds.count = (uint16_t)(c.st_ntrees[i] * P.npt);   // records
+        ds.thr = c.hid_thr[i];
+        // double products only on the reference's stump fast path (tempcv.cpp:862,872)
+        ds.flags = ((!c.is_tree && c.is_stump_based && c.two_rects[i]) ? 1u : 0u) | (any3 ? 2u : 0u) |
+                   (c.order_free[i] ? 4u : 0u);
+        // FP32 summation of n alphas in any order: |error| <= (n-1) 2^-24 sum|alpha|; 2x slack
+        const double er = (double)(c.st_ntrees[i] * P.npt) * ldexp(1.0, -23) * abs_sum;
+        ds.sum_eps = std::isfinite(er) ? (float)(er * 1.0000002) + FLT_MIN : INFINITY;
+        if (walk_tree) {
+            const uint32_t pass = c.st_child[i] >= 0 ? (uint32_t)pos[c.st_child[i]] : kRouteAccept;
+            int p = i;
+            while (p >= 0 && c.st_next[p] < 0) p = c.st_parent[p];   // tempcv.cpp:853-855
+            const uint32_t fail = p >= 0 ? (uint32_t)pos[c.st_next[p]] : kRouteReject;
+            ds.flags |= ((uint32_t)i << 8) | (pass << 16) | (fail << 24);
+            stage_tab[e] = ds;
+        }
+        if (e < elig) P.stage[e] = ds;
+    }
+    // parameter-resident copy of the leading stages that fit the kernel-parameter budget.  Inside a
+    // stage the copy is REORDERED (the FP32 filters do not depend on the order; the exact fallback
+    // reads the global records, which stay in tree order): first the two-rect stumps whose rects have
+    // two corners in common -- the usual edge feature, a rectangle and one of its halves -- in a
+    // six-offset form E0,E1,F0,F1,G0,G1 with rect0 = (E0-E1)+(F0-F1), rect1 = (E0-E1)+(G0-G1): six
+    // corner loads instead of eight.  With p0,p3 entering a rect sum with + and p1,p2 with -, the
+    // common pair can only be (p0,p2), (p3,p1), (p0,p1) or (p3,p2).
+    const bool share_corners = !getenv("CLFD_NO_SHARED_CORNERS");   // test hook
+    int ns = 0, nstump = 0;
+    while (ns < elig && nstump + c.st_ntrees[ns] * P.npt <= kMaxDenseStumps) {
+        P.stage[ns].first = (uint16_t)nstump;
+        std::vector<DenseStump> six, rest;
+        for (int t = c.st_first_tree[ns] * P.npt; t < c.st_first_tree[ns + 1] * P.npt; t++) {
+            DenseStump st = tail[t];
+            bool shared = false;
+            if (share_corners && P.npt == 1 && c.hid_nrects[c.tr_first_node[t]] == 2) {   // (multi-node trees keep their order)
+                const uint32_t *A = st.off, *B = st.off + 4;
+                static const int pairs[4][2] = {{0, 2}, {3, 1}, {0, 1}, {3, 2}};   // (plus, minus) corner
+                for (const auto &pr : pairs) {
+                    const int pl = pr[0], mi = pr[1];
+                    if (A[pl] != B[pl] || A[mi] != B[mi]) continue;
+                    const int opl = pl == 0 ? 3 : 0, omi = mi == 1 ? 2 : 1;   // the other plus / minus corner
+                    const uint32_t o[6] = {A[pl], A[mi], A[opl], A[omi], B[opl], B[omi]};
+                    for (int q = 0; q < 12; q++) st.off[q] = q < 6 ? o[q] : 0;
+                    shared = true;
+                    break;
+                }
+            }
+            (shared ? six : rest).push_back(st);
+        }
+        P.stage[ns].n_shared = (uint32_t)six.size();
+        for (const auto &st : six) P.stump[nstump++] = st;
+        for (const auto &st : rest) P.stump[nstump++] = st;
+        ns++;
+    }
+    P.n_stages = ns;
+    // stages run in fixed geometry before the first compaction (tunable for experiments)
+    int nf = 3;
+    if (const char *e = getenv("CLFD_N_FIXED")) nf = atoi(e);
+    P.n_fixed = nf < 0 ? 0 : (nf > ns ? ns : nf);
+}
+
 void pack_cascade(const HostCascade &c, PackedCascade &out) {
     const int S = c.n_stages(), T = c.n_trees(), N = c.n_nodes();
     out.deep_stages.resize(S);
@@ -264,192 +452,51 @@ void pack_cascade(const HostCascade &c, PackedCascade &out) {
         d.flags = (nd.tilted ? 1 : 0) | (c.hid_nrects[n] << 8);
     }
 
-    // Tile-kernel blobs.  `elig` = leading stages the tile kernel can evaluate: one-node upright
-    // trees, and in a stage tree only the unconditional linear prefix (stage i the single child
-    // of stage i-1 with no `next` alternative).  Every eligible stump gets a TailStump record
-    // (global memory, warp-autonomous phase); the stumps of the first n_fixed stages are also
-    // parameter resident (DenseStump, fixed-geometry phase).
-    for (int yi = 0; yi < 2; yi++) {
-        const int ystep = yi + 1;
-        DenseParams &P = out.dense[yi];
-        memset(&P, 0, sizeof P);
-        P.total_stages = S;
-        P.win_w = c.win_w; P.win_h = c.win_h;
-        P.tile_stride = dense_tile_stride(c.win_w, ystep);
-        P.is_tree = c.is_tree ? 1 : 0;
-        P.ystep = ystep;
-        P.filter_eps = 9.5367431640625e-07f;  // 2^-20
-        if (const char *e = getenv("CLFD_FORCE_EXACT")) P.force_exact = atoi(e) != 0;   // test hook: bypass the FP32 filters
-        P.inv_area = 1. / ((c.win_w - 2) * (c.win_h - 2));
-        // a cascade with tilted features keeps a second tile (the tilted integral) behind the first; on
-        // ystep-2 levels (more integral rows per tile) the tiles are half as high then, or the two tiles
-        // leave room for only one or two CTAs per SM
-        P.tilted_tile = c.has_tilted && !getenv("CLFD_NO_TILTED_TILE") ? 1 : 0;
-        P.tile_h = kTileH;
-        if (P.tilted_tile && ystep == 2 && !c.is_tree && !getenv("CLFD_NO_SMALL_TILES")) P.tile_h = kTileHSmall;
-        const size_t tile_bytes = (size_t)dense_tile_rows(c.win_h, ystep, P.tile_h) * P.tile_stride * 4;
-        const size_t tilt_base = (tile_bytes + 127) & ~(size_t)127;
-        const bool dense_ok = tile_bytes <= 65536 && (!P.tilted_tile || 2 * tilt_base <= 160 * 1024) && c.win_w <= 255 && c.win_h <= 255;
-        // multi-node trees (<= kMaxTreeNodes nodes, children after their parent) are evaluated node by node
-        // with a per-window "node I am at" state; every tree is padded to npt = the cascade's largest tree
-        int npt = 1;
-        for (int t = 0; t < T; t++) npt = std::max(npt, c.tr_nnodes[t]);
-        if (getenv("CLFD_NO_NODE_TILES") && npt > 1) npt = kMaxTreeNodes + 1;   // test hook: leave trees to the mid / deep kernels
-        P.npt = npt <= kMaxTreeNodes ? npt : 1;
-        auto stage_ok = [&](int i) {   // tilted only with the second tile
-            for (int t = c.st_first_tree[i]; t < c.st_first_tree[i + 1]; t++) {
-                if (c.tr_nnodes[t] > P.npt) return false;
-                for (int j = 0; j < c.tr_nnodes[t]; j++) {
-                    const HostNode &nd = c.nodes[c.tr_first_node[t] + j];
-                    if (!P.tilted_tile && nd.tilted) return false;
-                    if ((nd.left > 0 && (nd.left <= j || nd.left >= c.tr_nnodes[t])) ||
-                        (nd.right > 0 && (nd.right <= j || nd.right >= c.tr_nnodes[t])))
-                        return false;
-                }
+    for (int yi = 0; yi < 2; yi++) pack_dense_one(c, yi + 1, out.dense[yi], out.tail[yi], out.stage_tab[yi], out.dense_stumps);
+}
+
+// Tile-kernel blob of ONE scale of the scale-cascade mode, for the scales whose window step is
+// exactly 2 (factor <= 2, tempcv.cpp:1365): on the full-resolution integral image those windows
+// are a ystep-2 level like any other, with the cascade's rectangles scaled and its weights
+// re-normalised for this scale (cvSetImagesForHaarClassifierCascade, tempcv.cpp:614-618, 636-760
+// -- the same arithmetic as pack_sc_level).  Built by packing a scaled copy of the cascade whose
+// "window" is the extent the scaled rectangles reach (cvRound(x*s) + cvRound(w*s) may exceed
+// cvRound((x+w)*s) by one), then putting this scale's variance rectangle and area in.
+bool pack_sc_dense(const HostCascade &c, double scale, DenseParams &P, std::vector<TailStump> &tail,
+                   std::vector<DenseStage> &stage_tab) {
+    HostCascade s = c;
+    const int ex = cv_round_d(scale), ey = ex;
+    const int ew = cv_round_d((c.win_w - 2) * scale), eh = cv_round_d((c.win_h - 2) * scale);
+    const double weight_scale = 1. / (ew * eh);
+    int ext_w = std::max(cv_round_d(c.win_w * scale), ex + ew), ext_h = std::max(cv_round_d(c.win_h * scale), ey + eh);
+    for (int n = 0; n < c.n_nodes(); n++) {
+        const HostNode &nd = c.nodes[n];
+        HostNode &d = s.nodes[n];
+        const int nr = c.hid_nrects[n];
+        double sum0 = 0, area0 = 0;
+        const double correction_ratio = weight_scale * (!nd.tilted ? 1 : 0.5);   // :733
+        for (int k = 0; k < nr; k++) {
+            d.rect[k][0] = cv_round_d(nd.rect[k][0] * scale); d.rect[k][2] = cv_round_d(nd.rect[k][2] * scale);   // :704-716
+            d.rect[k][1] = cv_round_d(nd.rect[k][1] * scale); d.rect[k][3] = cv_round_d(nd.rect[k][3] * scale);
+            int dx[4], dy[4];
+            corner_coords(d, k, dx, dy);
+            for (int q = 0; q < 4; q++) {
+                if (dx[q] < 0 || dy[q] < 0) return false;
+                ext_w = std::max(ext_w, dx[q]); ext_h = std::max(ext_h, dy[q]);
             }
-            return true;
-        };
-        int elig = 0;   // the linear prefix
-        while (dense_ok && elig < S && elig < kMaxDenseStages) {
-            if (c.is_tree && (c.st_next[elig] != -1 || c.st_parent[elig] != elig - 1 ||
-                              (elig > 0 && c.st_child[elig - 1] != elig)))
-                break;
-            if (!stage_ok(elig)) break;
-            elig++;
+            float &w = s.hid_weight[(size_t)n * 3 + k];
+            w = (float)(nd.weight[k] * correction_ratio);   // :752
+            if (k == 0) area0 = d.rect[k][2] * d.rect[k][3];
+            else sum0 += w * d.rect[k][2] * d.rect[k][3];   // float*int*int evaluated in float, :757
         }
-        // A stage tree of stumps is walked by the tile kernel itself (tempcv.cpp:834-861): the stages in
-        // depth-first preorder (a stage, its child subtree, then its `next` alternative) -- both the
-        // stage a passing window goes to (child) and the one a failing window goes to (the `next` of the
-        // nearest ancestor-or-self that has one) lie later in that order, so one sweep over the order
-        // with a per-window target position evaluates every window's path.
-        std::vector<int> order;
-        if (c.is_tree && P.npt == 1 && dense_ok && elig > 0 && elig < S && S < (int)kRouteReject && !getenv("CLFD_NO_TREE_TILES")) {
-            std::vector<int> stack{0};
-            std::vector<char> seen(S, 0);
-            bool ok = true;
-            while (!stack.empty() && ok) {
-                const int i = stack.back();
-                stack.pop_back();
-                ok = !seen[i] && stage_ok(i);
-                seen[i] = 1;
-                order.push_back(i);
-                if (c.st_next[i] >= 0) stack.push_back(c.st_next[i]);
-                if (c.st_child[i] >= 0) stack.push_back(c.st_child[i]);
-            }
-            if (!ok || (int)order.size() != S) order.clear();
-            for (int e = 0; e < elig && !order.empty(); e++) if (order[e] != e) order.clear();
-        }
-        const bool walk_tree = !order.empty();
-        if (!walk_tree) { order.resize(elig); for (int e = 0; e < elig; e++) order[e] = e; }
-        const int E = (int)order.size();
-        std::vector<int> pos(S, -1);
-        for (int e = 0; e < E; e++) pos[order[e]] = e;
-        P.tail_stages = elig;
-        P.exec_stages = E;
-        P.g1_min = 16;
-        if (const char *e = getenv("CLFD_G1_MIN")) P.g1_min = std::max(1, std::min(16, atoi(e)));
-        int n_elig_stumps = 0;
-        for (int e = 0; e < E; e++) n_elig_stumps += c.st_ntrees[order[e]] * P.npt;
-        out.dense_stumps = n_elig_stumps;
-        out.tail[yi].assign(n_elig_stumps, TailStump());
-        out.stage_tab[yi].assign(walk_tree ? E : 0, DenseStage());
-        auto tile_offset = [&](int dy, int dx) {
-            const int word = ystep == 1 ? dy * P.tile_stride + dx
-                                        : dy * P.tile_stride + (dx & 1) * (P.tile_stride / 2) + (dx >> 1);
-            return (uint32_t)(word * 4);
-        };
-        int tail_at = 0;   // records in execution order (== tree order for the linear prefix)
-        for (int e = 0; e < E; e++) {
-            const int i = order[e];
-            DenseStage ds;
-            memset(&ds, 0, sizeof ds);
-            bool any3 = false;
-            double abs_sum = 0;
-            ds.tail_first = (uint32_t)tail_at;
-            for (int t = c.st_first_tree[i]; t < c.st_first_tree[i + 1]; t++) {
-                const int a = c.tr_first_node[t] + t;            // alpha base of tree t
-                double amax = 0;
-                for (int j = 0; j < P.npt; j++) {
-                    TailStump &ts = out.tail[yi][tail_at++];
-                    memset(&ts, 0, sizeof ts);
-                    if (j >= c.tr_nnodes[t]) { ts.meta = kNodePad | (kNodeLeaf << 8) | (kNodeLeaf << 16); continue; }
-                    const int n = c.tr_first_node[t] + j;
-                    const HostNode &nd = c.nodes[n];
-                    any3 |= c.hid_nrects[n] == 3;
-                    for (int k = 0; k < c.hid_nrects[n]; k++) {
-                        int dx[4], dy[4];
-                        corner_coords(nd, k, dx, dy);
-                        for (int q = 0; q < 4; q++) ts.off[k * 4 + q] = tile_offset(dy[q], dx[q]) + (nd.tilted ? (uint32_t)tilt_base : 0u);
-                        ts.w[k] = c.hid_weight[(size_t)n * 3 + k];
-                    }
-                    ts.thr = nd.threshold;
-                    ts.a0 = nd.left <= 0 ? c.alpha[a + (-nd.left)] : 0.f;     // sum <  t -> left  (tempcv.cpp:788)
-                    ts.a1 = nd.right <= 0 ? c.alpha[a + (-nd.right)] : 0.f;   // sum >= t -> right
-                    ts.meta = (uint32_t)j | ((nd.left > 0 ? (uint32_t)nd.left : kNodeLeaf) << 8) |
-                              ((nd.right > 0 ? (uint32_t)nd.right : kNodeLeaf) << 16);
-                    amax = fmax(amax, fmax(fabs((double)ts.a0), fabs((double)ts.a1)));
-                }
-                abs_sum += amax;
-            }
-            ds.first = 0; ds.count = (uint16_t)(c.st_ntrees[i] * P.npt);   // records
-            ds.thr = c.hid_thr[i];
-            // double products only on the reference's stump fast path (tempcv.cpp:862,872)
-            ds.flags = ((!c.is_tree && c.is_stump_based && c.two_rects[i]) ? 1u : 0u) | (any3 ? 2u : 0u) |
-                       (c.order_free[i] ? 4u : 0u);
-            // FP32 summation of n alphas in any order: |error| <= (n-1) 2^-24 sum|alpha|; 2x slack
-            const double er = (double)(c.st_ntrees[i] * P.npt) * ldexp(1.0, -23) * abs_sum;
-            ds.sum_eps = std::isfinite(er) ? (float)(er * 1.0000002) + FLT_MIN : INFINITY;
-            if (walk_tree) {
-                const uint32_t pass = c.st_child[i] >= 0 ? (uint32_t)pos[c.st_child[i]] : kRouteAccept;
-                int p = i;
-                while (p >= 0 && c.st_next[p] < 0) p = c.st_parent[p];   // tempcv.cpp:853-855
-                const uint32_t fail = p >= 0 ? (uint32_t)pos[c.st_next[p]] : kRouteReject;
-                ds.flags |= ((uint32_t)i << 8) | (pass << 16) | (fail << 24);
-                out.stage_tab[yi][e] = ds;
-            }
-            if (e < elig) P.stage[e] = ds;
-        }
-        // parameter-resident copy of the leading stages that fit the kernel-parameter budget.  Inside a
-        // stage the copy is REORDERED (the FP32 filters do not depend on the order; the exact fallback
-        // reads the global records, which stay in tree order): first the two-rect stumps whose rects have
-        // two corners in common -- the usual edge feature, a rectangle and one of its halves -- in a
-        // six-offset form E0,E1,F0,F1,G0,G1 with rect0 = (E0-E1)+(F0-F1), rect1 = (E0-E1)+(G0-G1): six
-        // corner loads instead of eight.  With p0,p3 entering a rect sum with + and p1,p2 with -, the
-        // common pair can only be (p0,p2), (p3,p1), (p0,p1) or (p3,p2).
-        const bool share_corners = !getenv("CLFD_NO_SHARED_CORNERS");   // test hook
-        int ns = 0, nstump = 0;
-        while (ns < elig && nstump + c.st_ntrees[ns] * P.npt <= kMaxDenseStumps) {
-            P.stage[ns].first = (uint16_t)nstump;
-            std::vector<DenseStump> six, rest;
-            for (int t = c.st_first_tree[ns] * P.npt; t < c.st_first_tree[ns + 1] * P.npt; t++) {
-                DenseStump st = out.tail[yi][t];
-                bool shared = false;
-                if (share_corners && P.npt == 1 && c.hid_nrects[c.tr_first_node[t]] == 2) {   // (multi-node trees keep their order)
-                    const uint32_t *A = st.off, *B = st.off + 4;
-                    static const int pairs[4][2] = {{0, 2}, {3, 1}, {0, 1}, {3, 2}};   // (plus, minus) corner
-                    for (const auto &pr : pairs) {
-                        const int pl = pr[0], mi = pr[1];
-                        if (A[pl] != B[pl] || A[mi] != B[mi]) continue;
-                        const int opl = pl == 0 ? 3 : 0, omi = mi == 1 ? 2 : 1;   // the other plus / minus corner
-                        const uint32_t o[6] = {A[pl], A[mi], A[opl], A[omi], B[opl], B[omi]};
-                        for (int q = 0; q < 12; q++) st.off[q] = q < 6 ? o[q] : 0;
-                        shared = true;
-                        break;
-                    }
-                }
-                (shared ? six : rest).push_back(st);
-            }
-            P.stage[ns].n_shared = (uint32_t)six.size();
-            for (const auto &st : six) P.stump[nstump++] = st;
-            for (const auto &st : rest) P.stump[nstump++] = st;
-            ns++;
-        }
-        P.n_stages = ns;
-        // stages run in fixed geometry before the first compaction (tunable for experiments)
-        int nf = 3;
-        if (const char *e = getenv("CLFD_N_FIXED")) nf = atoi(e);
-        P.n_fixed = nf < 0 ? 0 : (nf > ns ? ns : nf);
+        s.hid_weight[(size_t)n * 3] = (float)(-sum0 / area0);   // :760
     }
+    s.win_w = ext_w; s.win_h = ext_h;
+    int dense_stumps = 0;
+    pack_dense_one(s, 2, P, tail, stage_tab, dense_stumps);
+    P.inv_area = weight_scale;
+    P.eq_x = ex; P.eq_y = ey; P.eq_w = ew; P.eq_h = eh;
+    return P.tail_stages > 0 && P.exec_stages == P.total_stages;
 }
 
 }  // namespace clfd

@@ -102,6 +102,7 @@ struct ScArgs {
     const ScNode *nodes;            // device, n_levels x n_nodes
     int n_levels, rows_per_frame, n_frames, cascade_index, frame_base;
     long long windows_per_frame;
+    long long first_window;         // grid positions below this one are evaluated by the tile kernel (step-2 scales)
     int16_t *codes;                 // device, [n_frames][windows_per_frame] (always present in this mode)
     DevRect *rects; unsigned long long rect_cap;
     unsigned long long *counters;   // [0] rects [2] rect overflow [3] queue overflow

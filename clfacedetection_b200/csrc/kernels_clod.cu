@@ -75,6 +75,7 @@ __device__ __forceinline__ double window_sigma(int s4, ull q4, double inv_area) 
 }
 
 __device__ __forceinline__ void emit_rect(const CascadeArgs &a, const CasLevel &CL, int frame, int px, int py) {
+    if (!a.rects) return;   // scale-cascade mode: k_sc_rows makes the rects from the exit codes
     const ull slot = atomicAdd(a.counters + 0, 1ull);
     if (slot < a.rect_cap) {
         DevRect r;
@@ -182,12 +183,12 @@ __device__ __forceinline__ void dense_write_code(const DenseCtx &c, int wid, int
 // FP64 sigma of window `wid` (tempcv.cpp:824-832): int32 corners from the tile, uint64 from global
 __device__ __forceinline__ double dense_sigma(const DenseParams &P, const DenseCtx &c, int wid) {
     const int wx = wid & (kTileW - 1), wy = wid / kTileW;
-    const int eq_w = P.win_w - 2, eq_h = P.win_h - 2;
+    const int ex = P.eq_x, ey = P.eq_y, eq_w = P.eq_w, eq_h = P.eq_h;
     const uint32_t base = dense_base(c, wid);
-    const int s4 = lds32(base + dense_tile_off(c, 1, 1)) - lds32(base + dense_tile_off(c, 1, 1 + eq_w)) -
-                   lds32(base + dense_tile_off(c, 1 + eq_h, 1)) + lds32(base + dense_tile_off(c, 1 + eq_h, 1 + eq_w));
+    const int s4 = lds32(base + dense_tile_off(c, ey, ex)) - lds32(base + dense_tile_off(c, ey, ex + eq_w)) -
+                   lds32(base + dense_tile_off(c, ey + eq_h, ex)) + lds32(base + dense_tile_off(c, ey + eq_h, ex + eq_w));
     const ull *q = c.gsq + (size_t)(wy * c.ystep) * c.sq_pitch + wx * c.ystep;
-    const int g0 = c.sq_pitch + 1, g1 = g0 + eq_w, g2 = (1 + eq_h) * c.sq_pitch + 1, g3 = g2 + eq_w;
+    const int g0 = ey * c.sq_pitch + ex, g1 = g0 + eq_w, g2 = (ey + eq_h) * c.sq_pitch + ex, g3 = g2 + eq_w;
     const ull q4 = __ldg(q + g0) - __ldg(q + g1) - __ldg(q + g2) + __ldg(q + g3);
     return window_sigma(s4, q4, P.inv_area);
 }

@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(128) k_sc_eval(const __grid_constant__ ScArgs 
     const DeepCascadeDev &D = a.deep;
     const int lane = threadIdx.x & 31;
     const bool from_grid = a.in == nullptr;
-    ull n = from_grid ? (ull)a.windows_per_frame * a.n_frames : *a.in_count;
+    const ull grid_per_frame = (ull)(a.windows_per_frame - a.first_window);   // the tile kernel took the rest
+    ull n = from_grid ? grid_per_frame * a.n_frames : *a.in_count;
     if (!from_grid && n > a.queue_cap) n = a.queue_cap;
     const bool last_pass = a.stage_end >= D.n_stages;
     const ull stride = (ull)gridDim.x * 128;
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(128) k_sc_eval(const __grid_constant__ ScArgs 
         int frame = 0;
         long long w = 0;
         if (valid) {
-            if (from_grid) { frame = (int)(item / (ull)a.windows_per_frame); w = (long long)(item - (ull)frame * a.windows_per_frame); }
+            if (from_grid) { frame = (int)(item / grid_per_frame); w = a.first_window + (long long)(item - (ull)frame * grid_per_frame); }
             else { const QueueItem q = a.in[item]; frame = (int)q.key; w = (long long)q.xy; }
         }
         bool pass_on = false;

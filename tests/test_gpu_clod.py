@@ -364,9 +364,11 @@ def test_submit_collect_pipeline_keeps_batches_apart(gpu_ctx):
     det.close()
 
 
+@pytest.mark.parametrize("tiles", [True, False])
 @pytest.mark.parametrize("name,sf,shape", [("frontalface_alt", 1.2, (640, 480)), ("frontalface_alt2", 1.3, (500, 380)),
-                                           ("frontalface_alt_tree", 1.25, (480, 360)), ("fullbody", 1.2, (400, 420))])
-def test_scale_cascade_mode_equals_ref_sc_oracle(gpu_ctx, name, sf, shape):
+                                           ("frontalface_alt_tree", 1.25, (480, 360)), ("fullbody", 1.2, (400, 420)),
+                                           ("eye_tree_eyeglasses", 1.1, (330, 250)), ("frontalface_default", 1.15, (700, 300))])
+def test_scale_cascade_mode_equals_ref_sc_oracle(gpu_ctx, monkeypatch, name, sf, shape, tiles):
     """CLFD_MODE_SCALE_CASCADE: one integral image, features scaled per factor,
     step max(2, factor) and the skip rule of HaarDetectObjects_ScaleCascade_Invoker -- exit codes
     (including skipped / out-of-bounds markers) and the rect set identical to the REF-SC oracle."""
