@@ -64,7 +64,6 @@ constexpr int kTileWindows = kTileW * kTileH;
 constexpr int kDenseThreads = 256;
 constexpr int kDenseWarps = kDenseThreads / 32;
 constexpr int kDenseSlots = kTileWindows / kDenseThreads;   // windows per thread (8)
-constexpr int kDenseChunk = 4;                               // windows a thread carries through a stage at once
 constexpr int kMaxDenseStumps = 392;   // parameter-resident stumps (constant bank): the leading stages that fit
 constexpr int kMaxDenseStages = 32;    // stages the tile kernel can evaluate (a cascade with more keeps a deep tail)
 
@@ -120,7 +119,8 @@ struct DenseParams {
     int exec_stages;    // == tail_stages, or for a stage tree the tile kernel walks itself: all stages, in
                         // execution order (stage_g; the first tail_stages of them are the linear prefix)
     int npt;            // records per tree: 1 = stumps; 2..4 = multi-node trees, every tree padded to npt node records
-    int tile_h;         // window rows per tile: kTileH, or kTileHSmall where two tiles (tilted) would leave one CTA per SM
+    int tile_h;         // window rows per tile: kTileH; kTileHSmall where two tiles (tilted) would leave one CTA per SM;
+                        // 24 for plain stump cascades on ystep-2 levels
     int eq_x, eq_y, eq_w, eq_h;   // the variance rectangle inside the window (tempcv.cpp:614-616): (1, 1, w-2, h-2) at scale 1
     double inv_area;
     const TailStump *tail;   // device, layout of this blob's ystep (patched in by the detector)

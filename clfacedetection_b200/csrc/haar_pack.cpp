@@ -253,6 +253,12 @@ static void pack_dense_one(const HostCascade &c, int ystep, DenseParams &P, std:
     P.tilted_tile = c.has_tilted && !getenv("CLFD_NO_TILTED_TILE") ? 1 : 0;
     P.tile_h = kTileH;
     if (P.tilted_tile && ystep == 2 && !c.is_tree && !getenv("CLFD_NO_SMALL_TILES")) P.tile_h = kTileHSmall;
+    // plain stump cascades on ystep-2 levels: 24-row tiles bring the tile under 56 KB, i.e. 4 CTAs per SM
+    // instead of 3 (+1 % frontalface_alt, +2 % frontalface_default, measured); CLFD_TILE_H2=32 switches it off
+    if (ystep == 2 && !P.tilted_tile && !c.is_tree && c.is_stump_based) {
+        const char *e = getenv("CLFD_TILE_H2");
+        if (!e || atoi(e) == 24) P.tile_h = 24;
+    }
     const size_t tile_bytes = (size_t)dense_tile_rows(c.win_h, ystep, P.tile_h) * P.tile_stride * 4;
     const size_t tilt_base = (tile_bytes + 127) & ~(size_t)127;
     const bool dense_ok = tile_bytes <= 65536 && (!P.tilted_tile || 2 * tilt_base <= 160 * 1024) && c.win_w <= 255 && c.win_h <= 255;

@@ -410,7 +410,8 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     const int tx = local % CL.tiles_x, ty = local / CL.tiles_x;
     const int ystep = P.ystep;   // == CL.ystep by construction of the launch
     constexpr int kTileWindows = kTileW * TILE_H, kDenseSlots = kTileWindows / kDenseThreads;   // (shadow the 32-row constants)
-    static_assert(kDenseSlots % kDenseChunk == 0, "tile height must be a multiple of 16");
+    constexpr int kDenseChunk = kDenseSlots % 4 == 0 ? 4 : 3;   // windows a thread carries through a fixed stage at once
+    static_assert(kDenseSlots % kDenseChunk == 0 && kDenseSlots <= 8, "tile height: 12, 16, 24 or 32 window rows");
     const int px0 = tx * kTileW * ystep, py0 = ty * TILE_H * ystep;   // tile origin in the integral image
     const int n_wx = min(kTileW, CL.nx - tx * kTileW), n_wy = min(TILE_H, CL.ny - ty * TILE_H);
     const int rows = min((TILE_H - 1) * ystep + P.win_h + 1, L.h + 1 - py0);
@@ -778,6 +779,10 @@ static cudaError_t launch_tiles_t(const DenseParams &P, const CascadeArgs &a, in
     if (P.tile_h == kTileHSmall) {   // tilted cascades on ystep-2 levels
         if (P.npt > 1) return launch_tiles_tt<R, false, true, kTileHSmall>(P, a, tile0, n_tiles, smem, stream);
         return launch_tiles_tt<R, false, false, kTileHSmall>(P, a, tile0, n_tiles, smem, stream);
+    }
+    if (P.tile_h == 24) {   // plain stump cascades on ystep-2 levels (4 CTAs per SM)
+        if (P.exec_stages > P.tail_stages || P.npt > 1) return cudaErrorInvalidValue;
+        return launch_tiles_tt<ROWSTEP_T, false, false, 24>(P, a, tile0, n_tiles, smem, stream);
     }
     if (P.tile_h != kTileH) return cudaErrorInvalidValue;
     if (P.npt > 1) return launch_tiles_tt<R, false, true>(P, a, tile0, n_tiles, smem, stream);
