@@ -158,3 +158,31 @@ def test_group_batch_equals_per_frame_grouping():
         assert o == len(got)
     empty, _ = clfd.group_batch(rects[:0], 3)
     assert len(empty) == 0
+
+
+def test_tile_kernel_register_budget():
+    """The headline instantiations of k_cascade_tiles (plain stump cascades) must stay at 64 registers:
+    at 256 threads that is 4 CTAs per SM; a stray launch-bounds argument once let ptxas take 88
+    (2 CTAs per SM, -20 % frames/s).  cuobjdump -res-usage is the authority (tools/regs.sh)."""
+    import re
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("no cuobjdump")
+    from clfacedetection_b200 import abi
+    out = subprocess.run([exe, "-res-usage", abi.LIB_PATH], capture_output=True, text=True).stdout
+    regs = {}
+    name = None
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+        m = re.search(r"REG:(\d+)", line)
+        if m and name:
+            regs[name] = int(m.group(1))
+    tiles = {k: v for k, v in regs.items() if "k_cascade_tilesILi" in k}
+    assert len(tiles) >= 12, sorted(regs)
+    plain = {k: v for k, v in tiles.items() if "ELb0ELb0ELi" in k}
+    assert plain and all(v <= 64 for v in plain.values()), plain
+    assert all(v <= 80 for v in tiles.values()), tiles
