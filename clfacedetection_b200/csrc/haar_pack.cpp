@@ -417,6 +417,28 @@ static void pack_dense_one(const HostCascade &c, int ystep, DenseParams &P, std:
         ns++;
     }
     P.n_stages = ns;
+    // the global records go into blocks of 32 stumps with the five 16-byte chunks of a record 512 bytes apart
+    // (kernels_clod.cu, stump_from_global): chunk q of a stage's record j at (j / 32) * 160 + q * 32 + j % 32;
+    // every stage starts a new block, tail_first (in records) is remapped
+    {
+        static_assert(sizeof(TailStump) == 80, "five 16-byte chunks per record");
+        struct Chunk { uint32_t v[4]; };
+        std::vector<TailStump> blocked;
+        const Chunk *src = reinterpret_cast<const Chunk *>(tail.data());
+        int at = 0;
+        for (int e = 0; e < E; e++) {
+            const int count = c.st_ntrees[order[e]] * P.npt;
+            const size_t first = blocked.size();
+            blocked.resize(first + (size_t)((count + 31) / 32) * 32);
+            Chunk *blk = reinterpret_cast<Chunk *>(blocked.data() + first);
+            for (int j = 0; j < count; j++)
+                for (int q = 0; q < 5; q++) blk[(size_t)(j >> 5) * 160 + q * 32 + (j & 31)] = src[(size_t)(at + j) * 5 + q];
+            if (e < elig) P.stage[e].tail_first = (uint32_t)first;
+            if (walk_tree) stage_tab[e].tail_first = (uint32_t)first;
+            at += count;
+        }
+        tail.swap(blocked);
+    }
     // stages run in fixed geometry before the first compaction (tunable for experiments)
     int nf = 3;
     if (const char *e = getenv("CLFD_N_FIXED")) nf = atoi(e);

@@ -206,11 +206,17 @@ __device__ __forceinline__ StumpRegs stump_from_param(const DenseStump &q) {   /
     r.w0 = q.w[0]; r.w1 = q.w[1]; r.w2 = q.w[2]; r.thr = q.thr; r.a0 = q.a0; r.a1 = q.a1; r.meta = q.meta;
     return r;
 }
-__device__ __forceinline__ StumpRegs stump_from_global(const DenseStump *__restrict__ p, bool any3) {   // 4-5 x LDG.128
-    const uint4 *rec = reinterpret_cast<const uint4 *>(p);
-    const uint4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q3 = __ldg(rec + 3), q4 = __ldg(rec + 4);
+// Global records of a stage are stored in blocks of 32 stumps, chunk-interleaved: the five 16-byte chunks of
+// a record (offsets 0-3, 4-7, 8-11, weights + threshold, leaf values + meta) lie 512 bytes apart, chunk c of
+// stump j at rec[(j / 32) * 160 + c * 32 + j % 32].  When the lanes of a warp are on different stumps (window x
+// group mode: G consecutive stumps) one LDG.128 touches G/8 cache lines instead of the 0.6 G lines of
+// 80-byte records -- 22 % of the kernel's L1 data-pipe wavefronts were record fetches (profiles/README.md) --
+// and the chunks are still one pointer plus immediates.
+__device__ __forceinline__ StumpRegs stump_from_global(const uint4 *__restrict__ rec, int j, bool any3) {   // 4-5 x LDG.128
+    rec += (j >> 5) * 160 + (j & 31);
+    const uint4 q0 = __ldg(rec), q1 = __ldg(rec + 32), q3 = __ldg(rec + 96), q4 = __ldg(rec + 128);
     uint4 q2 = make_uint4(0u, 0u, 0u, 0u);
-    if (any3) q2 = __ldg(rec + 2);
+    if (any3) q2 = __ldg(rec + 64);
     StumpRegs r;
     r.o[0] = q0.x; r.o[1] = q0.y; r.o[2] = q0.z; r.o[3] = q0.w;
     r.o[4] = q1.x; r.o[5] = q1.y; r.o[6] = q1.z; r.o[7] = q1.w;
@@ -226,11 +232,11 @@ __device__ __noinline__ bool dense_stage_exact(const DenseParams &P, const Dense
                                                float sthr, int wid) {
     const uint32_t base = dense_base(c, wid);
     const double sigma = dense_sigma(P, c, wid);
-    const DenseStump *rec = P.tail + tail_first;
+    const uint4 *rec = reinterpret_cast<const uint4 *>(P.tail + tail_first);
     double S = 0.0;
     uint32_t at = 0;   // multi-node trees: the node this window is at (icvEvalHidHaarClassifier, tempcv.cpp:771-792)
     for (int j = 0; j < count; j++) {
-        const StumpRegs q = stump_from_global(rec + j, true);
+        const StumpRegs q = stump_from_global(rec, j, true);
         if (NODES) {
             if ((q.meta & 255u) == 0u) at = 0;
             if ((q.meta & 255u) != at) continue;
@@ -350,17 +356,17 @@ __device__ __forceinline__ void stage_filter(const DenseParams &P, const DenseSt
 #pragma unroll 1
         for (int j = n6; j < count; j++) stump_filter<K, FIXED, ROWSTEP, false, NODES>(stump_from_param(P.stump[first + j]), dbl, any3, eps, base, sg, S, near, at);
     } else {
-        const DenseStump *__restrict__ rec = P.tail + st.tail_first;
+        const uint4 *__restrict__ rec = reinterpret_cast<const uint4 *>(P.tail + st.tail_first);
         if (NODES) {   // the groups split the stage by whole trees
             const int npt = P.npt;
 #pragma unroll 1
             for (int j = grp * npt; j < count; j += G * npt)
 #pragma unroll 1
                 for (int i = 0; i < npt; i++)
-                    stump_filter<K, FIXED, ROWSTEP, false, true>(stump_from_global(rec + j + i, any3), dbl, any3, eps, base, sg, S, near, at);
+                    stump_filter<K, FIXED, ROWSTEP, false, true>(stump_from_global(rec, j + i, any3), dbl, any3, eps, base, sg, S, near, at);
         } else {
 #pragma unroll 1
-            for (int j = grp; j < count; j += G) stump_filter<K, FIXED, ROWSTEP, false, false>(stump_from_global(rec + j, any3), dbl, any3, eps, base, sg, S, near, at);
+            for (int j = grp; j < count; j += G) stump_filter<K, FIXED, ROWSTEP, false, false>(stump_from_global(rec, j, any3), dbl, any3, eps, base, sg, S, near, at);
         }
     }
 }
