@@ -318,7 +318,7 @@ static void pack_dense_one(const HostCascade &c, int ystep, DenseParams &P, std:
     for (int e = 0; e < E; e++) pos[order[e]] = e;
     P.tail_stages = elig;
     P.exec_stages = E;
-    P.g1_min = 16;
+    P.g1_min = 12;   // measured: 8, 12, 16 within 0.6 % of each other, 12 best
     if (const char *e = getenv("CLFD_G1_MIN")) P.g1_min = std::max(1, std::min(16, atoi(e)));
     int n_elig_stumps = 0;
     for (int e = 0; e < E; e++) n_elig_stumps += c.st_ntrees[order[e]] * P.npt;

@@ -3,7 +3,8 @@
 (profiles/summarize_ncu.py output).  bench.py reads it for `roofline.traffic` and the L1 data-pipe
 figures.
 
-usage: python profiles/make_traffic.py profiles/r1j_step_full_batch8.csv 8 > profiles/traffic.json
+usage: python profiles/make_traffic.py 8 profiles/r1j_step_full_batch8.csv [profiles/r1k_tiles_full.csv ...] > profiles/traffic.json
+(several summaries of the same batch size: a kernel takes its figures from the LAST file that captured it)
 """
 import csv
 import json
@@ -13,8 +14,7 @@ GROUPS = {"k_resize_colsum": "resize_colsum", "k_colscan": "colscan", "k_integra
           "k_tilted": "tilted", "k_cascade_tiles": "cascade_tiles"}
 
 
-def main():
-    path, batch = sys.argv[1], int(sys.argv[2])
+def one(path, batch):
     rows = list(csv.reader(open(path)))
     head = rows[0][2:]
     metric = {r[0]: (r[1], r[2:]) for r in rows[1:]}
@@ -48,7 +48,17 @@ def main():
             kernels[k]["l1_wavefronts_per_frame"] = round(o["wavefronts"] / batch)
             kernels[k]["l1_wavefronts_note"] = ("all L1 data-pipe wavefronts (shared + global) of both tile launches per frame: "
                                                 "shared-memory wavefronts x (total pipe % / shared pipe %) from the same capture")
-    json.dump({"source": "%s (ncu --set full, bench.py --batch %d; per-frame figures = capture / %d)" % (path, batch, batch),
+    for k in kernels:
+        kernels[k]["capture"] = path
+    return kernels
+
+
+def main():
+    batch, paths = int(sys.argv[1]), sys.argv[2:]
+    kernels = {}
+    for p in paths:
+        kernels.update(one(p, batch))
+    json.dump({"source": "%s (ncu --set full, bench.py --batch %d; per-frame figures = capture / %d)" % (", ".join(paths), batch, batch),
                "batch": batch, "kernels": kernels}, sys.stdout, indent=1)
     print()
 
