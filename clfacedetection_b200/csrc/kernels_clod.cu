@@ -4,23 +4,26 @@
 // window semantics of cvRunHaarClassifierCascadeSum (tempcv.cpp:795-972) on the pyramid
 // grid of HaarDetectObjects_ScaleImage_Invoker (tempcv.cpp:1011-1103).
 //
-// One or two kernels per cascade per batch, no host round trip in between:
-//   k_cascade_tiles : one CTA per 64x32-window tile of one level of one frame.  The int32
-//       integral tile is staged into shared memory (TMA bulk row copies, cp.async.bulk +
-//       mbarrier, on ystep-1 levels), sigma is computed once per window in FP64, and the
+// One kernel (two launches: ystep-2 and ystep-1 levels) per cascade per batch, no host round trip:
+//   k_cascade_tiles<ROWSTEP, TREE, NODES, TILE_H> : one CTA per 64 x TILE_H-window tile of one level
+//       of one frame.  The int32 integral tile (and, for cascades with tilted features, the tilted
+//       integral tile behind it) is staged into shared memory (TMA bulk row copies, cp.async.bulk
+//       + mbarrier, on ystep-1 levels), sigma is computed once per window in FP64, and the
 //       cascade is evaluated in two phases: fixed geometry (thread per window column, no
 //       compaction, stumps from the constant bank: the packed cascade is a __grid_constant__
 //       kernel parameter, <= 32 KB) while most windows are alive, then warp-autonomous: a
-//       warp carries 32 survivors through all remaining stages, re-dividing its lanes between
+//       warp carries its survivors through all remaining stages, re-dividing its lanes between
 //       windows and stumps as windows die (stump records from global memory).
-//       Stump-based upright cascades (frontalface_alt / _default, eye, profileface) are
-//       finished inside this kernel.
-//   k_cascade_deep  : for cascades the tile kernel cannot finish (multi-node trees, tilted
-//       features, the alt_tree stage tree) the survivors of the dense prefix from all tiles /
-//       levels / frames are pooled in one global queue and evaluated one WARP per window,
-//       lanes striding over the trees of a stage.  The stage sum is reduced with shuffles
-//       when the packer proved the alpha sum exact in any order, otherwise accumulated in
-//       tree order.
+//       Every stock cascade is finished inside this kernel: stumps, tilted features, trees of
+//       up to four nodes (NODES: per-window "node I am at" state over padded node records),
+//       the alt_tree stage tree (TREE: stages in depth-first order, per-window target position).
+//       The scale-cascade mode runs its step-2 scales through it as well (clfd_api.cu).
+//   k_cascade_mid / k_cascade_deep : generic fallback for cascades the tile kernel cannot finish
+//       (larger trees, a tile that does not fit shared memory): the survivors of the tile prefix
+//       (or every window) are pooled in one global queue and evaluated one thread / one WARP per
+//       window, lanes striding over the trees of a stage.  The stage sum is reduced with shuffles
+//       when the packer proved the alpha sum exact in any order, otherwise accumulated in tree order.
+//   k_roc_collect : reject-level output (tempcv.cpp:1084-1094) as a pass over the exit codes.
 //
 // Arithmetic is bit-identical to the reference's C expressions: integer rect sums; FP64
 // variance with separately rounded mul/sub/sqrt; two_rects stages multiply in double
