@@ -335,6 +335,8 @@ def main():
                 if ncu and nm in ncu["kernels"]:
                     k["ncu_dram_bytes"] = int(ncu["kernels"][nm]["dram_bytes_per_frame"]) * B
                     k["ncu_l1_data_pipe_pct"] = ncu["kernels"][nm]["l1_data_pipe_pct"]
+                    if "warp_execution_efficiency" in ncu["kernels"][nm]:
+                        k["ncu_warp_execution_efficiency"] = ncu["kernels"][nm]["warp_execution_efficiency"]
                 kernels[nm] = k
         dom = "cascade_tiles"
         roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
@@ -391,6 +393,30 @@ def main():
                                     "windows_per_sec": round(w / t, 1)}
         default_run = (CASCADE == "frontalface_alt" and (W, H) == (1920, 1080) and SCALE == 1.2 and args.mode == "pyramid"
                        and world == 1 and not args.no_extra)
+        if args.mode == "pyramid" and not args.no_extra:
+            # survivor counts per stage (north star's evidence list): the exit codes of frame 0 of the batch,
+            # from a second, one-frame detector with want_codes -- outside every timed region
+            try:
+                d2 = clfd.Detector(ctx, cas, W, H, max_batch=1, scale_factor=SCALE, min_size=MIN_SIZE, want_codes=True)
+                d2.detect(base[:1])
+                surv = []
+                for ci, cc in enumerate(cas):
+                    codes = d2.codes(ci, 1)[0].astype(np.int64)
+                    S = cc.info.n_stages
+                    if cc.info.is_tree:   # code = 2 * last evaluated stage + accepted
+                        hist = np.bincount(codes >> 1, minlength=S)
+                        surv.append({"cascade": XML[ci].split("haarcascade_")[-1][:-4], "windows": int(codes.size),
+                                     "stage_tree": True, "windows_whose_last_stage_is": hist.tolist(),
+                                     "accepted": int((codes & 1).sum())})
+                    else:                 # code = stages passed
+                        hist = np.bincount(codes, minlength=S + 1)
+                        reach = hist[::-1].cumsum()[::-1]   # windows that reach stage s = exit code >= s
+                        surv.append({"cascade": XML[ci].split("haarcascade_")[-1][:-4], "windows": int(codes.size),
+                                     "windows_reaching_stage": reach[:S].tolist(), "accepted": int(hist[S])})
+                d2.close()
+                line["survivors_per_stage"] = {"frame": 0, "cascades": surv}
+            except Exception as e:   # evidence only: never fail the headline line
+                line["survivors_per_stage"] = {"error": str(e)[:200]}
         det.close()
         ctx.close()
         if default_run:

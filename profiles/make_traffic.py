@@ -31,11 +31,12 @@ def one(path, batch):
         key = next((g for k, g in GROUPS.items() if k in name), None)
         if key is None:
             continue
-        o = out.setdefault(key, {"dram": 0.0, "ms": 0.0, "pipe_ms": 0.0, "wavefronts": 0.0})
+        o = out.setdefault(key, {"dram": 0.0, "ms": 0.0, "pipe_ms": 0.0, "wavefronts": 0.0, "eff_ms": 0.0})
         ms = val("gpu__time_duration.sum", i)
         o["dram"] += val("dram__bytes_read.sum", i) + val("dram__bytes_write.sum", i)
         o["ms"] += ms
         o["pipe_ms"] += ms * val("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", i)
+        o["eff_ms"] += ms * val("smsp__thread_inst_executed_per_inst_executed.ratio", i) / 32.0
         # all data-pipe wavefronts (shared + global): the shared-memory count scaled by total pipe % / shared pipe %
         sh, sh_pct = val("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", i), val("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", i)
         if sh_pct > 0:
@@ -43,6 +44,7 @@ def one(path, batch):
     kernels = {}
     for k, o in out.items():
         kernels[k] = {"dram_bytes_per_frame": round(o["dram"] / batch), "l1_data_pipe_pct": round(o["pipe_ms"] / o["ms"], 1),
+                      "warp_execution_efficiency": round(o["eff_ms"] / o["ms"], 3),   # active threads per executed instruction / 32
                       "ncu_ms_batch%d" % batch: round(o["ms"], 4)}
         if k == "cascade_tiles":
             kernels[k]["l1_wavefronts_per_frame"] = round(o["wavefronts"] / batch)
