@@ -335,6 +335,9 @@ def main():
                 if ncu and nm in ncu["kernels"]:
                     k["ncu_dram_bytes"] = int(ncu["kernels"][nm]["dram_bytes_per_frame"]) * B
                     k["ncu_l1_data_pipe_pct"] = ncu["kernels"][nm]["l1_data_pipe_pct"]
+                    for lvl in ("l1", "l2"):   # bytes through L1 (global) / L2 per frame in the capture over this run's kernel time
+                        if ncu["kernels"][nm].get(lvl + "_bytes_per_frame") and kernel_ms[i] > 0:
+                            k["ncu_%s_gbs" % lvl] = round(ncu["kernels"][nm][lvl + "_bytes_per_frame"] * B / (kernel_ms[i] * 1e-3) / 1e9, 1)
                     if "warp_execution_efficiency" in ncu["kernels"][nm]:
                         k["ncu_warp_execution_efficiency"] = ncu["kernels"][nm]["warp_execution_efficiency"]
                 kernels[nm] = k

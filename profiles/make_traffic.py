@@ -21,7 +21,10 @@ def one(path, batch):
 
     def val(name, i):
         unit, vals = metric[name]
-        v = float(vals[i].replace(",", ""))
+        try:
+            v = float(vals[i].replace(",", ""))
+        except ValueError:   # "no data" for a launch that did not collect the metric
+            return 0.0
         scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1, "us": 1e-3, "ms": 1, "ns": 1e-6, "s": 1e3}.get(unit, 1)
         return v * scale
 
@@ -31,11 +34,15 @@ def one(path, batch):
         key = next((g for k, g in GROUPS.items() if k in name), None)
         if key is None:
             continue
-        o = out.setdefault(key, {"dram": 0.0, "ms": 0.0, "pipe_ms": 0.0, "wavefronts": 0.0, "eff_ms": 0.0})
+        o = out.setdefault(key, {"dram": 0.0, "ms": 0.0, "pipe_ms": 0.0, "wavefronts": 0.0, "eff_ms": 0.0, "l1": 0.0, "l2": 0.0})
         ms = val("gpu__time_duration.sum", i)
         o["dram"] += val("dram__bytes_read.sum", i) + val("dram__bytes_write.sum", i)
         o["ms"] += ms
         o["pipe_ms"] += ms * val("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", i)
+        if "SM_B.TriageCompute.l1tex__t_sectors.sum" in metric:   # 32-byte sectors through the L1 tag stage (global) / L2
+            o["l1"] += 32 * val("SM_B.TriageCompute.l1tex__t_sectors.sum", i)
+        if "lts__t_sectors.sum" in metric:
+            o["l2"] += 32 * val("lts__t_sectors.sum", i)
         o["eff_ms"] += ms * val("smsp__thread_inst_executed_per_inst_executed.ratio", i) / 32.0
         # all data-pipe wavefronts (shared + global): the shared-memory count scaled by total pipe % / shared pipe %
         sh, sh_pct = val("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", i), val("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", i)
@@ -44,6 +51,7 @@ def one(path, batch):
     kernels = {}
     for k, o in out.items():
         kernels[k] = {"dram_bytes_per_frame": round(o["dram"] / batch), "l1_data_pipe_pct": round(o["pipe_ms"] / o["ms"], 1),
+                      "l1_bytes_per_frame": round(o["l1"] / batch) or None, "l2_bytes_per_frame": round(o["l2"] / batch) or None,
                       "warp_execution_efficiency": round(o["eff_ms"] / o["ms"], 3),   # active threads per executed instruction / 32
                       "ncu_ms_batch%d" % batch: round(o["ms"], 4)}
         if k == "cascade_tiles":

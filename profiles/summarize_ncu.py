@@ -14,7 +14,8 @@ KEEP = [
     "dram__bytes_read.sum", "dram__bytes_write.sum",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "dram__throughput.avg.pct_of_peak_sustained_elapsed",
-    "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
+    "lts__t_bytes.sum", "lts__t_sectors.sum", "lts__t_sector_hit_rate.pct",
+    "SM_B.TriageCompute.l1tex__t_sectors.sum",
     "l1tex__t_bytes.sum", "l1tex__t_sector_hit_rate.pct",
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
     "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
