@@ -159,36 +159,11 @@ __global__ void __launch_bounds__(NT) k_integral_rows(const PyramidArgs a, const
         q[0] = q[1] = q[2] = q[3] = make_ulonglong2(0, 0);
     }
 
-    uint2 nxt = make_uint2(0, 0);
-    if (in_pyr) nxt = __ldg(reinterpret_cast<const uint2 *>(pyr + (size_t)y0 * L.pyr_pitch + X0));
-    int buf = 0;
-    for (int y = y0; y < y1; y++) {
-        const uint2 cur = nxt;
-        if (in_pyr && y + 1 < y1) nxt = __ldg(reinterpret_cast<const uint2 *>(pyr + (size_t)(y + 1) * L.pyr_pitch + X0));
-        uint32_t ts = 0, tq32 = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const uint32_t word = i < 4 ? cur.x : cur.y;
-            const uint32_t p = (word >> (8 * (i & 3))) & 255u;
-            ca[i] += p;
-            cq[i] += p * p;
-            ts += ca[i];
-        }
-        // 8 column square sums (each < 2^28 up to 4K height) cannot overflow 32 bits pairwise,
-        // but their total can approach 2^32 -> widen before the last adds
-        tq32 = cq[0] + cq[1] + cq[2] + cq[3];
-        const ull tq = (ull)tq32 + (ull)(cq[4] + cq[5] + cq[6] + cq[7]);
-
-        uint32_t is = ts; ull iq = tq;  // warp inclusive scan of the thread totals
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t vs = __shfl_up_sync(0xffffffffu, is, d);
-            const ull vq = __shfl_up_sync(0xffffffffu, iq, d);
-            if (lane >= d) { is += vs; iq += vq; }
-        }
-        uint32_t os = 0; ull oq = 0;  // sum of the warps to the left
+    // cross-warp exclusive prefix of per-warp totals (lane 31 holds the warp's inclusive total)
+    auto left_of_warp = [&](int buf, uint32_t tot_s, ull tot_q, uint32_t &os, ull &oq) {
+        os = 0; oq = 0;
         if (NW > 1) {
-            if (lane == 31) { wtot_s[buf][warp] = is; wtot_q[buf][warp] = iq; }
+            if (lane == 31) { wtot_s[buf][warp] = tot_s; wtot_q[buf][warp] = tot_q; }
             __syncthreads();
             if (NW <= 8) {
                 for (int w = 0; w < warp; w++) { os += wtot_s[buf][w]; oq += wtot_q[buf][w]; }
@@ -202,20 +177,71 @@ __global__ void __launch_bounds__(NT) k_integral_rows(const PyramidArgs a, const
                 }
                 os = ws; oq = wq;
             }
-            buf ^= 1;
         }
-        if (in_sum) {
-            uint32_t es = os + is - ts;  // exclusive prefix at column X0
-            ull eq = oq + iq - tq;
-            int32_t o[8]; ull oq8[8];
+    };
+
+    // Integral row y0 of this thread's 8 columns = exclusive horizontal prefix of the column carries
+    // (64-bit scan, ONCE per row block).  After that every row only adds its own exclusive pixel
+    // prefix -- out[y+1][x] = out[y][x] + sum_{x' < x} p[y][x'] -- whose scans fit 32 bits: a row of
+    // 8-bit pixels sums to < 2^21 and its squares to < 2^30 up to 16384 columns.
+    uint32_t Is[8];
+    ull Iq[8];
+    {
+        uint32_t ts = 0;
+        ull tq = 0;
 #pragma unroll
-            for (int i = 0; i < 8; i++) { o[i] = (int32_t)es; oq8[i] = eq; es += ca[i]; eq += cq[i]; }
+        for (int i = 0; i < 8; i++) { ts += ca[i]; tq += cq[i]; }
+        uint32_t is = ts;
+        ull iq = tq;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t vs = __shfl_up_sync(0xffffffffu, is, d);
+            const ull vq = __shfl_up_sync(0xffffffffu, iq, d);
+            if (lane >= d) { is += vs; iq += vq; }
+        }
+        uint32_t os; ull oq;
+        left_of_warp(0, is, iq, os, oq);
+        uint32_t es = os + is - ts;
+        ull eq = oq + iq - tq;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { Is[i] = es; Iq[i] = eq; es += ca[i]; eq += cq[i]; }
+    }
+
+    uint2 nxt = make_uint2(0, 0);
+    if (in_pyr) nxt = __ldg(reinterpret_cast<const uint2 *>(pyr + (size_t)y0 * L.pyr_pitch + X0));
+    int buf = 1;
+    for (int y = y0; y < y1; y++) {
+        const uint2 cur = nxt;
+        if (in_pyr && y + 1 < y1) nxt = __ldg(reinterpret_cast<const uint2 *>(pyr + (size_t)(y + 1) * L.pyr_pitch + X0));
+        uint32_t p[8], ts = 0, tq = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t word = i < 4 ? cur.x : cur.y;
+            p[i] = (word >> (8 * (i & 3))) & 255u;
+            ts += p[i];
+            tq += p[i] * p[i];
+        }
+        uint32_t is = ts, iq = tq;  // warp inclusive scan of the thread totals, 32 bits each
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t vs = __shfl_up_sync(0xffffffffu, is, d);
+            const uint32_t vq = __shfl_up_sync(0xffffffffu, iq, d);
+            if (lane >= d) { is += vs; iq += vq; }
+        }
+        uint32_t os; ull oq;
+        left_of_warp(buf, is, (ull)iq, os, oq);
+        buf ^= 1;
+        if (in_sum) {
+            uint32_t rs = os + is - ts;              // exclusive pixel prefix of this row at column X0
+            uint32_t rq = (uint32_t)oq + iq - tq;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { Is[i] += rs; Iq[i] += rq; rs += p[i]; rq += p[i] * p[i]; }
             int4 *s = reinterpret_cast<int4 *>(sum + (size_t)(y + 1) * L.sum_pitch + X0);
-            s[0] = make_int4(o[0], o[1], o[2], o[3]);
-            s[1] = make_int4(o[4], o[5], o[6], o[7]);
+            s[0] = make_int4((int)Is[0], (int)Is[1], (int)Is[2], (int)Is[3]);
+            s[1] = make_int4((int)Is[4], (int)Is[5], (int)Is[6], (int)Is[7]);
             ulonglong2 *q = reinterpret_cast<ulonglong2 *>(sq + (size_t)(y + 1) * L.sum_pitch + X0);
-            q[0] = make_ulonglong2(oq8[0], oq8[1]); q[1] = make_ulonglong2(oq8[2], oq8[3]);
-            q[2] = make_ulonglong2(oq8[4], oq8[5]); q[3] = make_ulonglong2(oq8[6], oq8[7]);
+            q[0] = make_ulonglong2(Iq[0], Iq[1]); q[1] = make_ulonglong2(Iq[2], Iq[3]);
+            q[2] = make_ulonglong2(Iq[4], Iq[5]); q[3] = make_ulonglong2(Iq[6], Iq[7]);
         }
     }
 }
