@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(kResizeThreads) k_resize_colsum(const PyramidA
         }
     }
     uint32_t cs[4] = {0, 0, 0, 0}, cq[4] = {0, 0, 0, 0};
+    int prev_r1[4] = {0, 0, 0, 0}, prev_sy1 = -1;
     const int y0 = it.y * kRowBlock, y1 = min(y0 + kRowBlock, L.h);
     for (int y = y0; y < y1; y++) {
         const int sy = __ldg(a.yofs + L.ytab_off + y);
@@ -63,10 +64,15 @@ __global__ void __launch_bounds__(kResizeThreads) k_resize_colsum(const PyramidA
         const uint8_t *__restrict__ S0 = src + (size_t)sy0 * a.row_stride;
         const uint8_t *__restrict__ S1 = src + (size_t)sy1 * a.row_stride;
         uint32_t packed = 0;
+        // the horizontal pass of a source row is kept for the next output row: at factors < 2 most rows'
+        // upper source row is the previous row's lower one (block-uniform test, no divergence)
+        const bool reuse = sy0 == prev_sy1;
+        prev_sy1 = sy1;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const int r0 = (int)__ldg(S0 + sx0[i]) * a0[i] + (int)__ldg(S0 + sx1[i]) * a1[i];
+            const int r0 = reuse ? prev_r1[i] : (int)__ldg(S0 + sx0[i]) * a0[i] + (int)__ldg(S0 + sx1[i]) * a1[i];
             const int r1 = (int)__ldg(S1 + sx0[i]) * a0[i] + (int)__ldg(S1 + sx1[i]) * a1[i];
+            prev_r1[i] = r1;
             const int v = ((((int)b.x * (r0 >> 4)) >> 16) + (((int)b.y * (r1 >> 4)) >> 16) + 2) >> 2;
             const uint32_t u = (uint32_t)v & 255u;
             packed |= u << (8 * i);
