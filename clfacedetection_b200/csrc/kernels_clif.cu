@@ -56,6 +56,9 @@ __global__ void __launch_bounds__(kResizeThreads) k_resize_colsum(const PyramidA
     }
     uint32_t cs[4] = {0, 0, 0, 0}, cq[4] = {0, 0, 0, 0};
     int prev_r1[4] = {0, 0, 0, 0}, prev_sy1 = -1;
+    // whole groups of 4 pixels of an unscaled level with 4-byte aligned source rows
+    const bool copy4 = L.w == a.W && L.h == a.H && x0 + 4 <= L.w && (a.row_stride & 3) == 0 && (a.frame_stride & 3) == 0 &&
+                       (reinterpret_cast<uintptr_t>(a.frames) & 3) == 0;
     const int y0 = it.y * kRowBlock, y1 = min(y0 + kRowBlock, L.h);
     for (int y = y0; y < y1; y++) {
         const int sy = __ldg(a.yofs + L.ytab_off + y);
@@ -64,6 +67,17 @@ __global__ void __launch_bounds__(kResizeThreads) k_resize_colsum(const PyramidA
         const uint8_t *__restrict__ S0 = src + (size_t)sy0 * a.row_stride;
         const uint8_t *__restrict__ S1 = src + (size_t)sy1 * a.row_stride;
         uint32_t packed = 0;
+        if (copy4) {   // the level of factor 1: the resize is the identity (coefficients 2048 / 0), 4 pixels per load
+            packed = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)y * a.row_stride + x0));
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t u = (packed >> (8 * i)) & 255u;
+                cs[i] += u;
+                cq[i] += u * u;
+            }
+            *reinterpret_cast<uint32_t *>(dst + (size_t)y * L.pyr_pitch + x0) = packed;
+            continue;
+        }
         // the horizontal pass of a source row is kept for the next output row: at factors < 2 most rows'
         // upper source row is the previous row's lower one (block-uniform test, no divergence)
         const bool reuse = sy0 == prev_sy1;
