@@ -122,11 +122,21 @@ __global__ void __launch_bounds__(kColscanThreads) k_colscan(const PyramidArgs a
     for (int plane = 0; plane < 2; plane++) {
         uint32_t *p = a.col + (size_t)blockIdx.y * a.col_frame_stride + plane * a.col_plane_stride + L.col_off + X;
         uint4 acc = make_uint4(0, 0, 0, 0);
-        for (int rb = 0; rb < L.nrb; rb++) {
-            uint4 *q = reinterpret_cast<uint4 *>(p + (size_t)rb * L.sum_pitch);
-            const uint4 v = *q;
-            *q = acc;
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        // eight row blocks per step: all loads first (independent, in flight together), then the stores --
+        // a load behind a store to the same array is otherwise serialised, one DRAM latency per row block
+        constexpr int kAhead = 8;
+        for (int rb0 = 0; rb0 < L.nrb; rb0 += kAhead) {
+            uint4 v[kAhead];
+#pragma unroll
+            for (int k = 0; k < kAhead; k++)
+                if (rb0 + k < L.nrb) v[k] = *reinterpret_cast<const uint4 *>(p + (size_t)(rb0 + k) * L.sum_pitch);
+#pragma unroll
+            for (int k = 0; k < kAhead; k++) {
+                if (rb0 + k < L.nrb) {
+                    *reinterpret_cast<uint4 *>(p + (size_t)(rb0 + k) * L.sum_pitch) = acc;
+                    acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w;
+                }
+            }
         }
     }
 }
