@@ -208,3 +208,40 @@ def test_new_format_files_shipped_with_cv2_if_present():
         old, new = clfd.Cascade(cascade_path(name)), clfd.Cascade(os.path.join(d, f"haarcascade_{name}.xml"))
         a, b = old.arrays(), new.arrays()
         assert all(np.array_equal(a[k], b[k]) for k in a)
+
+
+def test_packer_tile_eligibility_of_synthetic_tree_shapes(monkeypatch):
+    """Host-side packing decisions need no GPU: trees of up to four nodes (children after their parent)
+    are tile-evaluated with padded node records; the test hooks switch each tile-kernel extension off."""
+    from test_gpu_clod import _mixed_tree_cascade
+    flat = _mixed_tree_cascade()
+    c = clfd.Cascade(flat=flat)
+    assert c.info.max_nodes_per_tree == 4 and c.info.dense_stages == c.info.n_stages
+    assert c.info.dense_stumps == 4 * c.info.n_trees   # every tree padded to 4 records
+    monkeypatch.setenv("CLFD_NO_NODE_TILES", "1")
+    assert clfd.Cascade(flat=flat).info.dense_stages == 0
+    assert clfd.Cascade(cascade_path("frontalface_alt2")).info.dense_stages == 0
+    monkeypatch.delenv("CLFD_NO_NODE_TILES")
+    monkeypatch.setenv("CLFD_NO_TREE_TILES", "1")
+    assert clfd.Cascade(cascade_path("frontalface_alt_tree")).info.dense_stages == 5   # the linear prefix only
+    monkeypatch.delenv("CLFD_NO_TREE_TILES")
+    monkeypatch.setenv("CLFD_NO_TILTED_TILE", "1")
+    assert clfd.Cascade(cascade_path("fullbody")).info.dense_stages == 2               # first tilted stump in stage 2
+    assert clfd.Cascade(cascade_path("mcs_nose")).info.dense_stages == 0
+    # a child that precedes its parent is left to the generic kernels
+    bad = _mixed_tree_cascade()
+    import numpy as _np
+    nn = _np.array(bad.tr_nnodes)
+    first4 = int(_np.flatnonzero(nn == 4)[0])
+    n0 = int(nn[:first4].sum())
+    left, right = _np.array(bad.nd_left).copy(), _np.array(bad.nd_right).copy()
+    # 4-node shape (0,1),(2,3),(-1,-2),(-3,-4): make node 2 point back to node 1 -> cycle-free but out of order
+    left[n0 + 2] = 1
+    import dataclasses
+    bad = dataclasses.replace(bad, nd_left=left, nd_right=right)
+    monkeypatch.delenv("CLFD_NO_TILTED_TILE")
+    try:
+        info = clfd.Cascade(flat=bad).info
+        assert info.dense_stages == 0   # stage 0 already holds a 4-node tree
+    except clfd.ClfdError:
+        pass                            # or rejected outright as a broken tree
