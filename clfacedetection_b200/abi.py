@@ -85,6 +85,8 @@ def lib() -> C.CDLL:
                                            C.POINTER(vp)]
     L.clfd_cascade_destroy.argtypes = [vp]
     L.clfd_cascade_destroy.restype = None
+    L.clfd_cascade_id.argtypes = [vp]
+    L.clfd_cascade_id.restype = C.c_uint64
     L.clfd_cascade_get_info.argtypes = [vp, C.POINTER(CascadeInfo)]
     L.clfd_cascade_get_arrays.argtypes = [vp, ip, fp, ip, ip, ip, ip, ip, ip, fp, fp, ip, ip, fp]
     L.clfd_cascade_get_hidden.argtypes = [vp, fp, ip, fp, ip]

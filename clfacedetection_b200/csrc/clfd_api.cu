@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -45,10 +46,18 @@ struct clfd_context {
     struct PyramidPlan *scratch = nullptr;   // cached plan of clfd_integral / clfd_resize
 };
 
+// Reference counted: a detector keeps the cascades of its plan alive, so destroying a cascade
+// before its detectors is safe.  `id` is unique per process (never reused, unlike the address).
 struct clfd_cascade {
     HostCascade host;
     PackedCascade packed;
+    std::atomic<int> refs{1};
+    uint64_t id = 0;
 };
+static std::atomic<uint64_t> g_next_cascade_id{1};
+static void cascade_release(const clfd_cascade *c) {
+    if (c && const_cast<clfd_cascade *>(c)->refs.fetch_sub(1) == 1) delete c;
+}
 
 template <class T>
 struct DevBuf {
@@ -224,7 +233,8 @@ int PyramidPlan::run(clfd_context *ctx, const uint8_t *frames, size_t frame_stri
 }
 
 struct CascadePlan {
-    const clfd_cascade *cascade = nullptr;
+    const clfd_cascade *cascade = nullptr;   // retained
+    ~CascadePlan() { cascade_release(cascade); }
     std::vector<CasLevel> levels;
     std::vector<clfd_level> pub_levels;
     int n_tiles = 0;
@@ -364,6 +374,7 @@ int clfd_cascade_load_xml(const char *path, clfd_cascade **out) {
     int rc = load_cascade_xml(path, c->host);
     if (rc) return rc;
     pack_cascade(c->host, c->packed);
+    c->id = g_next_cascade_id.fetch_add(1);
     *out = c.release();
     return 0;
 }
@@ -410,11 +421,13 @@ int clfd_cascade_from_arrays(int win_w, int win_h, int n_stages, const int *st_n
     int rc = build_hidden(h);
     if (rc) return rc;
     pack_cascade(h, c->packed);
+    c->id = g_next_cascade_id.fetch_add(1);
     *out = c.release();
     return 0;
 }
 
-void clfd_cascade_destroy(clfd_cascade *c) { delete c; }
+void clfd_cascade_destroy(clfd_cascade *c) { cascade_release(c); }
+uint64_t clfd_cascade_id(const clfd_cascade *c) { return c ? c->id : 0; }
 
 int clfd_cascade_get_info(const clfd_cascade *c, clfd_cascade_info *info) {
     if (!c || !info) INVALID("NULL argument");
@@ -605,6 +618,7 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
         if (!cascades[ci]) INVALID("cascade %d is NULL", ci);
         det->cas.emplace_back(new CascadePlan());
         det->cas.back()->cascade = cascades[ci];
+        const_cast<clfd_cascade *>(cascades[ci])->refs.fetch_add(1);   // released by ~CascadePlan
         any_tilted |= cascades[ci]->host.has_tilted;
     }
     if (scale_cascade) {

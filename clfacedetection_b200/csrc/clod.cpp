@@ -14,8 +14,9 @@
 
 namespace {
 
+// keyed by the cascade's ID, not its address: a released cascade's address can be handed out again
 struct DetKey {
-    const clfd_cascade* cascade; int w, h, min_w, min_h, max_w, max_h; double sf; int mode;
+    uint64_t cascade; int w, h, min_w, min_h, max_w, max_h; double sf; int mode;
     bool operator<(const DetKey& o) const {
         return std::tie(cascade, w, h, min_w, min_h, max_w, max_h, sf, mode) <
                std::tie(o.cascade, o.w, o.h, o.min_w, o.min_h, o.max_w, o.max_h, o.sf, o.mode);
@@ -27,6 +28,7 @@ struct ClodState {
     double scale_factor = 1.1;                       // clod.cpp:1349
     int mode = CLFD_MODE_SCALE_IMAGE;
     std::map<DetKey, clfd_detector*> detectors;      // plans are cached per (cascade, shape, limits)
+    unsigned long long release_generation = 0;       // cvShimReleaseGeneration() at the last sweep
     std::vector<clfd_rect> rects;
     std::vector<unsigned char> gray;
 };
@@ -93,7 +95,15 @@ CLODDetectObjectsResult clodDetectObjects(const IplImage* image, const CvHaarCla
     const clfd_cascade* cas = cvShimCascadeHandle(cascade);
     const int W = image->width, H = image->height;
 
-    DetKey key{cas, W, H, min_window_size.width, min_window_size.height, max_window_size.width, max_window_size.height,
+    // plans of cascades released since the last call go now (cvReleaseHaarClassifierCascade)
+    if (const unsigned long long gen = cvShimReleaseGeneration(); gen != s->release_generation) {
+        s->release_generation = gen;
+        for (auto it = s->detectors.begin(); it != s->detectors.end();) {
+            if (!cvShimCascadeIdAlive(it->first.cascade)) { clfd_detector_destroy(it->second); it = s->detectors.erase(it); }
+            else ++it;
+        }
+    }
+    DetKey key{clfd_cascade_id(cas), W, H, min_window_size.width, min_window_size.height, max_window_size.width, max_window_size.height,
                s->scale_factor, s->mode};
     clfd_detector*& det = s->detectors[key];
     if (!det) {
@@ -116,7 +126,7 @@ CLODDetectObjectsResult clodDetectObjects(const IplImage* image, const CvHaarCla
         r4[4 * i] = s->rects[i].x; r4[4 * i + 1] = s->rects[i].y; r4[4 * i + 2] = s->rects[i].w; r4[4 * i + 3] = s->rects[i].h;
     }
     int m = (int)n;
-    if (min_neighbors != 0)   // clod.cpp:1325-1326 -> filterResult; semantics of tempcv.cpp:1462-1472
+    if (min_neighbors != 0 && n > 0)   // clod.cpp:1325-1326 -> filterResult; semantics of tempcv.cpp:1462-1472
         CHECK(clfd_group_rectangles(r4.data(), &m, (int)MAX(min_neighbors, 1u), 0.2, weights.data()));
 
     CLODDetectObjectsResult result;

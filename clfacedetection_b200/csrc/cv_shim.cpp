@@ -24,6 +24,10 @@ namespace {
 std::mutex g_mu;
 std::map<int, clfd_context*> g_ctx;
 std::map<const CvHaarClassifierCascade*, clfd_cascade*> g_cascades;
+// detector plans of cvHaarDetectObjects, keyed by cascade ID (never reused; an address can be)
+typedef std::tuple<uint64_t, int, int, double, int, int, int, int, int> DetCacheKey;
+std::map<DetCacheKey, clfd_detector*> g_det_cache;
+uint64_t g_release_generation = 0;   // bumped by every cvReleaseHaarClassifierCascade
 
 bool file_exists(const std::string& p) { FILE* f = fopen(p.c_str(), "rb"); if (f) fclose(f); return f != nullptr; }
 std::string base_name(const std::string& p) { size_t i = p.find_last_of('/'); return i == std::string::npos ? p : p.substr(i + 1); }
@@ -99,6 +103,15 @@ clfd_cascade* cvShimCascadeHandle(const CvHaarClassifierCascade* c) {
     return h;
 }
 
+unsigned long long cvShimReleaseGeneration() { std::lock_guard<std::mutex> lock(g_mu); return g_release_generation; }
+
+bool cvShimCascadeIdAlive(unsigned long long id) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    for (auto& kv : g_cascades)
+        if (clfd_cascade_id(kv.second) == id) return true;
+    return false;
+}
+
 // ---- cascade I/O -----------------------------------------------------------------------
 void* cvLoad(const char* filename, CvMemStorage*, const char*, const char**) {
     const std::string path = resolve_data_path(filename);
@@ -156,7 +169,17 @@ void cvReleaseHaarClassifierCascade(CvHaarClassifierCascade** pc) {
     {
         std::lock_guard<std::mutex> lock(g_mu);
         auto it = g_cascades.find(c);
-        if (it != g_cascades.end()) { clfd_cascade_destroy(it->second); g_cascades.erase(it); }
+        if (it != g_cascades.end()) {
+            // plans cached for this cascade go with it (they would never be hit again: ids are unique)
+            const uint64_t id = clfd_cascade_id(it->second);
+            for (auto d = g_det_cache.begin(); d != g_det_cache.end();) {
+                if (std::get<0>(d->first) == id) { clfd_detector_destroy(d->second); d = g_det_cache.erase(d); }
+                else ++d;
+            }
+            clfd_cascade_destroy(it->second);
+            g_cascades.erase(it);
+            g_release_generation++;
+        }
     }
     for (int i = 0; i < c->count; i++) {
         for (int j = 0; j < c->stage_classifier[i].count; j++) free(c->stage_classifier[i].classifier[j].haar_feature);
@@ -302,9 +325,13 @@ CvSeq* cvHaarDetectObjects(const CvArr* image, CvHaarClassifierCascade* cascade,
     const clfd_cascade* cas = cvShimCascadeHandle(cascade);
     // detector plans are cached per (cascade, shape, parameters): OpenCV keeps its hidden cascade too
     const int mode = (flags & CV_HAAR_SCALE_IMAGE) ? CLFD_MODE_SCALE_IMAGE : CLFD_MODE_SCALE_CASCADE;
-    typedef std::tuple<const clfd_cascade*, int, int, double, int, int, int, int, int> Key;
-    static std::map<Key, clfd_detector*> cache;
-    clfd_detector*& det = cache[Key(cas, s.w, s.h, scale_factor, min_size.width, min_size.height, max_size.width, max_size.height, mode)];
+    // one call at a time: the plan cache and the detector it hands out are shared state (the
+    // reference's API is single-threaded, SURVEY 8-b "Threading")
+    static std::mutex call_mu;
+    std::lock_guard<std::mutex> call_lock(call_mu);
+    std::unique_lock<std::mutex> lock(g_mu);
+    clfd_detector*& det = g_det_cache[DetCacheKey(clfd_cascade_id(cas), s.w, s.h, scale_factor, min_size.width, min_size.height,
+                                                  max_size.width, max_size.height, mode)];
     if (!det) {
         clfd_detector_config cfg;
         memset(&cfg, 0, sizeof cfg);
@@ -313,13 +340,15 @@ CvSeq* cvHaarDetectObjects(const CvArr* image, CvHaarClassifierCascade* cascade,
         cfg.mode = mode;
         CHECK(clfd_detector_create(ctx, &cas, 1, &cfg, &det));
     }
-    static std::vector<clfd_rect> rects(1 << 20);
+    clfd_detector* const d = det;
+    lock.unlock();
+    static std::vector<clfd_rect> rects(1 << 20);   // guarded by call_mu
     int64_t n = 0;
-    CHECK(clfd_detect_image(det, s.data, s.channels, s.step, rects.data(), (int64_t)rects.size(), &n));
+    CHECK(clfd_detect_image(d, s.data, s.channels, s.step, rects.data(), (int64_t)rects.size(), &n));
     std::vector<int32_t> r4((size_t)n * 4), w(n > 0 ? n : 1, 0);
     for (int64_t i = 0; i < n; i++) { r4[4 * i] = rects[i].x; r4[4 * i + 1] = rects[i].y; r4[4 * i + 2] = rects[i].w; r4[4 * i + 3] = rects[i].h; }
     int m = (int)n;
-    if (min_neighbors != 0) CHECK(clfd_group_rectangles(r4.data(), &m, MAX(min_neighbors, 1), 0.2, w.data()));   // tempcv.cpp:1462-1472
+    if (min_neighbors != 0 && n > 0) CHECK(clfd_group_rectangles(r4.data(), &m, MAX(min_neighbors, 1), 0.2, w.data()));   // tempcv.cpp:1462-1472
     CvSeq* seq = (CvSeq*)calloc(1, sizeof(CvSeq));
     seq->total = m; seq->elem_size = sizeof(CvAvgComp); seq->capacity = m;
     seq->data = (char*)calloc(m > 0 ? m : 1, sizeof(CvAvgComp));

@@ -45,8 +45,10 @@ inline int trunc_sat(float v) { return v > (float)INT_MAX ? INT_MAX : (int)v; }
 // weights: out = neighbour counts; with level_weights (the ROC variant, tempcv.cpp:255-258) weights carries
 // the reject levels in and the winning level of each kept class out
 static int group_impl(int32_t *rects_xywh, int *n_io, int group_threshold, double eps, int32_t *weights, double *level_weights) {
-    if (!rects_xywh || !n_io || *n_io < 0) { clfd::set_error("bad argument"); return CLFD_ERR_INVALID; }
+    if (!n_io || *n_io < 0) { clfd::set_error("bad argument"); return CLFD_ERR_INVALID; }
     const int n = *n_io;
+    if (n == 0) return 0;   // an empty list needs no storage (std::vector::data() of one is NULL); tempcv.cpp:147
+    if (!rects_xywh) { clfd::set_error("bad argument"); return CLFD_ERR_INVALID; }
     if (group_threshold <= 0 || n == 0) {  // tempcv.cpp:147-157
         if (weights) for (int i = 0; i < n; i++) weights[i] = 1;
         return 0;
@@ -96,7 +98,9 @@ static int group_impl(int32_t *rects_xywh, int *n_io, int group_threshold, doubl
             const int n2 = count[j];
             if (j == i || n2 <= group_threshold) continue;
             const R4 r2 = mean[j];
-            const int dx = trunc_sat((float)(r2.w * eps)), dy = trunc_sat((float)(r2.h * eps));
+            // the double product is truncated as is (tempcv.cpp:221-222)
+            const double vx = r2.w * eps, vy = r2.h * eps;
+            const int dx = vx > INT_MAX ? INT_MAX : (int)vx, dy = vy > INT_MAX ? INT_MAX : (int)vy;
             nested = r1.x >= r2.x - dx && r1.y >= r2.y - dy && r1.x + r1.w <= r2.x + r2.w + dx &&
                      r1.y + r1.h <= r2.y + r2.h + dy && (n2 > std::max(3, n1) || n1 < 3);
         }

@@ -58,6 +58,24 @@ int build_hidden(HostCascade &c) {
     if ((int)c.nodes.size() != N) FMT_FAIL("node count does not match the tree headers");
     if ((int)c.alpha.size() != N + T) FMT_FAIL("alpha count does not match the tree headers");
 
+    for (int i = 0; i < S; i++) {   // the reader's range checks (tempcv.cpp:2054-2071), before any use as an index
+        if (c.st_parent[i] < -1 || c.st_parent[i] >= S) FMT_FAIL("parent must be integer number. (stage %d)", i);
+        if (c.st_next[i] < -1 || c.st_next[i] >= S) FMT_FAIL("next must be integer number. (stage %d)", i);
+    }
+    // A stage tree is walked pass -> child, fail -> `next` of the nearest ancestor-or-self that has one
+    // (tempcv.cpp:839-860).  That terminates iff the links form a forest whose `next` chains run through
+    // later siblings; the reference's reader only range-checks them and its evaluator would spin on a
+    // cycle, so anything else is rejected here (no stock cascade is affected).
+    {
+        bool any_next = false;
+        for (int i = 0; i < S; i++) any_next |= c.st_next[i] != -1;
+        for (int i = 0; any_next && i < S; i++) {
+            if (c.st_parent[i] >= i) FMT_FAIL("stage tree is not a forest: parent of stage %d is %d", i, c.st_parent[i]);
+            const int nx = c.st_next[i];
+            if (nx != -1 && (nx <= i || c.st_parent[nx] != c.st_parent[i]))
+                FMT_FAIL("stage tree is not a forest: next of stage %d is %d", i, nx);
+        }
+    }
     if ((int)c.st_child.size() != S) {  // derive child links (tempcv.cpp:2076-2083)
         c.st_child.assign(S, -1);
         for (int i = 0; i < S; i++) {
@@ -88,7 +106,10 @@ int build_hidden(HostCascade &c) {
             for (int l = 0; l < cnt; l++) {
                 const int n = c.tr_first_node[t] + l;
                 const HostNode &nd = c.nodes[n];
-                if (nd.left >= cnt || nd.right >= cnt || -nd.left > cnt || -nd.right > cnt)
+                // a link to another node must lead FORWARD (tempcv.cpp:1981-1982, 2019-2020: "<= k" is
+                // rejected): a back edge would make the device tree walk loop forever
+                if (nd.left >= cnt || nd.right >= cnt || -nd.left > cnt || -nd.right > cnt ||
+                    (nd.left > 0 && nd.left <= l) || (nd.right > 0 && nd.right <= l))
                     FMT_FAIL("Tree structure is broken (stage %d, tree %d, node %d)", i, t - c.st_first_tree[i], l);
                 for (int k = 0; k < 3; k++) {  // :365-387
                     const int *r = nd.rect[k];

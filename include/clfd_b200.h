@@ -79,7 +79,12 @@ CLFD_API int clfd_cascade_from_arrays(int win_w, int win_h, int n_stages,
                                       const float *nd_thr, const int *nd_left,
                                       const int *nd_right, const float *alpha,
                                       clfd_cascade **out);
+/* Cascades are reference counted: detectors created from a cascade keep it alive, so it may be
+ * destroyed before them (cvReleaseHaarClassifierCascade, tempcv.cpp:1702-1719, has no such
+ * ordering rule either). */
 CLFD_API void clfd_cascade_destroy(clfd_cascade *c);
+/* Unique per process and never reused (an address can be): the key for caches of detector plans. */
+CLFD_API uint64_t clfd_cascade_id(const clfd_cascade *c);
 
 typedef struct clfd_cascade_info {
     int win_w, win_h;

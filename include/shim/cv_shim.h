@@ -192,6 +192,8 @@ struct clfd_context;
 struct clfd_cascade;
 clfd_context* cvShimContext(int device_index);                     /* lazily created, one per device */
 clfd_cascade* cvShimCascadeHandle(const CvHaarClassifierCascade* cascade);   /* packed once, cached */
+unsigned long long cvShimReleaseGeneration();            /* changes whenever a cascade is released */
+bool cvShimCascadeIdAlive(unsigned long long cascade_id); /* is a cascade with this clfd_cascade_id still loaded */
 }  /* extern "C++" */
 
 #endif

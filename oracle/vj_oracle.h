@@ -5,16 +5,18 @@
  * call this; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs use it, and only as the checker / CPU baseline.
  *
- * PARITY STATUS: the reference (GabrieleCocco/CLFaceDetection) ships no tests, golden
- * vectors or recorded outputs, and cannot be compiled here (needs OpenCV 2.4.2, the
- * author's un-vendored CLUtil library and an OpenCL runtime).  The cascade evaluator
- * below is therefore "parity unpinned" by the reference itself: it is a literal
- * restatement of tempcv.cpp (C expression types kept as written).  The pieces that
- * live in OpenCV (resize, integral, tilted integral, groupRectangles) ARE pinned,
- * bit-for-bit, against cv2 4.13 in tests/test_oracle_pins.py and by the committed
- * fixtures under tests/golden/.  The evaluator has a SOFT pin there too: at the unscaled
- * pyramid level its raw candidates equal those of OpenCV 4.13's own CascadeClassifier (an
- * independent implementation) for the upright cascades; see DESIGN.md section 2.
+ * PARITY STATUS: PINNED to the reference's own code.  oracle/build_ref.py compiles the reference's
+ * Haar functions themselves -- tempcv.cpp:40-1516 (AgroupRectangles, hidden-cascade builder,
+ * cvSetImagesForHaarClassifierCascade, cvRunHaarClassifierCascadeSum, both invokers,
+ * cvHaarDetectObjectsForROC) and 1702-2089 (icvReadHaarClassifier) -- from where they lie under
+ * /root/reference into oracle/_ref/libtempcv_ref.so, against a test-only stand-in for the OpenCV
+ * 2.4 names they touch (oracle/ref_shim/).  tests/test_oracle_vs_reference.py holds this file equal
+ * to that library: per-window return codes, stage sums, raw / grouped / reject-level rect lists
+ * of the whole drivers (image-pyramid and scale-cascade), hidden-cascade weights and geometry, the
+ * XML reader, on all 19 cascade files; tests/golden/reference_tempcv.npz keeps the library's
+ * outputs for machines without it.  What the reference leaves to the OpenCV 2.4.2 dylibs (resize,
+ * integral, tilted integral, colour conversion) is pinned bit-for-bit against cv2 4.13 in
+ * tests/test_oracle_pins.py and tests/golden/opencv_pins.npz.
  *
  * All file:line citations are relative to /root/reference/CLFaceDetection/.
  */

@@ -18,8 +18,13 @@ def cascade_path(name: str) -> str:
     return os.path.join(DATA, f"haarcascade_{name}.xml")
 
 
+# all 19 cascade files the reference ships; the first six are BASELINE.json's
 ALL_CASCADES = ["frontalface_alt", "frontalface_default", "frontalface_alt_tree", "eye", "profileface",
-                "fullbody", "frontalface_alt2", "eye_tree_eyeglasses", "mcs_nose"]
+                "fullbody", "frontalface_alt2", "eye_tree_eyeglasses", "mcs_nose",
+                "lefteye_2splits", "righteye_2splits", "lowerbody", "upperbody", "mcs_eyepair_big",
+                "mcs_eyepair_small", "mcs_lefteye", "mcs_mouth", "mcs_righteye", "mcs_upperbody"]
+# the nine round-1 cascades (regression fixtures tests/golden/refsi_*.npz exist for these)
+CORE_CASCADES = ALL_CASCADES[:9]
 
 
 @pytest.fixture(scope="session")

@@ -186,3 +186,57 @@ def test_tile_kernel_register_budget():
     plain = {k: v for k, v in tiles.items() if "ELb0ELb0ELi" in k}
     assert plain and all(v <= 64 for v in plain.values()), plain
     assert all(v <= 80 for v in tiles.values()), tiles
+
+
+def test_grouping_an_empty_list_is_not_an_error():
+    """a frame without detections hands clfd_group_rectangles n = 0 and the NULL
+    data() of an empty std::vector; the reference returns match_count = 0 there (tempcv.cpp:147)."""
+    import ctypes as C
+    from clfacedetection_b200 import abi
+    L = abi.lib()
+    n = C.c_int(0)
+    assert L.clfd_group_rectangles(None, C.byref(n), 2, 0.2, None) == 0 and n.value == 0
+    n = C.c_int(3)
+    assert L.clfd_group_rectangles(None, C.byref(n), 2, 0.2, None) < 0      # rects missing for n > 0
+    n = C.c_int(-1)
+    assert L.clfd_group_rectangles(None, C.byref(n), 2, 0.2, None) < 0
+
+
+def test_cascade_ids_are_never_reused():
+    """plan caches are keyed by clfd_cascade_id, which -- unlike the address of a
+    released cascade -- is never handed out twice."""
+    import clfacedetection_b200 as clfd
+    from clfacedetection_b200 import abi
+    from conftest import cascade_path
+    seen = set()
+    for _ in range(6):
+        c = clfd.Cascade(cascade_path("lefteye_2splits"))
+        cid = int(abi.lib().clfd_cascade_id(c._h))
+        assert cid > 0 and cid not in seen
+        seen.add(cid)
+        del c
+
+
+def test_broken_tree_links_are_rejected():
+    """through clfd_cascade_from_arrays an out-of-range parent, a backward node link or
+    a stage-tree cycle must fail cleanly (the XML reader rejects the first two itself)."""
+    import copy
+    import clfacedetection_b200 as clfd
+    import oracle
+    from conftest import cascade_path
+    flat = oracle.load_cascade_xml(cascade_path("frontalface_alt2"))   # 2-node trees
+    bad = copy.deepcopy(flat)
+    bad.st_parent = bad.st_parent.copy(); bad.st_parent[3] = 999
+    with pytest.raises(clfd.ClfdError, match="parent must be integer number"):
+        clfd.Cascade(flat=bad)
+    bad = copy.deepcopy(flat)
+    n = int(np.flatnonzero(flat.nd_left > 0)[0]) if (flat.nd_left > 0).any() else int(np.flatnonzero(flat.nd_right > 0)[0])
+    bad.nd_left = bad.nd_left.copy(); bad.nd_left[n + 1] = 1   # node 1 of the tree links back to itself
+    with pytest.raises(clfd.ClfdError, match="Tree structure is broken"):
+        clfd.Cascade(flat=bad)
+    tree = oracle.load_cascade_xml(cascade_path("frontalface_alt_tree"))
+    bad = copy.deepcopy(tree)
+    bad.st_next = bad.st_next.copy(); bad.st_next[6] = 5       # 5 -> 6 -> 5
+    with pytest.raises(clfd.ClfdError, match="not a forest"):
+        clfd.Cascade(flat=bad)
+    clfd.Cascade(flat=tree)   # the stock stage tree passes

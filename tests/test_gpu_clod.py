@@ -67,6 +67,29 @@ def test_cfg4_profileface_fullbody_sf11(gpu_ctx):
     _compare(gpu_ctx, ["profileface", "fullbody"], frames, 1.1)
 
 
+def test_cfg3_full_size_3840x2160_alt_tree_and_eye(gpu_ctx):
+    """BASELINE config 3 at its real size: one 4K frame, 26 levels, 11 094 920 windows per cascade,
+    the widest integral-row kernels (k_integral_rows<512/1024>)"""
+    frames = np.stack([octave_frame(3840, 2160, 3)])
+    _compare(gpu_ctx, ["frontalface_alt_tree", "eye"], frames, 1.2)
+
+
+def test_cfg4_full_size_1080p_sf11_profileface_fullbody(gpu_ctx):
+    """BASELINE config 4 at its real size: 1080p, scale 1.1 (42 / 39 levels), tilted integral"""
+    frames = np.stack([octave_frame(1920, 1080, 4)])
+    _compare(gpu_ctx, ["profileface", "fullbody"], frames, 1.1)
+
+
+@pytest.mark.parametrize("name", ["lefteye_2splits", "righteye_2splits", "lowerbody", "upperbody", "mcs_eyepair_big",
+                                  "mcs_eyepair_small", "mcs_lefteye", "mcs_mouth", "mcs_righteye", "mcs_upperbody"])
+def test_the_other_ten_cascade_files(gpu_ctx, name):
+    """the 10 reference cascades outside BASELINE's configs: generic row step (19x23, 22x18, 18x12 ...
+    windows), wide / flat tiles (45x11, 22x5), 2-split trees with tilted features, the largest stages
+    (415 trees), the lenient-XML headers"""
+    frames = np.stack([octave_frame(480, 360, 5), uniform_frame(480, 360, 5)])
+    _compare(gpu_ctx, [name], frames, 1.2)
+
+
 @pytest.mark.parametrize("name", ["frontalface_alt2", "eye_tree_eyeglasses", "mcs_nose"])
 def test_tree_nodes_tilted_and_lenient_xml(gpu_ctx, name):
     frames = np.stack([octave_frame(480, 360, 5), uniform_frame(480, 360, 5)])

@@ -72,3 +72,68 @@ def test_reference_main_runs_unchanged():
     assert out.returncode == 0, out.stderr
     for label in ("OpenCV:", "OpenCL (optimized):", "OpenCL (per-stage):"):
         assert label in out.stdout
+
+
+def test_blank_frame_with_grouping_returns_no_matches(tmp_path):
+    """ADVICE r1 (high): zero raw detections + min_neighbors != 0 used to abort in the grouping call;
+    the reference returns match_count = 0 (the most common real input: a frame without a face)."""
+    pgm = str(tmp_path / "blank.pgm")
+    _write_pgm(pgm, np.full((240, 320), 128, np.uint8))
+    out = subprocess.run([os.path.join(ROOT, "examples", "clod_demo"), cascade_path("frontalface_alt"), pgm, "1.2", "2"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip().splitlines()[1] == "matches 0"
+
+
+def test_release_and_reload_never_reuses_a_stale_plan(tmp_path):
+    """load A, detect, release A, load B, detect on the same frame shape -- B's
+    malloc'd cascade often lands on A's address; the cached plan must not be A's.  Both entry points
+    (clodDetectObjects, cvHaarDetectObjects), two rounds over three cascades."""
+    from clfacedetection_b200.frames import octave_frame
+    img = octave_frame(480, 360, 5)
+    pgm = str(tmp_path / "frame.pgm")
+    _write_pgm(pgm, img)
+    names = ["eye", "mcs_lefteye", "frontalface_alt2"]
+    out = subprocess.run([os.path.join(ROOT, "examples", "clod_lifecycle"), pgm, "1.2", "2"] + [cascade_path(n) for n in names],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    want = {}
+    for n in names:
+        raw, _, _, _, _ = oracle_cascade(n).detect(img, 1.2)
+        g, w = oracle.group_rectangles(raw, 2)
+        want[cascade_path(n)] = [[int(v) for v in r] + [float(x)] for r, x in zip(g, w)]
+    assert sum(len(v) for v in want.values()) > 0
+    i = 0
+    blocks = 0
+    while i < len(lines):
+        tag, rnd, path, n = lines[i].split()
+        got = [[float(v) for v in ln.split()] for ln in lines[i + 1:i + 1 + int(n)]]
+        assert got == [[float(v) for v in r] for r in want[path]], (tag, rnd, path)
+        i += 1 + int(n)
+        blocks += 1
+    assert blocks == 2 * 2 * len(names)
+
+
+def test_bgr_to_gray_colour_pixels(gpu_ctx):
+    """random COLOUR pixels (a gray image replicated to B, G, R converts to itself
+    under any coefficient permutation) against OpenCV's fixed point (B*1868 + G*9617 + R*4899 + 8192) >> 14
+    -- what cvCvtColor(BGR2GRAY) at tempcv.cpp:1250 / clif.cpp:249,328 computes -- and, where cv2 is
+    installed, against cv2.cvtColor itself; 3 and 4 channels, padded rows."""
+    rng = np.random.default_rng(11)
+    for (h, w, c) in ((37, 53, 3), (240, 321, 3), (64, 100, 4), (1, 1, 3), (1080, 1920, 3)):
+        img = rng.integers(0, 256, size=(h, w + 3, c), dtype=np.uint8)[:, :w]   # row stride > w*c
+        exp = ((img[..., 0].astype(np.int64) * 1868 + img[..., 1].astype(np.int64) * 9617 +
+                img[..., 2].astype(np.int64) * 4899 + 8192) >> 14).astype(np.uint8)
+        got = gpu_ctx.bgr_to_gray(np.ascontiguousarray(img))
+        assert np.array_equal(got, exp), (h, w, c)
+        try:
+            import cv2
+        except ImportError:
+            continue
+        ref = cv2.cvtColor(np.ascontiguousarray(img), cv2.COLOR_BGR2GRAY if c == 3 else cv2.COLOR_BGRA2GRAY)
+        assert np.array_equal(got, ref), (h, w, c)
+    # pure primaries pin which channel gets which coefficient
+    prim = np.zeros((1, 3, 3), np.uint8)
+    prim[0, 0, 0] = prim[0, 1, 1] = prim[0, 2, 2] = 255
+    assert gpu_ctx.bgr_to_gray(prim).tolist() == [[29, 150, 76]]

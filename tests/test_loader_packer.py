@@ -22,6 +22,16 @@ CENSUS = {
     "fullbody": (14, 28, 30, 1464, 1464, 107, 1, 201, 227, 0),
     "mcs_nose": (18, 15, 20, 3365, 3365, 377, 1, 990, 557, 0),
     "profileface": (20, 20, 26, 2609, 2609, 195, 1, 0, 415, 0),
+    "lefteye_2splits": (20, 20, 20, 366, 732, 33, 2, 185, 58, 0),
+    "righteye_2splits": (20, 20, 20, 368, 736, 34, 2, 186, 47, 0),
+    "lowerbody": (19, 23, 27, 1221, 1221, 89, 1, 110, 128, 0),
+    "upperbody": (22, 18, 30, 2423, 2423, 152, 1, 474, 368, 0),
+    "mcs_eyepair_big": (45, 11, 19, 748, 748, 85, 1, 135, 127, 0),
+    "mcs_eyepair_small": (22, 5, 17, 860, 860, 133, 1, 76, 177, 0),
+    "mcs_lefteye": (18, 12, 14, 1648, 1648, 279, 1, 346, 273, 0),
+    "mcs_mouth": (25, 15, 17, 1515, 1515, 218, 1, 223, 295, 0),
+    "mcs_righteye": (18, 12, 18, 2942, 2942, 415, 1, 672, 433, 0),
+    "mcs_upperbody": (22, 20, 19, 3224, 3224, 334, 1, 657, 495, 0),
 }
 
 

@@ -9,7 +9,7 @@ import pytest
 
 import oracle
 from clfacedetection_b200.frames import octave_frame, uniform_frame
-from conftest import ALL_CASCADES, cascade_path, oracle_cascade
+from conftest import CORE_CASCADES, cascade_path, oracle_cascade
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 cv2 = pytest.importorskip("cv2")
@@ -81,7 +81,7 @@ def test_golden_opencv_pins():
     assert np.array_equal(w, g["group_w"]) and np.abs(a - g["group_out"]).max(initial=0) <= 1
 
 
-@pytest.mark.parametrize("name", ALL_CASCADES)
+@pytest.mark.parametrize("name", CORE_CASCADES)
 def test_golden_refsi_detection(name):
     g = np.load(os.path.join(GOLD, f"refsi_{name}.npz"))
     cas = oracle_cascade(name)
