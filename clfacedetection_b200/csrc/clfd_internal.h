@@ -122,6 +122,8 @@ struct DenseParams {
     int tile_h;         // window rows per tile: kTileH; kTileHSmall where two tiles (tilted) would leave one CTA per SM;
                         // 24 for plain stump cascades on ystep-2 levels
     int eq_x, eq_y, eq_w, eq_h;   // the variance rectangle inside the window (tempcv.cpp:614-616): (1, 1, w-2, h-2) at scale 1
+    int pool_min;       // stages after the fixed ones run POOLED (rows drawn from the whole tile's survivors, re-sorted by
+                        // bank class before every stage) while the tile has more than this many windows; 0: never
     double inv_area;
     const TailStump *tail;   // device, layout of this blob's ystep (patched in by the detector)
     const struct DenseStage *stage_g;   // device: stage table in execution order (stage trees only)

@@ -4,6 +4,7 @@
 // trip each (clod.cpp:1212-1321) and the CPU variants are replaced by ONE enqueue of the
 // whole pyramid + cascade pipeline (clfd_detect).  Grouping stays on the host
 // (clfd_group_rectangles = AgroupRectangles semantics), as the north star asks.
+#include <algorithm>
 #include <cstdio>
 #include <map>
 #include <tuple>
@@ -121,6 +122,12 @@ CLODDetectObjectsResult clodDetectObjects(const IplImage* image, const CvHaarCla
     CHECK(clfd_detect_image(det, (const uint8_t*)image->imageData, image->nChannels, image->widthStep, s->rects.data(),
                             (int64_t)s->rects.size(), &n));
 
+    // the device appends accepted windows in no particular order; the reference emits them scale by
+    // scale in raster order (tempcv.cpp:1079-1102), and AgroupRectangles numbers its classes by first
+    // appearance -- so sort into that order to make the (grouped) result deterministic and the reference's
+    std::sort(s->rects.begin(), s->rects.begin() + n, [](const clfd_rect& a, const clfd_rect& b) {
+        return std::tie(a.w, a.h, a.y, a.x) < std::tie(b.w, b.h, b.y, b.x);
+    });
     std::vector<int32_t> r4((size_t)n * 4), weights(n > 0 ? n : 1, 0);
     for (int64_t i = 0; i < n; i++) {
         r4[4 * i] = s->rects[i].x; r4[4 * i + 1] = s->rects[i].y; r4[4 * i + 2] = s->rects[i].w; r4[4 * i + 3] = s->rects[i].h;

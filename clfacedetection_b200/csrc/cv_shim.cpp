@@ -2,6 +2,7 @@
 // entry points the reference's main.cpp / clif / clod use, on top of the clfd C ABI.
 // Pixel work on the hot path (resize, BGR->gray, integral, Haar detection) runs on the GPU;
 // the rest is demo plumbing.  See SURVEY.md 8-b "shim surface".
+#include <algorithm>
 #include <cstdio>
 #include <map>
 #include <mutex>
@@ -345,6 +346,10 @@ CvSeq* cvHaarDetectObjects(const CvArr* image, CvHaarClassifierCascade* cascade,
     static std::vector<clfd_rect> rects(1 << 20);   // guarded by call_mu
     int64_t n = 0;
     CHECK(clfd_detect_image(d, s.data, s.channels, s.step, rects.data(), (int64_t)rects.size(), &n));
+    // the reference's output order: scale by scale, raster (tempcv.cpp:1079-1102, 1146-1160)
+    std::sort(rects.begin(), rects.begin() + n, [](const clfd_rect& a, const clfd_rect& b) {
+        return std::tie(a.w, a.h, a.y, a.x) < std::tie(b.w, b.h, b.y, b.x);
+    });
     std::vector<int32_t> r4((size_t)n * 4), w(n > 0 ? n : 1, 0);
     for (int64_t i = 0; i < n; i++) { r4[4 * i] = rects[i].x; r4[4 * i + 1] = rects[i].y; r4[4 * i + 2] = rects[i].w; r4[4 * i + 3] = rects[i].h; }
     int m = (int)n;

@@ -460,6 +460,12 @@ static void pack_dense_one(const HostCascade &c, int ystep, DenseParams &P, std:
         }
         tail.swap(blocked);
     }
+    // pooled stages (kernels_clod.cu): rows drawn from the whole tile's survivors while it holds more than pool_min
+    // windows.  OFF by default: on B200 they cut the shared-memory wavefronts by 17 % and the instructions by 5 %
+    // (ncu, profiles/r2_pooled_*.csv) but the block barrier per stage costs as much again (21.6 -> 22.0 ms per 64
+    // frames at pool_min = 64); kept as a tested A/B hook (CLFD_POOL_MIN=n, best with CLFD_N_FIXED=2)
+    P.pool_min = 0;
+    if (const char *e = getenv("CLFD_POOL_MIN")) P.pool_min = std::max(0, atoi(e));
     // stages run in fixed geometry before the first compaction (tunable for experiments)
     int nf = 3;
     if (const char *e = getenv("CLFD_N_FIXED")) nf = atoi(e);

@@ -138,11 +138,11 @@ __device__ __forceinline__ int lds32i(uint32_t addr) {
 }
 
 struct DenseSmemPlan {
-    size_t tile, sgf, list, ctl, bar, act, tgt, total;
+    size_t tile, sgf, list, pool, ctl, bar, act, tgt, total;
 };
-// control block (ints): [0..31] survivors of phase 1 per bank class, [32..63] their exclusive prefix,
-// [64] total
-constexpr int kCtlCount = 0, kCtlPrefix = 32, kCtlAlive = 64, kCtlInts = 72;
+// control block (ints): three sets of 32 per-class window counters (this stage's class lists, the next
+// stage's, and the set being cleared for the stage after)
+constexpr int kCtlCount = 0, kCtlCountB = 32, kCtlCountC = 64, kCtlInts = 96;
 __host__ __device__ inline DenseSmemPlan dense_smem_plan(const DenseParams &P) {
     DenseSmemPlan p;
     const size_t rows = (size_t)(P.tile_h - 1) * P.ystep + P.win_h + 1, windows = (size_t)kTileW * P.tile_h;
@@ -150,7 +150,8 @@ __host__ __device__ inline DenseSmemPlan dense_smem_plan(const DenseParams &P) {
     p.sgf = (rows * P.tile_stride * 4 + 127) & ~(size_t)127;
     if (P.tilted_tile) p.sgf *= 2;   // second tile: the tilted integral (same geometry)
     p.list = p.sgf + windows * sizeof(float);
-    p.ctl = p.list + windows * sizeof(uint16_t);
+    p.pool = p.list + windows * sizeof(uint16_t);    // second class-list / per-warp-list buffer
+    p.ctl = p.pool + windows * sizeof(uint16_t);
     p.bar = p.ctl + kCtlInts * sizeof(int);
     p.act = p.tgt = p.total = p.bar + 16;
     if (P.exec_stages > P.tail_stages) {   // stage tree: the windows of the current stage, every window's target position
@@ -518,51 +519,128 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
         }
     }
 
-    // ---- phase-1 survivors -> per-warp lists, dealt by bank class ----
+    // ---- phase-1 survivors -> class lists -> (pooled stages) -> per-warp lists ----
     // A window's bank class is (wx + 8*wy) mod 32 (the skew of the tile rows): two windows of a
-    // list row conflict on every corner load iff their classes are equal.  Counting-sort the
-    // survivors by class (rank i), deal them round-robin to the warps (warp i % 4, position
-    // p = i / 4) and, inside a warp, column-major over its R rows (row p % R): windows of one
-    // class end up in different warps / rows, which cuts the conflict degree of the first
-    // compacted stages from ~2.6 to ~2.1 wavefronts per load (profiles/).
-    uint32_t slots_lo = 0, slots_hi = 0;   // this thread's 8 bucket slots, one byte each
+    // row conflict on every corner load iff their classes are equal, and a load costs as many
+    // wavefronts as the row's most frequent class has members.
+    //   * CLASS LISTS: cls[c][0 .. h_c) holds the tile's live windows of class c; a window never
+    //     changes its class, so a survivor is appended to the next stage's list of its class with one
+    //     shared-memory atomic, and one block barrier per stage completes the lists.
+    //   * POOLED stages (optional, P.pool_min > 0, while the tile has more than pool_min windows): the
+    //     class-sorted windows (rank i = windows of lower classes + position in the class) are dealt
+    //     column-major over R rows (row i % R, lane i / R) that belong to the TILE; the eight warps take
+    //     ceil(R / 8) consecutive rows each.  With the whole tile to draw from the rows are full and R
+    //     can be chosen against the class histogram.  Measured (ncu, profiles/): -17 % shared-memory
+    //     wavefronts, -5 % instructions, but +2 % time -- the barrier per stage costs what the rows
+    //     save -- so it is off by default (CLFD_POOL_MIN, haar_pack.cpp).
+    //   * below pool_min windows per tile (or with pool_min = 0) the windows are dealt to the warps
+    //     in class-sorted order (rank i: warp i % 8, position p = i / 8, column-major over the warp's
+    //     R rows: row p % R) -- windows of one class end up in different warps / rows -- and every
+    //     warp finishes its share on its own, without block barriers.
+    constexpr int kClassCap = kTileWindows / 32;       // windows per class in a tile
+    constexpr int kSeg = kTileWindows / kDenseWarps;   // list segment of a warp (its share is at most this)
+    uint16_t *cl_in = list, *cl_out = reinterpret_cast<uint16_t *>(smem_raw + plan.pool);
+    int *cnt_in = ctl + kCtlCount, *cnt_out = ctl + kCtlCountB, *cnt_zero = ctl + kCtlCountC;
+    {
+        // the (up to 8) windows of a thread share one class: wy advances by 4 rows = 32 in 8*wy
+        const int na = __popc(alive);
+        if (na) {
+            const int cq = (wx + 8 * wy0) & 31;
+            int at = atomicAdd(cnt_in + cq, na);
 #pragma unroll
-    for (int k = 0; k < kDenseSlots; k++) {
-        if ((alive >> k) & 1u) {
-            const int wid = (wy0 + k * kRowsPerSlot) * kTileW + wx;
-            const uint32_t sl = (uint32_t)atomicAdd(ctl + kCtlCount + ((wid + 8 * (wid / kTileW)) & 31), 1);
-            if (k < 4) slots_lo |= sl << (8 * k); else slots_hi |= sl << (8 * (k - 4));
+            for (int k = 0; k < kDenseSlots; k++)
+                if ((alive >> k) & 1u) cl_in[cq * kClassCap + at++] = (uint16_t)((wy0 + k * kRowsPerSlot) * kTileW + wx);
         }
     }
     __syncthreads();
-    if (warp == 0) {
-        const int cnt = ctl[kCtlCount + lane];
-        int incl = cnt;
+    int n_alive;
+    for (;; s++) {
+        const int h = cnt_in[lane];
+        int incl = h, hmax = h;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += v;
+            hmax = max(hmax, __shfl_xor_sync(0xffffffffu, hmax, d));
         }
-        ctl[kCtlPrefix + lane] = incl - cnt;
-        if (lane == 31) ctl[kCtlAlive] = incl;
-    }
-    __syncthreads();
-    const int n_alive = ctl[kCtlAlive];
-    if (n_alive == 0) return;
-    constexpr int kSeg = kTileWindows / kDenseWarps;   // list segment of a warp (its share is at most this)
+        const int excl = incl - h, tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (tot == 0) return;
+        n_alive = tot;
+        if (!(P.pool_min > 0 && tot > P.pool_min && s < P.tail_stages)) {
+            // deal the class lists to the warps: rank i = (windows of lower classes) + position in the class
+            for (int r = warp; r < h; r += kDenseWarps) {
+                const int i = excl + r;
+                const int w = i % kDenseWarps, p = i / kDenseWarps;
+                const int nw = (tot - w + kDenseWarps - 1) / kDenseWarps, Rw = (nw + 31) >> 5;
+                const int col = p / Rw, row = p - col * Rw;
+                cl_out[w * kSeg + row * 32 + col] = cl_in[lane * kClassCap + r];
+            }
+            __syncthreads();
+            break;
+        }
+        // ---- one pooled stage: the class-sorted windows (rank i) dealt column-major over R rows (row i % R, lane
+        //      i / R), R from the class histogram: ceil(n / 32) rows cost the fewest instructions, R = the largest
+        //      class makes every row conflict free; minimise rows * 1.8 + rows that keep a duplicate ----
+        int R = (tot + 31) >> 5;
+        {
+            int best = 0x7fffffff;
+            for (int r = R; r <= hmax; r++) {
+                int e = max(h - r, 0);
 #pragma unroll
-    for (int k = 0; k < kDenseSlots; k++) {
-        if ((alive >> k) & 1u) {
-            const int wid = (wy0 + k * kRowsPerSlot) * kTileW + wx;
-            const uint32_t sl = ((k < 4 ? slots_lo >> (8 * k) : slots_hi >> (8 * (k - 4))) & 255u);
-            const int i = ctl[kCtlPrefix + ((wid + 8 * (wid / kTileW)) & 31)] + (int)sl;
-            const int w = i % kDenseWarps, p = i / kDenseWarps;
-            const int nw = (n_alive - w + kDenseWarps - 1) / kDenseWarps, R = (nw + 31) >> 5;
-            const int col = p / R, row = p - col * R;
-            list[w * kSeg + row * 32 + col] = (uint16_t)wid;
+                for (int d = 16; d > 0; d >>= 1) e += __shfl_xor_sync(0xffffffffu, e, d);
+                const int cost = r * 9 + 5 * min(r, e);
+                if (cost < best) { best = cost; R = r; }
+            }
         }
+        const int q = (R + kDenseWarps - 1) / kDenseWarps;
+        const int r_begin = warp * q, r_end = min(R, r_begin + q);
+        if (tid < 32) cnt_zero[tid] = 0;   // last read before the previous barrier, next written after the next one
+        const float sthr = P.stage[s].thr, seps = P.force_exact ? inf : P.stage[s].sum_eps;
+        auto fetch = [&](int r, bool &valid) -> int {   // the window of rank r + lane * R
+            const int i = r + lane * R;
+            valid = i < tot;
+            int cc = 0;   // its class: the last one with excl <= i
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int e_t = __shfl_sync(0xffffffffu, excl, (cc + step) & 31);
+                if (e_t <= i) cc += step;   // (cc + step <= 31 always: steps 16, 8, 4, 2, 1 from 0)
+            }
+            const int e_c = __shfl_sync(0xffffffffu, excl, cc);
+            return valid ? (int)cl_in[cc * kClassCap + (i - e_c)] : 0;   // (an idle lane computes on window 0: any valid tile address)
+        };
+        auto keep_pool = [&](bool valid, int wid, float Ssum, bool near) {
+            const bool pass = valid && stage_verdict<NODES>(P, c, P.stage[s], sthr, seps, wid, Ssum, near);
+            if (pass) {
+                const int cq = (wid + 8 * (wid / kTileW)) & 31;
+                cl_out[cq * kClassCap + atomicAdd(cnt_out + cq, 1)] = (uint16_t)wid;
+            }
+            if (valid && !pass && c.codes) dense_write_code(c, wid, s * c.code_mul);
+        };
+        for (int r = r_begin; r < r_end; r += 2) {
+            bool v0, v1 = false;
+            const int wid0 = fetch(r, v0);
+            if (r + 1 < r_end) {
+                const int wid1 = fetch(r + 1, v1);
+                const uint32_t base[2] = {dense_base(c, wid0), dense_base(c, wid1)};
+                const float sg[2] = {sgf[wid0], sgf[wid1]};
+                float Ssum[2] = {0.f, 0.f};
+                bool near[2] = {false, false};
+                stage_filter<2, false, 0, NODES>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near);
+                keep_pool(v0, wid0, Ssum[0], near[0]);
+                keep_pool(v1, wid1, Ssum[1], near[1]);
+            } else {
+                const uint32_t base[1] = {dense_base(c, wid0)};
+                const float sg[1] = {sgf[wid0]};
+                float Ssum[1] = {0.f};
+                bool near[1] = {false};
+                stage_filter<1, false, 0, NODES>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near);
+                keep_pool(v0, wid0, Ssum[0], near[0]);
+            }
+        }
+        __syncthreads();   // the next stage's class lists are complete
+        uint16_t *tl = cl_in; cl_in = cl_out; cl_out = tl;
+        int *tc = cnt_in; cnt_in = cnt_out; cnt_out = cnt_zero; cnt_zero = tc;
     }
-    __syncthreads();
 
     // ---- phase 2: every warp takes its share of the survivors through all remaining stages
     //      on its own: no block barrier, warp-local in-place re-compaction after every stage.
@@ -572,7 +650,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     //      evaluates stumps grp, grp + G, ... for window `slot`, and the G partial sums meet
     //      through xor-shuffles -- with one window left the warp does 32 stumps per pass. ----
     int n = (n_alive - warp + kDenseWarps - 1) / kDenseWarps;
-    uint16_t *cur = list + warp * kSeg;
+    uint16_t *cur = cl_out + warp * kSeg;
     bool dealt = true;   // first compacted stage: balanced rows (row r holds (n - r + R - 1) / R entries)
     for (; s < P.tail_stages && n > 0; s++) {
         const float sthr = P.stage[s].thr, seps = P.force_exact ? inf : P.stage[s].sum_eps;

@@ -118,8 +118,8 @@ def test_release_and_reload_never_reuses_a_stale_plan(tmp_path):
 def test_bgr_to_gray_colour_pixels(gpu_ctx):
     """random COLOUR pixels (a gray image replicated to B, G, R converts to itself
     under any coefficient permutation) against OpenCV's fixed point (B*1868 + G*9617 + R*4899 + 8192) >> 14
-    -- what cvCvtColor(BGR2GRAY) at tempcv.cpp:1250 / clif.cpp:249,328 computes -- and, where cv2 is
-    installed, against cv2.cvtColor itself; 3 and 4 channels, padded rows."""
+    -- what OpenCV 2.4's cvCvtColor(BGR2GRAY) at tempcv.cpp:1250 / clif.cpp:249,328 computes -- and, where cv2
+    is installed, within one grey level of cv2 4.x's cvtColor; 3 and 4 channels."""
     rng = np.random.default_rng(11)
     for (h, w, c) in ((37, 53, 3), (240, 321, 3), (64, 100, 4), (1, 1, 3), (1080, 1920, 3)):
         img = rng.integers(0, 256, size=(h, w + 3, c), dtype=np.uint8)[:, :w]   # row stride > w*c
@@ -131,8 +131,10 @@ def test_bgr_to_gray_colour_pixels(gpu_ctx):
             import cv2
         except ImportError:
             continue
+        # OpenCV 4.x moved to 15-bit coefficients (3735, 19235, 9798): same weights, one more bit, so it
+        # may differ from the 2.4-era 14-bit formula by one grey level -- a sanity check, not the pin
         ref = cv2.cvtColor(np.ascontiguousarray(img), cv2.COLOR_BGR2GRAY if c == 3 else cv2.COLOR_BGRA2GRAY)
-        assert np.array_equal(got, ref), (h, w, c)
+        assert np.abs(got.astype(np.int32) - ref.astype(np.int32)).max() <= 1, (h, w, c)
     # pure primaries pin which channel gets which coefficient
     prim = np.zeros((1, 3, 3), np.uint8)
     prim[0, 0, 0] = prim[0, 1, 1] = prim[0, 2, 2] = 255
