@@ -322,7 +322,7 @@ def main():
         fps = frames_total / (ms / 1e3)
         peak, peak_src = measured_peak_gbs()
         alg = {"resize_colsum": stats["bytes_resize"] * B, "integral_rows": stats["bytes_integral"] * B,
-               "cascade_tiles": stats["bytes_cascade"] * B}
+               "tilted": stats["bytes_tilted"] * B, "cascade_tiles": stats["bytes_cascade"] * B}
         kernels = {}
         ncu = ncu_traffic()
         for i, nm in enumerate(KERNEL_NAMES):

@@ -50,7 +50,7 @@ class Level(C.Structure):
 class RunStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "windows", "rects", "deep_windows", "kernel_launches", "pyramid_pixels",
-        "bytes_resize", "bytes_integral", "bytes_cascade")]
+        "bytes_resize", "bytes_integral", "bytes_cascade", "bytes_tilted")]
 
 
 def exported_symbols_in_header() -> list[str]:

@@ -86,7 +86,7 @@ struct PyramidPlan {
     std::vector<PyrLevel> levels;
     size_t pyr_frame_stride = 0, sum_frame_stride = 0, col_frame_stride = 0, col_plane_stride = 0;
     int max_level_w = 0;
-    int64_t pyramid_pixels = 0, bytes_resize = 0, bytes_integral = 0;
+    int64_t pyramid_pixels = 0, bytes_resize = 0, bytes_integral = 0, bytes_tilted = 0;
     DevBuf<uint8_t> pyr;
     DevBuf<int32_t> sum, tilted;
     DevBuf<unsigned long long> sq;
@@ -94,7 +94,8 @@ struct PyramidPlan {
     DevBuf<PyrLevel> d_levels;
     DevBuf<int> xofs, yofs;
     DevBuf<short2> xalpha, ybeta;
-    DevBuf<int4> resize_items, colscan_items, tilted_items, integral_items[6];
+    DevBuf<int4> resize_items, colscan_items, integral_items[6], tilt_tile_items, tilt_diag_items, tilt_tc_items;
+    DevBuf<int32_t> tcar;   // tilted integral: six carry planes per frame
 
     int build(int W_, int H_, const std::vector<std::pair<int, int>> &sizes, int batch, bool tilt, cudaStream_t s);
     void fill_args(PyramidArgs &a, const uint8_t *frames, size_t frame_stride, int row_stride, int n_frames) const;
@@ -109,9 +110,9 @@ int PyramidPlan::build(int W_, int H_, const std::vector<std::pair<int, int>> &s
     levels.clear();
     std::vector<int> h_xofs, h_yofs;
     std::vector<short2> h_xalpha, h_ybeta;
-    std::vector<int4> h_resize, h_colscan, h_tilted, h_integral[6];
+    std::vector<int4> h_resize, h_colscan, h_integral[6], h_tilt_tile, h_tilt_diag, h_tilt_tc;
     size_t pyr_off = 0, sum_off = 0, col_off = 0;
-    max_level_w = 0; pyramid_pixels = 0; bytes_resize = 0; bytes_integral = 0;
+    max_level_w = 0; pyramid_pixels = 0; bytes_resize = 0; bytes_integral = 0; bytes_tilted = 0;
     for (size_t li = 0; li < sizes.size(); li++) {
         const int w = sizes[li].first, h = sizes[li].second;
         if (w <= 0 || h <= 0) INVALID("pyramid level %zu has empty size %dx%d", li, w, h);
@@ -130,7 +131,8 @@ int PyramidPlan::build(int W_, int H_, const std::vector<std::pair<int, int>> &s
         pyramid_pixels += (int64_t)w * h;
         // algorithmic bytes: resize min(W*H, 4*w*h) + w*h ; integral w*h + (w+1)(h+1)(4+8+4T)
         bytes_resize += std::min<int64_t>((int64_t)W * H, 4ll * w * h) + (int64_t)w * h;
-        bytes_integral += (int64_t)w * h + (int64_t)(w + 1) * (h + 1) * (4 + 8 + (tilt ? 4 : 0));
+        bytes_integral += (int64_t)w * h + (int64_t)(w + 1) * (h + 1) * (4 + 8);
+        if (tilt) bytes_tilted += (int64_t)w * h + (int64_t)(w + 1) * (h + 1) * 4;   // the tilted kernels read the level again
 
         // cv::resize INTER_LINEAR coefficient tables (OpenCV imgproc)
         const double scale_x = 1. / ((double)w / W), scale_y = 1. / ((double)h / H);
@@ -158,7 +160,13 @@ int PyramidPlan::build(int W_, int H_, const std::vector<std::pair<int, int>> &s
         while (cls < 6 && (32 << cls) * 8 < L.sum_pitch) cls++;
         if (cls >= 6) INVALID("level width %d exceeds the supported maximum of 8191 pixels", w);
         for (int rb = 0; rb < L.nrb; rb++) h_integral[cls].push_back(make_int4((int)li, rb, 0, 0));
-        h_tilted.push_back(make_int4((int)li, 0, 0, 0));
+        if (tilt) {
+            const int interior = tilt_tile_interior();
+            for (int rb = 0; rb < L.nrb; rb++)
+                for (int t = 0; t * interior < w + 1; t++) h_tilt_tile.push_back(make_int4((int)li, rb, t, 0));
+            for (int c = 0; c * 256 <= w + (L.nrb - 1) * kRowBlock; c++) h_tilt_diag.push_back(make_int4((int)li, c, 0, 0));
+            for (int c = 0; c * 256 < L.sum_pitch; c++) h_tilt_tc.push_back(make_int4((int)li, c, 0, 0));
+        }
         levels.push_back(L);
     }
     pyr_frame_stride = round_up(pyr_off, 256);
@@ -171,12 +179,17 @@ int PyramidPlan::build(int W_, int H_, const std::vector<std::pair<int, int>> &s
     if ((rc = sum.alloc(sum_frame_stride * batch + 4096))) return rc;
     if ((rc = sq.alloc(sum_frame_stride * batch + 4096))) return rc;
     if (tilt && (rc = tilted.alloc(sum_frame_stride * batch + 4096))) return rc;
+    if (tilt && (rc = tcar.alloc(6 * col_plane_stride * batch + 64))) return rc;
     if ((rc = col.alloc(col_frame_stride * batch + 64))) return rc;
     if ((rc = d_levels.upload(levels, s))) return rc;
     if ((rc = xofs.upload(h_xofs, s)) || (rc = yofs.upload(h_yofs, s))) return rc;
     if ((rc = xalpha.upload(h_xalpha, s)) || (rc = ybeta.upload(h_ybeta, s))) return rc;
     if ((rc = resize_items.upload(h_resize, s)) || (rc = colscan_items.upload(h_colscan, s))) return rc;
-    if ((rc = tilted_items.upload(h_tilted, s))) return rc;
+    if (tilt && ((rc = tilt_tile_items.upload(h_tilt_tile, s)) || (rc = tilt_diag_items.upload(h_tilt_diag, s)) ||
+                 (rc = tilt_tc_items.upload(h_tilt_tc, s))))
+        return rc;
+    // carry entries beyond a level's last column are read as zeros and never written
+    if (tilt) CK(cudaMemsetAsync(tcar.p, 0, tcar.n * sizeof(int32_t), s));
     for (int k = 0; k < 6; k++)
         if ((rc = integral_items[k].upload(h_integral[k], s))) return rc;
     // the slack regions are read (never used) by TMA row copies: keep them defined
@@ -199,7 +212,10 @@ void PyramidPlan::fill_args(PyramidArgs &a, const uint8_t *frames, size_t frame_
     a.resize_items = resize_items.p; a.n_resize_items = (int)resize_items.n;
     a.colscan_items = colscan_items.p; a.n_colscan_items = (int)colscan_items.n;
     for (int k = 0; k < 6; k++) { a.integral_items[k] = integral_items[k].p; a.n_integral_items[k] = (int)integral_items[k].n; }
-    a.tilted_items = tilted_items.p; a.n_tilted_items = want_tilted ? (int)tilted_items.n : 0;
+    a.tcar = tcar.p; a.tcar_frame_stride = 6 * col_plane_stride;
+    a.tilt_tile_items = tilt_tile_items.p; a.n_tilt_tile_items = want_tilted ? (int)tilt_tile_items.n : 0;
+    a.tilt_diag_items = tilt_diag_items.p; a.n_tilt_diag_items = (int)tilt_diag_items.n;
+    a.tilt_tc_items = tilt_tc_items.p; a.n_tilt_tc_items = (int)tilt_tc_items.n;
     a.max_level_w = max_level_w;
 }
 
@@ -216,7 +232,7 @@ int PyramidPlan::run(clfd_context *ctx, const uint8_t *frames, size_t frame_stri
     a.col += (size_t)frame_base * a.col_frame_stride;
     a.sum += (size_t)frame_base * a.sum_frame_stride;
     a.sq += (size_t)frame_base * a.sum_frame_stride;
-    if (a.tilted) a.tilted += (size_t)frame_base * a.sum_frame_stride;
+    if (a.tilted) { a.tilted += (size_t)frame_base * a.sum_frame_stride; a.tcar += (size_t)frame_base * a.tcar_frame_stride; }
     int launches = 0, nint = 0;
     if (ev) CK(cudaEventRecord(ev[0], s));
     CK(launch_resize_colsum(a, s)); launches++;
@@ -225,7 +241,7 @@ int PyramidPlan::run(clfd_context *ctx, const uint8_t *frames, size_t frame_stri
     if (ev) CK(cudaEventRecord(ev[2], s));
     CK(launch_integral_rows(a, s, &nint)); launches += nint;
     if (ev) CK(cudaEventRecord(ev[3], s));
-    if (want_tilted) { CK(launch_tilted(a, s)); launches++; }
+    if (want_tilted) { CK(launch_tilted(a, s)); launches += tilted_launches(); }
     if (ev) CK(cudaEventRecord(ev[4], s));
     ctx->launches += launches;
     if (n_launch) *n_launch = launches;
@@ -789,6 +805,7 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
     det->stats.pyramid_pixels = det->pyr.pyramid_pixels;
     det->stats.bytes_resize = det->pyr.bytes_resize;
     det->stats.bytes_integral = det->pyr.bytes_integral;
+    det->stats.bytes_tilted = det->pyr.bytes_tilted;
     for (auto &cpp : det->cas) det->stats.bytes_cascade += cpp->bytes_cascade;
     *out = det.release();
     return 0;

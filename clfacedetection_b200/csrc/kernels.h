@@ -26,7 +26,11 @@ struct PyramidArgs {
     const int4 *colscan_items; int n_colscan_items;    // (level, column chunk, -, -)
     // integral row-block items grouped by CTA width class: class k uses 32<<k threads
     const int4 *integral_items[6]; int n_integral_items[6];
-    const int4 *tilted_items; int n_tilted_items;      // (level, -, -, -)
+    // tilted integral: carry planes (kernels_clif.cu, K4), laid out like one plane of `col` each
+    int32_t *tcar; size_t tcar_frame_stride;           // elements
+    const int4 *tilt_tile_items; int n_tilt_tile_items;   // (level, row block, column tile, -), one warp each
+    const int4 *tilt_diag_items; int n_tilt_diag_items;   // (level, chunk of 256 diagonals, -, -)
+    const int4 *tilt_tc_items; int n_tilt_tc_items;       // (level, chunk of 8 x 32 columns, -, -)
     int max_level_w;
 };
 
@@ -55,6 +59,8 @@ cudaError_t launch_resize_colsum(const PyramidArgs &a, cudaStream_t stream);
 cudaError_t launch_colscan(const PyramidArgs &a, cudaStream_t stream);
 cudaError_t launch_integral_rows(const PyramidArgs &a, cudaStream_t stream, int *n_launches);
 cudaError_t launch_tilted(const PyramidArgs &a, cudaStream_t stream);
+int tilted_launches();       // kernels launch_tilted enqueues
+int tilt_tile_interior();    // output columns per warp tile of k_tilt_tiles
 
 cudaError_t launch_bgr_to_gray(const uint8_t *bgr, int w, int h, int stride, int channels,
                                uint8_t *gray, int gstride, cudaStream_t stream);

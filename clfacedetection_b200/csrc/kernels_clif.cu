@@ -16,15 +16,42 @@
 //                      thread-serial + warp-shuffle + cross-warp prefix along the row, and
 //                      16-byte vector stores of int32 sums and uint64 square sums.  The image
 //                      is read once (8 B loads) and every output byte is written once.
-//   K4 tilted        : row-sequential diagonal recurrences, only for cascades with tilted
-//                      features (fullbody & co).
+//   K4 tilted        : four launches, only for cascades with tilted features (fullbody & co): block-local
+//                      diagonal sums, carries along the diagonals, column carries, then the rows -- warp
+//                      tiles with halo columns, no barriers (see K4 below).
 #include <cstdint>
+#include <cstdlib>
 
 #include "kernels.h"
 
 namespace clfd {
 
 typedef unsigned long long ull;
+
+// mbarrier + TMA bulk copy (cp.async.bulk, SASS: UBLKCP / SYNCS), as in kernels_clod.cu
+__device__ __forceinline__ uint32_t clif_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void clif_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(clif_smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void clif_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(clif_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void clif_mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "CLIF_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra CLIF_DONE;\n"
+        "bra CLIF_WAIT;\n"
+        "CLIF_DONE:\n"
+        "}" ::"r"(clif_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void clif_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(clif_smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(clif_smem_u32(bar)) : "memory");
+}
 
 // ------------------------------------------------------------------------------------
 // K1: pyramid level pixels + per-row-block column sums
@@ -295,63 +322,265 @@ cudaError_t launch_integral_rows(const PyramidArgs &a, cudaStream_t stream, int 
 }
 
 // ------------------------------------------------------------------------------------
-// K4: tilted integral.  tilted[Y][X] = sum_{y<Y, |x-(X-1)| <= (Y-1)-y} I[y][x]
-//     T(Y,X) = T(Y-1,X) + A(Y-1,X-1) + B(Y-1,X-1) - I(Y-1,X-1), A/B = up-left / up-right
-//     diagonal prefix sums; X = 0 only picks up B(Y-2,0).
+// K4: tilted integral.  tilted[Y][X] = sum_{y<Y, |x-(X-1)| <= (Y-1)-y} I[y][x]   (cvIntegral's third output,
+//     tempcv.cpp:1302; the cone above pixel (Y-1, X-1)).
+//
+//     With A(y,x) = I(y,x) + A(y-1,x-1) and B(y,x) = I(y,x) + B(y-1,x+1) (the up-left / up-right diagonal
+//     prefix sums, zero outside the image, one virtual zero column x = -1 that B runs into) the cone grows
+//     from row to row by its two edges:  T(Y,X) = T(Y-1,X) + A(Y-1,X-1) + B(Y-1,X-1) - I(Y-1,X-1),  i.e.
+//     T is the COLUMN prefix sum of G = A + B - I, and A, B are prefix sums along diagonals.  That makes it a
+//     bandwidth problem with the same carry structure as the upright integral, only sheared:
+//
+//     k_tilt_tiles<false>  per (level, 32-row block, 192-column tile) one WARP: the block's own diagonal sums
+//                          at its last row (LA, LB) and its column sums of G (LG), all from zero carries
+//     k_tilt_diag          A / B carries at the top of every row block: a prefix over row blocks ALONG the
+//                          diagonal (column shifts by 32 per block), one thread per diagonal
+//     k_tilt_tcarry        T carries: prefix over row blocks of LG + the 32-wide window sums of the A / B
+//                          carries that flow through the block (warp scans), one thread per column
+//     k_tilt_tiles<true>   the same row loop seeded with the carries; writes T
+//
+//     The row loop is barrier free: a lane owns 8 columns, the diagonal shift is one shuffle per array and
+//     row, and instead of exchanging diagonals between warps a tile carries 32 halo columns on either side
+//     (inside a 32-row block a diagonal moves at most 31 columns), recomputing A / B there.  The pixel tile of
+//     a warp is staged in shared memory by TMA bulk row copies; T is written 32 bytes per lane and row.
 // ------------------------------------------------------------------------------------
-constexpr int kTiltedThreads = 1024;
-constexpr int kTiltedMaxCols = 8;  // columns per thread -> level width <= 8192
+constexpr int kTiltCols = 8;                        // columns per lane (16 was measured too: 84-106 registers, 16-20
+                                                    // warps per SM, latency bound; 8 columns halve the register need)
+constexpr int kTiltWords = kTiltCols / 4;           // 32-bit words of pixels / int4 vectors of sums per lane and row
+constexpr int kTiltHalo = 32;                       // halo columns on either side
+constexpr int kTiltHaloLanes = kTiltHalo / kTiltCols;
+constexpr int kTiltInterior = 32 * kTiltCols - 2 * kTiltHalo;   // output columns per warp tile
+constexpr int kTiltWarps = 4;                       // warp tiles per CTA
+constexpr int kTiltRowBytes = 32 * kTiltCols;       // pixel bytes of one tile row
+constexpr int kTiltSmemLocal = kRowBlock * kTiltRowBytes + 16;   // the warp's pixel tile + its mbarrier
+static_assert(kTiltHalo >= kRowBlock && kTiltHalo % kTiltCols == 0, "a diagonal crosses < kRowBlock columns inside a block");
+static_assert(kTiltCols == 8 || kTiltCols == 16, "pixel vectors of 8 or 16 bytes");
 
-__global__ void __launch_bounds__(kTiltedThreads) k_tilted(const PyramidArgs a) {
-    extern __shared__ int32_t sm_t[];
-    const int4 it = a.tilted_items[blockIdx.x];
+// planes of the carry buffer (each laid out like one plane of the column-sum buffer: [row block][X], pitch sum_pitch)
+enum { kTcLA = 0, kTcLB, kTcLG, kTcAC, kTcBC, kTcTC, kTcPlanes };
+
+struct TiltPix { uint32_t w[kTiltWords]; };
+__device__ __forceinline__ TiltPix tilt_load_pix(const void *p) {
+    TiltPix r;
+    if (kTiltWords == 2) { const uint2 v = *reinterpret_cast<const uint2 *>(p); r.w[0] = v.x; r.w[1] = v.y; }
+    else { const uint4 v = *reinterpret_cast<const uint4 *>(p); r.w[0] = v.x; r.w[1] = v.y; r.w[kTiltWords - 2] = v.z; r.w[kTiltWords - 1] = v.w; }
+    return r;
+}
+
+template <bool FINAL>
+__global__ void __launch_bounds__(32 * kTiltWarps) k_tilt_tiles(const PyramidArgs a) {
+    extern __shared__ __align__(128) unsigned char tilt_smem[];
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * kTiltWarps + (threadIdx.x >> 5);
+    if (item >= a.n_tilt_tile_items) return;
+    const int4 it = a.tilt_tile_items[item];   // (level, row block, column tile, -)
     const PyrLevel L = a.levels[it.x];
-    const int frame = blockIdx.y, t = threadIdx.x;
-    const int wpad = L.w + 2;
-    int32_t *A0 = sm_t, *A1 = sm_t + wpad, *B0 = sm_t + 2 * wpad, *B1 = sm_t + 3 * wpad;
-    for (int i = t; i < 4 * wpad; i += kTiltedThreads) sm_t[i] = 0;
+    const int frame = blockIdx.y, rb = it.y;
+    // output columns X = x + 1 of this lane: [X0, X0 + kTiltCols); its pixel columns x = X0 - 1 + i
+    const int X0 = it.z * kTiltInterior - kTiltHalo + lane * kTiltCols;
+    const bool interior = lane >= kTiltHaloLanes && lane < 32 - kTiltHaloLanes && X0 < L.sum_pitch;
     const uint8_t *__restrict__ pyr = a.pyr + (size_t)frame * a.pyr_frame_stride + L.pyr_off;
     int32_t *__restrict__ til = a.tilted + (size_t)frame * a.sum_frame_stride + L.sum_off;
-    for (int X = t; X < L.sum_pitch; X += kTiltedThreads) til[X] = 0;
-    int32_t acc[kTiltedMaxCols];
+    int32_t *__restrict__ car = a.tcar + (size_t)frame * a.tcar_frame_stride + L.col_off + (size_t)rb * L.sum_pitch;
+    const bool in_car = X0 >= 0 && X0 < L.sum_pitch;   // (sum_pitch and X0 are multiples of 8: whole int4 pairs)
+    const bool in_pix = X0 >= 0 && X0 < L.pyr_pitch;   // aligned pixel vectors; padding bytes are zero
+
+    int A[kTiltCols], B[kTiltCols], T[kTiltCols];
 #pragma unroll
-    for (int k = 0; k < kTiltedMaxCols; k++) acc[k] = 0;
-    int32_t acc0 = 0;  // column X = 0 (thread 0)
-    __syncthreads();
-    for (int Y = 1; Y <= L.h; Y++) {
-        const uint8_t *__restrict__ p = pyr + (size_t)(Y - 1) * L.pyr_pitch;
-        int32_t *__restrict__ out = til + (size_t)Y * L.sum_pitch;
-        if (t == 0) { acc0 += B0[1]; out[0] = acc0; }
+    for (int i = 0; i < kTiltCols; i++) A[i] = B[i] = T[i] = 0;
+    const int n_vec = in_car ? min(kTiltCols, L.sum_pitch - X0) / 4 : 0;   // int4 vectors of this lane inside the row
+    if (FINAL) {
 #pragma unroll
-        for (int k = 0; k < kTiltedMaxCols; k++) {
-            const int x = t + k * kTiltedThreads;
-            if (x < L.w) {
-                const int32_t pix = p[x];
-                const int32_t a1 = pix + A0[x];      // A(y,x) = I + A(y-1,x-1)   (arrays are x+1 based)
-                const int32_t b1 = pix + B0[x + 2];  // B(y,x) = I + B(y-1,x+1)
-                A1[x + 1] = a1; B1[x + 1] = b1;
-                acc[k] += a1 + b1 - pix;
-                out[x + 1] = acc[k];
+        for (int v = 0; v < kTiltWords; v++) {
+            if (v < n_vec) {
+                const int4 va = *reinterpret_cast<const int4 *>(car + kTcAC * a.col_plane_stride + X0 + 4 * v);
+                const int4 vb = *reinterpret_cast<const int4 *>(car + kTcBC * a.col_plane_stride + X0 + 4 * v);
+                const int4 vt = *reinterpret_cast<const int4 *>(car + kTcTC * a.col_plane_stride + X0 + 4 * v);
+                A[4 * v] = va.x; A[4 * v + 1] = va.y; A[4 * v + 2] = va.z; A[4 * v + 3] = va.w;
+                B[4 * v] = vb.x; B[4 * v + 1] = vb.y; B[4 * v + 2] = vb.z; B[4 * v + 3] = vb.w;
+                T[4 * v] = vt.x; T[4 * v + 1] = vt.y; T[4 * v + 2] = vt.z; T[4 * v + 3] = vt.w;
             }
         }
-        __syncthreads();
-        int32_t *sw;
-        sw = A0; A0 = A1; A1 = sw;
-        sw = B0; B0 = B1; B1 = sw;
     }
+    const int y0 = rb * kRowBlock, y1 = min(y0 + kRowBlock, L.h);
+    if (FINAL && rb == 0 && interior) {   // row 0 of the tilted integral is zero
+        for (int v = 0; v < n_vec; v++) *reinterpret_cast<int4 *>(til + X0 + 4 * v) = make_int4(0, 0, 0, 0);
+    }
+    // The warp's whole pixel tile (32 rows) is staged with one TMA bulk copy per row, all in flight at once: a warp
+    // walks its rows one after the other, and register prefetching of a row or four ahead left it latency bound
+    // (one DRAM round trip per row).  Lane r copies row y0 + r; columns outside [0, pyr_pitch) are not copied
+    // (those lanes use zeros).
+    unsigned char *wsm = tilt_smem + (size_t)(threadIdx.x >> 5) * kTiltSmemLocal;
+    {
+        uint64_t *bar = reinterpret_cast<uint64_t *>(wsm + kRowBlock * kTiltRowBytes);
+        const int Xs = it.z * kTiltInterior - kTiltHalo;   // pixel column of the tile's first byte
+        const int cs = max(Xs, 0), ce = min(Xs + kTiltRowBytes, L.pyr_pitch);
+        const int nrows = y1 - y0;
+        if (lane == 0) clif_mbar_init(bar, 1);
+        __syncwarp();
+        if (ce > cs) {
+            if (lane == 0) clif_mbar_expect_tx(bar, (uint32_t)(nrows * (ce - cs)));
+            __syncwarp();
+            if (lane < nrows)
+                clif_bulk_g2s(wsm + lane * kTiltRowBytes + (cs - Xs), pyr + (size_t)(y0 + lane) * L.pyr_pitch + cs, (uint32_t)(ce - cs), bar);
+            clif_mbar_wait(bar, 0);
+        }
+    }
+    for (int y = y0; y < y1; y++) {
+        TiltPix cur;
+#pragma unroll
+        for (int k = 0; k < kTiltWords; k++) cur.w[k] = 0u;
+        if (in_pix) cur = tilt_load_pix(wsm + (y - y0) * kTiltRowBytes + lane * kTiltCols);
+        // p[i] = I(y, X0 - 1 + i): the left neighbour's last byte, then my first kTiltCols - 1
+        int p[kTiltCols];
+        p[0] = (int)(__shfl_up_sync(0xffffffffu, cur.w[kTiltWords - 1], 1) >> 24);
+        if (lane == 0) p[0] = 0;
+#pragma unroll
+        for (int i = 1; i < kTiltCols; i++) p[i] = (int)((cur.w[(i - 1) >> 2] >> (8 * ((i - 1) & 3))) & 255u);
+        int a_in = __shfl_up_sync(0xffffffffu, A[kTiltCols - 1], 1);     // A(y-1, x-1) for my first column
+        int b_in = __shfl_down_sync(0xffffffffu, B[0], 1);              // B(y-1, x+1) for my last column
+        if (lane == 0) a_in = 0;
+        if (lane == 31) b_in = 0;
+        // B(y,x) = I + B(y-1,x+1): ascending, in place
+#pragma unroll
+        for (int i = 0; i < kTiltCols; i++) B[i] = p[i] + (i + 1 < kTiltCols ? B[i + 1] : b_in);
+        // A(y,x) = I + A(y-1,x-1): descending, in place;  G = A + B - I = A(y-1,x-1) + B(y,x)
+#pragma unroll
+        for (int i = kTiltCols - 1; i >= 0; i--) {
+            const int up_left = i ? A[i - 1] : a_in;
+            T[i] += up_left + B[i];
+            A[i] = p[i] + up_left;
+        }
+        if (FINAL && interior) {
+            int32_t *out = til + (size_t)(y + 1) * L.sum_pitch + X0;
+#pragma unroll
+            for (int v = 0; v < kTiltWords; v++)
+                if (v < n_vec) *reinterpret_cast<int4 *>(out + 4 * v) = make_int4(T[4 * v], T[4 * v + 1], T[4 * v + 2], T[4 * v + 3]);
+        }
+    }
+    if (!FINAL && interior) {
+        // block-local diagonal sums at the last row and column sums of G; columns beyond the image hold zeros
+#pragma unroll
+        for (int i = 0; i < kTiltCols; i++)
+            if (X0 + i > L.w) A[i] = B[i] = T[i] = 0;
+#pragma unroll
+        for (int v = 0; v < kTiltWords; v++) {
+            if (v < n_vec) {
+                *reinterpret_cast<int4 *>(car + kTcLA * a.col_plane_stride + X0 + 4 * v) = make_int4(A[4 * v], A[4 * v + 1], A[4 * v + 2], A[4 * v + 3]);
+                *reinterpret_cast<int4 *>(car + kTcLB * a.col_plane_stride + X0 + 4 * v) = make_int4(B[4 * v], B[4 * v + 1], B[4 * v + 2], B[4 * v + 3]);
+                *reinterpret_cast<int4 *>(car + kTcLG * a.col_plane_stride + X0 + 4 * v) = make_int4(T[4 * v], T[4 * v + 1], T[4 * v + 2], T[4 * v + 3]);
+            }
+        }
+    }
+}
+
+// A / B carries.  AC_b(X) = A(32 b - 1, X - 1) = AC_{b-1}(X - 32) + LA_{b-1}(X): a prefix over row blocks along
+// the diagonal X - 32 b = const; BC_b(X) = BC_{b-1}(X + 32) + LB_{b-1}(X) along X + 32 b = const.  blockIdx.z
+// selects A or B; one thread per diagonal (all row blocks but the last are 32 rows high, and nobody needs the
+// carries below the last one).
+__global__ void __launch_bounds__(256) k_tilt_diag(const PyramidArgs a) {
+    const int4 it = a.tilt_diag_items[blockIdx.x];   // (level, chunk of 256 diagonals, -, -)
+    const PyrLevel L = a.levels[it.x];
+    const int frame = blockIdx.y;
+    const bool is_b = blockIdx.z != 0;
+    const int span = (L.nrb - 1) * kRowBlock;         // diagonals start up to this far outside the image
+    const int d = it.y * 256 + threadIdx.x;           // 0 .. w + span
+    if (d > L.w + span) return;
+    int32_t *__restrict__ car = a.tcar + (size_t)frame * a.tcar_frame_stride + L.col_off;
+    const int32_t *__restrict__ loc = car + (is_b ? kTcLB : kTcLA) * a.col_plane_stride;
+    int32_t *__restrict__ out = car + (is_b ? kTcBC : kTcAC) * a.col_plane_stride;
+    // A: X_b = d - span + 32 b (enters from the left);  B: X_b = d - 32 b (enters from the right)
+    // AC_b(X_b) = AC_{b-1}(X_{b-1}) + LA_{b-1}(X_b) while the diagonal is inside the image (the block's local sum
+    // belongs to the column the diagonal LEAVES the block at), zero where it enters
+    const int step = is_b ? -kRowBlock : kRowBlock;
+    const int X0 = is_b ? d : d - span;
+    int b_lo, b_hi;   // row blocks whose X_b = X0 + step * b lies in [0, w]
+    if (is_b) { b_lo = X0 > L.w ? (X0 - L.w + kRowBlock - 1) / kRowBlock : 0; b_hi = X0 / kRowBlock; }
+    else { b_lo = X0 < 0 ? (-X0 + kRowBlock - 1) / kRowBlock : 0; b_hi = (L.w - X0) / kRowBlock; }
+    b_hi = min(b_hi, L.nrb - 1);
+    int acc = 0;
+    constexpr int kBatch = 8;    // loads in flight per thread, then the dependent adds and the stores (a 1080p level has 34 steps)
+    for (int b0 = b_lo; b0 <= b_hi; b0 += kBatch) {
+        int v[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; k++) {
+            const int b = b0 + k;
+            v[k] = (b <= b_hi && b > 0) ? __ldg(loc + (size_t)(b - 1) * L.sum_pitch + X0 + step * b) : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < kBatch; k++) {
+            const int b = b0 + k;
+            if (b <= b_hi) { acc += v[k]; out[(size_t)b * L.sum_pitch + X0 + step * b] = acc; }
+        }
+    }
+}
+
+// T carries.  TC_b(X) = T(32 b, X) = sum over the row blocks above of their column sums of G, where a block's
+// G column sum = LG (its own pixels) + what the carries contribute while they cross the block:
+// sum_{j=1..32} AC(X - j) + sum_{j=1..32} BC(X + j).  One warp per 32 columns; the window sums come from four
+// warp scans (this group and its left neighbour for A, this group and its right neighbour for B).
+__global__ void __launch_bounds__(256) k_tilt_tcarry(const PyramidArgs a) {
+    const int4 it = a.tilt_tc_items[blockIdx.x];     // (level, chunk of 8 column groups, -, -)
+    const PyrLevel L = a.levels[it.x];
+    const int frame = blockIdx.y, lane = threadIdx.x & 31;
+    const int X = (it.y * 8 + (threadIdx.x >> 5)) * 32 + lane;
+    if (X - lane >= L.sum_pitch) return;   // (whole warps)
+    int32_t *__restrict__ car = a.tcar + (size_t)frame * a.tcar_frame_stride + L.col_off;
+    const size_t ps = a.col_plane_stride;
+    auto at = [&](int plane, int b, int x) -> int {   // zero outside [0, w]
+        return (x >= 0 && x <= L.w) ? car[plane * ps + (size_t)b * L.sum_pitch + x] : 0;
+    };
+    auto incl_scan = [&](int v) {
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += u;
+        }
+        return v;
+    };
+    int acc = 0;
+    constexpr int kSteps = 4;   // row blocks whose loads are in flight together (8 measured slower: registers)
+    for (int b0 = 0; b0 + 1 < L.nrb; b0 += kSteps) {
+        int a_cur[kSteps], a_prev[kSteps], b_cur[kSteps], b_next[kSteps], lg[kSteps];
+#pragma unroll
+        for (int k = 0; k < kSteps; k++) {
+            const int b = min(b0 + k, L.nrb - 1);
+            a_cur[k] = at(kTcAC, b, X); a_prev[k] = at(kTcAC, b, X - 32);
+            b_cur[k] = at(kTcBC, b, X); b_next[k] = at(kTcBC, b, X + 32);
+            lg[k] = at(kTcLG, b, X);
+        }
+#pragma unroll
+        for (int k = 0; k < kSteps; k++) {
+            const int b = b0 + k;
+            if (b + 1 >= L.nrb) break;
+            if (X <= L.w) car[kTcTC * ps + (size_t)b * L.sum_pitch + X] = acc;
+            const int sa_cur = incl_scan(a_cur[k]), sa_prev = incl_scan(a_prev[k]);
+            const int sb_cur = incl_scan(b_cur[k]), sb_next = incl_scan(b_next[k]);
+            // columns X-32 .. X-1: the previous group's lanes >= mine, this group's lanes < mine
+            const int wa = (__shfl_sync(0xffffffffu, sa_prev, 31) - (sa_prev - a_prev[k])) + (sa_cur - a_cur[k]);
+            // columns X+1 .. X+32: this group's lanes > mine, the next group's lanes <= mine
+            const int wb = (__shfl_sync(0xffffffffu, sb_cur, 31) - sb_cur) + sb_next;
+            acc += lg[k] + wa + wb;
+        }
+    }
+    if (X <= L.w) car[kTcTC * ps + (size_t)(L.nrb - 1) * L.sum_pitch + X] = acc;
 }
 
 cudaError_t launch_tilted(const PyramidArgs &a, cudaStream_t stream) {
-    if (a.n_tilted_items == 0 || a.n_frames == 0 || !a.tilted) return cudaSuccess;
-    if (a.max_level_w > kTiltedThreads * kTiltedMaxCols) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)4 * (a.max_level_w + 2) * sizeof(int32_t);
-    static SmemLimitCache limit;
-    if (smem > 48 * 1024) {
-        if (cudaError_t e = limit.ensure(k_tilted, smem)) return e;
-    }
-    k_tilted<<<dim3(a.n_tilted_items, a.n_frames), kTiltedThreads, smem, stream>>>(a);
+    if (a.n_tilt_tile_items == 0 || a.n_frames == 0 || !a.tilted) return cudaSuccess;
+    const dim3 tiles((a.n_tilt_tile_items + kTiltWarps - 1) / kTiltWarps, a.n_frames);
+    const size_t smem = (size_t)kTiltWarps * kTiltSmemLocal;
+    static SmemLimitCache lim_local, lim_final;
+    if (cudaError_t e = lim_local.ensure(k_tilt_tiles<false>, smem)) return e;
+    if (cudaError_t e = lim_final.ensure(k_tilt_tiles<true>, smem)) return e;
+    k_tilt_tiles<false><<<tiles, 32 * kTiltWarps, smem, stream>>>(a);
+    k_tilt_diag<<<dim3(a.n_tilt_diag_items, a.n_frames, 2), 256, 0, stream>>>(a);
+    k_tilt_tcarry<<<dim3(a.n_tilt_tc_items, a.n_frames), 256, 0, stream>>>(a);
+    k_tilt_tiles<true><<<tiles, 32 * kTiltWarps, smem, stream>>>(a);
     return cudaGetLastError();
 }
+int tilted_launches() { return 4; }
+int tilt_tile_interior() { return kTiltInterior; }
 
 // ------------------------------------------------------------------------------------
 // BGR(A) -> gray, OpenCV fixed point: (B*1868 + G*9617 + R*4899 + 8192) >> 14

@@ -177,7 +177,9 @@ typedef struct clfd_run_stats {
     int64_t deep_windows;     /* windows handed from the tile kernel to the deep kernel */
     int64_t kernel_launches;  /* kernels launched by the last enqueue */
     int64_t pyramid_pixels;   /* per frame */
-    int64_t bytes_resize, bytes_integral, bytes_cascade; /* algorithmic bytes per frame */
+    int64_t bytes_resize, bytes_integral, bytes_cascade; /* algorithmic bytes per frame; bytes_integral:
+                                                            the upright pair, w*h + (w+1)(h+1)*12 per level */
+    int64_t bytes_tilted;     /* tilted integral, w*h + (w+1)(h+1)*4 per level; 0 without tilted features */
 } clfd_run_stats;
 
 CLFD_API int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
