@@ -401,7 +401,13 @@ def main():
             # from a second, one-frame detector with want_codes -- outside every timed region
             try:
                 d2 = clfd.Detector(ctx, cas, W, H, max_batch=1, scale_factor=SCALE, min_size=MIN_SIZE, want_codes=True)
-                d2.detect(base[:1])
+                r2 = d2.detect(base[:1])
+                # counted and reported (north star): stage sums within 1e-5 relative of a threshold, FP64 fallbacks
+                line["near_threshold"] = {"frame": 0, "windows": int(r2.stats["windows"]),
+                                          "stage_sums_within_1e-5_of_threshold": int(r2.stats["near_threshold_events"]),
+                                          "stage_evaluations_redone_in_fp64": int(r2.stats["exact_stage_evals"]),
+                                          "note": "per (window, stage); results are identical to the reference's for these windows "
+                                                  "too (exact FP64 path), the tolerance is not used"}
                 surv = []
                 for ci, cc in enumerate(cas):
                     codes = d2.codes(ci, 1)[0].astype(np.int64)

@@ -11,7 +11,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libclfd_b200.so")
+LIB_PATH = os.environ.get("CLFD_LIB") or os.path.join(_HERE, "libclfd_b200.so")   # CLFD_LIB: A/B builds of the same ABI
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "clfd_b200.h")
 _lib = None
 
@@ -50,7 +50,7 @@ class Level(C.Structure):
 class RunStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "windows", "rects", "deep_windows", "kernel_launches", "pyramid_pixels",
-        "bytes_resize", "bytes_integral", "bytes_cascade", "bytes_tilted")]
+        "bytes_resize", "bytes_integral", "bytes_cascade", "bytes_tilted", "exact_stage_evals", "near_threshold_events")]
 
 
 def exported_symbols_in_header() -> list[str]:

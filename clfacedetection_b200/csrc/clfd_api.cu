@@ -248,6 +248,10 @@ int PyramidPlan::run(clfd_context *ctx, const uint8_t *frames, size_t frame_stri
     return 0;
 }
 
+// device counters per cascade and slot: [0] rects [1] queue items [2] rect overflow [3] queue overflow
+// [4] stage evaluations redone in FP64 (exact path of the tile kernel) [5] of those, stage sums within 1e-5 relative of the threshold
+constexpr int kCnt = 8;
+
 struct CascadePlan {
     const clfd_cascade *cascade = nullptr;   // retained
     ~CascadePlan() { cascade_release(cascade); }
@@ -280,7 +284,7 @@ struct CascadePlan {
     DevBuf<unsigned long long> d_count_b;   // second-queue counter, one per slot
     int mid_begin = 0, mid_end = 0;         // stages of the thread-per-window mid kernel (equal: none)
     std::vector<int> mid_cuts;              // pass boundaries: mid_begin = cuts[0] < ... < cuts.back() = mid_end
-    unsigned long long h_counters[4] = {0, 0, 0, 0};
+    unsigned long long h_counters[kCnt] = {0};
 };
 
 constexpr int kMaxChunks = 8;
@@ -301,7 +305,7 @@ struct clfd_detector {
     DevBuf<unsigned long long> roc_count;
     DevRect *h_rects = nullptr;           // pinned, kSlots x rect_cap... slot 1 holds kEagerRects only
     DevRect *h_rects1 = nullptr;
-    unsigned long long *h_counters = nullptr;  // pinned, kSlots x (4 per cascade, 16 cascades)
+    unsigned long long *h_counters = nullptr;  // pinned, kSlots x (kCnt per cascade, 16 cascades)
     cudaEvent_t done[kSlots] = {nullptr, nullptr};
     int slot_frames[kSlots] = {0, 0};
     long long n_submitted = 0, n_collected = 0;
@@ -772,7 +776,7 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
             if (!pk.stage_tab[yi].empty() && (rc = cp.d_stage_tab[yi].upload(pk.stage_tab[yi], s))) return rc;
             cp.dense[yi].stage_g = cp.d_stage_tab[yi].p;
         }
-        if ((rc = cp.d_counters.alloc(4 * kSlots)) || (rc = cp.d_count_b.alloc(kSlots))) return rc;
+        if ((rc = cp.d_counters.alloc(kCnt * kSlots)) || (rc = cp.d_count_b.alloc(kSlots))) return rc;
         // mid kernel: the stages right after the tile prefix of a LINEAR cascade whose trees the tile
         // kernel cannot take, while they are too small for a warp per window (< 24 trees), at most 8
         if (!scale_cascade && !cp.cascade->host.is_tree && pk.dense[0].tail_stages < pk.dense[0].total_stages) {
@@ -800,7 +804,7 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
     if ((rc = det->queue.alloc(det->queue_cap)) || (rc = det->rects.alloc(det->rect_cap))) return rc;
     if ((need_queue_b || scale_cascade) && (rc = det->queue_b.alloc(det->queue_cap))) return rc;
     CK(cudaMallocHost((void **)&det->h_rects, det->rect_cap * sizeof(DevRect)));
-    CK(cudaMallocHost((void **)&det->h_counters, kSlots * 4 * 16 * sizeof(unsigned long long)));
+    CK(cudaMallocHost((void **)&det->h_counters, kSlots * kCnt * 16 * sizeof(unsigned long long)));
     CK(cudaStreamSynchronize(s));
     det->stats.pyramid_pixels = det->pyr.pyramid_pixels;
     det->stats.bytes_resize = det->pyr.bytes_resize;
@@ -861,8 +865,8 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
     }
     const int pyr_launches = launches;
     for (auto &cpp : det->cas) {
-        if (first) CK(cudaMemsetAsync(cpp->d_counters.p + 4 * slot, 0, 4 * sizeof(unsigned long long), s));
-        else CK(cudaMemsetAsync(cpp->d_counters.p + 4 * slot + 1, 0, sizeof(unsigned long long), s));   // the queue is per range
+        if (first) CK(cudaMemsetAsync(cpp->d_counters.p + kCnt * slot, 0, kCnt * sizeof(unsigned long long), s));
+        else CK(cudaMemsetAsync(cpp->d_counters.p + kCnt * slot + 1, 0, sizeof(unsigned long long), s));   // the queue is per range
         CK(cudaMemsetAsync(cpp->d_count_b.p + slot, 0, sizeof(unsigned long long), s));
     }
     int ci = 0;
@@ -881,9 +885,10 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
             a.frame_base = frame_base;
             a.cascade_index = ci; a.windows_per_frame = cp.windows_per_frame;
             a.codes = det->cfg.want_codes ? cp.d_codes.p + (size_t)frame_base * cp.windows_per_frame : nullptr;
+            a.count_exact = det->cfg.want_codes ? 1 : 0;
             a.queue = det->queue.p; a.queue_cap = det->queue_cap;
             a.rects = slot ? det->rects2.p : det->rects.p; a.rect_cap = det->rect_cap;
-            a.counters = cp.d_counters.p + 4 * slot;
+            a.counters = cp.d_counters.p + kCnt * slot;
             a.deep.stages = cp.d_stages.p; a.deep.tree_first_node = cp.d_tree_first.p;
             a.deep.nodes = cp.d_nodes.p; a.deep.alpha = cp.d_alpha.p;
             a.deep.n_stages = cp.cascade->host.n_stages(); a.deep.is_tree = cp.cascade->host.is_tree;
@@ -962,7 +967,7 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
                 launches++;
                 if (ev && ci == 0) { CK(cudaEventRecord(ev[6], s)); CK(cudaEventRecord(ev[7], s)); }
                 if (ci + 1 < (int)det->cas.size())
-                    CK(cudaMemcpyAsync(det->cas[ci + 1]->d_counters.p + 4 * slot, cp.d_counters.p + 4 * slot, sizeof(unsigned long long),
+                    CK(cudaMemcpyAsync(det->cas[ci + 1]->d_counters.p + kCnt * slot, cp.d_counters.p + kCnt * slot, sizeof(unsigned long long),
                                        cudaMemcpyDeviceToDevice, s));
                 ci++;
                 continue;
@@ -1010,7 +1015,7 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
         }
         // all cascades append to one rect buffer: carry the rect count over
         if (ci + 1 < (int)det->cas.size())
-            CK(cudaMemcpyAsync(det->cas[ci + 1]->d_counters.p + 4 * slot, cp.d_counters.p + 4 * slot, sizeof(unsigned long long),
+            CK(cudaMemcpyAsync(det->cas[ci + 1]->d_counters.p + kCnt * slot, cp.d_counters.p + kCnt * slot, sizeof(unsigned long long),
                                cudaMemcpyDeviceToDevice, s));
         ci++;
     }
@@ -1042,20 +1047,25 @@ int clfd_detector_fetch(clfd_detector *det, clfd_rect *rects, int64_t cap, int64
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     const int nc = (int)det->cas.size();
     for (int ci = 0; ci < nc; ci++)
-        CK(cudaMemcpyAsync(det->h_counters + 4 * ci, det->cas[ci]->d_counters.p, 4 * sizeof(unsigned long long),
+        CK(cudaMemcpyAsync(det->h_counters + kCnt * ci, det->cas[ci]->d_counters.p, kCnt * sizeof(unsigned long long),
                            cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    unsigned long long total = det->h_counters[4 * (nc - 1)];
+    unsigned long long total = det->h_counters[kCnt * (nc - 1)];
     unsigned long long deep = 0, rect_over = 0, queue_over = 0;
     for (int ci = 0; ci < nc; ci++) {
-        memcpy(det->cas[ci]->h_counters, det->h_counters + 4 * ci, 4 * sizeof(unsigned long long));
-        deep += det->h_counters[4 * ci + 1];
-        rect_over += det->h_counters[4 * ci + 2];
-        queue_over += det->h_counters[4 * ci + 3];
+        memcpy(det->cas[ci]->h_counters, det->h_counters + kCnt * ci, kCnt * sizeof(unsigned long long));
+        deep += det->h_counters[kCnt * ci + 1];
+        rect_over += det->h_counters[kCnt * ci + 2];
+        queue_over += det->h_counters[kCnt * ci + 3];
     }
     if (queue_over) { set_error("survivor queue overflow (%llu windows dropped)", queue_over); return CLFD_ERR_CAPACITY; }
     det->stats.rects = (int64_t)total;
     det->stats.deep_windows = (int64_t)deep;
+    det->stats.exact_stage_evals = det->stats.near_threshold_events = det->cfg.want_codes ? 0 : -1;   // -1: not counted
+    for (int ci = 0; ci < nc && det->cfg.want_codes; ci++) {
+        det->stats.exact_stage_evals += (int64_t)det->h_counters[kCnt * ci + 4];
+        det->stats.near_threshold_events += (int64_t)det->h_counters[kCnt * ci + 5];
+    }
     det->stats.windows = 0;
     for (auto &cpp : det->cas) det->stats.windows += cpp->windows_per_frame * det->last_frames;
     *n_rects = (int64_t)total;
@@ -1146,9 +1156,9 @@ int clfd_detect_submit(clfd_detector *det, const uint8_t *frames_host, int n_fra
     det->stats.kernel_launches = launches;
     // results: counters of every cascade + the first rects, behind the kernels
     const int nc = (int)det->cas.size();
-    unsigned long long *hc = det->h_counters + (size_t)slot * 4 * 16;
+    unsigned long long *hc = det->h_counters + (size_t)slot * kCnt * 16;
     for (int ci = 0; ci < nc; ci++)
-        CK(cudaMemcpyAsync(hc + 4 * ci, det->cas[ci]->d_counters.p + 4 * slot, 4 * sizeof(unsigned long long),
+        CK(cudaMemcpyAsync(hc + kCnt * ci, det->cas[ci]->d_counters.p + kCnt * slot, kCnt * sizeof(unsigned long long),
                            cudaMemcpyDeviceToHost, ctx->stream));
     const size_t eager = (size_t)std::min<unsigned long long>(det->rect_cap, kEagerRects);
     CK(cudaMemcpyAsync(slot ? det->h_rects1 : det->h_rects, slot ? det->rects2.p : det->rects.p, eager * sizeof(DevRect),
@@ -1168,18 +1178,23 @@ int clfd_detect_collect(clfd_detector *det, clfd_rect *rects, int64_t cap, int64
     det->n_collected++;
     CK(cudaEventSynchronize(det->done[slot]));
     const int nc = (int)det->cas.size();
-    const unsigned long long *hc = det->h_counters + (size_t)slot * 4 * 16;
-    const unsigned long long total = hc[4 * (nc - 1)];
+    const unsigned long long *hc = det->h_counters + (size_t)slot * kCnt * 16;
+    const unsigned long long total = hc[kCnt * (nc - 1)];
     unsigned long long deep = 0, rect_over = 0, queue_over = 0;
     for (int ci = 0; ci < nc; ci++) {
-        memcpy(det->cas[ci]->h_counters, hc + 4 * ci, 4 * sizeof(unsigned long long));
-        deep += hc[4 * ci + 1];
-        rect_over += hc[4 * ci + 2];
-        queue_over += hc[4 * ci + 3];
+        memcpy(det->cas[ci]->h_counters, hc + kCnt * ci, kCnt * sizeof(unsigned long long));
+        deep += hc[kCnt * ci + 1];
+        rect_over += hc[kCnt * ci + 2];
+        queue_over += hc[kCnt * ci + 3];
     }
     if (queue_over) { set_error("survivor queue overflow (%llu windows dropped)", queue_over); return CLFD_ERR_CAPACITY; }
     det->stats.rects = (int64_t)total;
     det->stats.deep_windows = (int64_t)deep;
+    det->stats.exact_stage_evals = det->stats.near_threshold_events = det->cfg.want_codes ? 0 : -1;   // -1: not counted
+    for (int ci = 0; ci < nc && det->cfg.want_codes; ci++) {
+        det->stats.exact_stage_evals += (int64_t)hc[kCnt * ci + 4];
+        det->stats.near_threshold_events += (int64_t)hc[kCnt * ci + 5];
+    }
     det->stats.windows = 0;
     for (auto &cpp : det->cas) det->stats.windows += cpp->windows_per_frame * det->slot_frames[slot];
     *n_rects = (int64_t)total;

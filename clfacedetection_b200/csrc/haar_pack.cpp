@@ -392,6 +392,9 @@ static void pack_dense_one(const HostCascade &c, int ystep, DenseParams &P, std:
         // FP32 summation of n alphas in any order: |error| <= (n-1) 2^-24 sum|alpha|; 2x slack
         const double er = (double)(c.st_ntrees[i] * P.npt) * ldexp(1.0, -23) * abs_sum;
         ds.sum_eps = std::isfinite(er) ? (float)(er * 1.0000002) + FLT_MIN : INFINITY;
+        // + 1e-5 |thr|: windows whose stage sum lies within the north star's tolerance of the threshold all take the
+        // FP64 path, where they are counted exactly (clfd_run_stats::near_threshold_events); ~1e-4 of the windows
+        ds.sum_eps += 1.0001e-5f * std::fabs(ds.thr);
         if (walk_tree) {
             const uint32_t pass = c.st_child[i] >= 0 ? (uint32_t)pos[c.st_child[i]] : kRouteAccept;
             int p = i;

@@ -73,6 +73,7 @@ struct CascadeArgs {
     const CasLevel *cas_levels;     // device
     int n_cas_levels, n_tiles, n_frames, cascade_index;
     int frame_base;                 // added to the frame index of emitted rects (ranges of a batch)
+    int count_exact;                // tile kernel: the instantiation that counts FP64 fallbacks / near-threshold sums (counters[4], [5])
     long long windows_per_frame;
     int16_t *codes;                 // device, [n_frames][windows_per_frame] or NULL
     QueueItem *queue; unsigned long long queue_cap;   // written by the tile kernel / k_enqueue_all, counted in counters[1]

@@ -5,7 +5,7 @@
 // grid of HaarDetectObjects_ScaleImage_Invoker (tempcv.cpp:1011-1103).
 //
 // One kernel (two launches: ystep-2 and ystep-1 levels) per cascade per batch, no host round trip:
-//   k_cascade_tiles<ROWSTEP, TREE, NODES, TILE_H> : one CTA per 64 x TILE_H-window tile of one level
+//   k_cascade_tiles<ROWSTEP, TREE, NODES, TILE_H, COUNT> : one CTA per 64 x TILE_H-window tile of one level
 //       of one frame.  The int32 integral tile (and, for cascades with tilted features, the tilted
 //       integral tile behind it) is staged into shared memory (TMA bulk row copies, cp.async.bulk
 //       + mbarrier, on ystep-1 levels), sigma is computed once per window in FP64, and the
@@ -150,8 +150,8 @@ __host__ __device__ inline DenseSmemPlan dense_smem_plan(const DenseParams &P) {
     p.sgf = (rows * P.tile_stride * 4 + 127) & ~(size_t)127;
     if (P.tilted_tile) p.sgf *= 2;   // second tile: the tilted integral (same geometry)
     p.list = p.sgf + windows * sizeof(float);
-    p.pool = p.list + windows * sizeof(uint16_t);    // second class-list / per-warp-list buffer
-    p.ctl = p.pool + windows * sizeof(uint16_t);
+    p.pool = p.list + windows * sizeof(uint16_t);    // pooled stages only: second class-list / per-warp-list buffer
+    p.ctl = p.pool + (P.pool_min > 0 ? windows * sizeof(uint16_t) : 0);   // (3-4 KB that cost frontalface_default its fourth CTA per SM)
     p.bar = p.ctl + kCtlInts * sizeof(int);
     p.act = p.tgt = p.total = p.bar + 16;
     if (P.exec_stages > P.tail_stages) {   // stage tree: the windows of the current stage, every window's target position
@@ -160,7 +160,12 @@ __host__ __device__ inline DenseSmemPlan dense_smem_plan(const DenseParams &P) {
     }
     return p;
 }
+#ifdef CLFD_TILES_COUNT_TU
+constexpr bool kTilesCount = true;
+#else
+constexpr bool kTilesCount = false;
 size_t dense_smem_bytes(const DenseParams &P) { return dense_smem_plan(P).total; }
+#endif
 
 struct DenseCtx {
     uint32_t tile;    // shared-window address of the tile
@@ -230,9 +235,14 @@ __device__ __forceinline__ StumpRegs stump_from_global(const uint4 *__restrict__
     return r;
 }
 
+// FP64 fallbacks / near-threshold stage sums of this CTA (clfd_run_stats): counted in shared memory -- a 32-bit
+// address known at link time, so the rare path costs the hot kernel no register -- and added to
+// CascadeArgs::counters[4], [5] by the last warp that leaves the CTA.
+__shared__ unsigned int s_dense_exact, s_dense_near, s_dense_done;
+
 // Exact evaluation of one stage for one window: the reference's arithmetic, stumps in tree order.
 template <bool NODES>
-__device__ __noinline__ bool dense_stage_exact(const DenseParams &P, const DenseCtx &c, uint32_t tail_first, int count, bool dbl,
+__device__ __noinline__ int dense_stage_exact(const DenseParams &P, const DenseCtx &c, uint32_t tail_first, int count, bool dbl,
                                                float sthr, int wid) {
     const uint32_t base = dense_base(c, wid);
     const double sigma = dense_sigma(P, c, wid);
@@ -264,7 +274,11 @@ __device__ __noinline__ bool dense_stage_exact(const DenseParams &P, const Dense
         }
         S = __dadd_rn(S, (double)(sum >= t ? q.a1 : q.a0));
     }
-    return S >= (double)sthr;
+    // counted and reported (north star): FP64 fallbacks, and stage sums within 1e-5 relative of the threshold --
+    // the packer widens the FP32 band by that much, so every such event comes through here
+    // bit 0: the verdict; bit 1: the stage sum lies within 1e-5 relative of the threshold (counted by the caller)
+    const double thr = (double)sthr;
+    return (S >= thr ? 1 : 0) | (fabs(__dsub_rn(S, thr)) <= __dmul_rn(1e-5, fabs(thr)) ? 2 : 0);
 }
 
 // FP32 filter: one stump for K windows of this thread.  The stump decision sign(s - t) is taken
@@ -378,10 +392,17 @@ __device__ __forceinline__ void stage_filter(const DenseParams &P, const DenseSt
 // Stage verdict of one window from its FP32 stage sum.  |S32 - S| <= sum_eps for any summation
 // order, so outside that band (and with no stump inside its own band) the FP32 verdict is the
 // reference's; inside, the stage is redone exactly.
-template <bool NODES>
+template <bool NODES, bool COUNT>
 __device__ __forceinline__ bool stage_verdict(const DenseParams &P, const DenseCtx &c, const DenseStage &st, float sthr, float seps,
                                               int wid, float S, bool near) {
-    if (near || !(fabsf(__fadd_rn(S, -sthr)) > seps)) return dense_stage_exact<NODES>(P, c, st.tail_first, st.count, st.flags & 1u, st.thr, wid);
+    if (near || !(fabsf(__fadd_rn(S, -sthr)) > seps)) {
+        const int r = dense_stage_exact<NODES>(P, c, st.tail_first, st.count, st.flags & 1u, st.thr, wid);
+        if (COUNT) {   // diagnostic instantiation only: even these two lines cost the hot kernel 1.5-4.5 % (code growth at 8 sites)
+            atomicAdd(&s_dense_exact, 1u);
+            if (r & 2) atomicAdd(&s_dense_near, 1u);
+        }
+        return r & 1;
+    }
     return S >= sthr;
 }
 
@@ -390,10 +411,8 @@ __device__ __forceinline__ bool stage_verdict(const DenseParams &P, const DenseC
 // TREE: the cascade is a stage tree the kernel walks itself (DenseParams::exec_stages > tail_stages).
 // NODES: multi-node trees (DenseParams::npt > 1).
 // TILE_H: window rows per tile (== DenseParams::tile_h).
-template <int ROWSTEP_T, bool TREE, bool NODES, int TILE_H>
-__global__ void __launch_bounds__(kDenseThreads)   // (no min-blocks argument: even "1" lets ptxas take 88 registers and costs a CTA per SM)
-k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ CascadeArgs a, const int tile0) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+template <int ROWSTEP_T, bool TREE, bool NODES, int TILE_H, bool COUNT>
+__device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const CascadeArgs &a, const int tile0, unsigned char *smem_raw) {
     const DenseSmemPlan plan = dense_smem_plan(P);
     unsigned char *tile = smem_raw + plan.tile;
     float *sgf = reinterpret_cast<float *>(smem_raw + plan.sgf);
@@ -434,6 +453,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
 
     // ---- stage the integral tile ----
     for (int i = tid; i < kCtlInts; i += kDenseThreads) ctl[i] = 0;
+    if (tid == 0) s_dense_exact = s_dense_near = s_dense_done = 0u;   // (a block barrier follows on either staging path)
     const int n_tiles_smem = P.tilted_tile ? 2 : 1;
     const size_t tile2_off = ((size_t)((TILE_H - 1) * ystep + P.win_h + 1) * S * 4 + 127) & ~(size_t)127;
     const int32_t *__restrict__ gtil = a.tilted ? a.tilted + frame_off + (size_t)py0 * L.sum_pitch + px0 : gsum;
@@ -511,7 +531,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
             for (int k = 0; k < kDenseChunk; k++) {
                 if (!((m4 >> k) & 1u)) continue;
                 const int wid = (wy0 + (k0 + k) * kRowsPerSlot) * kTileW + wx;
-                if (!stage_verdict<NODES>(P, c, P.stage[s], sthr, seps, wid, Ssum[k], near[k])) {
+                if (!stage_verdict<NODES, COUNT>(P, c, P.stage[s], sthr, seps, wid, Ssum[k], near[k])) {
                     alive &= ~(1u << (k0 + k));
                     if (c.codes) dense_write_code(c, wid, s * c.code_mul);
                 }
@@ -539,107 +559,140 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     //     warp finishes its share on its own, without block barriers.
     constexpr int kClassCap = kTileWindows / 32;       // windows per class in a tile
     constexpr int kSeg = kTileWindows / kDenseWarps;   // list segment of a warp (its share is at most this)
-    uint16_t *cl_in = list, *cl_out = reinterpret_cast<uint16_t *>(smem_raw + plan.pool);
-    int *cnt_in = ctl + kCtlCount, *cnt_out = ctl + kCtlCountB, *cnt_zero = ctl + kCtlCountC;
-    {
-        // the (up to 8) windows of a thread share one class: wy advances by 4 rows = 32 in 8*wy
-        const int na = __popc(alive);
-        if (na) {
-            const int cq = (wx + 8 * wy0) & 31;
-            int at = atomicAdd(cnt_in + cq, na);
-#pragma unroll
-            for (int k = 0; k < kDenseSlots; k++)
-                if ((alive >> k) & 1u) cl_in[cq * kClassCap + at++] = (uint16_t)((wy0 + k * kRowsPerSlot) * kTileW + wx);
-        }
-    }
-    __syncthreads();
     int n_alive;
-    for (;; s++) {
-        const int h = cnt_in[lane];
-        int incl = h, hmax = h;
+    uint16_t *cur;
+    if (P.pool_min > 0) {
+        uint16_t *cl_in = list, *cl_out = reinterpret_cast<uint16_t *>(smem_raw + plan.pool);
+        int *cnt_in = ctl + kCtlCount, *cnt_out = ctl + kCtlCountB, *cnt_zero = ctl + kCtlCountC;
+        {
+            // the (up to 8) windows of a thread share one class: wy advances by 4 rows = 32 in 8*wy
+            const int na = __popc(alive);
+            if (na) {
+                const int cq = (wx + 8 * wy0) & 31;
+                int at = atomicAdd(cnt_in + cq, na);
+    #pragma unroll
+                for (int k = 0; k < kDenseSlots; k++)
+                    if ((alive >> k) & 1u) cl_in[cq * kClassCap + at++] = (uint16_t)((wy0 + k * kRowsPerSlot) * kTileW + wx);
+            }
+        }
+        __syncthreads();
+            for (;; s++) {
+            const int h = cnt_in[lane];
+            int incl = h, hmax = h;
+    #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+                hmax = max(hmax, __shfl_xor_sync(0xffffffffu, hmax, d));
+            }
+            const int excl = incl - h, tot = __shfl_sync(0xffffffffu, incl, 31);
+            if (tot == 0) return;
+            n_alive = tot;
+            if (!(P.pool_min > 0 && tot > P.pool_min && s < P.tail_stages)) {
+                // deal the class lists to the warps: rank i = (windows of lower classes) + position in the class
+                for (int r = warp; r < h; r += kDenseWarps) {
+                    const int i = excl + r;
+                    const int w = i % kDenseWarps, p = i / kDenseWarps;
+                    const int nw = (tot - w + kDenseWarps - 1) / kDenseWarps, Rw = (nw + 31) >> 5;
+                    const int col = p / Rw, row = p - col * Rw;
+                    cl_out[w * kSeg + row * 32 + col] = cl_in[lane * kClassCap + r];
+                }
+                __syncthreads();
+                break;
+            }
+            // ---- one pooled stage: the class-sorted windows (rank i) dealt column-major over R rows (row i % R, lane
+            //      i / R), R from the class histogram: ceil(n / 32) rows cost the fewest instructions, R = the largest
+            //      class makes every row conflict free; minimise rows * 1.8 + rows that keep a duplicate ----
+            int R = (tot + 31) >> 5;
+            {
+                int best = 0x7fffffff;
+                for (int r = R; r <= hmax; r++) {
+                    int e = max(h - r, 0);
+    #pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) e += __shfl_xor_sync(0xffffffffu, e, d);
+                    const int cost = r * 9 + 5 * min(r, e);
+                    if (cost < best) { best = cost; R = r; }
+                }
+            }
+            const int q = (R + kDenseWarps - 1) / kDenseWarps;
+            const int r_begin = warp * q, r_end = min(R, r_begin + q);
+            if (tid < 32) cnt_zero[tid] = 0;   // last read before the previous barrier, next written after the next one
+            const float sthr = P.stage[s].thr, seps = P.force_exact ? inf : P.stage[s].sum_eps;
+            auto fetch = [&](int r, bool &valid) -> int {   // the window of rank r + lane * R
+                const int i = r + lane * R;
+                valid = i < tot;
+                int cc = 0;   // its class: the last one with excl <= i
+    #pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int e_t = __shfl_sync(0xffffffffu, excl, (cc + step) & 31);
+                    if (e_t <= i) cc += step;   // (cc + step <= 31 always: steps 16, 8, 4, 2, 1 from 0)
+                }
+                const int e_c = __shfl_sync(0xffffffffu, excl, cc);
+                return valid ? (int)cl_in[cc * kClassCap + (i - e_c)] : 0;   // (an idle lane computes on window 0: any valid tile address)
+            };
+            auto keep_pool = [&](bool valid, int wid, float Ssum, bool near) {
+                const bool pass = valid && stage_verdict<NODES, COUNT>(P, c, P.stage[s], sthr, seps, wid, Ssum, near);
+                if (pass) {
+                    const int cq = (wid + 8 * (wid / kTileW)) & 31;
+                    cl_out[cq * kClassCap + atomicAdd(cnt_out + cq, 1)] = (uint16_t)wid;
+                }
+                if (valid && !pass && c.codes) dense_write_code(c, wid, s * c.code_mul);
+            };
+            for (int r = r_begin; r < r_end; r += 2) {
+                bool v0, v1 = false;
+                const int wid0 = fetch(r, v0);
+                if (r + 1 < r_end) {
+                    const int wid1 = fetch(r + 1, v1);
+                    const uint32_t base[2] = {dense_base(c, wid0), dense_base(c, wid1)};
+                    const float sg[2] = {sgf[wid0], sgf[wid1]};
+                    float Ssum[2] = {0.f, 0.f};
+                    bool near[2] = {false, false};
+                    stage_filter<2, false, 0, NODES>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near);
+                    keep_pool(v0, wid0, Ssum[0], near[0]);
+                    keep_pool(v1, wid1, Ssum[1], near[1]);
+                } else {
+                    const uint32_t base[1] = {dense_base(c, wid0)};
+                    const float sg[1] = {sgf[wid0]};
+                    float Ssum[1] = {0.f};
+                    bool near[1] = {false};
+                    stage_filter<1, false, 0, NODES>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near);
+                    keep_pool(v0, wid0, Ssum[0], near[0]);
+                }
+            }
+            __syncthreads();   // the next stage's class lists are complete
+            uint16_t *tl = cl_in; cl_in = cl_out; cl_out = tl;
+            int *tc = cnt_in; cnt_in = cnt_out; cnt_out = cnt_zero; cnt_zero = tc;
+        }
+
+        cur = cl_out + warp * kSeg;
+    } else {
+        // no pooled stages: deal the survivors straight from the phase-1 `alive` bits.  One atomic per thread reserves
+        // its windows' positions in their (common) class; every warp derives the class prefix itself.
+        const int na = __popc(alive), cq = (wx + 8 * wy0) & 31;
+        int at = na ? atomicAdd(ctl + kCtlCount + cq, na) : 0;
+        __syncthreads();
+        const int h = ctl[kCtlCount + lane];
+        int incl = h;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += v;
-            hmax = max(hmax, __shfl_xor_sync(0xffffffffu, hmax, d));
         }
-        const int excl = incl - h, tot = __shfl_sync(0xffffffffu, incl, 31);
-        if (tot == 0) return;
-        n_alive = tot;
-        if (!(P.pool_min > 0 && tot > P.pool_min && s < P.tail_stages)) {
-            // deal the class lists to the warps: rank i = (windows of lower classes) + position in the class
-            for (int r = warp; r < h; r += kDenseWarps) {
-                const int i = excl + r;
+        n_alive = __shfl_sync(0xffffffffu, incl, 31);
+        if (n_alive == 0) return;
+        at += __shfl_sync(0xffffffffu, incl - h, cq);   // rank i = windows of lower classes + position in the class
+#pragma unroll
+        for (int k = 0; k < kDenseSlots; k++) {
+            if ((alive >> k) & 1u) {
+                const int i = at++;
                 const int w = i % kDenseWarps, p = i / kDenseWarps;
-                const int nw = (tot - w + kDenseWarps - 1) / kDenseWarps, Rw = (nw + 31) >> 5;
+                const int nw = (n_alive - w + kDenseWarps - 1) / kDenseWarps, Rw = (nw + 31) >> 5;
                 const int col = p / Rw, row = p - col * Rw;
-                cl_out[w * kSeg + row * 32 + col] = cl_in[lane * kClassCap + r];
-            }
-            __syncthreads();
-            break;
-        }
-        // ---- one pooled stage: the class-sorted windows (rank i) dealt column-major over R rows (row i % R, lane
-        //      i / R), R from the class histogram: ceil(n / 32) rows cost the fewest instructions, R = the largest
-        //      class makes every row conflict free; minimise rows * 1.8 + rows that keep a duplicate ----
-        int R = (tot + 31) >> 5;
-        {
-            int best = 0x7fffffff;
-            for (int r = R; r <= hmax; r++) {
-                int e = max(h - r, 0);
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) e += __shfl_xor_sync(0xffffffffu, e, d);
-                const int cost = r * 9 + 5 * min(r, e);
-                if (cost < best) { best = cost; R = r; }
+                list[w * kSeg + row * 32 + col] = (uint16_t)((wy0 + k * kRowsPerSlot) * kTileW + wx);
             }
         }
-        const int q = (R + kDenseWarps - 1) / kDenseWarps;
-        const int r_begin = warp * q, r_end = min(R, r_begin + q);
-        if (tid < 32) cnt_zero[tid] = 0;   // last read before the previous barrier, next written after the next one
-        const float sthr = P.stage[s].thr, seps = P.force_exact ? inf : P.stage[s].sum_eps;
-        auto fetch = [&](int r, bool &valid) -> int {   // the window of rank r + lane * R
-            const int i = r + lane * R;
-            valid = i < tot;
-            int cc = 0;   // its class: the last one with excl <= i
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-                const int e_t = __shfl_sync(0xffffffffu, excl, (cc + step) & 31);
-                if (e_t <= i) cc += step;   // (cc + step <= 31 always: steps 16, 8, 4, 2, 1 from 0)
-            }
-            const int e_c = __shfl_sync(0xffffffffu, excl, cc);
-            return valid ? (int)cl_in[cc * kClassCap + (i - e_c)] : 0;   // (an idle lane computes on window 0: any valid tile address)
-        };
-        auto keep_pool = [&](bool valid, int wid, float Ssum, bool near) {
-            const bool pass = valid && stage_verdict<NODES>(P, c, P.stage[s], sthr, seps, wid, Ssum, near);
-            if (pass) {
-                const int cq = (wid + 8 * (wid / kTileW)) & 31;
-                cl_out[cq * kClassCap + atomicAdd(cnt_out + cq, 1)] = (uint16_t)wid;
-            }
-            if (valid && !pass && c.codes) dense_write_code(c, wid, s * c.code_mul);
-        };
-        for (int r = r_begin; r < r_end; r += 2) {
-            bool v0, v1 = false;
-            const int wid0 = fetch(r, v0);
-            if (r + 1 < r_end) {
-                const int wid1 = fetch(r + 1, v1);
-                const uint32_t base[2] = {dense_base(c, wid0), dense_base(c, wid1)};
-                const float sg[2] = {sgf[wid0], sgf[wid1]};
-                float Ssum[2] = {0.f, 0.f};
-                bool near[2] = {false, false};
-                stage_filter<2, false, 0, NODES>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near);
-                keep_pool(v0, wid0, Ssum[0], near[0]);
-                keep_pool(v1, wid1, Ssum[1], near[1]);
-            } else {
-                const uint32_t base[1] = {dense_base(c, wid0)};
-                const float sg[1] = {sgf[wid0]};
-                float Ssum[1] = {0.f};
-                bool near[1] = {false};
-                stage_filter<1, false, 0, NODES>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near);
-                keep_pool(v0, wid0, Ssum[0], near[0]);
-            }
-        }
-        __syncthreads();   // the next stage's class lists are complete
-        uint16_t *tl = cl_in; cl_in = cl_out; cl_out = tl;
-        int *tc = cnt_in; cnt_in = cnt_out; cnt_out = cnt_zero; cnt_zero = tc;
+        __syncthreads();
+        cur = list + warp * kSeg;
     }
 
     // ---- phase 2: every warp takes its share of the survivors through all remaining stages
@@ -650,7 +703,6 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     //      evaluates stumps grp, grp + G, ... for window `slot`, and the G partial sums meet
     //      through xor-shuffles -- with one window left the warp does 32 stumps per pass. ----
     int n = (n_alive - warp + kDenseWarps - 1) / kDenseWarps;
-    uint16_t *cur = cl_out + warp * kSeg;
     bool dealt = true;   // first compacted stage: balanced rows (row r holds (n - r + R - 1) / R entries)
     for (; s < P.tail_stages && n > 0; s++) {
         const float sthr = P.stage[s].thr, seps = P.force_exact ? inf : P.stage[s].sum_eps;
@@ -658,7 +710,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
         // append the survivors among this pass's windows at cur[n_next..]: always at or below the
         // positions the pass has already read (in-place compaction)
         auto keep = [&](bool valid, int wid, float Ssum, bool near) {
-            const bool pass = valid && stage_verdict<NODES>(P, c, P.stage[s], sthr, seps, wid, Ssum, near);
+            const bool pass = valid && stage_verdict<NODES, COUNT>(P, c, P.stage[s], sthr, seps, wid, Ssum, near);
             const unsigned m = __ballot_sync(0xffffffffu, pass);
             if (pass) cur[n_next + __popc(m & ((1u << lane) - 1u))] = (uint16_t)wid;
             n_next += __popc(m);
@@ -754,7 +806,7 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
                 uint32_t to = kRouteReject;
                 bool pass = false;
                 if (valid) {
-                    pass = stage_verdict<NODES>(P, c, st, sthr, seps, wid, Ssum, near);
+                    pass = stage_verdict<NODES, COUNT>(P, c, st, sthr, seps, wid, Ssum, near);
                     to = pass ? to_pass : to_fail;
                 }
                 const bool on = valid && to < kRouteReject;
@@ -841,6 +893,26 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
     }
 }
 
+// COUNT: the diagnostic instantiation (detectors created with want_codes) that counts FP64 fallbacks and
+// near-threshold stage sums; the production instantiation carries none of that code.
+template <int ROWSTEP_T, bool TREE, bool NODES, int TILE_H, bool COUNT>
+__global__ void __launch_bounds__(kDenseThreads)   // (no min-blocks argument: even "1" lets ptxas take 88 registers and costs a CTA per SM)
+k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ CascadeArgs a, const int tile0) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cascade_tiles_body<ROWSTEP_T, TREE, NODES, TILE_H, COUNT>(P, a, tile0, smem_raw);
+    // every warp ends up here (the body's returns are warp uniform); the last one flushes the CTA's counters
+    if (!COUNT) return;
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        __threadfence_block();
+        if (atomicAdd(&s_dense_done, 1u) == kDenseWarps - 1) {
+            const unsigned int ne = s_dense_exact, nn = s_dense_near;
+            if (ne) atomicAdd(a.counters + 4, (ull)ne);
+            if (nn) atomicAdd(a.counters + 5, (ull)nn);
+        }
+    }
+}
+
 // row steps of the stock window sizes (bytes between a thread's consecutive phase-1 windows)
 constexpr int dense_stride_ce(int win_w, int ystep) {
     int cols = ((kTileW - 1) * ystep + win_w + 1 + 3) & ~3;
@@ -854,8 +926,8 @@ constexpr int dense_rowstep_ce(int win_w, int ystep) { return (kDenseThreads / k
 template <int ROWSTEP_T, bool TREE, bool NODES, int TILE_H = kTileH>
 static cudaError_t launch_tiles_tt(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, size_t smem, cudaStream_t stream) {
     static SmemLimitCache limit;
-    if (cudaError_t e = limit.ensure(k_cascade_tiles<ROWSTEP_T, TREE, NODES, TILE_H>, smem)) return e;
-    k_cascade_tiles<ROWSTEP_T, TREE, NODES, TILE_H><<<dim3(n_tiles, a.n_frames), kDenseThreads, smem, stream>>>(P, a, tile0);
+    if (cudaError_t e = limit.ensure(k_cascade_tiles<ROWSTEP_T, TREE, NODES, TILE_H, kTilesCount>, smem)) return e;
+    k_cascade_tiles<ROWSTEP_T, TREE, NODES, TILE_H, kTilesCount><<<dim3(n_tiles, a.n_frames), kDenseThreads, smem, stream>>>(P, a, tile0);
     return cudaGetLastError();
 }
 template <int ROWSTEP_T>
@@ -876,9 +948,18 @@ static cudaError_t launch_tiles_t(const DenseParams &P, const CascadeArgs &a, in
     return launch_tiles_tt<ROWSTEP_T, false, false>(P, a, tile0, n_tiles, smem, stream);
 }
 
+// The tile kernel is compiled twice, in two translation units that build in parallel: this file as it is (the
+// production instantiations) and through kernels_clod_count.cu (CLFD_TILES_COUNT_TU: the diagnostic instantiations
+// that count FP64 fallbacks / near-threshold stage sums; only the tile kernel and this launcher are compiled there).
+#ifdef CLFD_TILES_COUNT_TU
+cudaError_t launch_cascade_tiles_count(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, cudaStream_t stream) {
+#else
+cudaError_t launch_cascade_tiles_count(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, cudaStream_t stream);
 cudaError_t launch_cascade_tiles(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, cudaStream_t stream) {
+    if (a.count_exact) return launch_cascade_tiles_count(P, a, tile0, n_tiles, stream);
+#endif
     if (n_tiles <= 0 || a.n_frames == 0) return cudaSuccess;
-    const size_t smem = dense_smem_bytes(P);
+    const size_t smem = dense_smem_plan(P).total;
     // byte distance between a thread's consecutive phase-1 windows: 2 window rows
     const int rowstep = (kDenseThreads / kTileW) * P.ystep * P.tile_stride * 4;
     // the common window widths (20 and 24 pixels) get immediate-offset code
@@ -893,6 +974,7 @@ cudaError_t launch_cascade_tiles(const DenseParams &P, const CascadeArgs &a, int
     }
 }
 
+#ifndef CLFD_TILES_COUNT_TU
 // ------------------------------------------------------------------------------------
 // enqueue-all: cascades without a dense prefix start every window in the deep kernel
 // ------------------------------------------------------------------------------------
@@ -1206,5 +1288,7 @@ cudaError_t launch_cascade_deep(const CascadeArgs &a, int n_sms, cudaStream_t st
     k_cascade_deep<<<n_sms * 8, kDeepThreads, 0, stream>>>(a);
     return cudaGetLastError();
 }
+
+#endif  // CLFD_TILES_COUNT_TU
 
 }  // namespace clfd

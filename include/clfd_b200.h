@@ -180,6 +180,15 @@ typedef struct clfd_run_stats {
     int64_t bytes_resize, bytes_integral, bytes_cascade; /* algorithmic bytes per frame; bytes_integral:
                                                             the upright pair, w*h + (w+1)(h+1)*12 per level */
     int64_t bytes_tilted;     /* tilted integral, w*h + (w+1)(h+1)*4 per level; 0 without tilted features */
+    /* The tile kernel decides stumps and stage sums with FP32 filters and redoes a window's stage in the reference's
+     * FP64 arithmetic whenever a decision could differ.  Counted per (window, stage):
+     *   exact_stage_evals     : stages redone in FP64
+     *   near_threshold_events : of those, |stage_sum - threshold| <= 1e-5 * |threshold| (the tolerance the north star
+     *                           allows for such windows; results are identical to the reference's anyway).  Every such
+     *                           event takes the FP64 path, so the count is exact.  Image-pyramid mode.
+     * Counted by detectors created with want_codes (a diagnostic instantiation of the tile kernel: the counting code
+     * costs the production kernel 1.5-4.5 % even when no window takes the path); -1 otherwise. */
+    int64_t exact_stage_evals, near_threshold_events;
 } clfd_run_stats;
 
 CLFD_API int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,

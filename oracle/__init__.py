@@ -39,7 +39,7 @@ class _Level(C.Structure):
 class _Stats(C.Structure):
     _fields_ = [("windows", C.c_int64), ("weak_evals", C.c_int64), ("node_evals", C.c_int64),
                 ("accepted", C.c_int64), ("near_stage_thr", C.c_int64),
-                ("stage_reach", C.c_int64 * 64)]
+                ("stage_reach", C.c_int64 * 64), ("near_stage_events", C.c_int64)]
 
 
 def _p(a, t):
@@ -110,11 +110,12 @@ class Stats:
     accepted: int
     near_stage_thr: int
     stage_reach: list
+    near_stage_events: int = 0
 
 
 def _stats(s: _Stats) -> Stats:
     return Stats(s.windows, s.weak_evals, s.node_evals, s.accepted, s.near_stage_thr,
-                 list(s.stage_reach))
+                 list(s.stage_reach), s.near_stage_events)
 
 
 CODE_SKIPPED, CODE_OUTSIDE = -32768, -32767

@@ -482,7 +482,7 @@ static int run_window(const vjo_cascade *c, const node_t *lvl_nodes, const level
     int64_t weak = 0, nodes = 0;
     int code;
 #define NEAR_CHECK(S, T) do { double _t = (double)(T); \
-        if (fabs((S) - _t) <= 1e-5 * fabs(_t)) near = 1; } while (0)
+        if (fabs((S) - _t) <= 1e-5 * fabs(_t)) { near = 1; st->near_stage_events++; } } while (0)
 
     if (c->is_tree) { /* tempcv.cpp:834-861 */
         int ptr = 0, last = 0, accepted = 0;
@@ -572,7 +572,7 @@ static int run_window(const vjo_cascade *c, const node_t *lvl_nodes, const level
 static void stats_add(vjo_stats *a, const vjo_stats *b)
 {
     a->windows += b->windows; a->weak_evals += b->weak_evals; a->node_evals += b->node_evals;
-    a->accepted += b->accepted; a->near_stage_thr += b->near_stage_thr;
+    a->accepted += b->accepted; a->near_stage_thr += b->near_stage_thr; a->near_stage_events += b->near_stage_events;
     for (int i = 0; i < 64; i++) a->stage_reach[i] += b->stage_reach[i];
 }
 

@@ -91,6 +91,7 @@ typedef struct vjo_stats {
     int64_t accepted;          /* windows accepted */
     int64_t near_stage_thr;    /* windows with |stage_sum-thr| <= 1e-5*|thr| at some stage */
     int64_t stage_reach[64];   /* windows that evaluated stage i (i<64) */
+    int64_t near_stage_events; /* (window, stage) pairs with |stage_sum-thr| <= 1e-5*|thr| */
 } vjo_stats;
 
 /* Whole REF-SI detection of one 8-bit gray frame.

@@ -23,6 +23,7 @@ def _compare(gpu_ctx, names, frames, sf, min_size=(0, 0), max_size=(0, 0)):
                         max_size=max_size, want_codes=True)
     res = det.detect(frames)
     report = {}
+    near_events = 0
     for ci, nm in enumerate(names):
         oc = oracle_cascade(nm)
         codes = det.codes(ci, n)
@@ -36,7 +37,13 @@ def _compare(gpu_ctx, names, frames, sf, min_size=(0, 0), max_size=(0, 0)):
                                   f"gpu {codes[f][bad[:5]]} oracle {ocodes[bad[:5]]}"
             assert np.array_equal(res.frame_rects(f, ci), _sorted(rects)), f"{nm} frame {f}: rect sets differ"
             near_total += st.near_stage_thr
+            near_events += st.near_stage_events
         report[nm] = near_total
+    # counted and reported: stage sums within 1e-5 relative of a threshold (all of them take the FP64 path of the
+    # tile kernel, which counts them), and FP64 fallbacks as a whole.  Cascades the tile kernel finishes itself.
+    if all(c.info.dense_stages == c.info.n_stages for c in cascades):
+        assert res.stats["near_threshold_events"] == near_events, (res.stats["near_threshold_events"], near_events)
+        assert res.stats["exact_stage_evals"] >= near_events
     det.close()
     return report
 
