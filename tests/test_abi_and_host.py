@@ -183,8 +183,10 @@ def test_tile_kernel_register_budget():
             regs[name] = int(m.group(1))
     tiles = {k: v for k, v in regs.items() if "k_cascade_tilesILi" in k}
     assert len(tiles) >= 12, sorted(regs)
-    plain = {k: v for k, v in tiles.items() if "ELb0ELb0ELi" in k}
-    assert plain and all(v <= 64 for v in plain.values()), plain
+    # plain stump cascades, 24- and 32-row tiles (the 16-row tiles of tilted cascades are bound to 2-3 CTAs per SM by
+    # their two shared-memory tiles anyway); both the production and the counting instantiation
+    plain = {k: v for k, v in tiles.items() if "ELb0ELb0ELi24E" in k or "ELb0ELb0ELi32E" in k}
+    assert len(plain) >= 8 and all(v <= 64 for v in plain.values()), plain
     assert all(v <= 80 for v in tiles.values()), tiles
 
 
