@@ -252,6 +252,11 @@ class Detector:
         assert (H, W) == (self.height, self.width)
         abi.check(abi.lib().clfd_detect_submit(self._h, _ptr(frames), n, fs, rs))
 
+    def submit_views(self, first_frame, n_frames: int, frame_stride: int, row_stride: int) -> None:
+        """submit n_frames frames that start frame_stride bytes apart at `first_frame` (a pinned tensor view or an
+        address); frames may overlap (frame_stride = row_stride: views of one canvas, one row apart)"""
+        abi.check(abi.lib().clfd_detect_submit(self._h, _ptr(first_frame), n_frames, frame_stride, row_stride))
+
     def collect(self) -> DetectResult:
         cnt = C.c_int64()
         abi.check(abi.lib().clfd_detect_collect(self._h, self._rects.ctypes.data_as(C.POINTER(abi.Rect)),

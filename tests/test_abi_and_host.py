@@ -242,3 +242,22 @@ def test_broken_tree_links_are_rejected():
     with pytest.raises(clfd.ClfdError, match="not a forest"):
         clfd.Cascade(flat=bad)
     clfd.Cascade(flat=tree)   # the stock stage tree passes
+
+
+def test_stream_source_is_a_function_of_the_global_frame_index():
+    """bench.py --stream / tests/test_gpu_multi.py: any sharding of the stream tiles it exactly, a batch's
+    overlapping canvas views are the frames, and the frames are distinct"""
+    from clfacedetection_b200 import sharding, stream
+    src = stream.StreamSource(160, 120, n_canvases=2, pinned=False)
+    N = 300
+    for world in (1, 3, 8):
+        seen = []
+        for r in range(world):
+            f, l = sharding.shard_range(N, r, world)
+            for g0, n, view in src.runs(f, l, 16):
+                assert 1 <= n <= 16
+                for j in (0, n - 1):
+                    assert np.array_equal(view[j:j + 120, :160].numpy(), src.frame(g0 + j))
+                seen += list(range(g0, g0 + n))
+        assert seen == list(range(N))
+    assert len({src.frame(g).tobytes() for g in range(N)}) == N
