@@ -2,7 +2,8 @@
 """bench.py -- 1080p frames/s (and windows/s) of the Viola-Jones hot path on N B200s.
 
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, C ABI)
-    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (its own code from oracle/_ref,
+                                                             # else the oracle port) on the host cores
 
 A "step" is one pass of the whole hot path (pyramid resize -> integral images -> cascade ->
 raw rects) over one batch of synthetic 1080p frames per GPU.  Workload = BASELINE.json's
@@ -112,9 +113,32 @@ class ClockSampler:
 
 
 def cpu_reference(frames: np.ndarray, threads: int):
-    """The reference's CPU path (REF-SI restatement = oracle port) on `frames`; returns
-    (seconds, windows, rects)."""
+    """The reference's CPU path on `frames` with `threads` host threads; returns (seconds, windows, rects, kind).
+
+    kind "reference": oracle/_ref/libtempcv_ref.so -- the reference's OWN cvHaarDetectObjects (tempcv.cpp:1188-1503,
+    CV_HAAR_SCALE_IMAGE, compiled from /root/reference by oracle/build_ref.py; the prebuilt library travels to the GPU
+    box), one frame per thread at a time, every thread with its own cascade (the reference mutates the hidden cascade
+    per level, tempcv.cpp:549-768, so a cascade cannot be shared).
+    kind "port": the REF-SI restatement (oracle/vj_oracle.c, held equal to that library by tests/), OpenMP over window
+    rows -- used when the library is absent."""
     import oracle
+    from oracle import ref
+    if ref.available():
+        from concurrent.futures import ThreadPoolExecutor
+        n_thr = max(1, min(threads, len(frames)))
+        cas = [[ref.RefCascade(x) for x in XML] for _ in range(n_thr)]
+        wpf = sum(sum(l.nx * l.ny for l in oracle.Cascade(x).plan_levels(W, H, SCALE, MIN_SIZE)) for x in XML)
+
+        def work(t):
+            n = 0
+            for i in range(t, len(frames), n_thr):   # ctypes releases the GIL for the duration of the call
+                for c in cas[t]:
+                    n += len(c.detect(frames[i], SCALE, 0, ref.CV_HAAR_SCALE_IMAGE, MIN_SIZE)[0])
+            return n
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(n_thr) as ex:
+            rects = sum(ex.map(work, range(n_thr)))
+        return time.perf_counter() - t0, wpf * len(frames), rects, "reference"
     cascades = [oracle.Cascade(x) for x in XML]
     t0 = time.perf_counter()
     windows = rects = 0
@@ -123,7 +147,31 @@ def cpu_reference(frames: np.ndarray, threads: int):
             r, _, _, st, _ = cas.detect(f, SCALE, MIN_SIZE, want_codes=False, n_threads=threads)
             windows += st.windows
             rects += len(r)
-    return time.perf_counter() - t0, windows, rects
+    return time.perf_counter() - t0, windows, rects, "port"
+
+
+def clod_cpu_baseline(frames: np.ndarray, threads: int):
+    """CLOD-CPU: the reference's own detector with use_cl = FALSE (clod.cpp:1339-1500, CLOD_PER_STAGE_ITERATIONS |
+    CLOD_PRECOMPUTE_FEATURES as main.cpp:79 -- "the reference's CPU path" of BASELINE.json), restated in
+    oracle/clod_cpu.c (pinned to the reference's compiled code by tests/test_clod_cpu.py) with the scale factor as a
+    parameter.  Different semantics from the metric's pipeline (float, scaled features, step max(2, scale)): a context
+    number, not a parity target.  None for cascades it cannot run (trees)."""
+    import oracle
+    try:
+        t0 = time.perf_counter()
+        matches = windows = evals = 0
+        for x in XML:
+            c, w, e = oracle.Cascade(x).clod_cpu_detect_batch(frames, SCALE, threads)
+            matches += int(c.sum()); windows += w; evals += e
+        dt = time.perf_counter() - t0
+    except ValueError:
+        return None
+    n = len(frames)
+    return {"value": round(n / dt, 3), "unit": "frames/s", "cores": min(threads, n), "kind": "port",
+            "sample": f"{n} frames, one frame per thread (the reference is single-threaded, clod.cpp:700)",
+            "windows_per_frame": windows // n, "windows_per_sec": round(windows / dt, 1),
+            "classifier_evals_per_sec": round(evals / dt, 1), "matches": matches,
+            "what": "clodDetectObjects(use_cl=FALSE), per-stage iterations + precomputed features, float (clod.cpp:1434-1482)"}
 
 
 def run_reference(args):
@@ -132,26 +180,28 @@ def run_reference(args):
         return 0
     from clfacedetection_b200.frames import make_frames
     cores = os.cpu_count() or 1
-    per_step = args.ref_frames
+    per_step = args.ref_frames if args.ref_frames > 0 else max(4, min(cores, 64))
     frames = make_frames("octave", W, H, per_step)
     for _ in range(args.warmup):
-        cpu_reference(frames[:1], cores)
+        cpu_reference(frames[:min(per_step, cores)], cores)
     t_total, win_total = 0.0, 0
     for _ in range(args.steps):
-        t, w, _ = cpu_reference(frames, cores)
+        t, w, _, kind = cpu_reference(frames, cores)
         t_total += t
         win_total += w
     fps = per_step * args.steps / t_total
-    # for the record: the scale-cascade formulation (REF-SC: what main.cpp:145 runs and the shape of
-    # clod's own CPU variants, clod.cpp:1339-1500) on the same frames, one pass
+    # for the record: the scale-cascade formulation (REF-SC: what main.cpp:145 runs) on a few of the frames, one pass,
+    # and the reference's own CPU detector (CLOD-CPU, clod.cpp:1339-1500)
     import oracle
     t0 = time.perf_counter()
     sc_windows = 0
-    for f in frames:
+    n_sc = min(per_step, 4)
+    for f in frames[:n_sc]:
         for x in XML:
             _, _, st, _ = oracle.Cascade(x).detect_sc(f, SCALE, MIN_SIZE, want_codes=False, n_threads=cores)
             sc_windows += st.windows
-    sc_fps = per_step / (time.perf_counter() - t0)
+    sc_fps = n_sc / (time.perf_counter() - t0)
+    how = ("one frame per thread, every thread its own cascade" if kind == "reference" else "OpenMP over window rows")
     line = {
         "impl": "reference", "metric": "frames_per_sec_1080p" if (W, H) == (1920, 1080) else f"frames_per_sec_{W}x{H}", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
@@ -159,9 +209,12 @@ def run_reference(args):
         "config": {"workload": f"haarcascade_{CASCADE} {W}x{H} scale {SCALE}, {per_step} octave-noise frames per step "
                                "(bounded sample of the 64-frame GPU batch)", "frames_per_step": per_step},
         "windows_per_sec": win_total / t_total,
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{per_step} frames/step x {args.steps} steps, OpenMP over window rows",
-                         "scale_cascade_formulation_value": sc_fps, "scale_cascade_windows_per_frame": sc_windows // per_step},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": min(cores, per_step) if kind == "reference" else cores, "kind": kind,
+                         "sample": f"{per_step} frames/step x {args.steps} steps, {how}",
+                         "what": ("oracle/_ref/libtempcv_ref.so: the reference's own cvHaarDetectObjects (tempcv.cpp, CV_HAAR_SCALE_IMAGE) "
+                                  "compiled from its sources" if kind == "reference" else "oracle/vj_oracle.c (REF-SI restatement)"),
+                         "scale_cascade_formulation_value": sc_fps, "scale_cascade_windows_per_frame": sc_windows // n_sc,
+                         "clod_cpu": clod_cpu_baseline(frames, cores)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -260,8 +313,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU")
-    ap.add_argument("--ref-frames", type=int, default=4, help="frames per step of the CPU reference arm")
-    ap.add_argument("--cpu-baseline-frames", type=int, default=8)
+    ap.add_argument("--ref-frames", type=int, default=0, help="frames per step of the CPU reference arm (0: one per host core, 4..64)")
+    ap.add_argument("--cpu-baseline-frames", type=int, default=0, help="0: one frame per host core (4..64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stream", type=int, default=0, help="strong scaling: a stream of this many distinct frames cut over the ranks "
                                                           "(BASELINE.json configs[4]: 8192); prints its own line")
@@ -476,11 +529,16 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            n = args.cpu_baseline_frames
-            t, w, _ = cpu_reference(base[:n] if n <= uniq else make_frames("octave", W, H, n), cores)
-            line["cpu_baseline"] = {"value": round(n / t, 3), "unit": "frames/s", "cores": cores, "kind": "port",
-                                    "sample": f"{n} of the batch's 1080p frames, REF-SI oracle, OpenMP over window rows",
-                                    "windows_per_sec": round(w / t, 1)}
+            n = args.cpu_baseline_frames if args.cpu_baseline_frames > 0 else max(4, min(cores, 64))
+            cpu_frames = base[:n] if n <= uniq else make_frames("octave", W, H, n)
+            t, w, _, kind = cpu_reference(cpu_frames, cores)
+            line["cpu_baseline"] = {"value": round(n / t, 3), "unit": "frames/s", "cores": min(cores, n) if kind == "reference" else cores,
+                                    "kind": kind,
+                                    "sample": (f"{n} 1080p frames of the batch's generator, the reference's own cvHaarDetectObjects "
+                                               "(oracle/_ref, CV_HAAR_SCALE_IMAGE), one frame per thread" if kind == "reference" else
+                                               f"{n} of the batch's 1080p frames, REF-SI oracle, OpenMP over window rows"),
+                                    "windows_per_sec": round(w / t, 1),
+                                    "clod_cpu": clod_cpu_baseline(cpu_frames, cores)}
         default_run = (CASCADE == "frontalface_alt" and (W, H) == (1920, 1080) and SCALE == 1.2 and args.mode == "pyramid"
                        and world == 1 and not args.no_extra)
         if args.mode == "pyramid" and not args.no_extra:

@@ -21,13 +21,15 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compile the C restatement with the committed Makefile."""
-    src = os.path.join(_HERE, "vj_oracle.c")
-    hdr = os.path.join(_HERE, "vj_oracle.h")
-    stale = (not os.path.exists(_LIB_PATH)
-             or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(hdr)))
+    deps = [os.path.join(_HERE, f) for f in ("vj_oracle.c", "vj_oracle.h", "clod_cpu.c", "Makefile")]
+    stale = not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(d) for d in deps)
     if force or stale:
         subprocess.check_call(["make", "-s", "-C", _HERE] + (["-B"] if force else []))
     return _LIB_PATH
+
+
+CLOD_PRECOMPUTE_FEATURES = 2 << 0     # clod.h:17
+CLOD_PER_STAGE_ITERATIONS = 2 << 2    # clod.h:19
 
 
 class _Level(C.Structure):
@@ -86,6 +88,14 @@ def lib():
                                      C.POINTER(C.c_int16), C.POINTER(C.c_uint8), C.POINTER(_Stats), C.c_int]
         L.vjo_group_rectangles.argtypes = [C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_double,
                                            C.POINTER(C.c_int32)]
+        i64p, u8p = C.POINTER(C.c_int64), C.POINTER(C.c_uint8)
+        cas = [C.c_int, C.c_int, C.c_int, ip, fp, ip, ip, fp, fp, fp]
+        L.clodcpu_detect.restype = C.c_int64
+        L.clodcpu_detect.argtypes = cas + [u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_uint, C.POINTER(C.c_int32), C.c_int64, i64p, i64p]
+        L.clodcpu_detect_batch.restype = C.c_int64
+        L.clodcpu_detect_batch.argtypes = cas + [u8p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float,
+                                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, i64p, i64p, i64p, C.c_int]
         _lib = L
     return _lib
 
@@ -187,6 +197,44 @@ class Cascade:
                 break
             cap = int(n)
         return rects[:n].copy(), codes, near, _stats(st), levels
+
+    def _clod_args(self):
+        f = self.flat
+        return [f.win_w, f.win_h, f.n_stages, _p(f.st_ntrees, C.c_int), _p(f.st_thr, C.c_float), _p(f.tr_nnodes, C.c_int),
+                _p(f.nd_rect, C.c_int), _p(f.nd_weight, C.c_float), _p(f.nd_thr, C.c_float), _p(f.alpha, C.c_float)]
+
+    def clod_cpu_detect(self, img: np.ndarray, scale_factor: float = 1.1, min_size=(0, 0), max_size=(0, 0),
+                        flags: int = CLOD_PER_STAGE_ITERATIONS | CLOD_PRECOMPUTE_FEATURES):
+        """CLOD-CPU (oracle/clod_cpu.c: clodDetectObjects(use_cl=FALSE), clod.cpp:1339-1500) on one gray frame
+        -> (raw matches [n,4], windows evaluated, classifier evaluations).  Stump cascades only."""
+        img = np.ascontiguousarray(img, np.uint8)
+        H, W = img.shape
+        cap = 1 << 16
+        nw, ne = C.c_int64(), C.c_int64()
+        while True:
+            rects = np.zeros((cap, 4), np.int32)
+            n = lib().clodcpu_detect(*self._clod_args(), _p(img, C.c_uint8), W, H, img.strides[0], scale_factor,
+                                     min_size[0], min_size[1], max_size[0], max_size[1], flags,
+                                     _p(rects, C.c_int32), cap, C.byref(nw), C.byref(ne))
+            if n < 0:
+                raise ValueError("CLOD-CPU runs stump cascades with at most 220 classifiers per stage (clod.cpp:13,458)")
+            if n <= cap:
+                break
+            cap = int(n)
+        return rects[:n].copy(), int(nw.value), int(ne.value)
+
+    def clod_cpu_detect_batch(self, frames: np.ndarray, scale_factor: float, n_threads: int,
+                              flags: int = CLOD_PER_STAGE_ITERATIONS | CLOD_PRECOMPUTE_FEATURES):
+        """frames [n, H, W] uint8, one frame per thread at a time -> (match counts [n], windows, classifier evaluations)"""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n, H, W = frames.shape
+        counts = np.zeros(n, np.int64)
+        nw, ne = C.c_int64(), C.c_int64()
+        r = lib().clodcpu_detect_batch(*self._clod_args(), _p(frames, C.c_uint8), n, frames.strides[0], W, H, frames.strides[1],
+                                       scale_factor, 0, 0, 0, 0, flags, _p(counts, C.c_int64), C.byref(nw), C.byref(ne), n_threads)
+        if r < 0:
+            raise ValueError("CLOD-CPU runs stump cascades with at most 220 classifiers per stage")
+        return counts, int(nw.value), int(ne.value)
 
     def detect_roc(self, img: np.ndarray, scale_factor: float, min_size=(0, 0), max_size=(0, 0), n_threads: int = 0):
         """REF-SI with outputRejectLevels (tempcv.cpp:1084-1094) -> (rects[n,4], reject_levels[n],

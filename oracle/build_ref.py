@@ -18,6 +18,16 @@ block.  The ranges taken are every function on the Haar path:
                           cvHaarDetectObjectsForROC, cvHaarDetectObjects
     tempcv.cpp 1702-2089  cvReleaseHaarClassifierCascade, icvReadHaarClassifier (XML reader)
 
+and the reference's own CPU detector ("CLOD-CPU", what BASELINE.json calls the reference's CPU path;
+clod.cpp as a whole needs the author's un-vendored CLUtil and <OpenCL/opencl.h>):
+
+    clod.h       17-21, 39-47   CLOD_* flags, CLODWeightedRect, CLODDetectObjectsResult
+    clod.cpp     11-38          macros, CLODOptimizedRect, CLODSubwindowData
+    clod.cpp    182-357         areRectSimilar, partitionData, filterResult (compiled, never called: min_neighbors = 0)
+    clod.cpp    371-527         setupScale, computeVariance, precomputeFeatures, precomputeWindows
+    clod.cpp    580-787         runClassifier, runClassifierWithPrecomputedFeatures, runSubwindow, runCascade
+    clod.cpp   1339-1500        clodDetectObjects
+
 On a machine without /root/reference (the GPU box) nothing is built: the prebuilt .so travels
 with the snapshot, and tests that need it skip if it is absent.
 """
@@ -36,10 +46,15 @@ LIB = os.path.join(OUT, "libtempcv_ref.so")
 RANGES = {
     "tempcv_hpp_extract.inc": ("tempcv.hpp", [(60, 155)]),
     "tempcv_cpp_extract.inc": ("tempcv.cpp", [(40, 1516), (1702, 2089)]),
+    # the reference's own CPU detector, clodDetectObjects(use_cl = FALSE): flags and result structs; macros and list
+    # structs, filterResult, setupScale .. precomputeWindows, runClassifier .. runCascade, clodDetectObjects
+    "clod_h_extract.inc": ("clod.h", [(17, 21), (39, 47)]),
+    "clod_cpp_extract.inc": ("clod.cpp", [(11, 38), (182, 357), (371, 527), (580, 787), (1339, 1500)]),
 }
+SOURCES = ("tempcv.hpp", "tempcv.cpp", "clod.h", "clod.cpp")
 
 def reference_available() -> bool:
-    return all(os.path.exists(os.path.join(REF, f)) for f in ("tempcv.hpp", "tempcv.cpp"))
+    return all(os.path.exists(os.path.join(REF, f)) for f in SOURCES)
 
 
 def _extract() -> None:
@@ -56,7 +71,7 @@ def _extract() -> None:
         with open(os.path.join(OUT, out_name), "w") as f:
             f.write("\n".join(parts) + "\n")
     with open(os.path.join(OUT, "SOURCES.txt"), "w") as f:
-        for src in ("tempcv.hpp", "tempcv.cpp"):
+        for src in SOURCES:
             with open(os.path.join(REF, src), "rb") as g:
                 f.write(f"{hashlib.sha256(g.read()).hexdigest()}  {src}\n")
 
@@ -65,10 +80,11 @@ def build(force: bool = False) -> str | None:
     """Returns the path of the library, or None when neither the reference nor a prebuilt
     library is available."""
     deps = [os.path.join(HERE, "ref_shim", "cvmini.hpp"), os.path.join(HERE, "ref_shim", "ref_driver.cpp"),
+            os.path.join(HERE, "ref_shim", "clod_driver.cpp"),
             os.path.join(HERE, "vj_oracle.c"), os.path.join(HERE, "vj_oracle.h"), os.path.abspath(__file__)]
     if not reference_available():
         return LIB if os.path.exists(LIB) else None
-    deps += [os.path.join(REF, "tempcv.hpp"), os.path.join(REF, "tempcv.cpp")]
+    deps += [os.path.join(REF, f) for f in SOURCES]
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in deps):
         return LIB
     _extract()
@@ -77,7 +93,8 @@ def build(force: bool = False) -> str | None:
     subprocess.check_call(["/usr/bin/gcc", "-std=gnu11"] + cflags + ["-c", os.path.join(HERE, "vj_oracle.c"), "-o", obj])
     subprocess.check_call(["/usr/bin/g++", "-std=gnu++14", "-w"] + cflags +
                           ["-I", OUT, "-I", os.path.join(HERE, "ref_shim"), "-shared", "-o", LIB,
-                           os.path.join(HERE, "ref_shim", "ref_driver.cpp"), obj, "-lm"])
+                           os.path.join(HERE, "ref_shim", "ref_driver.cpp"), os.path.join(HERE, "ref_shim", "clod_driver.cpp"),
+                           obj, "-lm"])
     # the verbatim extracts were only needed by the compiler: nothing of the reference's text stays
     for name in list(RANGES) + ["vj_oracle.o"]:
         os.unlink(os.path.join(OUT, name))

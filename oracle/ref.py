@@ -56,6 +56,9 @@ def lib():
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32, i32, i32, dp, C.c_int64]
         L.tcv_group_rectangles.argtypes = [i32, C.c_int, C.c_int, C.c_double, i32]
         L.tcv_group_rectangles_roc.argtypes = [i32, C.c_int, C.c_int, C.c_double, i32, dp]
+        L.tcv_clod_detect.restype = C.c_int64
+        L.tcv_clod_detect.argtypes = [C.c_void_p, u8, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_uint, i32, C.c_int64]
         _lib = L
     return _lib
 
@@ -175,6 +178,25 @@ class RefCascade:
                 break
             cap = int(n)
         return rects[:n].copy(), nb[:n].copy(), lv[:n].copy(), wt[:n].copy()
+
+
+def _clod_detect(self, img: np.ndarray, flags: int = (2 << 2) | (2 << 0), min_size=(0, 0), max_size=(0, 0)):
+    """The reference's clodDetectObjects(use_cl=FALSE, min_neighbors=0), clod.cpp:1339-1500 (scale factor 1.1, hard-coded
+    at clod.cpp:1349) -> raw matches [n,4].  flags: CLOD_PER_STAGE_ITERATIONS | CLOD_PRECOMPUTE_FEATURES as main.cpp:79."""
+    img = np.ascontiguousarray(img, np.uint8)
+    H, W = img.shape
+    cap = 1 << 16
+    while True:
+        rects = np.zeros((cap, 4), np.int32)
+        n = lib().tcv_clod_detect(self._h, _p(img, C.c_uint8), W, H, img.strides[0], min_size[0], min_size[1],
+                                  max_size[0], max_size[1], flags, _p(rects, C.c_int32), cap)
+        if n <= cap:
+            break
+        cap = int(n)
+    return rects[:n].copy()
+
+
+RefCascade.clod_detect = _clod_detect
 
 
 def group_rectangles(rects: np.ndarray, group_threshold: int, eps: float = 0.2):

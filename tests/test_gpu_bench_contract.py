@@ -34,6 +34,8 @@ def test_native_arm_line():
     assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
     c = d["cpu_baseline"]
     assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    # the reference's own CPU detector (CLOD-CPU, clod.cpp:1339-1500) beside it
+    assert c["clod_cpu"]["value"] > 0 and c["clod_cpu"]["cores"] >= 1 and c["clod_cpu"]["windows_per_frame"] > 0
 
 
 def test_reference_arm_line():
@@ -41,4 +43,4 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["metric"] == "frames_per_sec_1080p" and d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
-    assert d["gpu_launches"] == 0
+    assert d["gpu_launches"] == 0 and d["cpu_baseline"]["clod_cpu"]["value"] > 0
