@@ -145,6 +145,17 @@ int PyramidPlan::build(int W_, int H_, const std::vector<std::pair<int, int>> &s
             h_xofs.push_back(sx);
             h_xalpha.push_back(make_short2((short)lrintf((1.f - fx) * 2048), (short)lrintf(fx * 2048)));
         }
+        {   // which source-row access of k_resize_colsum this level's tap positions allow (kernels_clif.cu)
+            const int *sx = h_xofs.data() + L.xtab_off;
+            bool quad = true, pair = true;
+            for (int x = 0; x < w; x += 4) {
+                if (sx[std::min(x + 3, w - 1)] - sx[x] > 6) quad = false;
+                for (int j = 0; j < 4 && x + j < w; j += 2)
+                    if (sx[std::min(x + j + 1, w - 1)] - sx[x + j] > 6) pair = false;
+            }
+            L.resize_mode = quad ? kResizeQuad : pair ? kResizePair : kResizeBytes;
+            if (const char *e = getenv("CLFD_RESIZE_BYTES")) if (atoi(e)) L.resize_mode = kResizeBytes;   // test hook
+        }
         for (int dy = 0; dy < h; dy++) {
             float fy = (float)((dy + 0.5) * scale_y - 0.5);
             int sy = cv_floor(fy);

@@ -164,12 +164,15 @@ struct PyrLevel {
     int sum_pitch;       // elements, multiple of 8 (>= w+1)
     int nrb;             // row blocks of kRowBlock rows
     int xtab_off, ytab_off;
-    int pad;
+    int resize_mode;     // kResize*: how k_resize_colsum reads the source rows of this level
     long long pyr_off;   // byte offset inside a frame's pyramid block
     long long sum_off;   // element offset inside a frame's sum / sqsum / tilted block
     long long col_off;   // element offset inside a frame's column-sum block
 };
 constexpr int kRowBlock = 32;
+// k_resize_colsum: byte loads (any factor / alignment); word loads with the taps of four (factors < 2) or two
+// (factors up to 6) neighbouring pixels inside 8 source bytes
+constexpr int kResizeBytes = 0, kResizeQuad = 1, kResizePair = 2;
 
 // Per cascade, per level it evaluates
 struct CasLevel {

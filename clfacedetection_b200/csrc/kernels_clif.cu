@@ -59,43 +59,142 @@ __device__ __forceinline__ void clif_bulk_g2s(void *dst_smem, const void *src_gm
 constexpr int kResizeThreads = 128;  // x 4 px = 512 columns per CTA
 constexpr int kResizeCols = kResizeThreads * 4;
 
+// vertical pass of 4 pixels (OpenCV VResizeLinear, 8u: ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2),
+// r0s / r1s = the horizontal passes of the two source rows, already shifted right by 4.  The result is at most 255
+// (b0 + b1 = 2048, r >> 4 <= 32640), so the four bytes pack without masks.
+__device__ __forceinline__ uint32_t resize_vpass4(const int (&r0s)[4], const int (&r1s)[4], int b0, int b1, uint32_t (&cs)[4],
+                                                  uint32_t (&cq)[4]) {
+    uint32_t packed = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t u = (uint32_t)((((b0 * r0s[i]) >> 16) + ((b1 * r1s[i]) >> 16) + 2) >> 2);
+        packed |= u << (8 * i);
+        cs[i] += u;
+        cq[i] += u * u;
+    }
+    return packed;
+}
+
+// Word path of k_resize_colsum (source rows 4-byte aligned).  QUAD (factors < 2): the eight taps of the thread's
+// four pixels lie within 8 bytes of the first one -> three aligned 32-bit loads per source row, two funnel shifts that
+// put the first tap at byte 0, one PRMT + two IDP.2A per pixel pair.  !QUAD (factors up to 6): the same per pixel
+// pair.  (The byte path spends 8 LDG.U8 and 16 address instructions on the same row.)
+template <bool QUAD, bool GUARD>
+__device__ __forceinline__ void resize_rows_words(const PyramidArgs &a, const PyrLevel &L, const uint8_t *__restrict__ src,
+                                                  uint8_t *__restrict__ dst, int x0, int y0, int y1, const int (&sx0)[4],
+                                                  const uint32_t (&coef)[4], uint32_t (&cs)[4], uint32_t (&cq)[4]) {
+    const int last_word = (a.W - 1) & ~3;   // byte offset of the last source word that holds a pixel of the row
+    int boff[2], sh[2];
+    uint32_t sel[2];
+    bool p1[2], p2[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const int first = QUAD ? sx0[0] : sx0[2 * j];
+        boff[j] = first & ~3;
+        sh[j] = (first & 3) * 8;
+        const uint32_t o0 = (uint32_t)(sx0[2 * j] - first), o1 = (uint32_t)(sx0[2 * j + 1] - first);
+        sel[j] = o0 | ((o0 + 1) << 4) | (o1 << 8) | ((o1 + 1) << 12);
+        p1[j] = !GUARD || boff[j] + 4 <= last_word;
+        p2[j] = !GUARD || boff[j] + 8 <= last_word;
+    }
+    // per-row table entries: lane k of every warp holds row y0 + k's clamped source rows and coefficients (<< 16, for
+    // the multiply-high of the vertical pass); the row loop fetches them with shuffles instead of dependent loads
+    const int lane = threadIdx.x & 31;
+    const int ty = min(y0 + lane, L.h - 1);
+    const int tsy = __ldg(a.yofs + L.ytab_off + ty);
+    const short2 tb = __ldg(a.ybeta + L.ytab_off + ty);
+    const uint32_t my_sy = (uint32_t)min(max(tsy, 0), a.H - 1) | ((uint32_t)min(max(tsy + 1, 0), a.H - 1) << 16);
+    const uint32_t my_b0 = (uint32_t)tb.x << 16, my_b1 = (uint32_t)tb.y << 16;
+    const uint8_t *__restrict__ srcA = src + boff[0];
+    const uint8_t *__restrict__ srcB = src + boff[1];
+    const uint32_t rstride = (uint32_t)a.row_stride;
+    auto hrow = [&](uint32_t sy, uint32_t (&r)[4]) {
+        const uint32_t *__restrict__ p = reinterpret_cast<const uint32_t *>(srcA + (size_t)sy * rstride);
+        const uint32_t w0 = __ldg(p), w1 = p1[0] ? __ldg(p + 1) : 0u, w2 = p2[0] ? __ldg(p + 2) : 0u;
+        uint32_t lo = __funnelshift_r(w0, w1, sh[0]), hi = __funnelshift_r(w1, w2, sh[0]);
+        uint32_t P = __byte_perm(lo, hi, sel[0]);
+        r[0] = __dp2a_lo(coef[0], P, 0u) >> 4;
+        r[1] = __dp2a_hi(coef[1], P, 0u) >> 4;
+        if (!QUAD) {
+            const uint32_t *__restrict__ q = reinterpret_cast<const uint32_t *>(srcB + (size_t)sy * rstride);
+            const uint32_t v0 = __ldg(q), v1 = p1[1] ? __ldg(q + 1) : 0u, v2 = p2[1] ? __ldg(q + 2) : 0u;
+            lo = __funnelshift_r(v0, v1, sh[1]);
+            hi = __funnelshift_r(v1, v2, sh[1]);
+        }
+        P = __byte_perm(lo, hi, sel[1]);
+        r[2] = __dp2a_lo(coef[2], P, 0u) >> 4;
+        r[3] = __dp2a_hi(coef[3], P, 0u) >> 4;
+    };
+    // OpenCV VResizeLinear, 8u: (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2; (b * s) >> 16 is the high
+    // word of (b << 16) * s (b <= 2048, s <= 32640).  At most 255, so the bytes pack without masks.
+    auto vrow = [&](const uint32_t (&r0)[4], const uint32_t (&r1)[4], uint32_t b0, uint32_t b1, uint8_t *__restrict__ out) {
+        uint32_t u[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            u[i] = (__umulhi(b1, r1[i]) + (__umulhi(b0, r0[i]) + 2u)) >> 2;
+            cs[i] += u[i];
+            cq[i] += u[i] * u[i];
+        }
+        if (x0 < L.pyr_pitch)
+            *reinterpret_cast<uint32_t *>(out) = __byte_perm(__byte_perm(u[0], u[1], 0x0040), __byte_perm(u[2], u[3], 0x0040), 0x5410);
+    };
+    uint32_t ra[4] = {0, 0, 0, 0}, rb[4];
+    uint32_t prev_sy1 = 0xffffffffu;
+    uint8_t *__restrict__ out = dst + (size_t)y0 * L.pyr_pitch + x0;
+    // two output rows per iteration: the horizontal pass kept for the next row alternates between ra and rb
+    for (int k = 0; k < y1 - y0; k += 2) {
+        {
+            const uint32_t sy = __shfl_sync(0xffffffffu, my_sy, k);
+            const uint32_t b0 = __shfl_sync(0xffffffffu, my_b0, k), b1 = __shfl_sync(0xffffffffu, my_b1, k);
+            // the horizontal pass of a source row is reused: at factors < 2 most rows' upper source row is the
+            // previous row's lower one (block-uniform test, no divergence)
+            if ((sy & 0xffffu) != prev_sy1) hrow(sy & 0xffffu, ra);
+            hrow(sy >> 16, rb);
+            prev_sy1 = sy >> 16;
+            vrow(ra, rb, b0, b1, out);
+            out += L.pyr_pitch;
+        }
+        if (k + 1 < y1 - y0) {
+            const uint32_t sy = __shfl_sync(0xffffffffu, my_sy, k + 1);
+            const uint32_t b0 = __shfl_sync(0xffffffffu, my_b0, k + 1), b1 = __shfl_sync(0xffffffffu, my_b1, k + 1);
+            if ((sy & 0xffffu) != prev_sy1) hrow(sy & 0xffffu, rb);
+            hrow(sy >> 16, ra);
+            prev_sy1 = sy >> 16;
+            vrow(rb, ra, b0, b1, out);
+            out += L.pyr_pitch;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kResizeThreads) k_resize_colsum(const PyramidArgs a) {
     const int4 it = a.resize_items[blockIdx.x];
     const PyrLevel L = a.levels[it.x];
     const int frame = blockIdx.y;
     const int x0 = it.z * kResizeCols + threadIdx.x * 4;
-    if (x0 >= max(L.pyr_pitch, L.sum_pitch)) return;
+    const int xw = it.z * kResizeCols + (threadIdx.x & ~31) * 4;   // first column of this warp (128 columns)
+    if (xw >= max(L.pyr_pitch, L.sum_pitch)) return;               // whole warps only: the word path shuffles
 
     const uint8_t *__restrict__ src = a.frames + (size_t)frame * a.frame_stride;
     uint8_t *__restrict__ dst = a.pyr + (size_t)frame * a.pyr_frame_stride + L.pyr_off;
 
-    int sx0[4], sx1[4], a0[4], a1[4];
+    int sx0[4];
+    uint32_t coef[4];   // (a0, a1) as two u16: the table's short2
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int x = x0 + i;
-        if (x < L.w) {
-            const int s = __ldg(a.xofs + L.xtab_off + x);
-            const short2 c = __ldg(a.xalpha + L.xtab_off + x);
-            sx0[i] = s; sx1[i] = min(s + 1, a.W - 1); a0[i] = c.x; a1[i] = c.y;
-        } else {
-            sx0[i] = sx1[i] = 0; a0[i] = a1[i] = 0;
-        }
+        sx0[i] = x < L.w ? __ldg(a.xofs + L.xtab_off + x) : (i ? sx0[i > 0 ? i - 1 : 0] : 0);
+        coef[i] = x < L.w ? __ldg(reinterpret_cast<const uint32_t *>(a.xalpha + L.xtab_off + x)) : 0u;
     }
     uint32_t cs[4] = {0, 0, 0, 0}, cq[4] = {0, 0, 0, 0};
-    int prev_r1[4] = {0, 0, 0, 0}, prev_sy1 = -1;
+    const bool aligned = (a.row_stride & 3) == 0 && (a.frame_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(a.frames) & 3) == 0;
     // whole groups of 4 pixels of an unscaled level with 4-byte aligned source rows
-    const bool copy4 = L.w == a.W && L.h == a.H && x0 + 4 <= L.w && (a.row_stride & 3) == 0 && (a.frame_stride & 3) == 0 &&
-                       (reinterpret_cast<uintptr_t>(a.frames) & 3) == 0;
+    const bool copy4 = L.w == a.W && L.h == a.H && xw + 128 <= L.w && aligned;   // (warp uniform)
+    const int mode = aligned ? L.resize_mode : kResizeBytes;
     const int y0 = it.y * kRowBlock, y1 = min(y0 + kRowBlock, L.h);
-    for (int y = y0; y < y1; y++) {
-        const int sy = __ldg(a.yofs + L.ytab_off + y);
-        const short2 b = __ldg(a.ybeta + L.ytab_off + y);
-        const int sy0 = min(max(sy, 0), a.H - 1), sy1 = min(max(sy + 1, 0), a.H - 1);
-        const uint8_t *__restrict__ S0 = src + (size_t)sy0 * a.row_stride;
-        const uint8_t *__restrict__ S1 = src + (size_t)sy1 * a.row_stride;
-        uint32_t packed = 0;
-        if (copy4) {   // the level of factor 1: the resize is the identity (coefficients 2048 / 0), 4 pixels per load
-            packed = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)y * a.row_stride + x0));
+
+    if (copy4) {   // the level of factor 1: the resize is the identity (coefficients 2048 / 0), 4 pixels per load
+        for (int y = y0; y < y1; y++) {
+            const uint32_t packed = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)y * a.row_stride + x0));
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const uint32_t u = (packed >> (8 * i)) & 255u;
@@ -103,24 +202,46 @@ __global__ void __launch_bounds__(kResizeThreads) k_resize_colsum(const PyramidA
                 cq[i] += u * u;
             }
             *reinterpret_cast<uint32_t *>(dst + (size_t)y * L.pyr_pitch + x0) = packed;
-            continue;
         }
-        // the horizontal pass of a source row is kept for the next output row: at factors < 2 most rows'
-        // upper source row is the previous row's lower one (block-uniform test, no divergence)
-        const bool reuse = sy0 == prev_sy1;
-        prev_sy1 = sy1;
+    } else if (mode == kResizeQuad || mode == kResizePair) {
+        // GUARD: the words behind a row's last pixel are not loaded.  Only the CTAs that read the last source row of
+        // the batch's last frame need that (everywhere else the bytes behind a row belong to the next row or frame);
+        // output row h - 2 reads it too when the factor is 1
+        const bool guard = frame == a.n_frames - 1 && y1 + 1 >= L.h;
+        if (mode == kResizeQuad) {
+            if (guard) resize_rows_words<true, true>(a, L, src, dst, x0, y0, y1, sx0, coef, cs, cq);
+            else resize_rows_words<true, false>(a, L, src, dst, x0, y0, y1, sx0, coef, cs, cq);
+        } else {
+            if (guard) resize_rows_words<false, true>(a, L, src, dst, x0, y0, y1, sx0, coef, cs, cq);
+            else resize_rows_words<false, false>(a, L, src, dst, x0, y0, y1, sx0, coef, cs, cq);
+        }
+    } else {
+        // byte path: any factor, any alignment
+        int sx1[4], a0[4], a1[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const int r0 = reuse ? prev_r1[i] : (int)__ldg(S0 + sx0[i]) * a0[i] + (int)__ldg(S0 + sx1[i]) * a1[i];
-            const int r1 = (int)__ldg(S1 + sx0[i]) * a0[i] + (int)__ldg(S1 + sx1[i]) * a1[i];
-            prev_r1[i] = r1;
-            const int v = ((((int)b.x * (r0 >> 4)) >> 16) + (((int)b.y * (r1 >> 4)) >> 16) + 2) >> 2;
-            const uint32_t u = (uint32_t)v & 255u;
-            packed |= u << (8 * i);
-            cs[i] += u;
-            cq[i] += u * u;
+            sx1[i] = min(sx0[i] + 1, a.W - 1);
+            a0[i] = (int)(coef[i] & 0xffffu); a1[i] = (int)(coef[i] >> 16);
         }
-        if (x0 < L.pyr_pitch) *reinterpret_cast<uint32_t *>(dst + (size_t)y * L.pyr_pitch + x0) = packed;
+        int prev[4] = {0, 0, 0, 0}, prev_sy1 = -1;
+        for (int y = y0; y < y1; y++) {
+            const int sy = __ldg(a.yofs + L.ytab_off + y);
+            const short2 b = __ldg(a.ybeta + L.ytab_off + y);
+            const int sy0 = min(max(sy, 0), a.H - 1), sy1 = min(max(sy + 1, 0), a.H - 1);
+            const uint8_t *__restrict__ S0 = src + (size_t)sy0 * a.row_stride;
+            const uint8_t *__restrict__ S1 = src + (size_t)sy1 * a.row_stride;
+            const bool reuse = sy0 == prev_sy1;
+            prev_sy1 = sy1;
+            int r0[4], r1[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                r0[i] = reuse ? prev[i] : ((int)__ldg(S0 + sx0[i]) * a0[i] + (int)__ldg(S0 + sx1[i]) * a1[i]) >> 4;
+                r1[i] = ((int)__ldg(S1 + sx0[i]) * a0[i] + (int)__ldg(S1 + sx1[i]) * a1[i]) >> 4;
+                prev[i] = r1[i];
+            }
+            const uint32_t packed = resize_vpass4(r0, r1, b.x, b.y, cs, cq);
+            if (x0 < L.pyr_pitch) *reinterpret_cast<uint32_t *>(dst + (size_t)y * L.pyr_pitch + x0) = packed;
+        }
     }
     if (x0 < L.sum_pitch) {
         uint32_t *c0 = a.col + (size_t)frame * a.col_frame_stride + L.col_off + (size_t)it.y * L.sum_pitch + x0;

@@ -52,6 +52,37 @@ def test_resize_bit_exact(gpu_ctx, src, dst):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("src,dst", [((1920, 1080), (401, 227)), ((1920, 1080), (320, 180)), ((1920, 1080), (275, 155)),
+                                     ((1919, 1079), (1600, 900)), ((1918, 1080), (1001, 563)), ((643, 481), (322, 241)),
+                                     ((1921, 1080), (1067, 600)), ((1920, 1080), (1919, 1079)), ((645, 480), (643, 479)),
+                                     ((1920, 1080), (6, 4)), ((9, 9), (7, 7)), ((4, 4), (3, 3)), ((5, 3), (1, 1))])
+def test_resize_word_paths_bit_exact(gpu_ctx, src, dst):
+    """k_resize_colsum reads source rows as 32-bit words where the taps of four (factor < 2) or two (factor <= 6)
+    neighbouring pixels fit 8 bytes: factors on either side of those limits, widths that are no multiple of 4
+    (partial pixel groups, the row's last word), tiny images"""
+    img = uniform_frame(src[0], src[1], 11)
+    assert np.array_equal(gpu_ctx.resize(img, dst[0], dst[1]), oracle.resize_linear(img, dst[0], dst[1]))
+
+
+@pytest.mark.parametrize("w,stride", [(1919, 1919), (1918, 1918), (1917, 1921), (1920, 1920), (1920, 2048)])
+def test_resize_device_source_any_alignment(gpu_ctx, w, stride):
+    """frames already on the device with any row stride / base alignment: unaligned rows take the byte path"""
+    import ctypes as C
+
+    import torch
+    from clfacedetection_b200 import abi
+    h, dw, dh = 270, int(round(w / 1.2)), 225
+    host = np.zeros((h, stride), np.uint8)
+    host[:, :w] = uniform_frame(w, h, 12)
+    for shift in (0, 1):   # base pointer 4-byte aligned or not
+        buf = torch.zeros(h * stride + 8, dtype=torch.uint8, device="cuda")
+        buf[shift:shift + h * stride] = torch.from_numpy(host.reshape(-1)).cuda()
+        out = torch.zeros((dh, dw), dtype=torch.uint8, device="cuda")
+        abi.check(abi.lib().clfd_resize(gpu_ctx._h, C.cast(buf.data_ptr() + shift, C.POINTER(C.c_uint8)), w, h, stride, 1,
+                                        C.cast(out.data_ptr(), C.POINTER(C.c_uint8)), dw, dh, dw, 1))
+        assert np.array_equal(out.cpu().numpy(), oracle.resize_linear(np.ascontiguousarray(host[:, :w]), dw, dh)), (w, stride, shift)
+
+
 def test_resize_uniform_noise_1080p_levels(gpu_ctx):
     img = uniform_frame(1920, 1080, 5)
     f = 1.0
