@@ -41,12 +41,29 @@ XML = [os.path.join(ROOT, "data", "haarcascades", f"haarcascade_{CASCADE}.xml")]
 KERNEL_NAMES = ["resize_colsum", "colscan", "integral_rows", "tilted", "cascade_tiles", "cascade_deep"]
 
 
+def kernel_source_stamp():
+    """sha256 over the CUDA sources the kernels are built from: profiles/traffic.json carries the stamp of the build its
+    ncu capture was taken from (profiles/make_traffic.py), and a capture of other kernels is not used"""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "clfacedetection_b200", "csrc")
+    for f in ("kernels_clif.cu", "kernels_clod.cu", "kernels_sc.cu", "kernels.h", "clfd_pack.h", "clfd_internal.h"):
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic():
-    """per-kernel DRAM bytes per frame and L1 data-pipe utilisation from the committed ncu capture"""
+    """per-kernel DRAM bytes per frame and L1 data-pipe utilisation from the committed ncu capture; None (and the
+    ncu_* fields of the line stay out) when the capture was taken from other kernel sources than the ones in the tree"""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         return None
+    if t.get("kernel_source_stamp") != kernel_source_stamp():
+        sys.stderr.write("bench.py: profiles/traffic.json is stale (kernel sources changed since its ncu capture): "
+                         "ncu figures left out; regenerate with tools/capture_step.sh\n")
+        return None
+    return t
 
 
 def measured_peak_gbs():
@@ -569,6 +586,35 @@ def main():
                                      "windows_reaching_stage": reach[:S].tolist(), "accepted": int(hist[S])})
                 d2.close()
                 line["survivors_per_stage"] = {"frame": 0, "cascades": surv}
+                # EFFICIENCY of the tile kernel's L1 data pipe (not its utilisation): the corner values the algorithm
+                # needs -- 4 per rectangle of every weak classifier a window evaluates, 4 bytes each --
+                # over the kernel's time, against one 128-byte wavefront per clock per SM.  Linear stump cascades only
+                # (a tree's evaluated nodes depend on the data).
+                if all("windows_reaching_stage" in x for x in surv) and clocks.get("sm_mhz"):
+                    import oracle
+                    corner_bytes = evals = 0
+                    for ci, x in enumerate(surv):
+                        f = oracle.load_cascade_xml(XML[ci])
+                        if int(f.tr_nnodes.max()) != 1:
+                            corner_bytes = 0
+                            break
+                        first = np.concatenate([[0], np.cumsum(f.st_ntrees)])
+                        nrect = (f.nd_weight != 0).sum(axis=1)
+                        for st, n_win in enumerate(x["windows_reaching_stage"]):
+                            corner_bytes += int(n_win) * int(nrect[first[st]:first[st + 1]].sum()) * 16
+                            evals += int(n_win) * int(f.st_ntrees[st])
+                    if corner_bytes:
+                        n_sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+                        t_frame = kernel_ms[KERNEL_NAMES.index("cascade_tiles")] * 1e-3 / B
+                        peak_bs = n_sms * 128 * clocks["sm_mhz"] * 1e6
+                        roof["l1_data_pipe"]["efficiency"] = {
+                            "useful_corner_bytes_per_frame": corner_bytes, "weak_classifier_evals_per_frame": evals,
+                            "achieved_tbs": round(corner_bytes / t_frame / 1e12, 2), "peak_tbs": round(peak_bs / 1e12, 2),
+                            "frac": round(corner_bytes / t_frame / peak_bs, 4),
+                            "note": "frame 0's survivor counts x 16 bytes per rectangle of every weak classifier evaluated, over the "
+                                    "tile kernel's time per frame, against SMs x 128 B x SM clock; the rest of the pipe's "
+                                    "wavefronts are dead lanes of the fixed-geometry stages, bank conflicts of the compacted "
+                                    "stages, stump records and staging"}
             except Exception as e:   # evidence only: never fail the headline line
                 line["survivors_per_stage"] = {"error": str(e)[:200]}
         det.close()

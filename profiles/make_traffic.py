@@ -3,15 +3,18 @@
 (profiles/summarize_ncu.py output).  bench.py reads it for `roofline.traffic` and the L1 data-pipe
 figures.
 
-usage: python profiles/make_traffic.py 8 profiles/r1j_step_full_batch8.csv [profiles/r1k_tiles_full.csv ...] > profiles/traffic.json
+usage: python profiles/make_traffic.py 8 STAMP profiles/r2x_step_full_batch8.csv [more.csv ...] > profiles/traffic.json
 (several summaries of the same batch size: a kernel takes its figures from the LAST file that captured it)
+
+STAMP = bench.kernel_source_stamp() of the tree the capture was taken from; tools/capture_step.sh writes it on the GPU
+box next to the report (gpurun_out/<tag>_stamp.txt).  bench.py leaves the ncu figures out when the tree's stamp differs.
 """
 import csv
 import json
 import sys
 
 GROUPS = {"k_resize_colsum": "resize_colsum", "k_colscan": "colscan", "k_integral_rows": "integral_rows",
-          "k_tilted": "tilted", "k_cascade_tiles": "cascade_tiles"}
+          "k_tilt": "tilted", "k_cascade_tiles": "cascade_tiles"}
 
 
 def one(path, batch):
@@ -64,12 +67,12 @@ def one(path, batch):
 
 
 def main():
-    batch, paths = int(sys.argv[1]), sys.argv[2:]
+    batch, stamp, paths = int(sys.argv[1]), sys.argv[2], sys.argv[3:]
     kernels = {}
     for p in paths:
         kernels.update(one(p, batch))
     json.dump({"source": "%s (ncu --set full, bench.py --batch %d; per-frame figures = capture / %d)" % (", ".join(paths), batch, batch),
-               "batch": batch, "kernels": kernels}, sys.stdout, indent=1)
+               "batch": batch, "kernel_source_stamp": stamp, "kernels": kernels}, sys.stdout, indent=1)
     print()
 
 
