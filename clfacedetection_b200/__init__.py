@@ -69,6 +69,20 @@ class Context:
         abi.check(abi.lib().clfd_integral(self._h, _ptr(img), w, h, img.strides[0], 0, _ptr(s), _ptr(q), _ptr(t), 0))
         return s, q, t
 
+    def integral_image(self, img: np.ndarray, tilted: bool = False, want_gray: bool = False):
+        """clifGrayscaleIntegral (clif.cpp:318-381) of one interleaved host image [H, W] or [H, W, 3 | 4] (BGR / BGRA):
+        colour conversion + integral images on the device, one upload -> sum, sqsum, tilted | None[, gray]"""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape[:2]
+        c = 1 if img.ndim == 2 else img.shape[2]
+        s = np.empty((h + 1, w + 1), np.int32)
+        q = np.empty((h + 1, w + 1), np.uint64)
+        t = np.empty((h + 1, w + 1), np.int32) if tilted else None
+        g = np.empty((h, w), np.uint8) if want_gray else None
+        abi.check(abi.lib().clfd_integral_image(self._h, _ptr(img), w, h, img.strides[0], c, _ptr(s), _ptr(q), _ptr(t),
+                                                _ptr(g) if want_gray else None, w))
+        return (s, q, t, g) if want_gray else (s, q, t)
+
     def resize(self, img: np.ndarray, dw: int, dh: int) -> np.ndarray:
         """cvResize(INTER_LINEAR) of one level (tempcv.cpp:1301)"""
         img = np.ascontiguousarray(img, np.uint8)

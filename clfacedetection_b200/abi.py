@@ -93,6 +93,7 @@ def lib() -> C.CDLL:
     L.clfd_integral.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int]
     L.clfd_resize.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.clfd_bgr_to_gray.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int]
+    L.clfd_integral_image.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, u8p, C.c_int]
     L.clfd_detector_create.argtypes = [vp, C.POINTER(vp), C.c_int, C.POINTER(DetectorConfig), C.POINTER(vp)]
     L.clfd_detector_destroy.argtypes = [vp]
     L.clfd_detector_destroy.restype = None

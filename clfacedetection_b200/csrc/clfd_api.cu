@@ -621,6 +621,33 @@ int clfd_bgr_to_gray(clfd_context *ctx, const uint8_t *bgr, int w, int h, int st
     return 0;
 }
 
+// clifGrayscaleIntegral (clif.cpp:318-381) in one call: the interleaved frame goes to the device once, the gray plane is
+// made there (and stays there) and feeds the integral kernels; the gray plane comes back only if asked for.
+int clfd_integral_image(clfd_context *ctx, const uint8_t *img, int w, int h, int stride, int channels, int32_t *sum,
+                        uint64_t *sqsum, int32_t *tilted, uint8_t *gray, int gstride) {
+    if (!ctx || !img) INVALID("NULL argument");
+    if (channels == 1) {
+        if (gray) {
+            if (gstride < w) INVALID("bad gray stride");
+            for (int y = 0; y < h; y++) memcpy(gray + (size_t)y * gstride, img + (size_t)y * stride, (size_t)w);
+        }
+        return clfd_integral(ctx, img, w, h, stride, 0, sum, sqsum, tilted, 0);
+    }
+    if (w <= 0 || h <= 0 || (channels != 3 && channels != 4) || stride < w * channels || (gray && gstride < w))
+        INVALID("bad geometry");
+    CK(cudaSetDevice(ctx->device));
+    InputImage in;
+    int rc = in.set(img, w * channels, h, stride, 0, ctx->stream);
+    if (rc) return rc;
+    DevBuf<uint8_t> g;
+    const int dstride = (int)round_up(w, 16);
+    if ((rc = g.alloc((size_t)dstride * h + 16))) return rc;
+    CK(launch_bgr_to_gray(in.dev, w, h, in.stride, channels, g.p, dstride, ctx->stream));
+    ctx->launches++;
+    if (gray) CK(cudaMemcpy2DAsync(gray, gstride, g.p, dstride, w, h, cudaMemcpyDeviceToHost, ctx->stream));
+    return clfd_integral(ctx, g.p, w, h, dstride, 1, sum, sqsum, tilted, 0);   // (synchronises the stream before it returns)
+}
+
 // ------------------------------------------------------------------------------------
 // detector
 // ------------------------------------------------------------------------------------

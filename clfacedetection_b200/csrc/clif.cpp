@@ -119,9 +119,9 @@ CLIFGrayscaleResult clifGrayscale(const IplImage* source, CLIFEnvironmentData* d
 static CLIFIntegralResult integral_of(const IplImage* source, CLIFEnvironmentData* data) {
     ClifState* s = state(data);
     ensure_headers(s, source->width, source->height);
-    int step = 0;
-    const unsigned char* g = gray_plane(s, source, &step);
-    CHECK(clfd_integral(s->ctx, g, source->width, source->height, step, 0, s->sum.data(), s->sqsum.data(), nullptr, 0));
+    // one upload of the frame as it is; colour conversion and integral images on the device (no gray round trip)
+    CHECK(clfd_integral_image(s->ctx, (const uint8_t*)source->imageData, source->width, source->height, source->widthStep,
+                              source->nChannels, s->sum.data(), s->sqsum.data(), nullptr, nullptr, 0));
     data->integral_image_data.ptr = s->sum.data();
     data->integral_image_data.square_ptr = s->sqsum.data();
     CLIFIntegralResult r;

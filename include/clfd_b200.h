@@ -129,6 +129,12 @@ CLFD_API int clfd_resize(clfd_context *ctx, const uint8_t *src, int sw, int sh, 
 CLFD_API int clfd_bgr_to_gray(clfd_context *ctx, const uint8_t *bgr, int w, int h, int stride,
                               int channels, int src_on_device, uint8_t *gray, int gstride,
                               int dst_on_device);
+/* clifGrayscaleIntegral (clif.cpp:318-381; clod.cpp:366 calls it for every frame): colour conversion and
+ * integral images of one interleaved HOST image (1, 3 = BGR or 4 = BGRA channels) in one call.  The frame is
+ * uploaded once and the gray plane never leaves the device (the reference's OpenCL branch downloads it and
+ * uploads it again, clif.cpp:339-364); `gray` (host, gstride >= w) receives it if not NULL. */
+CLFD_API int clfd_integral_image(clfd_context *ctx, const uint8_t *img, int w, int h, int stride, int channels,
+                                 int32_t *sum, uint64_t *sqsum, int32_t *tilted, uint8_t *gray, int gstride);
 
 /* ---- clod: multi-scale detection -----------------------------------------------------
  * Replaces clodInitBuffers / clodDetectObjects / clodReleaseBuffers (clod.cpp:102-170,

@@ -139,3 +139,20 @@ def test_bgr_to_gray_colour_pixels(gpu_ctx):
     prim = np.zeros((1, 3, 3), np.uint8)
     prim[0, 0, 0] = prim[0, 1, 1] = prim[0, 2, 2] = 255
     assert gpu_ctx.bgr_to_gray(prim).tolist() == [[29, 150, 76]]
+
+
+def test_integral_image_colour_in_one_call(gpu_ctx):
+    """clfd_integral_image (clifGrayscaleIntegral, clif.cpp:318-381): colour pixels -> gray -> integrals on the device
+    == oracle integral of the fixed-point gray plane; also 1-channel input and the optional gray output"""
+    rng = np.random.default_rng(8)
+    for shape in ((37, 53, 3), (240, 321, 3), (100, 64, 4), (75, 90)):
+        img = rng.integers(0, 256, size=shape, dtype=np.uint8)
+        if img.ndim == 3:
+            b, g, r = (img[..., k].astype(np.int64) for k in range(3))
+            gray = ((b * 1868 + g * 9617 + r * 4899 + 8192) >> 14).astype(np.uint8)
+        else:
+            gray = img
+        s, q, t, got_gray = gpu_ctx.integral_image(img, tilted=True, want_gray=True)
+        os_, oq, ot = oracle.integral(gray, tilted=True)
+        assert np.array_equal(got_gray, gray)
+        assert np.array_equal(s, os_) and np.array_equal(q, oq.astype(np.uint64)) and np.array_equal(t, ot)
