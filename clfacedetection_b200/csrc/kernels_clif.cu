@@ -638,14 +638,15 @@ __global__ void __launch_bounds__(256) k_tilt_diag(const PyramidArgs a) {
 
 // T carries.  TC_b(X) = T(32 b, X) = sum over the row blocks above of their column sums of G, where a block's
 // G column sum = LG (its own pixels) + what the carries contribute while they cross the block:
-// sum_{j=1..32} AC(X - j) + sum_{j=1..32} BC(X + j).  One warp per 32 columns; the window sums come from four
-// warp scans (this group and its left neighbour for A, this group and its right neighbour for B).
+// sum_{j=1..32} AC(X - j) + sum_{j=1..32} BC(X + j).  One warp per 32 columns, eight neighbouring groups per CTA:
+// every warp scans its own group's AC and BC once and the neighbours meet through shared memory (the first warp also
+// scans the group to its left, the last one the group to its right), one block barrier per row block on two buffers.
 __global__ void __launch_bounds__(256) k_tilt_tcarry(const PyramidArgs a) {
+    __shared__ int s_exa[2][9][32], s_tota[2][9], s_inb[2][9][32];   // [buffer][group -1 .. 7 (A) / 0 .. 8 (B)][lane]
     const int4 it = a.tilt_tc_items[blockIdx.x];     // (level, chunk of 8 column groups, -, -)
     const PyrLevel L = a.levels[it.x];
-    const int frame = blockIdx.y, lane = threadIdx.x & 31;
-    const int X = (it.y * 8 + (threadIdx.x >> 5)) * 32 + lane;
-    if (X - lane >= L.sum_pitch) return;   // (whole warps)
+    const int frame = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int X = (it.y * 8 + w) * 32 + lane;
     int32_t *__restrict__ car = a.tcar + (size_t)frame * a.tcar_frame_stride + L.col_off;
     const size_t ps = a.col_plane_stride;
     auto at = [&](int plane, int b, int x) -> int {   // zero outside [0, w]
@@ -662,25 +663,36 @@ __global__ void __launch_bounds__(256) k_tilt_tcarry(const PyramidArgs a) {
     int acc = 0;
     constexpr int kSteps = 4;   // row blocks whose loads are in flight together (8 measured slower: registers)
     for (int b0 = 0; b0 + 1 < L.nrb; b0 += kSteps) {
-        int a_cur[kSteps], a_prev[kSteps], b_cur[kSteps], b_next[kSteps], lg[kSteps];
+        int a_cur[kSteps], b_cur[kSteps], edge[kSteps], lg[kSteps];
 #pragma unroll
         for (int k = 0; k < kSteps; k++) {
             const int b = min(b0 + k, L.nrb - 1);
-            a_cur[k] = at(kTcAC, b, X); a_prev[k] = at(kTcAC, b, X - 32);
-            b_cur[k] = at(kTcBC, b, X); b_next[k] = at(kTcBC, b, X + 32);
+            a_cur[k] = at(kTcAC, b, X); b_cur[k] = at(kTcBC, b, X);
             lg[k] = at(kTcLG, b, X);
+            edge[k] = w == 0 ? at(kTcAC, b, X - 32) : w == 7 ? at(kTcBC, b, X + 32) : 0;   // (warp uniform)
         }
 #pragma unroll
         for (int k = 0; k < kSteps; k++) {
             const int b = b0 + k;
-            if (b + 1 >= L.nrb) break;
+            if (b + 1 >= L.nrb) break;   // (uniform over the CTA: one level)
+            const int buf = b & 1;
             if (X <= L.w) car[kTcTC * ps + (size_t)b * L.sum_pitch + X] = acc;
-            const int sa_cur = incl_scan(a_cur[k]), sa_prev = incl_scan(a_prev[k]);
-            const int sb_cur = incl_scan(b_cur[k]), sb_next = incl_scan(b_next[k]);
+            const int sa = incl_scan(a_cur[k]), sb = incl_scan(b_cur[k]);
+            s_exa[buf][w + 1][lane] = sa - a_cur[k];
+            s_inb[buf][w][lane] = sb;
+            if (lane == 31) s_tota[buf][w + 1] = sa;
+            if (w == 0) {
+                const int se = incl_scan(edge[k]);
+                s_exa[buf][0][lane] = se - edge[k];
+                if (lane == 31) s_tota[buf][0] = se;
+            } else if (w == 7) {
+                s_inb[buf][8][lane] = incl_scan(edge[k]);
+            }
+            __syncthreads();
             // columns X-32 .. X-1: the previous group's lanes >= mine, this group's lanes < mine
-            const int wa = (__shfl_sync(0xffffffffu, sa_prev, 31) - (sa_prev - a_prev[k])) + (sa_cur - a_cur[k]);
+            const int wa = (s_tota[buf][w] - s_exa[buf][w][lane]) + (sa - a_cur[k]);
             // columns X+1 .. X+32: this group's lanes > mine, the next group's lanes <= mine
-            const int wb = (__shfl_sync(0xffffffffu, sb_cur, 31) - sb_cur) + sb_next;
+            const int wb = (__shfl_sync(0xffffffffu, sb, 31) - sb) + s_inb[buf][w + 1][lane];
             acc += lg[k] + wa + wb;
         }
     }
