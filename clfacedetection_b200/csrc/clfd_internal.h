@@ -124,6 +124,9 @@ struct DenseParams {
     int eq_x, eq_y, eq_w, eq_h;   // the variance rectangle inside the window (tempcv.cpp:614-616): (1, 1, w-2, h-2) at scale 1
     int pool_min;       // stages after the fixed ones run POOLED (rows drawn from the whole tile's survivors, re-sorted by
                         // bank class before every stage) while the tile has more than this many windows; 0: never
+    int track_abs;      // some leaf value is a sentinel (|alpha| > 64: haarcascade_mcs_*): the static sum_eps of such a stage
+                        // would send every window through the FP64 path; stage verdicts bound the FP32 sum by the
+                        // magnitudes actually added instead (kernels_clod.cu, stage_verdict<TRACK>)
     double inv_area;
     const TailStump *tail;   // device, layout of this blob's ystep (patched in by the detector)
     const struct DenseStage *stage_g;   // device: stage table in execution order (stage trees only)

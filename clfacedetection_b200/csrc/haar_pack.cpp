@@ -469,6 +469,13 @@ static void pack_dense_one(const HostCascade &c, int ystep, DenseParams &P, std:
     // frames at pool_min = 64); kept as a tested A/B hook (CLFD_POOL_MIN=n, best with CLFD_N_FIXED=2)
     P.pool_min = 0;
     if (const char *e = getenv("CLFD_POOL_MIN")) P.pool_min = std::max(0, atoi(e));
+    // sentinel leaf values (haarcascade_mcs_upperbody has one of 2.2e6 in stage 2): sum_eps, built from the largest
+    // leaf of every stump, would exceed any real distance to the stage threshold and send every window of the stage
+    // through the FP64 path; such cascades use the kernel instantiation that bounds the FP32 sum by what was added
+    P.track_abs = 0;
+    for (float v : c.alpha)
+        if (std::fabs(v) > 64.f) P.track_abs = 1;
+    if (getenv("CLFD_NO_TRACK_ABS")) P.track_abs = 0;   // A/B hook
     // stages run in fixed geometry before the first compaction (tunable for experiments)
     int nf = 3;
     if (const char *e = getenv("CLFD_N_FIXED")) nf = atoi(e);

@@ -288,10 +288,12 @@ __device__ __noinline__ int dense_stage_exact(const DenseParams &P, const DenseC
 //   FIXED = false: window k lives at base[k]
 //   NODES = true : multi-node trees; at[k] = the node window k is at, a record only counts for the
 //                  windows that are at its node (the others still load its corners: uniform code)
-template <int KK, int K, bool FIXED, int ROWSTEP, bool SHARED, bool NODES>
+//   TRACK = true : also Sa[k] += |selected alpha| (cascades with sentinel leaf values: the stage verdict then bounds the
+//                  error of the FP32 sum by what was actually added, see stage_verdict)
+template <int KK, int K, bool FIXED, int ROWSTEP, bool SHARED, bool NODES, bool TRACK>
 __device__ __forceinline__ void stump_filter_window(const StumpRegs &q, bool dbl, bool three, float eps, const uint32_t (&c)[12],
                                                     const uint32_t (&base)[K], const float (&sg)[K], float (&S)[K], bool (&near)[K],
-                                                    uint32_t (&at)[K]) {
+                                                    uint32_t (&at)[K], float (&Sa)[K]) {
     const float eps4 = eps * 0.25f;
     constexpr int IMM = KK * ROWSTEP;
     const uint32_t b = base[FIXED ? 0 : KK];
@@ -331,13 +333,15 @@ __device__ __forceinline__ void stump_filter_window(const StumpRegs &q, bool dbl
         at[KK] = on ? ((d >= 0.f ? q.meta >> 16 : q.meta >> 8) & 255u) : at[KK];
     } else {
         near[KK] = near[KK] || (fabsf(d) <= m);
-        S[KK] = __fadd_rn(S[KK], d >= 0.f ? q.a1 : q.a0);
+        const float sel = d >= 0.f ? q.a1 : q.a0;
+        S[KK] = __fadd_rn(S[KK], sel);
+        if (TRACK) Sa[KK] = __fadd_rn(Sa[KK], fabsf(sel));
     }
 }
 
-template <int K, bool FIXED, int ROWSTEP, bool SHARED, bool NODES>
+template <int K, bool FIXED, int ROWSTEP, bool SHARED, bool NODES, bool TRACK>
 __device__ __forceinline__ void stump_filter(const StumpRegs &q, bool dbl, bool any3, float eps, const uint32_t (&base)[K],
-                                             const float (&sg)[K], float (&S)[K], bool (&near)[K], uint32_t (&at)[K]) {
+                                             const float (&sg)[K], float (&S)[K], bool (&near)[K], uint32_t (&at)[K], float (&Sa)[K]) {
     static_assert(K >= 1 && K <= 4, "1..4 windows per thread");
     const bool three = !SHARED && any3 && q.o[11] != 0u;   // warp-uniform per stump
     uint32_t c[12];
@@ -349,17 +353,18 @@ __device__ __forceinline__ void stump_filter(const StumpRegs &q, bool dbl, bool 
 #pragma unroll
         for (int k = 0; k < K; k++) at[k] = 0u;
     }
-    stump_filter_window<0, K, FIXED, ROWSTEP, SHARED, NODES>(q, dbl, three, eps, c, base, sg, S, near, at);
-    if (K > 1) stump_filter_window<(K > 1 ? 1 : 0), K, FIXED, ROWSTEP, SHARED, NODES>(q, dbl, three, eps, c, base, sg, S, near, at);
-    if (K > 2) stump_filter_window<(K > 2 ? 2 : 0), K, FIXED, ROWSTEP, SHARED, NODES>(q, dbl, three, eps, c, base, sg, S, near, at);
-    if (K > 3) stump_filter_window<(K > 3 ? 3 : 0), K, FIXED, ROWSTEP, SHARED, NODES>(q, dbl, three, eps, c, base, sg, S, near, at);
+    stump_filter_window<0, K, FIXED, ROWSTEP, SHARED, NODES, TRACK>(q, dbl, three, eps, c, base, sg, S, near, at, Sa);
+    if (K > 1) stump_filter_window<(K > 1 ? 1 : 0), K, FIXED, ROWSTEP, SHARED, NODES, TRACK>(q, dbl, three, eps, c, base, sg, S, near, at, Sa);
+    if (K > 2) stump_filter_window<(K > 2 ? 2 : 0), K, FIXED, ROWSTEP, SHARED, NODES, TRACK>(q, dbl, three, eps, c, base, sg, S, near, at, Sa);
+    if (K > 3) stump_filter_window<(K > 3 ? 3 : 0), K, FIXED, ROWSTEP, SHARED, NODES, TRACK>(q, dbl, three, eps, c, base, sg, S, near, at, Sa);
 }
 
 // Stumps grp, grp + G, ... of stage st for K windows of this lane.  Stumps come from the
 // constant bank when the stage is parameter resident (`resident`), else from global memory.
-template <int K, bool FIXED, int ROWSTEP, bool NODES>
+template <int K, bool FIXED, int ROWSTEP, bool NODES, bool TRACK>
 __device__ __forceinline__ void stage_filter(const DenseParams &P, const DenseStage &st, bool resident, int grp, int G,
-                                             const uint32_t (&base)[K], const float (&sg)[K], float (&S)[K], bool (&near)[K]) {
+                                             const uint32_t (&base)[K], const float (&sg)[K], float (&S)[K], bool (&near)[K],
+                                             float (&Sa)[K]) {
     uint32_t at[K];
 #pragma unroll
     for (int k = 0; k < K; k++) at[k] = 0u;
@@ -370,9 +375,9 @@ __device__ __forceinline__ void stage_filter(const DenseParams &P, const DenseSt
     if (resident && G == 1) {   // all lanes on the same stump: constant bank (reordered copy: six-load stumps first)
         const int first = st.first, n6 = (int)st.n_shared;
 #pragma unroll 1
-        for (int j = 0; j < n6; j++) stump_filter<K, FIXED, ROWSTEP, true, false>(stump_from_param(P.stump[first + j]), dbl, false, eps, base, sg, S, near, at);
+        for (int j = 0; j < n6; j++) stump_filter<K, FIXED, ROWSTEP, true, false, TRACK>(stump_from_param(P.stump[first + j]), dbl, false, eps, base, sg, S, near, at, Sa);
 #pragma unroll 1
-        for (int j = n6; j < count; j++) stump_filter<K, FIXED, ROWSTEP, false, NODES>(stump_from_param(P.stump[first + j]), dbl, any3, eps, base, sg, S, near, at);
+        for (int j = n6; j < count; j++) stump_filter<K, FIXED, ROWSTEP, false, NODES, TRACK>(stump_from_param(P.stump[first + j]), dbl, any3, eps, base, sg, S, near, at, Sa);
     } else {
         const uint4 *__restrict__ rec = reinterpret_cast<const uint4 *>(P.tail + st.tail_first);
         if (NODES) {   // the groups split the stage by whole trees
@@ -381,10 +386,10 @@ __device__ __forceinline__ void stage_filter(const DenseParams &P, const DenseSt
             for (int j = grp * npt; j < count; j += G * npt)
 #pragma unroll 1
                 for (int i = 0; i < npt; i++)
-                    stump_filter<K, FIXED, ROWSTEP, false, true>(stump_from_global(rec, j + i, any3), dbl, any3, eps, base, sg, S, near, at);
+                    stump_filter<K, FIXED, ROWSTEP, false, true, TRACK>(stump_from_global(rec, j + i, any3), dbl, any3, eps, base, sg, S, near, at, Sa);
         } else {
 #pragma unroll 1
-            for (int j = grp; j < count; j += G) stump_filter<K, FIXED, ROWSTEP, false, false>(stump_from_global(rec, j, any3), dbl, any3, eps, base, sg, S, near, at);
+            for (int j = grp; j < count; j += G) stump_filter<K, FIXED, ROWSTEP, false, false, TRACK>(stump_from_global(rec, j, any3), dbl, any3, eps, base, sg, S, near, at, Sa);
         }
     }
 }
@@ -392,9 +397,17 @@ __device__ __forceinline__ void stage_filter(const DenseParams &P, const DenseSt
 // Stage verdict of one window from its FP32 stage sum.  |S32 - S| <= sum_eps for any summation
 // order, so outside that band (and with no stump inside its own band) the FP32 verdict is the
 // reference's; inside, the stage is redone exactly.
-template <bool NODES, bool COUNT>
+// TRACK (cascades with sentinel leaf values, DenseParams::track_abs): sum_eps is built from the LARGEST leaf of every
+// stump; one leaf of 2e6 (haarcascade_mcs_upperbody, stage 2) makes it 24.5 and sends every window of the stage through
+// the FP64 path.  There the bound is taken from what was actually added, n 2^-23 Sa with Sa = sum |selected alpha|
+// (the same (n-1) 2^-24 sum|x| bound with 2x slack; Sa itself is an FP32 sum of non-negative terms, low by at most
+// n 2^-24 relative), plus the same 1e-5 |thr| band: a window that picked the sentinel is far from the threshold, one
+// that did not has a small Sa.
+template <bool NODES, bool COUNT, bool TRACK>
 __device__ __forceinline__ bool stage_verdict(const DenseParams &P, const DenseCtx &c, const DenseStage &st, float sthr, float seps,
-                                              int wid, float S, bool near) {
+                                              int wid, float S, bool near, float Sa) {
+    if (TRACK && !P.force_exact)
+        seps = __fadd_ru(__fmul_ru(__fmul_ru((float)st.count, 1.1920930e-7f), Sa), __fadd_ru(__fmul_ru(1.0001e-5f, fabsf(sthr)), 1.2e-38f));
     if (near || !(fabsf(__fadd_rn(S, -sthr)) > seps)) {
         const int r = dense_stage_exact<NODES>(P, c, st.tail_first, st.count, st.flags & 1u, st.thr, wid);
         if (COUNT) {   // diagnostic instantiation only: even these two lines cost the hot kernel 1.5-4.5 % (code growth at 8 sites)
@@ -411,7 +424,7 @@ __device__ __forceinline__ bool stage_verdict(const DenseParams &P, const DenseC
 // TREE: the cascade is a stage tree the kernel walks itself (DenseParams::exec_stages > tail_stages).
 // NODES: multi-node trees (DenseParams::npt > 1).
 // TILE_H: window rows per tile (== DenseParams::tile_h).
-template <int ROWSTEP_T, bool TREE, bool NODES, int TILE_H, bool COUNT>
+template <int ROWSTEP_T, bool TREE, bool NODES, int TILE_H, bool COUNT, bool TRACK>
 __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const CascadeArgs &a, const int tile0, unsigned char *smem_raw) {
     const DenseSmemPlan plan = dense_smem_plan(P);
     unsigned char *tile = smem_raw + plan.tile;
@@ -525,13 +538,16 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
                 Ssum[k] = 0.f;
                 near[k] = false;
             }
-            if (ROWSTEP_T) stage_filter<kDenseChunk, true, ROWSTEP_T, NODES>(P, P.stage[s], true, 0, 1, base, sg, Ssum, near);
-            else stage_filter<kDenseChunk, false, 0, NODES>(P, P.stage[s], true, 0, 1, base, sg, Ssum, near);
+            float Sabs[kDenseChunk];
+#pragma unroll
+            for (int k = 0; k < kDenseChunk; k++) Sabs[k] = 0.f;
+            if (ROWSTEP_T) stage_filter<kDenseChunk, true, ROWSTEP_T, NODES, TRACK>(P, P.stage[s], true, 0, 1, base, sg, Ssum, near, Sabs);
+            else stage_filter<kDenseChunk, false, 0, NODES, TRACK>(P, P.stage[s], true, 0, 1, base, sg, Ssum, near, Sabs);
 #pragma unroll
             for (int k = 0; k < kDenseChunk; k++) {
                 if (!((m4 >> k) & 1u)) continue;
                 const int wid = (wy0 + (k0 + k) * kRowsPerSlot) * kTileW + wx;
-                if (!stage_verdict<NODES, COUNT>(P, c, P.stage[s], sthr, seps, wid, Ssum[k], near[k])) {
+                if (!stage_verdict<NODES, COUNT, TRACK>(P, c, P.stage[s], sthr, seps, wid, Ssum[k], near[k], Sabs[k])) {
                     alive &= ~(1u << (k0 + k));
                     if (c.codes) dense_write_code(c, wid, s * c.code_mul);
                 }
@@ -630,8 +646,8 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
                 const int e_c = __shfl_sync(0xffffffffu, excl, cc);
                 return valid ? (int)cl_in[cc * kClassCap + (i - e_c)] : 0;   // (an idle lane computes on window 0: any valid tile address)
             };
-            auto keep_pool = [&](bool valid, int wid, float Ssum, bool near) {
-                const bool pass = valid && stage_verdict<NODES, COUNT>(P, c, P.stage[s], sthr, seps, wid, Ssum, near);
+            auto keep_pool = [&](bool valid, int wid, float Ssum, bool near, float Sabs) {
+                const bool pass = valid && stage_verdict<NODES, COUNT, TRACK>(P, c, P.stage[s], sthr, seps, wid, Ssum, near, Sabs);
                 if (pass) {
                     const int cq = (wid + 8 * (wid / kTileW)) & 31;
                     cl_out[cq * kClassCap + atomicAdd(cnt_out + cq, 1)] = (uint16_t)wid;
@@ -647,16 +663,18 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
                     const float sg[2] = {sgf[wid0], sgf[wid1]};
                     float Ssum[2] = {0.f, 0.f};
                     bool near[2] = {false, false};
-                    stage_filter<2, false, 0, NODES>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near);
-                    keep_pool(v0, wid0, Ssum[0], near[0]);
-                    keep_pool(v1, wid1, Ssum[1], near[1]);
+                    float Sabs[2] = {0.f, 0.f};
+                    stage_filter<2, false, 0, NODES, TRACK>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near, Sabs);
+                    keep_pool(v0, wid0, Ssum[0], near[0], Sabs[0]);
+                    keep_pool(v1, wid1, Ssum[1], near[1], Sabs[1]);
                 } else {
                     const uint32_t base[1] = {dense_base(c, wid0)};
                     const float sg[1] = {sgf[wid0]};
                     float Ssum[1] = {0.f};
                     bool near[1] = {false};
-                    stage_filter<1, false, 0, NODES>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near);
-                    keep_pool(v0, wid0, Ssum[0], near[0]);
+                    float Sabs[1] = {0.f};
+                    stage_filter<1, false, 0, NODES, TRACK>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near, Sabs);
+                    keep_pool(v0, wid0, Ssum[0], near[0], Sabs[0]);
                 }
             }
             __syncthreads();   // the next stage's class lists are complete
@@ -709,8 +727,8 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
         int n_next = 0;
         // append the survivors among this pass's windows at cur[n_next..]: always at or below the
         // positions the pass has already read (in-place compaction)
-        auto keep = [&](bool valid, int wid, float Ssum, bool near) {
-            const bool pass = valid && stage_verdict<NODES, COUNT>(P, c, P.stage[s], sthr, seps, wid, Ssum, near);
+        auto keep = [&](bool valid, int wid, float Ssum, bool near, float Sabs) {
+            const bool pass = valid && stage_verdict<NODES, COUNT, TRACK>(P, c, P.stage[s], sthr, seps, wid, Ssum, near, Sabs);
             const unsigned m = __ballot_sync(0xffffffffu, pass);
             if (pass) cur[n_next + __popc(m & ((1u << lane) - 1u))] = (uint16_t)wid;
             n_next += __popc(m);
@@ -729,9 +747,10 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
                     const float sg[2] = {sgf[wid0], sgf[wid1]};
                     float Ssum[2] = {0.f, 0.f};
                     bool near[2] = {false, false};
-                    stage_filter<2, false, 0, NODES>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near);
-                    keep(v0, wid0, Ssum[0], near[0]);
-                    keep(v1, wid1, Ssum[1], near[1]);
+                    float Sabs[2] = {0.f, 0.f};
+                    stage_filter<2, false, 0, NODES, TRACK>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near, Sabs);
+                    keep(v0, wid0, Ssum[0], near[0], Sabs[0]);
+                    keep(v1, wid1, Ssum[1], near[1], Sabs[1]);
                 } else {           // one row
                     const bool v0 = lane < c0;
                     const int wid0 = cur[32 * r + (v0 ? lane : 0)];
@@ -740,8 +759,9 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
                     const float sg[1] = {sgf[wid0]};
                     float Ssum[1] = {0.f};
                     bool near[1] = {false};
-                    stage_filter<1, false, 0, NODES>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near);
-                    keep(v0, wid0, Ssum[0], near[0]);
+                    float Sabs[1] = {0.f};
+                    stage_filter<1, false, 0, NODES, TRACK>(P, P.stage[s], s < P.n_stages, 0, 1, base, sg, Ssum, near, Sabs);
+                    keep(v0, wid0, Ssum[0], near[0], Sabs[0]);
                 }
             }
         } else {
@@ -755,14 +775,16 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
             const float sg[1] = {sgf[wid0]};
             float Ssum[1] = {0.f};
             bool near[1] = {false};
-            if (valid) stage_filter<1, false, 0, NODES>(P, P.stage[s], s < P.n_stages, grp, G, base, sg, Ssum, near);
-            float acc = Ssum[0];
+            float Sabs[1] = {0.f};
+            if (valid) stage_filter<1, false, 0, NODES, TRACK>(P, P.stage[s], s < P.n_stages, grp, G, base, sg, Ssum, near, Sabs);
+            float acc = Ssum[0], acc_abs = Sabs[0];
             unsigned nr = near[0];
             for (int d = 1 << lw; d < 32; d <<= 1) {
                 acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, d));
+                if (TRACK) acc_abs = __fadd_rn(acc_abs, __shfl_xor_sync(0xffffffffu, acc_abs, d));
                 nr |= __shfl_xor_sync(0xffffffffu, nr, d);
             }
-            keep(lane < n, wid0, acc, nr != 0);   // lane < n: slot == lane
+            keep(lane < n, wid0, acc, nr != 0, acc_abs);   // lane < n: slot == lane
         }
         __syncwarp();
         n = n_next;
@@ -802,11 +824,11 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
             const float sthr = st.thr, seps = P.force_exact ? inf : st.sum_eps;
             const int orig = (st.flags >> 8) & 255;
             const uint32_t to_pass = (st.flags >> 16) & 255u, to_fail = st.flags >> 24;
-            auto route = [&](bool valid, int wid, float Ssum, bool near) {
+            auto route = [&](bool valid, int wid, float Ssum, bool near, float Sabs) {
                 uint32_t to = kRouteReject;
                 bool pass = false;
                 if (valid) {
-                    pass = stage_verdict<NODES, COUNT>(P, c, st, sthr, seps, wid, Ssum, near);
+                    pass = stage_verdict<NODES, COUNT, TRACK>(P, c, st, sthr, seps, wid, Ssum, near, Sabs);
                     to = pass ? to_pass : to_fail;
                 }
                 const bool on = valid && to < kRouteReject;
@@ -830,16 +852,18 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
                         const float sg[2] = {sgf[wid0], sgf[wid1]};
                         float Ssum[2] = {0.f, 0.f};
                         bool near[2] = {false, false};
-                        stage_filter<2, false, 0, NODES>(P, st, false, 0, 1, base, sg, Ssum, near);
-                        route(v0, wid0, Ssum[0], near[0]);
-                        route(v1, wid1, Ssum[1], near[1]);
+                        float Sabs[2] = {0.f, 0.f};
+                        stage_filter<2, false, 0, NODES, TRACK>(P, st, false, 0, 1, base, sg, Ssum, near, Sabs);
+                        route(v0, wid0, Ssum[0], near[0], Sabs[0]);
+                        route(v1, wid1, Ssum[1], near[1], Sabs[1]);
                     } else {
                         const uint32_t base[1] = {dense_base(c, wid0)};
                         const float sg[1] = {sgf[wid0]};
                         float Ssum[1] = {0.f};
                         bool near[1] = {false};
-                        stage_filter<1, false, 0, NODES>(P, st, false, 0, 1, base, sg, Ssum, near);
-                        route(v0, wid0, Ssum[0], near[0]);
+                        float Sabs[1] = {0.f};
+                        stage_filter<1, false, 0, NODES, TRACK>(P, st, false, 0, 1, base, sg, Ssum, near, Sabs);
+                        route(v0, wid0, Ssum[0], near[0], Sabs[0]);
                     }
                 }
             } else {
@@ -852,14 +876,16 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
                 const float sg[1] = {sgf[wid0]};
                 float Ssum[1] = {0.f};
                 bool near[1] = {false};
-                if (valid) stage_filter<1, false, 0, NODES>(P, st, false, grp, G, base, sg, Ssum, near);
-                float acc = Ssum[0];
+                float Sabs[1] = {0.f};
+                if (valid) stage_filter<1, false, 0, NODES, TRACK>(P, st, false, grp, G, base, sg, Ssum, near, Sabs);
+                float acc = Ssum[0], acc_abs = Sabs[0];
                 unsigned nr = near[0];
                 for (int d = 1 << lw; d < 32; d <<= 1) {
                     acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, d));
+                    if (TRACK) acc_abs = __fadd_rn(acc_abs, __shfl_xor_sync(0xffffffffu, acc_abs, d));
                     nr |= __shfl_xor_sync(0xffffffffu, nr, d);
                 }
-                route(lane < n_act, wid0, acc, nr != 0);
+                route(lane < n_act, wid0, acc, nr != 0, acc_abs);
             }
             __syncwarp();
         }
@@ -895,11 +921,11 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
 
 // COUNT: the diagnostic instantiation (detectors created with want_codes) that counts FP64 fallbacks and
 // near-threshold stage sums; the production instantiation carries none of that code.
-template <int ROWSTEP_T, bool TREE, bool NODES, int TILE_H, bool COUNT>
+template <int ROWSTEP_T, bool TREE, bool NODES, int TILE_H, bool COUNT, bool TRACK = false>
 __global__ void __launch_bounds__(kDenseThreads)   // (no min-blocks argument: even "1" lets ptxas take 88 registers and costs a CTA per SM)
 k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ CascadeArgs a, const int tile0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    cascade_tiles_body<ROWSTEP_T, TREE, NODES, TILE_H, COUNT>(P, a, tile0, smem_raw);
+    cascade_tiles_body<ROWSTEP_T, TREE, NODES, TILE_H, COUNT, TRACK>(P, a, tile0, smem_raw);
     // every warp ends up here (the body's returns are warp uniform); the last one flushes the CTA's counters
     if (!COUNT) return;
     __syncwarp();
@@ -925,6 +951,16 @@ constexpr int dense_rowstep_ce(int win_w, int ystep) { return (kDenseThreads / k
 
 template <int ROWSTEP_T, bool TREE, bool NODES, int TILE_H = kTileH>
 static cudaError_t launch_tiles_tt(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, size_t smem, cudaStream_t stream) {
+    // cascades with sentinel leaf values (DenseParams::track_abs; haarcascade_mcs_*: generic window sizes, stumps): the
+    // instantiation whose stage verdicts bound the FP32 sum by the magnitudes actually added
+    if constexpr (ROWSTEP_T == 0 && !TREE && !NODES) {
+        if (P.track_abs) {
+            static SmemLimitCache limit_track;
+            if (cudaError_t e = limit_track.ensure(k_cascade_tiles<0, false, false, TILE_H, kTilesCount, true>, smem)) return e;
+            k_cascade_tiles<0, false, false, TILE_H, kTilesCount, true><<<dim3(n_tiles, a.n_frames), kDenseThreads, smem, stream>>>(P, a, tile0);
+            return cudaGetLastError();
+        }
+    }
     static SmemLimitCache limit;
     if (cudaError_t e = limit.ensure(k_cascade_tiles<ROWSTEP_T, TREE, NODES, TILE_H, kTilesCount>, smem)) return e;
     k_cascade_tiles<ROWSTEP_T, TREE, NODES, TILE_H, kTilesCount><<<dim3(n_tiles, a.n_frames), kDenseThreads, smem, stream>>>(P, a, tile0);
@@ -966,6 +1002,8 @@ cudaError_t launch_cascade_tiles(const DenseParams &P, const CascadeArgs &a, int
     constexpr int r20_1 = dense_rowstep_ce(20, 1), r20_2 = dense_rowstep_ce(20, 2);
     constexpr int r24_1 = dense_rowstep_ce(24, 1), r24_2 = dense_rowstep_ce(24, 2);
     static_assert(r20_1 == r24_1 && r20_2 != r24_2 && r20_2 != r20_1 && r24_2 != r20_1, "row steps must be distinct switch labels");
+    // sentinel-leaf cascades: only the generic row-step code has the TRACK instantiation (launch_tiles_tt)
+    if (P.track_abs && P.exec_stages <= P.tail_stages && P.npt == 1) return launch_tiles_t<0>(P, a, tile0, n_tiles, smem, stream);
     switch (rowstep) {
         case r20_1: return launch_tiles_t<r20_1>(P, a, tile0, n_tiles, smem, stream);
         case r20_2: return launch_tiles_t<r20_2>(P, a, tile0, n_tiles, smem, stream);
