@@ -185,8 +185,12 @@ def test_tile_kernel_register_budget():
     assert len(tiles) >= 12, sorted(regs)
     # plain stump cascades, 24- and 32-row tiles (the 16-row tiles of tilted cascades are bound to 2-3 CTAs per SM by
     # their two shared-memory tiles anyway); both the production and the counting instantiation
-    plain = {k: v for k, v in tiles.items() if "ELb0ELb0ELi24E" in k or "ELb0ELb0ELi32E" in k}
+    # (the TRACK instantiations -- last template flag set, sentinel-leaf cascades such as haarcascade_mcs_* only --
+    # carry one more accumulator per window and may take more)
+    track = {k for k in tiles if re.search(r"Lb1EEEvNS", k)}
+    plain = {k: v for k, v in tiles.items() if ("ELb0ELb0ELi24E" in k or "ELb0ELb0ELi32E" in k) and k not in track}
     assert len(plain) >= 8 and all(v <= 64 for v in plain.values()), plain
+    assert track, "no TRACK instantiation found"
     assert all(v <= 80 for v in tiles.values()), tiles
 
 
