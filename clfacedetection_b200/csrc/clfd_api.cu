@@ -289,6 +289,7 @@ struct CascadePlan {
     long long sc_tile_windows = 0;   // grid positions [0, sc_tile_windows) of a frame belong to those scales
     DevBuf<TailStump> d_tail[2];   // warp-per-window tail records of the tile kernel, [ystep-1]
     DevBuf<DenseStage> d_stage_tab[2];   // stage trees: stage table in execution order
+    DevBuf<int16_t> d_flat_code;         // exit codes of flat windows by pixel value (DenseParams::flat_code), see build_flat_table
     DenseParams dense[2];          // the cascade's parameter blobs with this detector's tail pointers
     DevBuf<int16_t> d_codes;
     DevBuf<unsigned long long> d_counters;
@@ -651,6 +652,49 @@ int clfd_integral_image(clfd_context *ctx, const uint8_t *img, int w, int h, int
 // ------------------------------------------------------------------------------------
 // detector
 // ------------------------------------------------------------------------------------
+// The exit code of a FLAT window (every pixel equal) depends on the pixel value alone: rect sums are value x area, sigma
+// follows from value and area.  The tile kernel looks such windows up instead of walking them through one FP64 fallback
+// per stage (kernels_clod.cu, flat_window_code).  The table is MEASURED, not derived: a 16 x 16 board of flat patches, one
+// per pixel value and a little larger than the window, goes through a diagnostic detector of the same cascade (want_codes:
+// the instantiation that evaluates flat windows like any other) at the unscaled level, and the exit code of the window
+// inside patch v is entry v.
+static int build_flat_table(clfd_context *ctx, CascadePlan &cp) {
+    const HostCascade &hc = cp.cascade->host;
+    const DenseParams &P0 = cp.dense[0];
+    // only where the tile kernel takes a window all the way (every stock cascade): codes then are final verdicts
+    if (!(P0.tail_stages == P0.total_stages || P0.exec_stages > P0.tail_stages) || P0.total_stages <= 0) return 0;
+    const int pw = (hc.win_w + 4 + 1) & ~1, ph = (hc.win_h + 4 + 1) & ~1;   // even: patch origins on the step-2 window grid
+    clfd_detector_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.width = 16 * pw; cfg.height = 16 * ph; cfg.max_batch = 1;
+    cfg.scale_factor = 1000.0;   // one level: the frame itself
+    cfg.want_codes = 1; cfg.max_rects = 4096; cfg.mode = CLFD_MODE_SCALE_IMAGE;
+    clfd_detector *probe = nullptr;
+    const clfd_cascade *one = cp.cascade;
+    int rc = clfd_detector_create(ctx, &one, 1, &cfg, &probe);
+    if (rc) return rc;
+    std::unique_ptr<clfd_detector, void (*)(clfd_detector *)> guard(probe, clfd_detector_destroy);
+    std::vector<uint8_t> board((size_t)cfg.width * cfg.height);
+    for (int y = 0; y < cfg.height; y++)
+        for (int x = 0; x < cfg.width; x++) board[(size_t)y * cfg.width + x] = (uint8_t)((y / ph) * 16 + x / pw);
+    int64_t n = 0;
+    if ((rc = clfd_detect(probe, board.data(), 1, board.size(), cfg.width, nullptr, 0, &n)) && rc != CLFD_ERR_CAPACITY) return rc;
+    const CascadePlan &pc = *probe->cas[0];
+    if (pc.levels.empty() || pc.levels[0].ystep != 2 || pc.levels[0].win_base != 0) return 0;   // (cannot happen at factor 1)
+    std::vector<int16_t> codes((size_t)pc.windows_per_frame);
+    if ((rc = clfd_detector_get_codes(probe, 0, codes.data(), (int64_t)codes.size()))) return rc;
+    std::vector<int16_t> table(256);
+    const int nx = pc.levels[0].nx;
+    for (int v = 0; v < 256; v++) {
+        const int x = (v % 16) * pw + 2, y = (v / 16) * ph + 2;   // the window [x, x + w) x [y, y + h) lies inside patch v
+        table[v] = codes[(size_t)(y / 2) * nx + x / 2];
+    }
+    if ((rc = cp.d_flat_code.upload(table, ctx->stream))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int yi = 0; yi < 2; yi++) cp.dense[yi].flat_code = cp.d_flat_code.p;
+    return 0;
+}
+
 int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades, int n_cascades,
                          const clfd_detector_config *cfg, clfd_detector **out) {
     if (!ctx || !cascades || !cfg || !out) INVALID("NULL argument");
@@ -849,6 +893,10 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
     det->stats.bytes_integral = det->pyr.bytes_integral;
     det->stats.bytes_tilted = det->pyr.bytes_tilted;
     for (auto &cpp : det->cas) det->stats.bytes_cascade += cpp->bytes_cascade;
+    // production detectors of the pyramid mode look flat windows up (the diagnostic ones, want_codes, measure the table)
+    if (!scale_cascade && !cfg->want_codes && !getenv("CLFD_NO_FLAT_TABLE"))
+        for (auto &cpp : det->cas)
+            if ((rc = build_flat_table(ctx, *cpp))) return rc;
     *out = det.release();
     return 0;
 }

@@ -130,6 +130,8 @@ struct DenseParams {
     double inv_area;
     const TailStump *tail;   // device, layout of this blob's ystep (patched in by the detector)
     const struct DenseStage *stage_g;   // device: stage table in execution order (stage trees only)
+    const int16_t *flat_code;           // device, 256 entries or NULL: the exit code of a FLAT window (every pixel = the index),
+                                        // measured once per detector with the detector's own kernels (clfd_api.cu, build_flat_table)
     DenseStage stage[kMaxDenseStages];
     DenseStump stump[kMaxDenseStumps];
 };

@@ -201,6 +201,40 @@ __device__ __forceinline__ double dense_sigma(const DenseParams &P, const DenseC
     const ull q4 = __ldg(q + g0) - __ldg(q + g1) - __ldg(q + g2) + __ldg(q + g3);
     return window_sigma(s4, q4, P.inv_area);
 }
+// the same, and whether the variance rectangle is FLAT (every pixel equal): Q A == S^2 exactly (Cauchy-Schwarz with equality)
+__device__ __forceinline__ double dense_sigma_flat(const DenseParams &P, const DenseCtx &c, int wid, bool &eq_flat) {
+    const int wx = wid & (kTileW - 1), wy = wid / kTileW;
+    const int ex = P.eq_x, ey = P.eq_y, eq_w = P.eq_w, eq_h = P.eq_h;
+    const uint32_t base = dense_base(c, wid);
+    const int s4 = lds32(base + dense_tile_off(c, ey, ex)) - lds32(base + dense_tile_off(c, ey, ex + eq_w)) -
+                   lds32(base + dense_tile_off(c, ey + eq_h, ex)) + lds32(base + dense_tile_off(c, ey + eq_h, ex + eq_w));
+    const ull *q = c.gsq + (size_t)(wy * c.ystep) * c.sq_pitch + wx * c.ystep;
+    const int g0 = ey * c.sq_pitch + ex, g1 = g0 + eq_w, g2 = (ey + eq_h) * c.sq_pitch + ex, g3 = g2 + eq_w;
+    const ull q4 = __ldg(q + g0) - __ldg(q + g1) - __ldg(q + g2) + __ldg(q + g3);
+    eq_flat = q4 * (ull)(eq_w * eq_h) == (ull)((long long)s4 * s4);
+    return window_sigma(s4, q4, P.inv_area);
+}
+
+// Flat windows -- every pixel of the window equal: black bars, saturated or empty regions -- are the one systematic
+// customer of the FP64 fallback: sigma is 0 or rounding noise and every feature sum cancels to (almost) nothing, so every
+// stump lands inside its guard band and the window walks its stages one exact evaluation after the other (an all-black
+// 1080p batch ran at 890 frames/s instead of 2300, frontalface_default at 306).  But a flat window's rect sums, its
+// sigma and with them its whole path through the cascade depend on the pixel value alone, so its exit code comes from a
+// table of 256 entries that the detector measured once with these same kernels (clfd_api.cu, build_flat_table).  The
+// variance rectangle's flatness falls out of the sums sigma needs anyway; only then is the whole window tested (rare
+// path, a function of its own).  Returns the window's exit code, or kNotFlat.
+constexpr int kNotFlat = -0x8000;
+static __device__ __noinline__ int flat_window_code(const DenseParams &P, const DenseCtx &c, int wid) {
+    const uint32_t base = dense_base(c, wid);
+    const int W = P.win_w, H = P.win_h;
+    const uint32_t S4 = (uint32_t)(lds32(base + dense_tile_off(c, 0, 0)) - lds32(base + dense_tile_off(c, 0, W)) -
+                                   lds32(base + dense_tile_off(c, H, 0)) + lds32(base + dense_tile_off(c, H, W)));   // <= 255 W H
+    const ull *q = c.gsq + (size_t)((wid / kTileW) * c.ystep) * c.sq_pitch + (wid & (kTileW - 1)) * c.ystep;
+    const ull Q4 = __ldg(q) - __ldg(q + W) - __ldg(q + (size_t)H * c.sq_pitch) + __ldg(q + (size_t)H * c.sq_pitch + W);
+    const uint32_t A = (uint32_t)(W * H);
+    if (Q4 * (ull)A != (ull)S4 * (ull)S4) return kNotFlat;
+    return (int)__ldg(P.flat_code + S4 / A);
+}
 
 // One stump in registers.
 struct StumpRegs {
@@ -512,8 +546,16 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
         const int wy = wy0 + k * kRowsPerSlot;
         const int wid = wy * kTileW + wx;
         if (wx < n_wx && wy < n_wy) {
-            alive |= 1u << k;
-            sgf[wid] = (float)dense_sigma(P, c, wid);
+            bool eq_flat, live = true;
+            sgf[wid] = (float)dense_sigma_flat(P, c, wid, eq_flat);
+            if (!COUNT && eq_flat && P.flat_code) {   // (the diagnostic instantiation evaluates flat windows like any other)
+                const int code = flat_window_code(P, c, wid);
+                if (code != kNotFlat) {
+                    live = false;
+                    if (P.is_tree ? (code & 1) : (code == P.total_stages)) emit_rect(a, CL, frame, px0 + wx * ystep, py0 + wy * ystep);
+                }
+            }
+            if (live) alive |= 1u << k;
         } else {
             sgf[wid] = 1.0f;
         }

@@ -493,3 +493,42 @@ def test_empty_ragged_and_odd_inputs(gpu_ctx):
         for f in range(3):
             assert np.array_equal(res2.frame_rects(f), _sorted(w))
         det.close()
+
+
+@pytest.mark.parametrize("name", ["frontalface_alt", "frontalface_default", "frontalface_alt_tree", "frontalface_alt2", "fullbody",
+                                  "mcs_nose", "eye"])
+def test_flat_regions_take_the_table_and_equal_the_oracle(gpu_ctx, monkeypatch, name):
+    """Flat windows (every pixel equal) are looked up in a table the detector measures at creation instead of walking one
+    FP64 fallback per stage.  Frames made of flat regions of every kind -- letterbox bars, a saturated half, a board of
+    flat patches of all 256 values with noise between them, all-black, all-white -- must give the oracle's rects, and the
+    same rects with the table switched off (CLFD_NO_FLAT_TABLE)."""
+    W, H = 640, 360
+    base = octave_frame(W, H, 77)
+    frames = []
+    lb = base.copy(); lb[:60] = 0; lb[-60:] = 16; frames.append(lb)
+    sat = base.copy(); sat[:, W // 2:] = 255; frames.append(sat)
+    board = base.copy()
+    for v in range(256):   # 40 x 32 patches of every value; noise strips between them
+        y, x = (v // 16) * 22, (v % 16) * 40
+        board[y:y + 20, x:x + 36] = v
+    frames.append(board)
+    big = base.copy(); big[40:200, 100:400] = 128; big[220:340, 50:300] = 3; frames.append(big)
+    frames += [np.zeros((H, W), np.uint8), np.full((H, W), 255, np.uint8), np.full((H, W), 77, np.uint8)]
+    frames = np.stack(frames)
+    cas = clfd.Cascade(cascade_path(name))
+    det = clfd.Detector(gpu_ctx, cas, W, H, max_batch=len(frames), scale_factor=1.2)
+    got = det.detect(frames)
+    det.close()
+    monkeypatch.setenv("CLFD_NO_FLAT_TABLE", "1")
+    det = clfd.Detector(gpu_ctx, cas, W, H, max_batch=len(frames), scale_factor=1.2)
+    plain = det.detect(frames)
+    det.close()
+    oc = oracle_cascade(name)
+    total = 0
+    for f in range(len(frames)):
+        rects, _, _, _, _ = oc.detect(frames[f], 1.2, want_codes=False)
+        want = _sorted(rects)
+        assert np.array_equal(got.frame_rects(f), want), (name, f)
+        assert np.array_equal(plain.frame_rects(f), want), (name, f)
+        total += len(want)
+    assert total > 0
