@@ -347,19 +347,21 @@ __device__ __forceinline__ void stump_filter_window(const StumpRegs &q, bool dbl
         r0 = lds32(b + q.o[0]) - lds32(b + q.o[1]) - lds32(b + q.o[2]) + lds32(b + q.o[3]);
         r1 = lds32(b + q.o[4]) - lds32(b + q.o[5]) - lds32(b + q.o[6]) + lds32(b + q.o[7]);
     }
-    const float p0 = __fmul_rn(__int2float_rn(r0), q.w0), p1 = __fmul_rn(__int2float_rn(r1), q.w1);
-    float s32 = __fadd_rn(p0, p1);
-    const float t32 = __fmul_rn(q.thr, sg[KK]);
-    float m = __fmul_rn(fabsf(t32), eps);
-    if (dbl) m = __fadd_rn(m, __fmul_rn(__fadd_rn(fabsf(p0), fabsf(p1)), eps4));   // the reference adds EXACT products: fp32 product errors do not cancel
+    // p0 is the reference's own float product; the second (and third) product goes into the sum unrounded (FFMA): that
+    // is closer to the double-product stages' exact sum, and differs from a float-product stage's rounded product by at
+    // most 2^-24 |r1 w1| <= 2^-24 (|p0| + |s32|).  Either way the band eps |t32| + eps/4 |p0| covers it.
+    const float p0 = __fmul_rn(__int2float_rn(r0), q.w0);
+    float s32 = __fmaf_rn(__int2float_rn(r1), q.w1, p0);
+    // eps is a power of two: |thr| (sg eps) == |thr sg| eps, and sg eps does not depend on the stump (hoisted)
+    float m = __fmaf_rn(fabsf(p0), eps4, __fmul_rn(fabsf(q.thr), __fmul_rn(sg[KK], eps)));
     if (!SHARED && three) {
         int r2;
         if (FIXED) r2 = lds32i<IMM>(c[8]) - lds32i<IMM>(c[9]) - lds32i<IMM>(c[10]) + lds32i<IMM>(c[11]);
         else r2 = lds32(b + q.o[8]) - lds32(b + q.o[9]) - lds32(b + q.o[10]) + lds32(b + q.o[11]);
-        m = __fadd_rn(m, __fmul_rn(fabsf(s32), eps4));   // rounding of the first add
-        s32 = __fadd_rn(s32, __fmul_rn(__int2float_rn(r2), q.w2));
+        m = __fmaf_rn(fabsf(s32), eps4, m);   // rounding of the first sum, the third product unrounded
+        s32 = __fmaf_rn(__int2float_rn(r2), q.w2, s32);
     }
-    const float d = __fadd_rn(s32, -t32);
+    const float d = __fmaf_rn(-q.thr, sg[KK], s32);   // s32 - thr sigma, rounded once
     if (NODES) {
         const bool on = at[KK] == (q.meta & 255u);
         near[KK] = near[KK] || (on && fabsf(d) <= m);
