@@ -79,10 +79,16 @@ struct DevBuf {
     }
 };
 
+// element `at` of a squared integral that holds 64-bit or (sq32) 32-bit elements, as the pointer the kernels take
+static inline unsigned long long *sq_at(unsigned long long *base, size_t at, bool sq32) {
+    return sq32 ? reinterpret_cast<unsigned long long *>(reinterpret_cast<uint32_t *>(base) + at) : base + at;
+}
+
 // Pyramid + integral plan for frames of W x H and a list of level sizes.
 struct PyramidPlan {
     int W = 0, H = 0, max_batch = 0;
     bool want_tilted = false;
+    bool sq32 = false;   // squared integral modulo 2^32 (pyramid-mode detectors; set before build())
     std::vector<PyrLevel> levels;
     size_t pyr_frame_stride = 0, sum_frame_stride = 0, col_frame_stride = 0, col_plane_stride = 0;
     int max_level_w = 0;
@@ -131,7 +137,7 @@ int PyramidPlan::build(int W_, int H_, const std::vector<std::pair<int, int>> &s
         pyramid_pixels += (int64_t)w * h;
         // algorithmic bytes: resize min(W*H, 4*w*h) + w*h ; integral w*h + (w+1)(h+1)(4+8+4T)
         bytes_resize += std::min<int64_t>((int64_t)W * H, 4ll * w * h) + (int64_t)w * h;
-        bytes_integral += (int64_t)w * h + (int64_t)(w + 1) * (h + 1) * (4 + 8);
+        bytes_integral += (int64_t)w * h + (int64_t)(w + 1) * (h + 1) * (4 + (sq32 ? 4 : 8));
         if (tilt) bytes_tilted += (int64_t)w * h + (int64_t)(w + 1) * (h + 1) * 4;   // the tilted kernels read the level again
 
         // cv::resize INTER_LINEAR coefficient tables (OpenCV imgproc)
@@ -188,7 +194,7 @@ int PyramidPlan::build(int W_, int H_, const std::vector<std::pair<int, int>> &s
     int rc = 0;
     if ((rc = pyr.alloc(pyr_frame_stride * batch + 256))) return rc;
     if ((rc = sum.alloc(sum_frame_stride * batch + 4096))) return rc;
-    if ((rc = sq.alloc(sum_frame_stride * batch + 4096))) return rc;
+    if ((rc = sq.alloc((sum_frame_stride * batch + 4096) / (sq32 ? 2 : 1)))) return rc;
     if (tilt && (rc = tilted.alloc(sum_frame_stride * batch + 4096))) return rc;
     if (tilt && (rc = tcar.alloc(6 * col_plane_stride * batch + 64))) return rc;
     if ((rc = col.alloc(col_frame_stride * batch + 64))) return rc;
@@ -217,7 +223,7 @@ void PyramidPlan::fill_args(PyramidArgs &a, const uint8_t *frames, size_t frame_
     a.pyr = pyr.p; a.pyr_frame_stride = pyr_frame_stride;
     a.col = col.p; a.col_frame_stride = col_frame_stride; a.col_plane_stride = col_plane_stride;
     a.sum = sum.p; a.sq = sq.p; a.tilted = want_tilted ? tilted.p : nullptr;
-    a.sum_frame_stride = sum_frame_stride;
+    a.sum_frame_stride = sum_frame_stride; a.sq32 = sq32 ? 1 : 0;
     a.levels = d_levels.p; a.n_levels = (int)levels.size();
     a.xofs = xofs.p; a.xalpha = xalpha.p; a.yofs = yofs.p; a.ybeta = ybeta.p;
     a.resize_items = resize_items.p; a.n_resize_items = (int)resize_items.n;
@@ -242,7 +248,7 @@ int PyramidPlan::run(clfd_context *ctx, const uint8_t *frames, size_t frame_stri
     a.pyr += (size_t)frame_base * a.pyr_frame_stride;
     a.col += (size_t)frame_base * a.col_frame_stride;
     a.sum += (size_t)frame_base * a.sum_frame_stride;
-    a.sq += (size_t)frame_base * a.sum_frame_stride;
+    a.sq = sq_at(a.sq, (size_t)frame_base * a.sum_frame_stride, sq32);
     if (a.tilted) { a.tilted += (size_t)frame_base * a.sum_frame_stride; a.tcar += (size_t)frame_base * a.tcar_frame_stride; }
     int launches = 0, nint = 0;
     if (ev) CK(cudaEventRecord(ev[0], s));
@@ -331,6 +337,10 @@ struct clfd_detector {
     // clfd_detect pipelines the H2D copy of a batch with its own compute, chunk by chunk
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copied[kMaxChunks] = {nullptr};
+    // chunk overlap (enqueue_overlapped): the HBM-bound pyramid kernels of chunk k+1 run beside the L1-bound tile
+    // kernel of chunk k
+    cudaStream_t pyr_stream = nullptr, tile_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_pyr[kMaxChunks] = {nullptr}, ev_tile[2] = {nullptr, nullptr};
     ~clfd_detector() {
         if (h_rects) cudaFreeHost(h_rects);
         if (h_rects1) cudaFreeHost(h_rects1);
@@ -339,6 +349,11 @@ struct clfd_detector {
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         for (auto &e : copied) if (e) cudaEventDestroy(e);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        for (auto &e : ev_pyr) if (e) cudaEventDestroy(e);
+        for (auto &e : ev_tile) if (e) cudaEventDestroy(e);
+        if (pyr_stream) cudaStreamDestroy(pyr_stream);
+        for (auto &t : tile_stream) if (t) cudaStreamDestroy(t);
     }
 };
 
@@ -839,6 +854,9 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
     }
     cudaStream_t s = ctx->stream;
     int rc = 0;
+    // pyramid mode: every sum of squares the kernels form is a cascade window's (< 2^32), so the squared integral is
+    // kept modulo 2^32 -- a third less integral traffic; the scale-cascade mode's windows grow with the scale: 64 bits
+    det->pyr.sq32 = !scale_cascade && !getenv("CLFD_SQ64");
     if (!sizes.empty() && (rc = det->pyr.build(W, H, sizes, cfg->max_batch, any_tilted, s))) return rc;
     else if (sizes.empty()) { det->pyr.W = W; det->pyr.H = H; det->pyr.max_batch = cfg->max_batch; }
 
@@ -940,20 +958,27 @@ int clfd_detector_set_profiling(clfd_detector *det, int enable) {
 // `first` resets the batch's rect / overflow counters; the kernels see frame numbers relative
 // to the range (the per-frame buffers are passed pre-offset) and add frame_base to the frame
 // index of the rects they emit.
+// parts: which halves of the range's work go onto stream s (enqueue_overlapped puts them on different streams)
+enum { kPartPyramid = 1, kPartCascades = 2, kPartCounters = 4, kPartAll = 7 };
 static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int frame_base, int n_frames, size_t frame_stride,
-                         int row_stride, cudaStream_t s, bool first, int *n_launches, int slot = 0) {
+                         int row_stride, cudaStream_t s, bool first, int *n_launches, int slot = 0, int parts = kPartAll) {
     clfd_context *ctx = det->ctx;
     int launches = 0;
     cudaEvent_t *ev = det->profiling ? det->ev : nullptr;
-    if (!det->pyr.levels.empty()) {
+    if (!det->pyr.levels.empty() && (parts & kPartPyramid)) {
         int rc = det->pyr.run(ctx, frames_dev, frame_stride, row_stride, frame_base, n_frames, s, ev, &launches);
         if (rc) return rc;
     }
     const int pyr_launches = launches;
-    for (auto &cpp : det->cas) {
-        if (first) CK(cudaMemsetAsync(cpp->d_counters.p + kCnt * slot, 0, kCnt * sizeof(unsigned long long), s));
-        else CK(cudaMemsetAsync(cpp->d_counters.p + kCnt * slot + 1, 0, sizeof(unsigned long long), s));   // the queue is per range
-        CK(cudaMemsetAsync(cpp->d_count_b.p + slot, 0, sizeof(unsigned long long), s));
+    if (parts & kPartCounters)
+        for (auto &cpp : det->cas) {
+            if (first) CK(cudaMemsetAsync(cpp->d_counters.p + kCnt * slot, 0, kCnt * sizeof(unsigned long long), s));
+            else CK(cudaMemsetAsync(cpp->d_counters.p + kCnt * slot + 1, 0, sizeof(unsigned long long), s));   // the queue is per range
+            CK(cudaMemsetAsync(cpp->d_count_b.p + slot, 0, sizeof(unsigned long long), s));
+        }
+    if (!(parts & kPartCascades)) {
+        *n_launches += launches;
+        return 0;
     }
     int ci = 0;
     for (auto &cpp : det->cas) {
@@ -963,7 +988,7 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
             const size_t fo = (size_t)frame_base * det->pyr.sum_frame_stride;
             CascadeArgs a;
             memset(&a, 0, sizeof a);
-            a.sum = det->pyr.sum.p + fo; a.sq = det->pyr.sq.p + fo;
+            a.sum = det->pyr.sum.p + fo; a.sq = sq_at(det->pyr.sq.p, fo, det->pyr.sq32); a.sq32 = det->pyr.sq32 ? 1 : 0;
             a.tilted = det->pyr.want_tilted ? det->pyr.tilted.p + fo : nullptr;
             a.sum_frame_stride = det->pyr.sum_frame_stride;
             a.levels = det->pyr.d_levels.p; a.cas_levels = cp.d_levels.p;
@@ -1111,6 +1136,65 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
     return 0;
 }
 
+// Chunk overlap.  The pyramid kernels are HBM-bound and the tile kernel is bound by the SMs' L1 data pipe, so they
+// overlap well: the batch is cut into chunks, the pyramid of chunk k+1 runs on a high-priority stream while the tile
+// kernel of chunk k runs (the per-frame buffers of different chunks are disjoint), and the tile launches of consecutive
+// chunks alternate between two streams so that one chunk's last wave overlaps the next chunk's first.  Forked from and
+// joined back into the caller's stream s.  Only for detectors whose (single) cascade the tile kernel finishes itself
+// (no survivor queue, no counter hand-over between cascades); profiling runs keep the serial order so that the
+// per-kernel event times mean something.  copied: per-chunk events of the host-to-device copies, or nullptr.
+static bool overlap_applies(const clfd_detector *det, int n_frames) {
+    if (det->profiling || det->cfg.mode == CLFD_MODE_SCALE_CASCADE || det->pyr.levels.empty() || det->cas.size() != 1) return false;
+    if (n_frames < 8 || getenv("CLFD_NO_OVERLAP")) return false;
+    const CascadePlan &cp = *det->cas[0];
+    const PackedCascade &pk = cp.cascade->packed;
+    return cp.windows_per_frame > 0 && pk.dense[0].tail_stages > 0 && pk.dense[0].exec_stages == pk.dense[0].total_stages;
+}
+static int overlap_chunks(int n_frames) {
+    int n = n_frames >= 32 ? 8 : 4;
+    if (const char *e = getenv("CLFD_OVERLAP_CHUNKS")) n = atoi(e);
+    return std::max(1, std::min({n, kMaxChunks, n_frames}));
+}
+static int overlap_setup(clfd_detector *det) {
+    if (det->pyr_stream) return 0;
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi: the numerically lowest value = the highest priority
+    CK(cudaStreamCreateWithPriority(&det->pyr_stream, cudaStreamNonBlocking, hi));
+    for (auto &t : det->tile_stream) CK(cudaStreamCreateWithPriority(&t, cudaStreamNonBlocking, lo));
+    CK(cudaEventCreateWithFlags(&det->ev_fork, cudaEventDisableTiming));
+    for (auto &e : det->ev_pyr) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : det->ev_tile) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return 0;
+}
+static int enqueue_overlapped(clfd_detector *det, const uint8_t *frames_dev, int n_frames, size_t frame_stride, int row_stride,
+                              cudaStream_t s, int n_chunks, const cudaEvent_t *copied, int *n_launches, int slot) {
+    int rc = overlap_setup(det);
+    if (rc) return rc;
+    rc = enqueue_range(det, frames_dev, 0, n_frames, frame_stride, row_stride, s, true, n_launches, slot, kPartCounters);
+    if (rc) return rc;
+    CK(cudaEventRecord(det->ev_fork, s));
+    CK(cudaStreamWaitEvent(det->pyr_stream, det->ev_fork, 0));
+    for (auto &t : det->tile_stream) CK(cudaStreamWaitEvent(t, det->ev_fork, 0));
+    for (int k = 0; k < n_chunks; k++) {
+        const int f0 = (int)((long long)n_frames * k / n_chunks), f1 = (int)((long long)n_frames * (k + 1) / n_chunks);
+        if (f1 <= f0) continue;
+        const uint8_t *src = frames_dev + (size_t)f0 * frame_stride;
+        if (copied) CK(cudaStreamWaitEvent(det->pyr_stream, copied[k], 0));
+        rc = enqueue_range(det, src, f0, f1 - f0, frame_stride, row_stride, det->pyr_stream, false, n_launches, slot, kPartPyramid);
+        if (rc) return rc;
+        CK(cudaEventRecord(det->ev_pyr[k], det->pyr_stream));
+        cudaStream_t t = det->tile_stream[k & 1];
+        CK(cudaStreamWaitEvent(t, det->ev_pyr[k], 0));
+        rc = enqueue_range(det, src, f0, f1 - f0, frame_stride, row_stride, t, false, n_launches, slot, kPartCascades);
+        if (rc) return rc;
+    }
+    for (int i = 0; i < 2; i++) {
+        CK(cudaEventRecord(det->ev_tile[i], det->tile_stream[i]));
+        CK(cudaStreamWaitEvent(s, det->ev_tile[i], 0));
+    }
+    return 0;
+}
+
 int clfd_detector_enqueue(clfd_detector *det, const uint8_t *frames_dev, int n_frames, size_t frame_stride,
                           int row_stride, void *cuda_stream) {
     if (!det || !frames_dev) INVALID("NULL argument");
@@ -1120,7 +1204,9 @@ int clfd_detector_enqueue(clfd_detector *det, const uint8_t *frames_dev, int n_f
     if (n_frames <= 0 || n_frames > det->cfg.max_batch) INVALID("n_frames %d outside 1..%d", n_frames, det->cfg.max_batch);
     det->last_frames = n_frames;
     int launches = 0;
-    int rc = enqueue_range(det, frames_dev, 0, n_frames, frame_stride, row_stride, s, true, &launches);
+    int rc = overlap_applies(det, n_frames)
+                 ? enqueue_overlapped(det, frames_dev, n_frames, frame_stride, row_stride, s, overlap_chunks(n_frames), nullptr, &launches, 0)
+                 : enqueue_range(det, frames_dev, 0, n_frames, frame_stride, row_stride, s, true, &launches);
     if (rc) return rc;
     det->stats.kernel_launches = launches;
     return 0;
@@ -1207,6 +1293,8 @@ int clfd_detect_submit(clfd_detector *det, const uint8_t *frames_host, int n_fra
     if (det->n_submitted > det->n_collected) n_chunks = 1;
     if (const char *e = getenv("CLFD_DETECT_CHUNKS")) n_chunks = std::max(1, std::min({atoi(e), kMaxChunks, n_frames}));
     if (det->cas.size() != 1) n_chunks = 1;
+    const bool overlap = overlap_applies(det, n_frames);
+    if (overlap) n_chunks = overlap_chunks(n_frames);   // the compute chunks are the copy chunks
     if (!det->copy_stream) CK(cudaStreamCreateWithFlags(&det->copy_stream, cudaStreamNonBlocking));
     for (int k = 0; k < n_chunks; k++)
         if (!det->copied[k]) CK(cudaEventCreateWithFlags(&det->copied[k], cudaEventDisableTiming));
@@ -1235,8 +1323,14 @@ int clfd_detect_submit(clfd_detector *det, const uint8_t *frames_host, int n_fra
                                      cudaMemcpyHostToDevice, cs));
         }
         CK(cudaEventRecord(det->copied[k], cs));
+        if (overlap) continue;
         CK(cudaStreamWaitEvent(ctx->stream, det->copied[k], 0));
         rc = enqueue_range(det, dst, f0, nf, dframe, (int)dstride, ctx->stream, k == 0, &launches, slot);
+        if (rc) return rc;
+    }
+    if (overlap) {   // pyramid of chunk k+1 beside the tile kernel of chunk k, each pyramid behind its chunk's copy
+        rc = enqueue_overlapped(det, det->dev_frames[slot].p, n_frames, dframe, (int)dstride, ctx->stream, n_chunks, det->copied,
+                                &launches, slot);
         if (rc) return rc;
     }
     det->stats.kernel_launches = launches;
@@ -1363,7 +1457,7 @@ int clfd_detector_reject_levels(clfd_detector *det, int cascade, clfd_rect *rect
     if (!det->roc.p && ((rc = det->roc.alloc(roc_cap)) || (rc = det->roc_count.alloc(1)))) return rc;
     CascadeArgs a;
     memset(&a, 0, sizeof a);
-    a.sum = det->pyr.sum.p; a.sq = det->pyr.sq.p;
+    a.sum = det->pyr.sum.p; a.sq = det->pyr.sq.p; a.sq32 = det->pyr.sq32 ? 1 : 0;
     a.tilted = det->pyr.want_tilted ? det->pyr.tilted.p : nullptr;
     a.sum_frame_stride = det->pyr.sum_frame_stride;
     a.levels = det->pyr.d_levels.p; a.cas_levels = cp.d_levels.p;
@@ -1413,7 +1507,14 @@ int clfd_detector_read_level(clfd_detector *det, int cascade, int level, int fra
     const size_t so = (size_t)frame * det->pyr.sum_frame_stride + L.sum_off;
     if (pyr) CK(cudaMemcpy2D(pyr, L.w, det->pyr.pyr.p + (size_t)frame * det->pyr.pyr_frame_stride + L.pyr_off, L.pyr_pitch, L.w, L.h, cudaMemcpyDeviceToHost));
     if (sum) CK(cudaMemcpy2D(sum, W1 * 4, det->pyr.sum.p + so, (size_t)L.sum_pitch * 4, W1 * 4, L.h + 1, cudaMemcpyDeviceToHost));
-    if (sqsum) CK(cudaMemcpy2D(sqsum, W1 * 8, det->pyr.sq.p + so, (size_t)L.sum_pitch * 8, W1 * 8, L.h + 1, cudaMemcpyDeviceToHost));
+    if (sqsum && det->pyr.sq32) {   // kept modulo 2^32 on the device: the low words, widened
+        std::vector<uint32_t> low(W1 * (L.h + 1));
+        CK(cudaMemcpy2D(low.data(), W1 * 4, reinterpret_cast<const uint32_t *>(det->pyr.sq.p) + so, (size_t)L.sum_pitch * 4, W1 * 4,
+                        L.h + 1, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < low.size(); i++) sqsum[i] = low[i];
+    } else if (sqsum) {
+        CK(cudaMemcpy2D(sqsum, W1 * 8, det->pyr.sq.p + so, (size_t)L.sum_pitch * 8, W1 * 8, L.h + 1, cudaMemcpyDeviceToHost));
+    }
     if (tilted) CK(cudaMemcpy2D(tilted, W1 * 4, det->pyr.tilted.p + so, (size_t)L.sum_pitch * 4, W1 * 4, L.h + 1, cudaMemcpyDeviceToHost));
     return 0;
 }

@@ -19,6 +19,9 @@ struct PyramidArgs {
     size_t col_plane_stride;                    // elements
     int32_t *sum; unsigned long long *sq; int32_t *tilted;   // tilted may be NULL
     size_t sum_frame_stride;                    // elements (same for sum / sq / tilted)
+    int sq32;                                   // the squared integral is kept modulo 2^32 (uint32 elements at `sq`, same
+                                                // element offsets): every difference the detector forms is a window's sum of
+                                                // squares < 255^2 x 257^2 < 2^32, so the low words give it exactly
     const PyrLevel *levels;                     // device
     int n_levels;
     const int *xofs; const short2 *xalpha; const int *yofs; const short2 *ybeta;   // device tables
@@ -69,6 +72,7 @@ cudaError_t launch_bgr_to_gray(const uint8_t *bgr, int w, int h, int stride, int
 struct CascadeArgs {
     const int32_t *sum; const unsigned long long *sq; const int32_t *tilted;
     size_t sum_frame_stride;
+    int sq32;                       // `sq` holds uint32 elements (squared integral modulo 2^32, PyramidArgs::sq32)
     const PyrLevel *levels;         // device
     const CasLevel *cas_levels;     // device
     int n_cas_levels, n_tiles, n_frames, cascade_index;

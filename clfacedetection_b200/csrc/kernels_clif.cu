@@ -20,6 +20,7 @@
 //                      diagonal sums, carries along the diagonals, column carries, then the rows -- warp
 //                      tiles with halo columns, no barriers (see K4 below).
 #include <cstdint>
+#include <type_traits>
 #include <cstdlib>
 
 #include "kernels.h"
@@ -298,11 +299,13 @@ cudaError_t launch_colscan(const PyramidArgs &a, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------
 // K3: integral rows.  sum[Y][X] = sum_{y<Y, x<X} I, written for Y in the row block.
 // ------------------------------------------------------------------------------------
-template <int NT>
+// SQ32: the squared integral modulo 2^32 (PyramidArgs::sq32): 32-bit scans and half the bytes written.
+template <int NT, bool SQ32>
 __global__ void __launch_bounds__(NT) k_integral_rows(const PyramidArgs a, const int4 *__restrict__ items) {
+    typedef typename std::conditional<SQ32, uint32_t, ull>::type sq_t;
     constexpr int NW = NT / 32;
     __shared__ uint32_t wtot_s[2][NW];
-    __shared__ ull wtot_q[2][NW];
+    __shared__ sq_t wtot_q[2][NW];
 
     const int4 it = items[blockIdx.x];
     const PyrLevel L = a.levels[it.x];
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(NT) k_integral_rows(const PyramidArgs a, const
 
     const uint8_t *__restrict__ pyr = a.pyr + (size_t)frame * a.pyr_frame_stride + L.pyr_off;
     int32_t *__restrict__ sum = a.sum + (size_t)frame * a.sum_frame_stride + L.sum_off;
-    ull *__restrict__ sq = a.sq + (size_t)frame * a.sum_frame_stride + L.sum_off;
+    sq_t *__restrict__ sq = reinterpret_cast<sq_t *>(a.sq) + (size_t)frame * a.sum_frame_stride + L.sum_off;
 
     uint32_t ca[8], cq[8];
     if (in_sum) {
@@ -333,12 +336,17 @@ __global__ void __launch_bounds__(NT) k_integral_rows(const PyramidArgs a, const
     if (rb == 0 && in_sum) {  // row 0 of every integral image is zero
         int4 *s = reinterpret_cast<int4 *>(sum + X0);
         s[0] = make_int4(0, 0, 0, 0); s[1] = make_int4(0, 0, 0, 0);
-        ulonglong2 *q = reinterpret_cast<ulonglong2 *>(sq + X0);
-        q[0] = q[1] = q[2] = q[3] = make_ulonglong2(0, 0);
+        if (SQ32) {
+            uint4 *q = reinterpret_cast<uint4 *>(sq + X0);
+            q[0] = q[1] = make_uint4(0, 0, 0, 0);
+        } else {
+            ulonglong2 *q = reinterpret_cast<ulonglong2 *>(sq + X0);
+            q[0] = q[1] = q[2] = q[3] = make_ulonglong2(0, 0);
+        }
     }
 
     // cross-warp exclusive prefix of per-warp totals (lane 31 holds the warp's inclusive total)
-    auto left_of_warp = [&](int buf, uint32_t tot_s, ull tot_q, uint32_t &os, ull &oq) {
+    auto left_of_warp = [&](int buf, uint32_t tot_s, sq_t tot_q, uint32_t &os, sq_t &oq) {
         os = 0; oq = 0;
         if (NW > 1) {
             if (lane == 31) { wtot_s[buf][warp] = tot_s; wtot_q[buf][warp] = tot_q; }
@@ -347,7 +355,7 @@ __global__ void __launch_bounds__(NT) k_integral_rows(const PyramidArgs a, const
                 for (int w = 0; w < warp; w++) { os += wtot_s[buf][w]; oq += wtot_q[buf][w]; }
             } else {
                 uint32_t ws = lane < warp ? wtot_s[buf][lane] : 0u;
-                ull wq = lane < warp ? wtot_q[buf][lane] : 0ull;
+                sq_t wq = lane < warp ? wtot_q[buf][lane] : (sq_t)0;
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) {
                     ws += __shfl_xor_sync(0xffffffffu, ws, d);
@@ -363,24 +371,24 @@ __global__ void __launch_bounds__(NT) k_integral_rows(const PyramidArgs a, const
     // prefix -- out[y+1][x] = out[y][x] + sum_{x' < x} p[y][x'] -- whose scans fit 32 bits: a row of
     // 8-bit pixels sums to < 2^21 and its squares to < 2^30 up to 16384 columns.
     uint32_t Is[8];
-    ull Iq[8];
+    sq_t Iq[8];
     {
         uint32_t ts = 0;
-        ull tq = 0;
+        sq_t tq = 0;
 #pragma unroll
         for (int i = 0; i < 8; i++) { ts += ca[i]; tq += cq[i]; }
         uint32_t is = ts;
-        ull iq = tq;
+        sq_t iq = tq;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t vs = __shfl_up_sync(0xffffffffu, is, d);
-            const ull vq = __shfl_up_sync(0xffffffffu, iq, d);
+            const sq_t vq = __shfl_up_sync(0xffffffffu, iq, d);
             if (lane >= d) { is += vs; iq += vq; }
         }
-        uint32_t os; ull oq;
+        uint32_t os; sq_t oq;
         left_of_warp(0, is, iq, os, oq);
         uint32_t es = os + is - ts;
-        ull eq = oq + iq - tq;
+        sq_t eq = oq + iq - tq;
 #pragma unroll
         for (int i = 0; i < 8; i++) { Is[i] = es; Iq[i] = eq; es += ca[i]; eq += cq[i]; }
     }
@@ -406,8 +414,8 @@ __global__ void __launch_bounds__(NT) k_integral_rows(const PyramidArgs a, const
             const uint32_t vq = __shfl_up_sync(0xffffffffu, iq, d);
             if (lane >= d) { is += vs; iq += vq; }
         }
-        uint32_t os; ull oq;
-        left_of_warp(buf, is, (ull)iq, os, oq);
+        uint32_t os; sq_t oq;
+        left_of_warp(buf, is, (sq_t)iq, os, oq);
         buf ^= 1;
         if (in_sum) {
             uint32_t rs = os + is - ts;              // exclusive pixel prefix of this row at column X0
@@ -417,9 +425,15 @@ __global__ void __launch_bounds__(NT) k_integral_rows(const PyramidArgs a, const
             int4 *s = reinterpret_cast<int4 *>(sum + (size_t)(y + 1) * L.sum_pitch + X0);
             s[0] = make_int4((int)Is[0], (int)Is[1], (int)Is[2], (int)Is[3]);
             s[1] = make_int4((int)Is[4], (int)Is[5], (int)Is[6], (int)Is[7]);
-            ulonglong2 *q = reinterpret_cast<ulonglong2 *>(sq + (size_t)(y + 1) * L.sum_pitch + X0);
-            q[0] = make_ulonglong2(Iq[0], Iq[1]); q[1] = make_ulonglong2(Iq[2], Iq[3]);
-            q[2] = make_ulonglong2(Iq[4], Iq[5]); q[3] = make_ulonglong2(Iq[6], Iq[7]);
+            if (SQ32) {
+                uint4 *q = reinterpret_cast<uint4 *>(sq + (size_t)(y + 1) * L.sum_pitch + X0);
+                q[0] = make_uint4((uint32_t)Iq[0], (uint32_t)Iq[1], (uint32_t)Iq[2], (uint32_t)Iq[3]);
+                q[1] = make_uint4((uint32_t)Iq[4], (uint32_t)Iq[5], (uint32_t)Iq[6], (uint32_t)Iq[7]);
+            } else {
+                ulonglong2 *q = reinterpret_cast<ulonglong2 *>(sq + (size_t)(y + 1) * L.sum_pitch + X0);
+                q[0] = make_ulonglong2(Iq[0], Iq[1]); q[1] = make_ulonglong2(Iq[2], Iq[3]);
+                q[2] = make_ulonglong2(Iq[4], Iq[5]); q[3] = make_ulonglong2(Iq[6], Iq[7]);
+            }
         }
     }
 }
@@ -428,7 +442,8 @@ cudaError_t launch_integral_rows(const PyramidArgs &a, cudaStream_t stream, int 
     int n = 0;
 #define CLFD_LAUNCH_INT(K, NT)                                                                          \
     if (a.n_integral_items[K] > 0 && a.n_frames > 0) {                                                  \
-        k_integral_rows<NT><<<dim3(a.n_integral_items[K], a.n_frames), NT, 0, stream>>>(a, a.integral_items[K]); \
+        if (a.sq32) k_integral_rows<NT, true><<<dim3(a.n_integral_items[K], a.n_frames), NT, 0, stream>>>(a, a.integral_items[K]); \
+        else k_integral_rows<NT, false><<<dim3(a.n_integral_items[K], a.n_frames), NT, 0, stream>>>(a, a.integral_items[K]); \
         n++;                                                                                            \
     }
     CLFD_LAUNCH_INT(0, 32)

@@ -77,6 +77,18 @@ __device__ __forceinline__ double window_sigma(int s4, ull q4, double inv_area) 
     return v >= 0. ? sqrt(v) : 1.;
 }
 
+// Sum of squares of a rectangle from the squared integral at element offset `at` (corner offsets g0..g3): 64-bit
+// elements, or the integral modulo 2^32 (CascadeArgs::sq32; a window's sum of squares is below 2^32, so the low
+// words' difference is the sum itself).
+__device__ __forceinline__ ull sq_rect(const ull *sq, bool sq32, size_t at, int g0, int g1, int g2, int g3) {
+    if (sq32) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(sq) + at;
+        return (ull)(uint32_t)(__ldg(q + g0) - __ldg(q + g1) - __ldg(q + g2) + __ldg(q + g3));
+    }
+    const ull *q = sq + at;
+    return __ldg(q + g0) - __ldg(q + g1) - __ldg(q + g2) + __ldg(q + g3);
+}
+
 __device__ __forceinline__ void emit_rect(const CascadeArgs &a, const CasLevel &CL, int frame, int px, int py) {
     if (!a.rects) return;   // scale-cascade mode: k_sc_rows makes the rects from the exit codes
     const ull slot = atomicAdd(a.counters + 0, 1ull);
@@ -137,6 +149,12 @@ __device__ __forceinline__ int lds32i(uint32_t addr) {
     return v;
 }
 
+// pooled stages (A/B hook CLFD_POOL_MIN) are compiled in only with -DCLFD_POOLED_STAGES
+#ifdef CLFD_POOLED_STAGES
+constexpr bool kPooledStages = true;
+#else
+constexpr bool kPooledStages = false;
+#endif
 struct DenseSmemPlan {
     size_t tile, sgf, list, pool, ctl, bar, act, tgt, total;
 };
@@ -169,7 +187,9 @@ size_t dense_smem_bytes(const DenseParams &P) { return dense_smem_plan(P).total;
 
 struct DenseCtx {
     uint32_t tile;    // shared-window address of the tile
-    const ull *gsq;   // squared integral at the tile origin
+    const ull *gsq;   // squared integral (frame base; 64-bit elements or, sq32, 32-bit ones)
+    size_t sq_at;     // element offset of the tile origin
+    bool sq32;
     int16_t *codes;   // this frame + level, or nullptr
     int sq_pitch;     // elements
     int row_mul;      // bytes between window rows in the tile
@@ -196,9 +216,8 @@ __device__ __forceinline__ double dense_sigma(const DenseParams &P, const DenseC
     const uint32_t base = dense_base(c, wid);
     const int s4 = lds32(base + dense_tile_off(c, ey, ex)) - lds32(base + dense_tile_off(c, ey, ex + eq_w)) -
                    lds32(base + dense_tile_off(c, ey + eq_h, ex)) + lds32(base + dense_tile_off(c, ey + eq_h, ex + eq_w));
-    const ull *q = c.gsq + (size_t)(wy * c.ystep) * c.sq_pitch + wx * c.ystep;
     const int g0 = ey * c.sq_pitch + ex, g1 = g0 + eq_w, g2 = (ey + eq_h) * c.sq_pitch + ex, g3 = g2 + eq_w;
-    const ull q4 = __ldg(q + g0) - __ldg(q + g1) - __ldg(q + g2) + __ldg(q + g3);
+    const ull q4 = sq_rect(c.gsq, c.sq32, c.sq_at + (size_t)(wy * c.ystep) * c.sq_pitch + wx * c.ystep, g0, g1, g2, g3);
     return window_sigma(s4, q4, P.inv_area);
 }
 // the same, and whether the variance rectangle is FLAT (every pixel equal): Q A == S^2 exactly (Cauchy-Schwarz with equality)
@@ -208,9 +227,8 @@ __device__ __forceinline__ double dense_sigma_flat(const DenseParams &P, const D
     const uint32_t base = dense_base(c, wid);
     const int s4 = lds32(base + dense_tile_off(c, ey, ex)) - lds32(base + dense_tile_off(c, ey, ex + eq_w)) -
                    lds32(base + dense_tile_off(c, ey + eq_h, ex)) + lds32(base + dense_tile_off(c, ey + eq_h, ex + eq_w));
-    const ull *q = c.gsq + (size_t)(wy * c.ystep) * c.sq_pitch + wx * c.ystep;
     const int g0 = ey * c.sq_pitch + ex, g1 = g0 + eq_w, g2 = (ey + eq_h) * c.sq_pitch + ex, g3 = g2 + eq_w;
-    const ull q4 = __ldg(q + g0) - __ldg(q + g1) - __ldg(q + g2) + __ldg(q + g3);
+    const ull q4 = sq_rect(c.gsq, c.sq32, c.sq_at + (size_t)(wy * c.ystep) * c.sq_pitch + wx * c.ystep, g0, g1, g2, g3);
     eq_flat = q4 * (ull)(eq_w * eq_h) == (ull)((long long)s4 * s4);
     return window_sigma(s4, q4, P.inv_area);
 }
@@ -229,8 +247,8 @@ static __device__ __noinline__ int flat_window_code(const DenseParams &P, const 
     const int W = P.win_w, H = P.win_h;
     const uint32_t S4 = (uint32_t)(lds32(base + dense_tile_off(c, 0, 0)) - lds32(base + dense_tile_off(c, 0, W)) -
                                    lds32(base + dense_tile_off(c, H, 0)) + lds32(base + dense_tile_off(c, H, W)));   // <= 255 W H
-    const ull *q = c.gsq + (size_t)((wid / kTileW) * c.ystep) * c.sq_pitch + (wid & (kTileW - 1)) * c.ystep;
-    const ull Q4 = __ldg(q) - __ldg(q + W) - __ldg(q + (size_t)H * c.sq_pitch) + __ldg(q + (size_t)H * c.sq_pitch + W);
+    const ull Q4 = sq_rect(c.gsq, c.sq32, c.sq_at + (size_t)((wid / kTileW) * c.ystep) * c.sq_pitch + (wid & (kTileW - 1)) * c.ystep,
+                           0, W, H * c.sq_pitch, H * c.sq_pitch + W);
     const uint32_t A = (uint32_t)(W * H);
     if (Q4 * (ull)A != (ull)S4 * (ull)S4) return kNotFlat;
     return (int)__ldg(P.flat_code + S4 / A);
@@ -498,7 +516,6 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
 
     const size_t frame_off = (size_t)frame * a.sum_frame_stride + L.sum_off;
     const int32_t *__restrict__ gsum = a.sum + frame_off + (size_t)py0 * L.sum_pitch + px0;
-    const ull *__restrict__ gsq = a.sq + frame_off + (size_t)py0 * L.sum_pitch + px0;
 
     // ---- stage the integral tile ----
     for (int i = tid; i < kCtlInts; i += kDenseThreads) ctl[i] = 0;
@@ -530,7 +547,7 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
     }
 
     DenseCtx c;
-    c.tile = smem_u32(tile); c.gsq = gsq;
+    c.tile = smem_u32(tile); c.gsq = a.sq; c.sq_at = frame_off + (size_t)py0 * L.sum_pitch + px0; c.sq32 = a.sq32 != 0;
     c.codes = a.codes ? a.codes + (size_t)frame * a.windows_per_frame + CL.win_base : nullptr;
     c.sq_pitch = L.sum_pitch;
     c.row_mul = ystep * S * 4;
@@ -621,7 +638,7 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
     constexpr int kSeg = kTileWindows / kDenseWarps;   // list segment of a warp (its share is at most this)
     int n_alive;
     uint16_t *cur;
-    if (P.pool_min > 0) {
+    if (kPooledStages && P.pool_min > 0) {
         uint16_t *cl_in = list, *cl_out = reinterpret_cast<uint16_t *>(smem_raw + plan.pool);
         int *cnt_in = ctl + kCtlCount, *cnt_out = ctl + kCtlCountB, *cnt_zero = ctl + kCtlCountC;
         {
@@ -966,7 +983,7 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
 // COUNT: the diagnostic instantiation (detectors created with want_codes) that counts FP64 fallbacks and
 // near-threshold stage sums; the production instantiation carries none of that code.
 template <int ROWSTEP_T, bool TREE, bool NODES, int TILE_H, bool COUNT, bool TRACK = false>
-__global__ void __launch_bounds__(kDenseThreads)   // (no min-blocks argument: even "1" lets ptxas take 88 registers and costs a CTA per SM)
+__global__ void __launch_bounds__(kDenseThreads)   // (no min-blocks argument: "1" lets ptxas take 88 registers and costs a CTA per SM; "4" caps at 64 but was measured 2 % slower)
 k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ CascadeArgs a, const int tile0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cascade_tiles_body<ROWSTEP_T, TREE, NODES, TILE_H, COUNT, TRACK>(P, a, tile0, smem_raw);
@@ -1182,11 +1199,10 @@ __global__ void __launch_bounds__(128) k_cascade_mid(const __grid_constant__ Cas
             const size_t off = (size_t)frame * a.sum_frame_stride + L.sum_off + (size_t)y * pitch + x;
             const int32_t *__restrict__ sum = a.sum + off;
             const int32_t *__restrict__ til = a.tilted ? a.tilted + off : sum;
-            const ull *__restrict__ sq = a.sq + off;
             const int eq_w = D.win_w - 2, eq_h = D.win_h - 2;
             const int g0 = pitch + 1, g1 = g0 + eq_w, g2 = (1 + eq_h) * pitch + 1, g3 = g2 + eq_w;
             const int s4 = __ldg(sum + g0) - __ldg(sum + g1) - __ldg(sum + g2) + __ldg(sum + g3);
-            const ull q4 = __ldg(sq + g0) - __ldg(sq + g1) - __ldg(sq + g2) + __ldg(sq + g3);
+            const ull q4 = sq_rect(a.sq, a.sq32 != 0, off, g0, g1, g2, g3);
             const double sigma = window_sigma(s4, q4, D.inv_area);
             for (; stage < D.mid_end; stage++) {
                 const DeepStage st = D.stages[stage];
@@ -1250,12 +1266,11 @@ __global__ void __launch_bounds__(kDeepThreads) k_cascade_deep(const __grid_cons
         const size_t off = (size_t)frame * a.sum_frame_stride + L.sum_off + (size_t)y * pitch + x;
         const int32_t *__restrict__ sum = a.sum + off;
         const int32_t *__restrict__ til = a.tilted ? a.tilted + off : sum;
-        const ull *__restrict__ sq = a.sq + off;
 
         const int eq_w = D.win_w - 2, eq_h = D.win_h - 2;
         const int g0 = pitch + 1, g1 = g0 + eq_w, g2 = (1 + eq_h) * pitch + 1, g3 = g2 + eq_w;
         const int s4 = __ldg(sum + g0) - __ldg(sum + g1) - __ldg(sum + g2) + __ldg(sum + g3);
-        const ull q4 = __ldg(sq + g0) - __ldg(sq + g1) - __ldg(sq + g2) + __ldg(sq + g3);
+        const ull q4 = sq_rect(a.sq, a.sq32 != 0, off, g0, g1, g2, g3);
         const double sigma = window_sigma(s4, q4, D.inv_area);
 
         int ptr = stage0, last = stage0, accepted = 0;
@@ -1339,11 +1354,10 @@ __global__ void __launch_bounds__(256) k_roc_collect(const CascadeArgs a, RocIte
     const size_t off = (size_t)frame * a.sum_frame_stride + L.sum_off + (size_t)y * pitch + x;
     const int32_t *__restrict__ sum = a.sum + off;
     const int32_t *__restrict__ til = a.tilted ? a.tilted + off : sum;
-    const ull *__restrict__ sq = a.sq + off;
     const int eq_w = D.win_w - 2, eq_h = D.win_h - 2;
     const int g0 = pitch + 1, g1 = g0 + eq_w, g2 = (1 + eq_h) * pitch + 1, g3 = g2 + eq_w;
     const int s4 = __ldg(sum + g0) - __ldg(sum + g1) - __ldg(sum + g2) + __ldg(sum + g3);
-    const ull q4 = __ldg(sq + g0) - __ldg(sq + g1) - __ldg(sq + g2) + __ldg(sq + g3);
+    const ull q4 = sq_rect(a.sq, a.sq32 != 0, off, g0, g1, g2, g3);
     const double sigma = window_sigma(s4, q4, D.inv_area);
     const DeepStage st = D.stages[last];
     double S = 0.0;

@@ -237,7 +237,9 @@ CLFD_API int clfd_detect_collect(clfd_detector *det, clfd_rect *rects, int64_t c
 CLFD_API int clfd_detector_get_codes(clfd_detector *det, int cascade, int16_t *codes,
                                      int64_t cap);
 /* Pyramid level `level` (index into the union pyramid = cascade 0's level list when there
- * is one cascade) of frame `frame` from the last batch, dense layouts; NULLs skipped. */
+ * is one cascade) of frame `frame` from the last batch, dense layouts; NULLs skipped.
+ * A pyramid-mode detector keeps its squared integral modulo 2^32 (all it ever needs are windows'
+ * sums of squares, which are below 2^32): sqsum then returns those low words, widened. */
 CLFD_API int clfd_detector_read_level(clfd_detector *det, int cascade, int level, int frame,
                                       uint8_t *pyr, int32_t *sum, uint64_t *sqsum,
                                       int32_t *tilted);

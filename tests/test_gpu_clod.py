@@ -194,6 +194,53 @@ def test_detect_pipelined_chunks_equal_one_shot(gpu_ctx, monkeypatch, chunks):
     det.close()
 
 
+@pytest.mark.parametrize("chunks", [1, 3, 8])
+def test_chunk_overlap_equals_serial_order(gpu_ctx, monkeypatch, chunks):
+    """Batches of 8+ frames run their pyramid kernels on a second stream beside the previous chunk's tile kernel
+    (clfd_api.cu, enqueue_overlapped).  Host path, device-resident path and the two-slot pipeline must return what
+    the serial order (CLFD_NO_OVERLAP=1) and the oracle return, for any cut."""
+    import torch
+    batches = [np.stack([octave_frame(640, 480, 20 * b + i) for i in range(11)]) for b in range(3)]
+    cas = clfd.Cascade(cascade_path("frontalface_alt"))
+    det = clfd.Detector(gpu_ctx, cas, 640, 480, max_batch=11, scale_factor=1.2)
+    monkeypatch.setenv("CLFD_NO_OVERLAP", "1")
+    want = [det.detect(b) for b in batches]
+    launches_serial = want[0].stats["kernel_launches"]
+    monkeypatch.delenv("CLFD_NO_OVERLAP")
+    monkeypatch.setenv("CLFD_OVERLAP_CHUNKS", str(chunks))
+    oc = oracle_cascade("frontalface_alt")
+    for f in (0, 5, 10):
+        assert np.array_equal(want[1].frame_rects(f), _sorted(oc.detect(batches[1][f], 1.2, want_codes=False)[0]))
+    # host path, blocking
+    for b in range(3):
+        got = det.detect(batches[b])
+        if chunks > 1:
+            assert got.stats["kernel_launches"] > launches_serial   # the cut really happened
+        for f in range(11):
+            assert np.array_equal(got.frame_rects(f), want[b].frame_rects(f)), (b, f)
+    # device-resident path, twice on the same stream (the second batch's pyramid must wait for the first one's tiles)
+    st = torch.cuda.current_stream().cuda_stream
+    t = [torch.from_numpy(b).cuda() for b in batches]
+    torch.cuda.synchronize()
+    for b in (2, 0):
+        det.enqueue(t[b], 11, t[b].stride(0), t[b].stride(1), st)
+        got = det.fetch(st)
+        for f in range(11):
+            assert np.array_equal(got.frame_rects(f), want[b].frame_rects(f)), (b, f)
+    # two batches in flight
+    pinned = [torch.from_numpy(b).pin_memory() for b in batches]
+    got = []
+    det.submit(pinned[0])
+    for b in (1, 2):
+        det.submit(pinned[b])
+        got.append(det.collect())
+    got.append(det.collect())
+    for b in range(3):
+        for f in range(11):
+            assert np.array_equal(got[b].frame_rects(f), want[b].frame_rects(f)), (b, f)
+    det.close()
+
+
 def _synthetic_cascade(big, n_stages=12):
     """frontalface_alt's first stages; with `big` != 0 the first stump of every stage votes +big
     and the last one -big whatever the window: the partial sums in between are rounded at the
