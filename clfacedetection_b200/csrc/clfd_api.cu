@@ -89,6 +89,7 @@ struct PyramidPlan {
     int W = 0, H = 0, max_batch = 0;
     bool want_tilted = false;
     bool sq32 = false;   // squared integral modulo 2^32 (pyramid-mode detectors; set before build())
+    std::vector<char> di_levels;   // per level (set before build(); empty: none): store the int32 integral column-de-interleaved (PyrLevel::di)
     std::vector<PyrLevel> levels;
     size_t pyr_frame_stride = 0, sum_frame_stride = 0, col_frame_stride = 0, col_plane_stride = 0;
     int max_level_w = 0;
@@ -128,6 +129,7 @@ int PyramidPlan::build(int W_, int H_, const std::vector<std::pair<int, int>> &s
         L.pyr_pitch = (int)round_up(w, 16);
         L.sum_pitch = (int)round_up(w + 1, 8);
         L.nrb = (h + kRowBlock - 1) / kRowBlock;
+        L.di = li < di_levels.size() && di_levels[li] ? 1 : 0;
         L.xtab_off = (int)h_xofs.size(); L.ytab_off = (int)h_yofs.size();
         L.pyr_off = (long long)pyr_off; L.sum_off = (long long)sum_off; L.col_off = (long long)col_off;
         pyr_off += round_up((size_t)L.pyr_pitch * h, 256);
@@ -334,6 +336,7 @@ struct clfd_detector {
     cudaEvent_t ev[16] = {nullptr};
     float kernel_ms[8] = {0};
     bool have_events = false;
+    bool sum_di = false;   // the ystep-2 levels of pyr.sum are column-de-interleaved (PyrLevel::di)
     // clfd_detect pipelines the H2D copy of a batch with its own compute, chunk by chunk
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copied[kMaxChunks] = {nullptr};
@@ -730,6 +733,7 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
     if (cfg->mode != CLFD_MODE_SCALE_IMAGE && cfg->mode != CLFD_MODE_SCALE_CASCADE) INVALID("unknown mode %d", cfg->mode);
     const bool scale_cascade = cfg->mode == CLFD_MODE_SCALE_CASCADE;
     std::vector<std::pair<int, int>> sizes;          // union pyramid
+    std::vector<char> sizes_y2;                      // ... and whether a level's windows are 2 pixels apart (factor <= 2)
     bool any_tilted = false;
     for (int ci = 0; ci < n_cascades; ci++) {
         if (!cascades[ci]) INVALID("cascade %d is NULL", ci);
@@ -829,7 +833,7 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
             const int xe = sz_w - hc.win_w, ye = sz_h - hc.win_h;                        // :1015-1020
             const int nx = xe > 0 ? (xe + ystep - 1) / ystep : 0, ny = ye > 0 ? (ye + ystep - 1) / ystep : 0;
             if (nx == 0 || ny == 0) continue;
-            if (!pyr_index.count(k)) { pyr_index[k] = (int)sizes.size(); sizes.push_back({sz_w, sz_h}); }
+            if (!pyr_index.count(k)) { pyr_index[k] = (int)sizes.size(); sizes.push_back({sz_w, sz_h}); sizes_y2.push_back(ystep == 2); }
             CascadePlan &cp = *det->cas[ci];
             CasLevel CL;
             memset(&CL, 0, sizeof CL);
@@ -857,6 +861,11 @@ int clfd_detector_create(clfd_context *ctx, const clfd_cascade *const *cascades,
     // pyramid mode: every sum of squares the kernels form is a cascade window's (< 2^32), so the squared integral is
     // kept modulo 2^32 -- a third less integral traffic; the scale-cascade mode's windows grow with the scale: 64 bits
     det->pyr.sq32 = !scale_cascade && !getenv("CLFD_SQ64");
+    // pyramid mode: the int32 integral of the ystep-2 levels is written column-de-interleaved -- the layout their tiles have
+    // in shared memory -- so that the tile kernel stages a tile row with two TMA bulk copies instead of LDG.128 + 2 x STS.64
+    // through the L1 data pipe it is bound by; the generic kernels (mid / deep / reject levels) address it through PyrLevel::di
+    det->sum_di = !scale_cascade && !getenv("CLFD_NO_DI");
+    if (det->sum_di) det->pyr.di_levels = sizes_y2;
     if (!sizes.empty() && (rc = det->pyr.build(W, H, sizes, cfg->max_batch, any_tilted, s))) return rc;
     else if (sizes.empty()) { det->pyr.W = W; det->pyr.H = H; det->pyr.max_batch = cfg->max_batch; }
 
@@ -991,6 +1000,7 @@ static int enqueue_range(clfd_detector *det, const uint8_t *frames_dev, int fram
             a.sum = det->pyr.sum.p + fo; a.sq = sq_at(det->pyr.sq.p, fo, det->pyr.sq32); a.sq32 = det->pyr.sq32 ? 1 : 0;
             a.tilted = det->pyr.want_tilted ? det->pyr.tilted.p + fo : nullptr;
             a.sum_frame_stride = det->pyr.sum_frame_stride;
+            a.sum_di = det->sum_di ? 1 : 0;
             a.levels = det->pyr.d_levels.p; a.cas_levels = cp.d_levels.p;
             a.n_cas_levels = (int)cp.levels.size(); a.n_tiles = cp.n_tiles; a.n_frames = n_frames;
             a.frame_base = frame_base;
@@ -1506,7 +1516,14 @@ int clfd_detector_read_level(clfd_detector *det, int cascade, int level, int fra
     const size_t W1 = (size_t)L.w + 1;
     const size_t so = (size_t)frame * det->pyr.sum_frame_stride + L.sum_off;
     if (pyr) CK(cudaMemcpy2D(pyr, L.w, det->pyr.pyr.p + (size_t)frame * det->pyr.pyr_frame_stride + L.pyr_off, L.pyr_pitch, L.w, L.h, cudaMemcpyDeviceToHost));
-    if (sum) CK(cudaMemcpy2D(sum, W1 * 4, det->pyr.sum.p + so, (size_t)L.sum_pitch * 4, W1 * 4, L.h + 1, cudaMemcpyDeviceToHost));
+    if (sum && L.di) {   // stored column-de-interleaved on the device (PyrLevel::di): back to the natural order
+        std::vector<int32_t> rows((size_t)L.sum_pitch * (L.h + 1));
+        CK(cudaMemcpy(rows.data(), det->pyr.sum.p + so, rows.size() * 4, cudaMemcpyDeviceToHost));
+        for (int y = 0; y <= L.h; y++)
+            for (size_t x = 0; x < W1; x++) sum[y * W1 + x] = rows[(size_t)y * L.sum_pitch + (x & 1) * (L.sum_pitch / 2) + (x >> 1)];
+    } else if (sum) {
+        CK(cudaMemcpy2D(sum, W1 * 4, det->pyr.sum.p + so, (size_t)L.sum_pitch * 4, W1 * 4, L.h + 1, cudaMemcpyDeviceToHost));
+    }
     if (sqsum && det->pyr.sq32) {   // kept modulo 2^32 on the device: the low words, widened
         std::vector<uint32_t> low(W1 * (L.h + 1));
         CK(cudaMemcpy2D(low.data(), W1 * 4, reinterpret_cast<const uint32_t *>(det->pyr.sq.p) + so, (size_t)L.sum_pitch * 4, W1 * 4,

@@ -97,7 +97,7 @@ struct DenseStage {
                              // stumps whose rects share two corners, stored in six-offset form (see haar_pack.cpp)
 };
 // Two blobs per cascade: [0] for ystep-1 levels (natural tile layout, addr = y*S + x) and
-// [1] for ystep-2 levels (columns de-interleaved: addr = y*S + (x&1)*S/2 + (x>>1)), so that in
+// [1] for ystep-2 levels (columns de-interleaved: addr = y*S + (x&1)*tile_half + (x>>1)), so that in
 // both a window's base word is  ystep*wy*S + wx  with ystep*S = 8 (mod 32): the bank of every
 // corner load is (wx + 8*wy + const) mod 32, so lanes whose windows have distinct
 // (wx + 8*wy) mod 32 never conflict, and a compact blob of survivors spreads over the banks.
@@ -105,6 +105,8 @@ struct DenseParams {
     int n_stages;       // stages whose stumps are parameter resident (>= n_fixed)
     int total_stages;   // stages in the whole cascade
     int tile_stride;    // ints per smem tile row (ystep * stride = 8 mod 32)
+    int tile_half;      // ystep-2 blob: word offset of a row's odd columns (a multiple of 4: both halves of a row are
+                        // 16-byte aligned for the TMA bulk copies from a column-de-interleaved integral); 0 in the ystep-1 blob
     int win_w, win_h;
     int is_tree;        // stage-tree cascade: exit codes are 2*last_stage (+accept)
     int ystep;          // 1 or 2
@@ -170,6 +172,10 @@ struct PyrLevel {
     int nrb;             // row blocks of kRowBlock rows
     int xtab_off, ytab_off;
     int resize_mode;     // kResize*: how k_resize_colsum reads the source rows of this level
+    int di;              // the int32 integral of this level is stored column-DE-INTERLEAVED: row y holds its even columns
+                         // at [y*sum_pitch, +sum_pitch/2) and its odd columns behind them (element (y, x) at
+                         // y*sum_pitch + (x&1)*sum_pitch/2 + (x>>1)), which is the layout the tile kernel wants in shared
+                         // memory on ystep-2 levels -- a tile row is then two TMA bulk copies (kernels_clod.cu)
     long long pyr_off;   // byte offset inside a frame's pyramid block
     long long sum_off;   // element offset inside a frame's sum / sqsum / tilted block
     long long col_off;   // element offset inside a frame's column-sum block

@@ -26,6 +26,7 @@ bool pack_sc_dense(const HostCascade &c, double scale, DenseParams &P, std::vect
 const char *get_error();
 
 int dense_tile_stride(int win_w, int ystep);  // ints per smem tile row (ystep * stride = 8 mod 32)
+int dense_tile_half(int win_w, int ystep);    // ystep 2: word offset of a row's odd columns inside a tile row (multiple of 4)
 int dense_tile_rows(int win_h, int ystep, int tile_h);    // integral rows a tile needs
 int dense_tile_cols(int win_w, int ystep);    // integral columns a tile needs (multiple of 4)
 

@@ -194,13 +194,20 @@ static void corner_coords(const HostNode &nd, int k, int dx[4], int dy[4]) {
 
 int dense_tile_cols(int win_w, int ystep) { return ((kTileW - 1) * ystep + win_w + 1 + 3) & ~3; }
 int dense_tile_rows(int win_h, int ystep, int tile_h) { return (tile_h - 1) * ystep + win_h + 1; }
+int dense_tile_half(int win_w, int ystep) {
+    // ystep 2: word offset of a row's odd columns.  A multiple of 4 words, so that both halves of a tile row are 16-byte
+    // aligned destinations of a TMA bulk copy (whose size is rounded up to 16 bytes as well: the even half may run
+    // up to `half` words, never into the odd half).
+    if (ystep == 1) return 0;
+    return (dense_tile_cols(win_w, ystep) / 2 + 3) & ~3;
+}
 int dense_tile_stride(int win_w, int ystep) {
-    // ystep 1: natural layout, stride >= cols.  ystep 2: even columns in the first half of a
-    // row, odd columns in the second half, stride/2 >= cols/2.  In both the word distance
+    // ystep 1: natural layout, stride >= cols.  ystep 2: even columns at the start of a row, odd columns
+    // `half` words behind them, stride >= 2 * half.  In both the word distance
     // between consecutive WINDOW rows, ystep * stride, is 8 (mod 32) and the stride is a
-    // multiple of 4 words (16-byte rows for the TMA bulk copies / 8-byte halves for STS.64).
+    // multiple of 4 words (16-byte rows / halves for the TMA bulk copies).
     const int cols = dense_tile_cols(win_w, ystep);
-    int s = ystep == 1 ? cols : 2 * ((cols + 1) / 2);
+    int s = ystep == 1 ? cols : 2 * dense_tile_half(win_w, ystep);
     s = (s + 3) & ~3;
     while ((ystep * s) % 32 != 8) s += 4;
     return s;
@@ -262,6 +269,7 @@ static void pack_dense_one(const HostCascade &c, int ystep, DenseParams &P, std:
     P.total_stages = S;
     P.win_w = c.win_w; P.win_h = c.win_h;
     P.tile_stride = dense_tile_stride(c.win_w, ystep);
+    P.tile_half = dense_tile_half(c.win_w, ystep);
     P.is_tree = c.is_tree ? 1 : 0;
     P.ystep = ystep;
     P.filter_eps = 9.5367431640625e-07f;  // 2^-20
@@ -348,7 +356,7 @@ static void pack_dense_one(const HostCascade &c, int ystep, DenseParams &P, std:
     stage_tab.assign(walk_tree ? E : 0, DenseStage());
     auto tile_offset = [&](int dy, int dx) {
         const int word = ystep == 1 ? dy * P.tile_stride + dx
-                                    : dy * P.tile_stride + (dx & 1) * (P.tile_stride / 2) + (dx >> 1);
+                                    : dy * P.tile_stride + (dx & 1) * P.tile_half + (dx >> 1);
         return (uint32_t)(word * 4);
     };
     int tail_at = 0;   // records in execution order (== tree order for the linear prefix)

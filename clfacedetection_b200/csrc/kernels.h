@@ -73,6 +73,8 @@ struct CascadeArgs {
     const int32_t *sum; const unsigned long long *sq; const int32_t *tilted;
     size_t sum_frame_stride;
     int sq32;                       // `sq` holds uint32 elements (squared integral modulo 2^32, PyramidArgs::sq32)
+    int sum_di;                     // the ystep-2 levels of `sum` are stored column-de-interleaved (PyrLevel::di): the tile
+                                    // kernel stages their tiles with TMA bulk copies; nothing else may read `sum` then
     const PyrLevel *levels;         // device
     const CasLevel *cas_levels;     // device
     int n_cas_levels, n_tiles, n_frames, cascade_index;

@@ -422,9 +422,15 @@ __global__ void __launch_bounds__(NT) k_integral_rows(const PyramidArgs a, const
             uint32_t rq = (uint32_t)oq + iq - tq;
 #pragma unroll
             for (int i = 0; i < 8; i++) { Is[i] += rs; Iq[i] += rq; rs += p[i]; rq += p[i] * p[i]; }
-            int4 *s = reinterpret_cast<int4 *>(sum + (size_t)(y + 1) * L.sum_pitch + X0);
-            s[0] = make_int4((int)Is[0], (int)Is[1], (int)Is[2], (int)Is[3]);
-            s[1] = make_int4((int)Is[4], (int)Is[5], (int)Is[6], (int)Is[7]);
+            if (L.di) {   // column-de-interleaved row: even columns in the first half, odd columns in the second
+                int32_t *row = sum + (size_t)(y + 1) * L.sum_pitch + (X0 >> 1);
+                *reinterpret_cast<int4 *>(row) = make_int4((int)Is[0], (int)Is[2], (int)Is[4], (int)Is[6]);
+                *reinterpret_cast<int4 *>(row + (L.sum_pitch >> 1)) = make_int4((int)Is[1], (int)Is[3], (int)Is[5], (int)Is[7]);
+            } else {
+                int4 *s = reinterpret_cast<int4 *>(sum + (size_t)(y + 1) * L.sum_pitch + X0);
+                s[0] = make_int4((int)Is[0], (int)Is[1], (int)Is[2], (int)Is[3]);
+                s[1] = make_int4((int)Is[4], (int)Is[5], (int)Is[6], (int)Is[7]);
+            }
             if (SQ32) {
                 uint4 *q = reinterpret_cast<uint4 *>(sq + (size_t)(y + 1) * L.sum_pitch + X0);
                 q[0] = make_uint4((uint32_t)Iq[0], (uint32_t)Iq[1], (uint32_t)Iq[2], (uint32_t)Iq[3]);

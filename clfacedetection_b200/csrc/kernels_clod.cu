@@ -193,7 +193,7 @@ struct DenseCtx {
     int16_t *codes;   // this frame + level, or nullptr
     int sq_pitch;     // elements
     int row_mul;      // bytes between window rows in the tile
-    int ystep, S;
+    int ystep, S, half;   // half: word offset of a row's odd columns (ystep-2 layout)
     int tx, wy_tile, nx;   // tile column; first window row of the tile
     int code_mul;
 };
@@ -202,7 +202,7 @@ __device__ __forceinline__ uint32_t dense_base(const DenseCtx &c, int wid) {
     return c.tile + (uint32_t)((wid / kTileW) * c.row_mul + (wid & (kTileW - 1)) * 4);
 }
 __device__ __forceinline__ uint32_t dense_tile_off(const DenseCtx &c, int y, int x) {   // byte offset of integral (y, x) from a window base
-    return 4u * (uint32_t)(c.ystep == 1 ? y * c.S + x : y * c.S + (x & 1) * (c.S >> 1) + (x >> 1));
+    return 4u * (uint32_t)(c.ystep == 1 ? y * c.S + x : y * c.S + (x & 1) * c.half + (x >> 1));
 }
 __device__ __forceinline__ void dense_write_code(const DenseCtx &c, int wid, int code) {
     const int wx = wid & (kTileW - 1), wy = wid / kTileW;
@@ -533,17 +533,34 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
                          (uint32_t)(cols * 4), bar);
         }
         mbar_wait(bar, 0);
-    } else {            // de-interleave columns: x -> (x&1)*S/2 + (x>>1)
+    } else {
+        // ystep-2 layout: x -> (x&1)*half + (x>>1).  A level whose integral is stored de-interleaved (PyrLevel::di,
+        // CascadeArgs::sum_di) is staged with two TMA bulk copies per row -- off the L1 data pipe this kernel is bound by;
+        // anything else (the tilted integral's tile, detectors without di) with LDG.128 + 2 x STS.64
+        const bool di = a.sum_di != 0;
+        const int half = P.tile_half;
+        if (di) {
+            if (tid == 0) mbar_init(bar, 1);
+            __syncthreads();
+            const uint32_t hb = (uint32_t)half * 4u;   // bytes of one half row (>= cols / 2 elements, a 16-byte multiple)
+            if (tid == 0) mbar_expect_tx(bar, (uint32_t)rows * 2u * hb);
+            const int32_t *__restrict__ gdi = a.sum + frame_off + (size_t)py0 * L.sum_pitch + (px0 >> 1);
+            for (int r = tid; r < rows * 2; r += kDenseThreads) {
+                const int odd = r >= rows, rr = odd ? r - rows : r;
+                tma_bulk_g2s(tile + (size_t)rr * S * 4 + (odd ? hb : 0u), gdi + (size_t)rr * L.sum_pitch + (odd ? (L.sum_pitch >> 1) : 0), hb, bar);
+            }
+        }
         const int c4 = cols >> 2, total = rows * c4;
-        for (int i = tid; i < total * n_tiles_smem; i += kDenseThreads) {
+        for (int i = (di ? total : 0) + tid; i < total * n_tiles_smem; i += kDenseThreads) {
             const int t2 = i >= total, ii = t2 ? i - total : i;
             const int r = ii / c4, cq = ii - r * c4;
             const int4 v = __ldg(reinterpret_cast<const int4 *>((t2 ? gtil : gsum) + (size_t)r * L.sum_pitch) + cq);
             int *row = reinterpret_cast<int *>(tile + (t2 ? tile2_off : 0)) + r * S;
             *reinterpret_cast<int2 *>(row + 2 * cq) = make_int2(v.x, v.z);
-            *reinterpret_cast<int2 *>(row + (S >> 1) + 2 * cq) = make_int2(v.y, v.w);
+            *reinterpret_cast<int2 *>(row + half + 2 * cq) = make_int2(v.y, v.w);
         }
         __syncthreads();
+        if (di) mbar_wait(bar, 0);
     }
 
     DenseCtx c;
@@ -551,7 +568,7 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
     c.codes = a.codes ? a.codes + (size_t)frame * a.windows_per_frame + CL.win_base : nullptr;
     c.sq_pitch = L.sum_pitch;
     c.row_mul = ystep * S * 4;
-    c.ystep = ystep; c.S = S;
+    c.ystep = ystep; c.S = S; c.half = P.tile_half;
     c.tx = tx; c.wy_tile = ty * TILE_H; c.nx = CL.nx;
     c.code_mul = P.is_tree ? 2 : 1;
     const float inf = __int_as_float(0x7f800000);
@@ -1001,9 +1018,9 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
 }
 
 // row steps of the stock window sizes (bytes between a thread's consecutive phase-1 windows)
-constexpr int dense_stride_ce(int win_w, int ystep) {
+constexpr int dense_stride_ce(int win_w, int ystep) {   // == dense_tile_stride (haar_pack.cpp)
     int cols = ((kTileW - 1) * ystep + win_w + 1 + 3) & ~3;
-    int s = ystep == 1 ? cols : 2 * ((cols + 1) / 2);
+    int s = ystep == 1 ? cols : 2 * ((cols / 2 + 3) & ~3);
     s = (s + 3) & ~3;
     while ((ystep * s) % 32 != 8) s += 4;
     return s;
@@ -1029,8 +1046,8 @@ static cudaError_t launch_tiles_tt(const DenseParams &P, const CascadeArgs &a, i
 }
 template <int ROWSTEP_T>
 static cudaError_t launch_tiles_t(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, size_t smem, cudaStream_t stream) {
-    // stage trees and multi-node trees: 20-pixel windows get the immediate-offset code, the rest the generic one
-    constexpr int R = ROWSTEP_T == dense_rowstep_ce(24, 2) ? 0 : ROWSTEP_T;
+    // (20- and 24-pixel windows share their row steps on both kinds of level: one set of instantiations)
+    constexpr int R = ROWSTEP_T;
     if (P.exec_stages > P.tail_stages) return launch_tiles_tt<R, true, false>(P, a, tile0, n_tiles, smem, stream);
     if (P.tile_h == kTileHSmall) {   // tilted cascades on ystep-2 levels
         if (P.npt > 1) return launch_tiles_tt<R, false, true, kTileHSmall>(P, a, tile0, n_tiles, smem, stream);
@@ -1062,13 +1079,12 @@ cudaError_t launch_cascade_tiles(const DenseParams &P, const CascadeArgs &a, int
     // the common window widths (20 and 24 pixels) get immediate-offset code
     constexpr int r20_1 = dense_rowstep_ce(20, 1), r20_2 = dense_rowstep_ce(20, 2);
     constexpr int r24_1 = dense_rowstep_ce(24, 1), r24_2 = dense_rowstep_ce(24, 2);
-    static_assert(r20_1 == r24_1 && r20_2 != r24_2 && r20_2 != r20_1 && r24_2 != r20_1, "row steps must be distinct switch labels");
+    static_assert(r20_1 == r24_1 && r20_2 == r24_2 && r20_2 != r20_1, "row steps must be distinct switch labels");
     // sentinel-leaf cascades: only the generic row-step code has the TRACK instantiation (launch_tiles_tt)
     if (P.track_abs && P.exec_stages <= P.tail_stages && P.npt == 1) return launch_tiles_t<0>(P, a, tile0, n_tiles, smem, stream);
     switch (rowstep) {
         case r20_1: return launch_tiles_t<r20_1>(P, a, tile0, n_tiles, smem, stream);
         case r20_2: return launch_tiles_t<r20_2>(P, a, tile0, n_tiles, smem, stream);
-        case r24_2: return launch_tiles_t<r24_2>(P, a, tile0, n_tiles, smem, stream);
         default:    return launch_tiles_t<0>(P, a, tile0, n_tiles, smem, stream);
     }
 }
@@ -1107,19 +1123,30 @@ cudaError_t launch_enqueue_all(const CascadeArgs &a, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------
 constexpr int kDeepThreads = 256;
 
-__device__ __forceinline__ int rect_sum_g(const int32_t *__restrict__ base, int pitch, uint32_t dxw, uint32_t dyw) {
+// A window's view of an int32 integral in global memory: element (dy, dx) relative to the window origin.  Natural
+// layout: sh = 0.  Column-de-interleaved level (PyrLevel::di; window origins have even x there): sh = 1, half =
+// sum_pitch / 2, p = level + y * pitch + x / 2.
+struct SumView {
+    const int32_t *__restrict__ p;
+    int pitch, half, sh;
+    __device__ __forceinline__ int at(int dy, int dx) const { return __ldg(p + dy * pitch + (dx & sh) * half + (dx >> sh)); }
+};
+__device__ __forceinline__ SumView sum_view(const int32_t *__restrict__ plane, const PyrLevel &L, size_t frame_level_off, int y, int x, bool di) {
+    SumView v;
+    v.pitch = L.sum_pitch; v.half = L.sum_pitch >> 1; v.sh = di ? 1 : 0;
+    v.p = plane + frame_level_off + (size_t)y * L.sum_pitch + (di ? x >> 1 : x);
+    return v;
+}
+__device__ __forceinline__ int rect_sum_g(const SumView &v, uint32_t dxw, uint32_t dyw) {
     // dxw / dyw hold the 4 corner coordinates of one rectangle, one byte each
-    const int o0 = (int)(dyw & 255u) * pitch + (int)(dxw & 255u);
-    const int o1 = (int)((dyw >> 8) & 255u) * pitch + (int)((dxw >> 8) & 255u);
-    const int o2 = (int)((dyw >> 16) & 255u) * pitch + (int)((dxw >> 16) & 255u);
-    const int o3 = (int)(dyw >> 24) * pitch + (int)(dxw >> 24);
-    return __ldg(base + o0) - __ldg(base + o1) - __ldg(base + o2) + __ldg(base + o3);
+    return v.at((int)(dyw & 255u), (int)(dxw & 255u)) - v.at((int)((dyw >> 8) & 255u), (int)((dxw >> 8) & 255u)) -
+           v.at((int)((dyw >> 16) & 255u), (int)((dxw >> 16) & 255u)) + v.at((int)(dyw >> 24), (int)(dxw >> 24));
 }
 
 // One tree of the generic cascade for one window: icvEvalHidHaarClassifier (tempcv.cpp:771-792) and
 // the stump fast paths (tempcv.cpp:872-930).  Returns the leaf value.
-__device__ __forceinline__ float deep_eval_tree(const DeepCascadeDev &D, int tree, const int32_t *__restrict__ sum,
-                                                const int32_t *__restrict__ til, int pitch, double sigma, bool dbl) {
+__device__ __forceinline__ float deep_eval_tree(const DeepCascadeDev &D, int tree, const SumView &sum, const SumView &til,
+                                                double sigma, bool dbl) {
     const int n0 = __ldg(D.tree_first_node + tree);
     int idx = 0;
     do {
@@ -1127,9 +1154,9 @@ __device__ __forceinline__ float deep_eval_tree(const DeepCascadeDev &D, int tre
         const uint4 c0 = __ldg(nd), c1 = __ldg(nd + 1), c2 = __ldg(nd + 2);
         const int flags = __ldg(reinterpret_cast<const int *>(nd + 3));
         // c0 = dx[0..11], dy[0..3]; c1 = dy[4..11], w0, w1; c2 = w2, thr, left, right
-        const int32_t *__restrict__ base = (flags & 1) ? til : sum;
-        const int r0 = rect_sum_g(base, pitch, c0.x, c0.w);
-        const int r1 = rect_sum_g(base, pitch, c0.y, c1.x);
+        const SumView &base = (flags & 1) ? til : sum;
+        const int r0 = rect_sum_g(base, c0.x, c0.w);
+        const int r1 = rect_sum_g(base, c0.y, c1.x);
         const float w0 = __uint_as_float(c1.z), w1 = __uint_as_float(c1.w);
         const float thr = __uint_as_float(c2.y);
         const double t = __dmul_rn((double)thr, sigma);
@@ -1139,7 +1166,7 @@ __device__ __forceinline__ float deep_eval_tree(const DeepCascadeDev &D, int tre
         } else {
             sv = __dadd_rn((double)__fmul_rn(__int2float_rn(r0), w0), (double)__fmul_rn(__int2float_rn(r1), w1));
             if ((flags >> 8) == 3) {
-                const int r2 = rect_sum_g(base, pitch, c0.z, c1.y);
+                const int r2 = rect_sum_g(base, c0.z, c1.y);
                 sv = __dadd_rn(sv, (double)__fmul_rn(__int2float_rn(r2), __uint_as_float(c2.x)));
             }
         }
@@ -1197,11 +1224,12 @@ __global__ void __launch_bounds__(128) k_cascade_mid(const __grid_constant__ Cas
             const PyrLevel L = a.levels[CL.pyr_level];
             const int pitch = L.sum_pitch;
             const size_t off = (size_t)frame * a.sum_frame_stride + L.sum_off + (size_t)y * pitch + x;
-            const int32_t *__restrict__ sum = a.sum + off;
-            const int32_t *__restrict__ til = a.tilted ? a.tilted + off : sum;
+            const size_t lvl = (size_t)frame * a.sum_frame_stride + L.sum_off;
+            const SumView sum = sum_view(a.sum, L, lvl, y, x, L.di != 0);
+            const SumView til = a.tilted ? sum_view(a.tilted, L, lvl, y, x, false) : sum;
             const int eq_w = D.win_w - 2, eq_h = D.win_h - 2;
             const int g0 = pitch + 1, g1 = g0 + eq_w, g2 = (1 + eq_h) * pitch + 1, g3 = g2 + eq_w;
-            const int s4 = __ldg(sum + g0) - __ldg(sum + g1) - __ldg(sum + g2) + __ldg(sum + g3);
+            const int s4 = sum.at(1, 1) - sum.at(1, 1 + eq_w) - sum.at(1 + eq_h, 1) + sum.at(1 + eq_h, 1 + eq_w);
             const ull q4 = sq_rect(a.sq, a.sq32 != 0, off, g0, g1, g2, g3);
             const double sigma = window_sigma(s4, q4, D.inv_area);
             for (; stage < D.mid_end; stage++) {
@@ -1209,7 +1237,7 @@ __global__ void __launch_bounds__(128) k_cascade_mid(const __grid_constant__ Cas
                 const bool dbl = st.flags & 1;
                 double S = 0.0;
                 for (int j = 0; j < st.ntrees; j++)
-                    S = __dadd_rn(S, (double)deep_eval_tree(D, st.first_tree + j, sum, til, pitch, sigma, dbl));
+                    S = __dadd_rn(S, (double)deep_eval_tree(D, st.first_tree + j, sum, til, sigma, dbl));
                 if (S < (double)st.thr) { alive = false; break; }
             }
         }
@@ -1264,12 +1292,13 @@ __global__ void __launch_bounds__(kDeepThreads) k_cascade_deep(const __grid_cons
         const PyrLevel L = a.levels[CL.pyr_level];
         const int pitch = L.sum_pitch;
         const size_t off = (size_t)frame * a.sum_frame_stride + L.sum_off + (size_t)y * pitch + x;
-        const int32_t *__restrict__ sum = a.sum + off;
-        const int32_t *__restrict__ til = a.tilted ? a.tilted + off : sum;
+        const size_t lvl = (size_t)frame * a.sum_frame_stride + L.sum_off;
+        const SumView sum = sum_view(a.sum, L, lvl, y, x, L.di != 0);
+        const SumView til = a.tilted ? sum_view(a.tilted, L, lvl, y, x, false) : sum;
 
         const int eq_w = D.win_w - 2, eq_h = D.win_h - 2;
         const int g0 = pitch + 1, g1 = g0 + eq_w, g2 = (1 + eq_h) * pitch + 1, g3 = g2 + eq_w;
-        const int s4 = __ldg(sum + g0) - __ldg(sum + g1) - __ldg(sum + g2) + __ldg(sum + g3);
+        const int s4 = sum.at(1, 1) - sum.at(1, 1 + eq_w) - sum.at(1 + eq_h, 1) + sum.at(1 + eq_h, 1 + eq_w);
         const ull q4 = sq_rect(a.sq, a.sq32 != 0, off, g0, g1, g2, g3);
         const double sigma = window_sigma(s4, q4, D.inv_area);
 
@@ -1282,7 +1311,7 @@ __global__ void __launch_bounds__(kDeepThreads) k_cascade_deep(const __grid_cons
             for (int j0 = 0; j0 < st.ntrees; j0 += 32) {
                 const int j = j0 + lane;
                 float av = 0.f;
-                if (j < st.ntrees) av = deep_eval_tree(D, st.first_tree + j, sum, til, pitch, sigma, dbl);
+                if (j < st.ntrees) av = deep_eval_tree(D, st.first_tree + j, sum, til, sigma, dbl);
                 if (order_free) {
                     part = __dadd_rn(part, (double)av);
                 } else {
@@ -1352,17 +1381,18 @@ __global__ void __launch_bounds__(256) k_roc_collect(const CascadeArgs a, RocIte
     const int x = ix * CL.ystep, y = iy * CL.ystep;
     const int pitch = L.sum_pitch;
     const size_t off = (size_t)frame * a.sum_frame_stride + L.sum_off + (size_t)y * pitch + x;
-    const int32_t *__restrict__ sum = a.sum + off;
-    const int32_t *__restrict__ til = a.tilted ? a.tilted + off : sum;
+    const size_t lvl = (size_t)frame * a.sum_frame_stride + L.sum_off;
+    const SumView sum = sum_view(a.sum, L, lvl, y, x, L.di != 0);
+    const SumView til = a.tilted ? sum_view(a.tilted, L, lvl, y, x, false) : sum;
     const int eq_w = D.win_w - 2, eq_h = D.win_h - 2;
     const int g0 = pitch + 1, g1 = g0 + eq_w, g2 = (1 + eq_h) * pitch + 1, g3 = g2 + eq_w;
-    const int s4 = __ldg(sum + g0) - __ldg(sum + g1) - __ldg(sum + g2) + __ldg(sum + g3);
+    const int s4 = sum.at(1, 1) - sum.at(1, 1 + eq_w) - sum.at(1 + eq_h, 1) + sum.at(1 + eq_h, 1 + eq_w);
     const ull q4 = sq_rect(a.sq, a.sq32 != 0, off, g0, g1, g2, g3);
     const double sigma = window_sigma(s4, q4, D.inv_area);
     const DeepStage st = D.stages[last];
     double S = 0.0;
     for (int j = 0; j < st.ntrees; j++)
-        S = __dadd_rn(S, (double)deep_eval_tree(D, st.first_tree + j, sum, til, pitch, sigma, st.flags & 1));
+        S = __dadd_rn(S, (double)deep_eval_tree(D, st.first_tree + j, sum, til, sigma, st.flags & 1));
     const ull slot = atomicAdd(counter, 1ull);
     if (slot >= cap) return;
     RocItem it;

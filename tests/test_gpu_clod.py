@@ -357,11 +357,14 @@ def test_generic_kernels_behind_the_tile_kernel(gpu_ctx, monkeypatch, hook, name
 
 @pytest.mark.parametrize("env", [{"CLFD_FORCE_EXACT": "1"}, {"CLFD_N_FIXED": "0"}, {"CLFD_N_FIXED": "5"}, {"CLFD_G1_MIN": "1"},
                                  {"CLFD_G1_MIN": "16"}, {"CLFD_TILE_H2": "32", "CLFD_NO_SMALL_TILES": "1"},
-                                 {"CLFD_POOL_MIN": "64", "CLFD_N_FIXED": "2"}, {"CLFD_POOL_MIN": "1", "CLFD_N_FIXED": "0"}])
+                                 {"CLFD_POOL_MIN": "64", "CLFD_N_FIXED": "2"}, {"CLFD_POOL_MIN": "1", "CLFD_N_FIXED": "0"},
+                                 {"CLFD_NO_DI": "1"}])
 def test_tile_kernel_variants_under_every_split(gpu_ctx, monkeypatch, env):
     """stage tree / multi-node / tilted variants of the tile kernel: all-FP64 evaluation, no fixed
     stages (the stage-tree walk starts from a dealt list when the linear prefix is all fixed:
-    N_FIXED=5), thread-per-window only, pooled stages (rows drawn from the whole tile, block barrier per stage)."""
+    N_FIXED=5), thread-per-window only, pooled stages (rows drawn from the whole tile, block barrier per stage),
+    the ystep-2 levels' integral in natural order (LDG + STS tile staging instead of the TMA copies from a
+    column-de-interleaved integral, which every other test runs with)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     _compare(gpu_ctx, ["frontalface_alt_tree", "frontalface_alt2", "eye_tree_eyeglasses", "fullbody", "frontalface_alt"],

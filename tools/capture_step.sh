@@ -8,6 +8,7 @@
 #   python profiles/summarize_ncu.py gpurun_out/<tag>_step.ncu-rep profiles/<tag>_step_full_batch8.csv
 #   python profiles/make_traffic.py 8 $(cat gpurun_out/<tag>_stamp.txt) profiles/<tag>_step_full_batch8.csv > profiles/traffic.json
 tag=$1; shift
+export CLFD_NO_OVERLAP=1   # serial order: under ncu the chunks of the overlapped schedule (2 frames each at batch 8) would be profiled as separate, tail-dominated launches
 B="python bench.py --batch 8 --steps 2 --warmup 3 --no-cpu-baseline --no-extra $*"
 $B > gpurun_out/${tag}_plain.json 2> gpurun_out/${tag}_plain.err || exit 1
 python -c "import bench; print(bench.kernel_source_stamp())" > gpurun_out/${tag}_stamp.txt

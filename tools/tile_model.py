@@ -24,9 +24,14 @@ TW = 64
 NWARP = 8
 
 
+def dense_half(win_w, ystep):
+    cols = ((TW - 1) * ystep + win_w + 1 + 3) & ~3
+    return 0 if ystep == 1 else (cols // 2 + 3) & ~3
+
+
 def dense_stride(win_w, ystep):
     cols = ((TW - 1) * ystep + win_w + 1 + 3) & ~3
-    s = cols if ystep == 1 else 2 * ((cols + 1) // 2)
+    s = cols if ystep == 1 else 2 * dense_half(win_w, ystep)
     s = (s + 3) & ~3
     while (ystep * s) % 32 != 8:
         s += 4
@@ -41,7 +46,7 @@ def stump_tables(cas, ystep):
     S = dense_stride(f.win_w, ystep)
 
     def off(y, x):
-        return y * S + x if ystep == 1 else y * S + (x & 1) * (S // 2) + (x >> 1)
+        return y * S + x if ystep == 1 else y * S + (x & 1) * dense_half(f.win_w, ystep) + (x >> 1)
     offs, loads6 = [], []
     for n in range(f.n_nodes):
         pts = []
