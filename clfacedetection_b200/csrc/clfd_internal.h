@@ -115,6 +115,8 @@ struct DenseParams {
     int n_fixed;        // leading stages run in fixed geometry (no compaction), <= n_stages
     int tail_stages;    // leading stages the tile kernel evaluates (upright stumps, linear): == total_stages
                         // when it finishes the cascade itself, otherwise survivors go to the deep kernel
+    int cut_stages;     // stages the tile kernel evaluates before it hands its survivors to the patch kernel (k_cascade_patch:
+                        // a warp per survivor, the window's own integral patch in shared memory); == tail_stages without one
     int g1_min;         // phase 2: more than this many windows in a warp -> thread per window (G = 1), max 16
     int tilted_tile;    // the cascade has tilted features: a second smem tile holds the tilted integral, right
                         // behind the first (tilted nodes' offsets already point into it)

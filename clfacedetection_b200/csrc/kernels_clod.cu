@@ -30,6 +30,7 @@
 // (products of a <2^24 integer and a 24-bit float are exact, so one FMA equals mul+add);
 // other stages multiply in FLOAT and accumulate in double (tempcv.cpp:782-786,907-910).
 // Tensor cores are not used: this is gather + compare work, not a contraction.
+#include <algorithm>
 #include <cstdint>
 
 #include "clfd_pack.h"
@@ -291,6 +292,9 @@ __device__ __forceinline__ StumpRegs stump_from_global(const uint4 *__restrict__
 // address known at link time, so the rare path costs the hot kernel no register -- and added to
 // CascadeArgs::counters[4], [5] by the last warp that leaves the CTA.
 __shared__ unsigned int s_dense_exact, s_dense_near, s_dense_done;
+#ifdef CLFD_TILE_TIMING   // diagnostic build (make EXTRA=-DCLFD_TILE_TIMING, tools/tile_timing.py): where a CTA's warp slots go
+__shared__ unsigned int s_dense_t_busy, s_dense_t_p1;   // sum over warps: cycles until the warp left the kernel / entered phase 2
+#endif
 
 // Exact evaluation of one stage for one window: the reference's arithmetic, stumps in tree order.
 template <bool NODES>
@@ -520,6 +524,10 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
     // ---- stage the integral tile ----
     for (int i = tid; i < kCtlInts; i += kDenseThreads) ctl[i] = 0;
     if (tid == 0) s_dense_exact = s_dense_near = s_dense_done = 0u;   // (a block barrier follows on either staging path)
+#ifdef CLFD_TILE_TIMING
+    const long long t_start = clock64();
+    if (tid == 0) s_dense_t_busy = s_dense_t_p1 = 0u;
+#endif
     const int n_tiles_smem = P.tilted_tile ? 2 : 1;
     const size_t tile2_off = ((size_t)((TILE_H - 1) * ystep + P.win_h + 1) * S * 4 + 127) & ~(size_t)127;
     const int32_t *__restrict__ gtil = a.tilted ? a.tilted + frame_off + (size_t)py0 * L.sum_pitch + px0 : gsum;
@@ -798,9 +806,12 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
     //      stump groups (w = smallest power of two >= windows, G = 32 / w): lane (slot, grp)
     //      evaluates stumps grp, grp + G, ... for window `slot`, and the G partial sums meet
     //      through xor-shuffles -- with one window left the warp does 32 stumps per pass. ----
+#ifdef CLFD_TILE_TIMING
+    if (lane == 0) atomicAdd(&s_dense_t_p1, (unsigned int)(clock64() - t_start));
+#endif
     int n = (n_alive - warp + kDenseWarps - 1) / kDenseWarps;
     bool dealt = true;   // first compacted stage: balanced rows (row r holds (n - r + R - 1) / R entries)
-    for (; s < P.tail_stages && n > 0; s++) {
+    for (; s < P.cut_stages && n > 0; s++) {
         const float sthr = P.stage[s].thr, seps = P.force_exact ? inf : P.stage[s].sum_eps;
         int n_next = 0;
         // append the survivors among this pass's windows at cur[n_next..]: always at or below the
@@ -973,7 +984,7 @@ __device__ __forceinline__ void cascade_tiles_body(const DenseParams &P, const C
     if (n == 0) return;
     ull qb = 0;
     if (s < P.total_stages) {
-        if (lane == 0) qb = atomicAdd(a.counters + 1, (ull)n);
+        if (lane == 0) qb = atomicAdd(a.qcount, (ull)n);
         qb = __shfl_sync(0xffffffffu, qb, 0);
     }
     const int Rn = (n + 31) >> 5;
@@ -1003,7 +1014,26 @@ template <int ROWSTEP_T, bool TREE, bool NODES, int TILE_H, bool COUNT, bool TRA
 __global__ void __launch_bounds__(kDenseThreads)   // (no min-blocks argument: "1" lets ptxas take 88 registers and costs a CTA per SM; "4" caps at 64 but was measured 2 % slower)
 k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ CascadeArgs a, const int tile0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+#ifdef CLFD_TILE_TIMING
+    const long long t_cta = clock64();
+#endif
     cascade_tiles_body<ROWSTEP_T, TREE, NODES, TILE_H, COUNT, TRACK>(P, a, tile0, smem_raw);
+#ifdef CLFD_TILE_TIMING
+    // counters[4] += sum over the CTA's warps of their busy cycles, [5] += 8 x the cycles of the CTA's last warp (the
+    // warp slots the CTA held), [6] += sum of the warps' cycles up to the hand-over (phase 1 + staging)
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        const unsigned int dt = (unsigned int)(clock64() - t_cta);
+        atomicAdd(&s_dense_t_busy, dt);
+        __threadfence_block();
+        if (atomicAdd(&s_dense_done, 1u) == kDenseWarps - 1) {
+            atomicAdd(a.counters + 4, (ull)s_dense_t_busy);
+            atomicAdd(a.counters + 5, (ull)dt * kDenseWarps);
+            atomicAdd(a.counters + 6, (ull)s_dense_t_p1);
+        }
+    }
+    return;
+#endif
     // every warp ends up here (the body's returns are warp uniform); the last one flushes the CTA's counters
     if (!COUNT) return;
     __syncwarp();
@@ -1015,6 +1045,157 @@ k_cascade_tiles(const __grid_constant__ DenseParams P, const __grid_constant__ C
             if (nn) atomicAdd(a.counters + 5, (ull)nn);
         }
     }
+}
+
+// ------------------------------------------------------------------------------------
+// patch kernel: the survivors the tile kernel handed over (DenseParams::cut_stages), one WARP per window.
+// The warp copies the window's own integral patch -- (win_h + 1) x (win_w + 1) values, 1.8 KB for a 20 x 20 window --
+// into shared memory and takes the window through its remaining stages with the 32 lanes on 32 different stumps
+// (the tile kernel's window x stump-group mode at G = 32): same FP32 filters, same exact fallback, same records, in
+// patch layout (P = PackedCascade::patch).  Warps are independent, so a window that goes deep holds one warp, not the
+// eight of a tile's CTA; the kernel runs beside the next chunk's tile kernel.
+// ------------------------------------------------------------------------------------
+constexpr int kPatchWarps = 8;
+__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+// words of one patch buffer: the patch, then the four corners of the squared integral sigma needs (8 words)
+__host__ __device__ inline int patch_buf_words(const DenseParams &P) { return (((P.win_h + 1) * P.tile_stride + 3) & ~3) + 8; }
+// Starts the asynchronous copy (LDGSTS) of one window's patch and squared-integral corners into a buffer: nothing
+// waits for it here, the warp goes on with the window it holds while the next one's data arrives.
+__device__ __forceinline__ void patch_issue(const DenseParams &P, const CascadeArgs &a, const QueueItem q, uint32_t buf, int lane) {
+    const int frame = q.key >> 16, cl = (q.key >> 8) & 255;
+    const int x = q.xy & 0xffff, y = q.xy >> 16;
+    const PyrLevel &L = a.levels[__ldg(&a.cas_levels[cl].pyr_level)];
+    const int pitch = __ldg(&L.sum_pitch);
+    const bool di = __ldg(&L.di) != 0;
+    const size_t lvl = (size_t)frame * a.sum_frame_stride + (size_t)__ldg(&L.sum_off);
+    const int32_t *__restrict__ src = a.sum + lvl + (size_t)y * pitch;
+    const int PS = P.tile_stride, prow = P.win_h + 1, pcol = P.win_w + 1, half = pitch >> 1;
+    int r = lane / pcol, cx = lane - r * pcol;
+    while (r < prow) {
+        const int X = x + cx;
+        cp_async4(buf + 4u * (uint32_t)(r * PS + cx), src + (size_t)r * pitch + (di ? (X & 1) * half + (X >> 1) : X));
+        cx += 32;
+        while (cx >= pcol) { cx -= pcol; r++; }
+    }
+    if (lane < 4) {   // corners of the variance rectangle in the squared integral (dense_sigma's g0..g3)
+        const int gy = P.eq_y + (lane >> 1) * P.eq_h, gx = P.eq_x + (lane & 1) * P.eq_w;
+        const size_t at = lvl + (size_t)(y + gy) * pitch + x + gx;
+        const uint32_t dst = buf + 4u * (uint32_t)(patch_buf_words(P) - 8 + 2 * lane);
+        if (a.sq32) cp_async4(dst, reinterpret_cast<const uint32_t *>(a.sq) + at);
+        else cp_async8(dst, a.sq + at);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <bool COUNT>
+__global__ void __launch_bounds__(32 * kPatchWarps) k_cascade_patch(const __grid_constant__ DenseParams P, const __grid_constant__ CascadeArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (COUNT) {
+        if (threadIdx.x == 0) s_dense_exact = s_dense_near = s_dense_done = 0u;
+        __syncthreads();
+    }
+    const int PS = P.tile_stride, bw = patch_buf_words(P);
+    const uint32_t buf0 = smem_u32(smem_raw) + 4u * (uint32_t)(warp * 2 * bw);   // two buffers per warp
+    const ull n_items = min(*a.qcount, a.queue_cap);
+    const ull stride = (ull)gridDim.x * kPatchWarps;
+    const float inf = __int_as_float(0x7f800000);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.counters + 1, n_items);   // reported: clfd_run_stats::deep_windows
+    ull item = (ull)blockIdx.x * kPatchWarps + warp;
+    QueueItem q = {0u, 0u};
+    if (item < n_items) { q = a.queue[item]; patch_issue(P, a, q, buf0, lane); }
+    int cur = 0;
+    for (; item < n_items; item += stride, cur ^= 1) {
+        // the next window's data start their way in before this one's are waited for
+        const bool more = item + stride < n_items;
+        QueueItem qn = q;
+        if (more) {
+            qn = a.queue[item + stride];
+            patch_issue(P, a, qn, buf0 + 4u * (uint32_t)((cur ^ 1) * bw), lane);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+        const int frame = q.key >> 16, cl = (q.key >> 8) & 255, stage0 = q.key & 255;
+        const int x = q.xy & 0xffff, y = q.xy >> 16;
+        const CasLevel CL = a.cas_levels[cl];
+        const PyrLevel L = a.levels[CL.pyr_level];
+        const int pitch = L.sum_pitch;
+        const size_t lvl = (size_t)frame * a.sum_frame_stride + L.sum_off;
+        DenseCtx c;
+        c.tile = buf0 + 4u * (uint32_t)(cur * bw); c.gsq = a.sq; c.sq_at = lvl + (size_t)y * pitch + x; c.sq32 = a.sq32 != 0;
+        c.codes = a.codes ? a.codes + (size_t)frame * a.windows_per_frame + CL.win_base + (size_t)(y / CL.ystep) * CL.nx + x / CL.ystep : nullptr;
+        c.sq_pitch = pitch; c.row_mul = 0; c.ystep = 1; c.S = PS; c.half = 0;
+        c.tx = 0; c.wy_tile = 0; c.nx = 0; c.code_mul = 1;   // window 0 of a "tile" that is the window itself
+        // sigma (tempcv.cpp:824-832) from the patch and the prefetched corners: the same value as dense_sigma()
+        float sgv;
+        {
+            const int ex = P.eq_x, ey = P.eq_y, ew = P.eq_w, eh = P.eq_h;
+            const int s4 = lds32(c.tile + dense_tile_off(c, ey, ex)) - lds32(c.tile + dense_tile_off(c, ey, ex + ew)) -
+                           lds32(c.tile + dense_tile_off(c, ey + eh, ex)) + lds32(c.tile + dense_tile_off(c, ey + eh, ex + ew));
+            const uint32_t qa = c.tile + 4u * (uint32_t)(bw - 8);
+            ull q4;
+            if (c.sq32) {
+                q4 = (ull)(uint32_t)(lds32(qa) - lds32(qa + 8) - lds32(qa + 16) + lds32(qa + 24));
+            } else {
+                ull v[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) v[i] = (ull)(uint32_t)lds32(qa + 8 * i) | ((ull)(uint32_t)lds32(qa + 8 * i + 4) << 32);
+                q4 = v[0] - v[1] - v[2] + v[3];
+            }
+            sgv = (float)window_sigma(s4, q4, P.inv_area);
+        }
+        const uint32_t base[1] = {c.tile};
+        const float sg[1] = {sgv};
+        int s = stage0;
+        bool alive = true;
+        for (; s < P.total_stages; s++) {
+            const float sthr = P.stage[s].thr, seps = P.force_exact ? inf : P.stage[s].sum_eps;
+            float Ssum[1] = {0.f}, Sabs[1] = {0.f};
+            bool near[1] = {false};
+            stage_filter<1, false, 0, false, false>(P, P.stage[s], false, lane, 32, base, sg, Ssum, near, Sabs);
+            float acc = Ssum[0];
+            unsigned nr = near[0];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, d));
+                nr |= __shfl_xor_sync(0xffffffffu, nr, d);
+            }
+            int pass = 0;
+            if (lane == 0) pass = stage_verdict<false, COUNT, false>(P, c, P.stage[s], sthr, seps, 0, acc, nr != 0, 0.f) ? 1 : 0;
+            pass = __shfl_sync(0xffffffffu, pass, 0);
+            if (!pass) { alive = false; break; }
+        }
+        if (lane == 0) {
+            if (alive) emit_rect(a, CL, frame, x, y);
+            if (c.codes) dense_write_code(c, 0, alive ? P.total_stages : s);
+        }
+        __syncwarp();   // every lane is done with this buffer before the window after the next overwrites it
+        q = qn;
+    }
+    if (!COUNT) return;
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();
+        if (atomicAdd(&s_dense_done, 1u) == kPatchWarps - 1) {
+            const unsigned int ne = s_dense_exact, nn = s_dense_near;
+            if (ne) atomicAdd(a.counters + 4, (ull)ne);
+            if (nn) atomicAdd(a.counters + 5, (ull)nn);
+        }
+    }
+}
+static cudaError_t launch_patch_tt(const DenseParams &P, const CascadeArgs &a, int n_sms, cudaStream_t stream) {
+    const size_t smem = (size_t)kPatchWarps * 2 * patch_buf_words(P) * 4;
+    static SmemLimitCache limit;
+    if (cudaError_t e = limit.ensure(k_cascade_patch<kTilesCount>, smem)) return e;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(smem, 1)));   // 64 registers: 4 CTAs
+    k_cascade_patch<kTilesCount><<<n_sms * per_sm, 32 * kPatchWarps, smem, stream>>>(P, a);
+    return cudaGetLastError();
 }
 
 // row steps of the stock window sizes (bytes between a thread's consecutive phase-1 windows)
@@ -1065,6 +1246,17 @@ static cudaError_t launch_tiles_t(const DenseParams &P, const CascadeArgs &a, in
 // The tile kernel is compiled twice, in two translation units that build in parallel: this file as it is (the
 // production instantiations) and through kernels_clod_count.cu (CLFD_TILES_COUNT_TU: the diagnostic instantiations
 // that count FP64 fallbacks / near-threshold stage sums; only the tile kernel and this launcher are compiled there).
+#ifdef CLFD_TILES_COUNT_TU
+cudaError_t launch_cascade_patch_count(const DenseParams &P, const CascadeArgs &a, int n_sms, cudaStream_t stream) {
+    return launch_patch_tt(P, a, n_sms, stream);
+}
+#else
+cudaError_t launch_cascade_patch_count(const DenseParams &P, const CascadeArgs &a, int n_sms, cudaStream_t stream);
+cudaError_t launch_cascade_patch(const DenseParams &P, const CascadeArgs &a, int n_sms, cudaStream_t stream) {
+    if (a.n_frames == 0) return cudaSuccess;
+    return a.count_exact ? launch_cascade_patch_count(P, a, n_sms, stream) : launch_patch_tt(P, a, n_sms, stream);
+}
+#endif
 #ifdef CLFD_TILES_COUNT_TU
 cudaError_t launch_cascade_tiles_count(const DenseParams &P, const CascadeArgs &a, int tile0, int n_tiles, cudaStream_t stream) {
 #else
