@@ -173,7 +173,7 @@ int PyramidPlan::build(int W_, int H_, const std::vector<std::pair<int, int>> &s
         }
         const int xspan = std::max(L.pyr_pitch, L.sum_pitch);
         for (int rb = 0; rb < L.nrb; rb++)
-            for (int c = 0; c * 512 < xspan; c++) h_resize.push_back(make_int4((int)li, rb, c, 0));
+            for (int c = 0; c * 128 < xspan; c++) h_resize.push_back(make_int4((int)li, rb, c, 0));   // one per warp
         for (int c = 0; c * 512 < L.sum_pitch; c++) h_colscan.push_back(make_int4((int)li, c, 0, 0));
         int cls = 0;
         while (cls < 6 && (32 << cls) * 8 < L.sum_pitch) cls++;
@@ -203,6 +203,7 @@ int PyramidPlan::build(int W_, int H_, const std::vector<std::pair<int, int>> &s
     if ((rc = d_levels.upload(levels, s))) return rc;
     if ((rc = xofs.upload(h_xofs, s)) || (rc = yofs.upload(h_yofs, s))) return rc;
     if ((rc = xalpha.upload(h_xalpha, s)) || (rc = ybeta.upload(h_ybeta, s))) return rc;
+    while (h_resize.size() % 4) h_resize.push_back(make_int4(-1, 0, 0, 0));   // whole CTAs of four warps
     if ((rc = resize_items.upload(h_resize, s)) || (rc = colscan_items.upload(h_colscan, s))) return rc;
     if (tilt && ((rc = tilt_tile_items.upload(h_tilt_tile, s)) || (rc = tilt_diag_items.upload(h_tilt_diag, s)) ||
                  (rc = tilt_tc_items.upload(h_tilt_tc, s))))

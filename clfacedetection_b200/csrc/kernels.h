@@ -25,7 +25,7 @@ struct PyramidArgs {
     const PyrLevel *levels;                     // device
     int n_levels;
     const int *xofs; const short2 *xalpha; const int *yofs; const short2 *ybeta;   // device tables
-    const int4 *resize_items; int n_resize_items;      // (level, row block, column chunk, -)
+    const int4 *resize_items; int n_resize_items;      // (level, row block, 128-column chunk, -), one per warp; padded with level -1 to a multiple of 4
     const int4 *colscan_items; int n_colscan_items;    // (level, column chunk, -, -)
     // integral row-block items grouped by CTA width class: class k uses 32<<k threads
     const int4 *integral_items[6]; int n_integral_items[6];

@@ -57,8 +57,8 @@ __device__ __forceinline__ void clif_bulk_g2s(void *dst_smem, const void *src_gm
 // ------------------------------------------------------------------------------------
 // K1: pyramid level pixels + per-row-block column sums
 // ------------------------------------------------------------------------------------
-constexpr int kResizeThreads = 128;  // x 4 px = 512 columns per CTA
-constexpr int kResizeCols = kResizeThreads * 4;
+constexpr int kResizeThreads = 128;  // four warps, each with a work item of its own: (level, row block, 128-column chunk)
+constexpr int kResizeCols = 32 * 4;  // columns per warp
 
 // vertical pass of 4 pixels (OpenCV VResizeLinear, 8u: ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2),
 // r0s / r1s = the horizontal passes of the two source rows, already shifted right by 4.  The result is at most 255
@@ -167,12 +167,17 @@ __device__ __forceinline__ void resize_rows_words(const PyramidArgs &a, const Py
     }
 }
 
-__global__ void __launch_bounds__(kResizeThreads) k_resize_colsum(const PyramidArgs a) {
-    const int4 it = a.resize_items[blockIdx.x];
+// (9 CTAs per SM: a cap of 56 registers costs 44 bytes of spills outside the row loop and buys 36 instead of 32 resident
+//  warps for a kernel that waits on its own loads: 0.435 -> 0.426 ms; 10 CTAs = 48 registers spill in the loop: 0.452)
+__global__ void __launch_bounds__(kResizeThreads, 9) k_resize_colsum(const PyramidArgs a) {
+    // items are per WARP (the warps of a CTA never meet): a level's last 512 columns do not leave idle warps behind in
+    // resident CTAs (14 % of the warp slots with 512-column items per CTA at 1080p, scale 1.2)
+    const int4 it = a.resize_items[blockIdx.x * (kResizeThreads / 32) + (threadIdx.x >> 5)];
+    if (it.x < 0) return;                                          // padding of the item list
     const PyrLevel L = a.levels[it.x];
     const int frame = blockIdx.y;
-    const int x0 = it.z * kResizeCols + threadIdx.x * 4;
-    const int xw = it.z * kResizeCols + (threadIdx.x & ~31) * 4;   // first column of this warp (128 columns)
+    const int x0 = it.z * kResizeCols + (threadIdx.x & 31) * 4;
+    const int xw = it.z * kResizeCols;                             // first column of this warp (128 columns)
     if (xw >= max(L.pyr_pitch, L.sum_pitch)) return;               // whole warps only: the word path shuffles
 
     const uint8_t *__restrict__ src = a.frames + (size_t)frame * a.frame_stride;
@@ -253,7 +258,7 @@ __global__ void __launch_bounds__(kResizeThreads) k_resize_colsum(const PyramidA
 
 cudaError_t launch_resize_colsum(const PyramidArgs &a, cudaStream_t stream) {
     if (a.n_resize_items == 0 || a.n_frames == 0) return cudaSuccess;
-    k_resize_colsum<<<dim3(a.n_resize_items, a.n_frames), kResizeThreads, 0, stream>>>(a);
+    k_resize_colsum<<<dim3(a.n_resize_items / (kResizeThreads / 32), a.n_frames), kResizeThreads, 0, stream>>>(a);   // (the list is padded to whole CTAs)
     return cudaGetLastError();
 }
 
