@@ -180,7 +180,7 @@ typedef struct clfd_level {
 typedef struct clfd_run_stats {
     int64_t windows;          /* windows evaluated (all frames, all cascades) */
     int64_t rects;            /* accepted windows */
-    int64_t deep_windows;     /* windows handed from the tile kernel to the deep kernel */
+    int64_t deep_windows;     /* windows handed from the tile kernel to the mid / deep kernels (or, CLFD_PATCH_CUT, the patch kernel) */
     int64_t kernel_launches;  /* kernels launched by the last enqueue */
     int64_t pyramid_pixels;   /* per frame */
     int64_t bytes_resize, bytes_integral, bytes_cascade; /* algorithmic bytes per frame; bytes_integral:
@@ -239,7 +239,9 @@ CLFD_API int clfd_detector_get_codes(clfd_detector *det, int cascade, int16_t *c
 /* Pyramid level `level` (index into the union pyramid = cascade 0's level list when there
  * is one cascade) of frame `frame` from the last batch, dense layouts; NULLs skipped.
  * A pyramid-mode detector keeps its squared integral modulo 2^32 (all it ever needs are windows'
- * sums of squares, which are below 2^32): sqsum then returns those low words, widened. */
+ * sums of squares, which are below 2^32): sqsum then returns those low words, widened.  It also stores the
+ * int32 integral of the levels whose windows are 2 pixels apart column-de-interleaved (the tile kernel's
+ * shared-memory order); `sum` is handed back in the natural order regardless. */
 CLFD_API int clfd_detector_read_level(clfd_detector *det, int cascade, int level, int frame,
                                       uint8_t *pyr, int32_t *sum, uint64_t *sqsum,
                                       int32_t *tilted);
